@@ -1,0 +1,336 @@
+// K2: HBM-bound normalisation kernels over NHWC / token-major bf16.
+//   aptp_groupnorm_stats : per-(sample, group) sum / sum-of-squares, one read of x
+//   aptp_groupnorm_apply : y = [silu]((g*x - g*mean) * rstd' * gamma + beta), one read + one write
+//   aptp_layernorm       : one warp per token row, values held in registers (exact two-pass)
+// Thread -> channel mapping is fixed (each thread owns one 16-byte vector of 8 channels and walks
+// down the pixels), so per-channel partial sums and the affine parameters live in registers and every
+// global access is a coalesced 16-byte vector.
+#include "common.cuh"
+#include "../../include/aptp_sm100.h"
+
+namespace aptp {
+
+constexpr int NORM_THREADS = 256;
+constexpr int MAX_SLOTS = 2;  // 8-channel vectors per thread: supports up to 256*2*8 = 4096 channels
+
+struct Src2 {
+  const __nv_bfloat16* x0;
+  const __nv_bfloat16* x1;
+  int c0, ld0, c1, ld1;
+};
+
+__device__ __forceinline__ uint4 load_vec(const Src2& s, long long pix, int c) {
+  // c is a multiple of 8; c0 is a multiple of 8 so a vector never straddles the two sources
+  if (c < s.c0) return __ldg(reinterpret_cast<const uint4*>(s.x0 + pix * s.ld0 + c));
+  return __ldg(reinterpret_cast<const uint4*>(s.x1 + pix * s.ld1 + (c - s.c0)));
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+// Merge a thread's 8 per-channel partial sums into per-group runs before touching shared memory.
+__device__ __forceinline__ void flush_runs(float* bins, const float* sum, const float* sq, int c_first, int ctot,
+                                           int gs) {
+  int g_run = -1;
+  float s_run = 0.f, q_run = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c_first + e;
+    if (c >= ctot) break;
+    const int g = c / gs;
+    if (g != g_run) {
+      if (g_run >= 0) {
+        atomicAdd(&bins[2 * g_run], s_run);
+        atomicAdd(&bins[2 * g_run + 1], q_run);
+      }
+      g_run = g;
+      s_run = 0.f;
+      q_run = 0.f;
+    }
+    s_run += sum[e];
+    q_run += sq[e];
+  }
+  if (g_run >= 0) {
+    atomicAdd(&bins[2 * g_run], s_run);
+    atomicAdd(&bins[2 * g_run + 1], q_run);
+  }
+}
+
+__global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(Src2 s, int hw, int gs, const int* __restrict__ sample_channels,
+                                                                float* __restrict__ stats, int stats_groups,
+                                                                int pix_per_cta) {
+  extern __shared__ float bins[];  // [2 * stats_groups]
+  const int b = blockIdx.y;
+  const int ctot = sample_channels ? sample_channels[b] : (s.c0 + s.c1);
+  if (ctot <= 0) return;
+  const int cv = (ctot + 7) / 8;
+  const int groups = (ctot + gs - 1) / gs;
+  for (int i = threadIdx.x; i < 2 * stats_groups; i += NORM_THREADS) bins[i] = 0.f;
+  __syncthreads();
+
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  float sum[MAX_SLOTS][8], sq[MAX_SLOTS][8];
+#pragma unroll
+  for (int q = 0; q < MAX_SLOTS; ++q)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum[q][e] = sq[q][e] = 0.f;
+
+  if (cv <= NORM_THREADS) {
+    const int rows_per_iter = NORM_THREADS / cv;
+    const int v = threadIdx.x % cv;
+    const int prow = threadIdx.x / cv;
+    if (prow < rows_per_iter) {
+      for (int p = p_begin + prow; p < p_end; p += rows_per_iter) {
+        float f[8];
+        unpack8(load_vec(s, (long long)b * hw + p, v * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sum[0][e] += f[e];
+          sq[0][e] += f[e] * f[e];
+        }
+      }
+      flush_runs(bins, sum[0], sq[0], v * 8, ctot, gs);
+    }
+  } else {
+    for (int p = p_begin; p < p_end; ++p) {
+#pragma unroll
+      for (int q = 0; q < MAX_SLOTS; ++q) {
+        const int v = threadIdx.x + q * NORM_THREADS;
+        if (v < cv) {
+          float f[8];
+          unpack8(load_vec(s, (long long)b * hw + p, v * 8), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            sum[q][e] += f[e];
+            sq[q][e] += f[e] * f[e];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MAX_SLOTS; ++q) {
+      const int v = threadIdx.x + q * NORM_THREADS;
+      if (v < cv) {
+        flush_runs(bins, sum[q], sq[q], v * 8, ctot, gs);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += NORM_THREADS)
+    atomicAdd(&stats[(size_t)b * stats_groups * 2 + i], bins[i]);
+}
+
+__global__ void __launch_bounds__(NORM_THREADS)
+    gn_apply_kernel(Src2 s, __nv_bfloat16* __restrict__ y, int ldy, int hw, int gs, float eps,
+                    const float* __restrict__ stats, int stats_groups, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int affine_ld, const int* __restrict__ sample_seg,
+                    const int* __restrict__ sample_channels, const float* __restrict__ gate, int gate_ld, int silu,
+                    int pix_per_cta) {
+  const int b = blockIdx.y;
+  const int ctot = sample_channels ? sample_channels[b] : (s.c0 + s.c1);
+  if (ctot <= 0) return;
+  int cstore = (ctot + 63) & ~63;
+  if (cstore > ldy) cstore = ldy;
+  const int cv = (cstore + 7) / 8;
+  const int seg = sample_seg ? sample_seg[b] : 0;
+  const float* gm = gamma + (size_t)seg * affine_ld;
+  const float* bt = beta + (size_t)seg * affine_ld;
+  const float inv_n = 1.f / ((float)hw * (float)gs);
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+
+  const int slots = (cv + NORM_THREADS - 1) / NORM_THREADS;
+  const int rows_per_iter = (cv <= NORM_THREADS) ? NORM_THREADS / cv : 1;
+  for (int q = 0; q < slots; ++q) {
+    const int v = (cv <= NORM_THREADS) ? (int)(threadIdx.x % cv) : (int)(threadIdx.x + q * NORM_THREADS);
+    const int prow = (cv <= NORM_THREADS) ? (int)(threadIdx.x / cv) : 0;
+    if (v >= cv || prow >= rows_per_iter) continue;
+    // per-channel scale/shift folded from (gate, mean, rstd, gamma, beta)
+    float a[8], sft[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = v * 8 + e;
+      if (c < ctot) {
+        const int g = c / gs;
+        const float su = stats[((size_t)b * stats_groups + g) * 2];
+        const float ss = stats[((size_t)b * stats_groups + g) * 2 + 1];
+        const float gt = gate ? gate[(size_t)b * gate_ld + g] : 1.f;
+        const float mean = su * inv_n;
+        float var = ss * inv_n - mean * mean;
+        var = fmaxf(var, 0.f);
+        // stats are of the un-gated tensor; GroupNorm(g*x) = (g*x - g*mean) * rsqrt(g^2 var + eps)
+        const float rstd = rsqrtf(gt * gt * var + eps);
+        const float w = gm[c] * rstd * gt;
+        a[e] = w;
+        sft[e] = bt[c] - mean * w;
+      } else {
+        a[e] = 0.f;
+        sft[e] = 0.f;
+      }
+    }
+    for (int p = p_begin + prow; p < p_end; p += rows_per_iter) {
+      const long long pix = (long long)b * hw + p;
+      float f[8];
+      if (v * 8 < ctot) {
+        unpack8(load_vec(s, pix, v * 8), f);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+      }
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = f[e] * a[e] + sft[e];
+        if (silu) t = silu_f(t);
+        o[e] = (v * 8 + e < ctot) ? t : 0.f;
+      }
+      uint4 out;
+      out.x = pack_bf16(o[0], o[1]);
+      out.y = pack_bf16(o[2], o[3]);
+      out.z = pack_bf16(o[4], o[5]);
+      out.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(y + pix * ldy + v * 8) = out;
+    }
+  }
+}
+
+// One warp per row; C <= 32*8*MAXV.
+constexpr int LN_MAXV = 8;
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                        __nv_bfloat16* __restrict__ y, int ldy, long long rows, int C,
+                                                        float eps, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta,
+                                                        const uint8_t* __restrict__ sample_active,
+                                                        int rows_per_sample) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  if (sample_active && !sample_active[row / rows_per_sample]) return;
+  const int cv = C / 8;
+  float f[LN_MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < LN_MAXV; ++q) {
+    const int v = lane + q * 32;
+    if (v < cv) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * ldx + v * 8)), f[q]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[q][e];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int q = 0; q < LN_MAXV; ++q) {
+    const int v = lane + q * 32;
+    if (v < cv) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[q][e] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+#pragma unroll
+  for (int q = 0; q < LN_MAXV; ++q) {
+    const int v = lane + q * 32;
+    if (v < cv) {
+      float o[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (f[q][e] - mean) * rstd * gg[e] + bb[e];
+      uint4 out;
+      out.x = pack_bf16(o[0], o[1]);
+      out.y = pack_bf16(o[2], o[3]);
+      out.z = pack_bf16(o[4], o[5]);
+      out.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(y + row * ldy + v * 8) = out;
+    }
+  }
+}
+
+static int pick_pix_per_cta(int hw, int batch) {
+  // aim for ~4 CTAs per SM across the grid, at least 16 pixels per CTA
+  int target_ctas = 4 * sm_count();
+  int chunks = (target_ctas + batch - 1) / batch;
+  if (chunks < 1) chunks = 1;
+  int ppc = (hw + chunks - 1) / chunks;
+  if (ppc < 16) ppc = 16;
+  if (ppc > hw) ppc = hw;
+  return ppc;
+}
+
+}  // namespace aptp
+
+using namespace aptp;
+
+static int check_src(const void* x0, int c0, int ld0, const void* x1, int c1, int ld1, const char* who) {
+  APTP_REQUIRE(x0 != nullptr && c0 > 0, "%s: x0 is null", who);
+  APTP_REQUIRE(c0 % 8 == 0 && ld0 % 8 == 0, "%s: c0/ld0 must be multiples of 8", who);
+  APTP_REQUIRE(c1 == 0 || (x1 != nullptr && c1 % 8 == 0 && ld1 % 8 == 0), "%s: bad second source", who);
+  APTP_REQUIRE(c0 + c1 <= NORM_THREADS * MAX_SLOTS * 8, "%s: too many channels (%d)", who, c0 + c1);
+  return APTP_OK;
+}
+
+extern "C" int aptp_groupnorm_stats(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
+                                    int32_t batch, int32_t hw, int32_t group_size, const int32_t* sample_channels,
+                                    float* stats, int32_t stats_groups, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = check_src(x0, c0, ld0, x1, c1, ld1, "aptp_groupnorm_stats");
+  if (rc) return rc;
+  APTP_REQUIRE(stats && group_size > 0 && batch > 0 && hw > 0, "aptp_groupnorm_stats: bad arguments");
+  APTP_REQUIRE((c0 + c1 + group_size - 1) / group_size <= stats_groups, "aptp_groupnorm_stats: stats_groups too small");
+  Src2 s{reinterpret_cast<const __nv_bfloat16*>(x0), reinterpret_cast<const __nv_bfloat16*>(x1), c0, ld0, c1, ld1};
+  const int ppc = pick_pix_per_cta(hw, batch);
+  dim3 grid((hw + ppc - 1) / ppc, batch);
+  gn_stats_kernel<<<grid, NORM_THREADS, 2 * stats_groups * sizeof(float), stream>>>(s, hw, group_size, sample_channels,
+                                                                                 stats, stats_groups, ppc);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
+                                    void* y, int32_t ldy, int32_t batch, int32_t hw, int32_t group_size, float eps,
+                                    const float* stats, int32_t stats_groups, const float* gamma, const float* beta,
+                                    int32_t affine_ld, const int32_t* sample_seg, const int32_t* sample_channels,
+                                    const float* gate, int32_t gate_ld, int32_t silu, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = check_src(x0, c0, ld0, x1, c1, ld1, "aptp_groupnorm_apply");
+  if (rc) return rc;
+  APTP_REQUIRE(y && stats && gamma && beta && ldy % 8 == 0, "aptp_groupnorm_apply: bad arguments");
+  Src2 s{reinterpret_cast<const __nv_bfloat16*>(x0), reinterpret_cast<const __nv_bfloat16*>(x1), c0, ld0, c1, ld1};
+  const int ppc = pick_pix_per_cta(hw, batch);
+  dim3 grid((hw + ppc - 1) / ppc, batch);
+  gn_apply_kernel<<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size, eps,
+                                                     stats, stats_groups, gamma, beta, affine_ld, sample_seg,
+                                                     sample_channels, gate, gate_ld, silu, ppc);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_layernorm(const void* x, int32_t ldx, void* y, int32_t ldy, int64_t rows, int32_t C, float eps,
+                              const float* gamma, const float* beta, const uint8_t* sample_active,
+                              int32_t rows_per_sample, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(x && y && gamma && beta, "aptp_layernorm: null pointer");
+  APTP_REQUIRE(C % 8 == 0 && C <= 32 * 8 * LN_MAXV && ldx % 8 == 0 && ldy % 8 == 0, "aptp_layernorm: unsupported C=%d", C);
+  APTP_REQUIRE(rows_per_sample > 0, "aptp_layernorm: rows_per_sample must be > 0");
+  if (rows == 0) return APTP_OK;
+  const long long blocks = (rows + 7) / 8;
+  layernorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                                                        reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, eps, gamma,
+                                                        beta, sample_active, rows_per_sample);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}

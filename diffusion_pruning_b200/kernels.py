@@ -1,0 +1,225 @@
+"""Host-side launchers for the sm_100a kernels: torch tensors in, C-ABI calls out (ctypes).
+
+PyTorch is only plumbing here (device memory, the current stream); every op below runs a
+hand-written kernel from libaptp_sm100.so and raises if the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (A_CONV3X3, A_CONV3X3_S2, A_LINEAR, EPI_GEGLU, EPI_SILU, OUT_BF16, OUT_F32, OUT_F32_NCHW, GemmArgs,
+                   check, load)
+
+BM = 128
+BK = 64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def check_abort() -> None:
+    rc = load().aptp_check_abort(_stream())
+    if rc != 0:
+        check(rc, "aptp_check_abort")
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM schedule (segments = expert buckets, tiles = 128-row x bn-column work items)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Segment:
+    row_begin: int
+    row_end: int
+    n_valid: int
+    k_chunks: int
+    w_row_off: int = 0
+    vec_off: int = 0
+    tab_off: int = 0
+    n_store: int = -1  # default: n_valid rounded up to 8
+    active: bool = True
+
+
+@dataclass
+class Schedule:
+    segs: torch.Tensor   # int32 [n_segs, 8] on device
+    tiles: torch.Tensor  # int32 [n_tiles, 4] on device
+    n_segs: int
+    n_tiles: int
+    bn: int
+    box: tuple           # (bw, bh, bb)
+    flops: float = 0.0   # 2 * kept MACs of this launch (for roofline accounting)
+
+
+def conv_box(W: int, H: int) -> tuple:
+    """Pick the 128-pixel output box (bw, bh, bb) that tiles a W x H image."""
+    for bw in (128, 64, 32, 16, 8, 4, 2, 1):
+        if bw <= W and W % bw == 0:
+            rest = BM // bw
+            for bh in (rest, rest // 2, rest // 4, rest // 8, rest // 16, rest // 32, rest // 64, rest // 128):
+                if bh >= 1 and bh <= H and H % bh == 0 and rest % bh == 0:
+                    return bw, bh, rest // bh
+    raise ValueError(f"no 128-pixel box tiles a {W}x{H} image")
+
+
+def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_LINEAR, Ho: int = 1, Wo: int = 1,
+                   geglu: bool = False, taps: Optional[int] = None) -> Schedule:
+    """Enumerate tiles (m outer, n inner so concurrently running CTAs share the A tile in L2)."""
+    segs = np.zeros((max(len(segments), 1), 8), dtype=np.int32)
+    tiles: List[tuple] = []
+    box = (BM, 1, 1) if mode == A_LINEAR else conv_box(Wo, Ho)
+    bw, bh, bb = box
+    hw = Ho * Wo
+    cols_per_tile = bn // 2 if geglu else bn
+    if taps is None:
+        taps = 1 if mode == A_LINEAR else 9
+    flops = 0.0
+    for si, s in enumerate(segments):
+        n_store = s.n_store if s.n_store >= 0 else (s.n_valid + 7) // 8 * 8
+        segs[si] = (s.row_begin, s.row_end, s.n_valid, n_store, s.k_chunks, s.w_row_off, s.vec_off, s.tab_off)
+        if not s.active or s.row_end <= s.row_begin or s.n_valid <= 0 or s.k_chunks <= 0:
+            continue
+        n_tiles_n = (max(s.n_valid, n_store) + cols_per_tile - 1) // cols_per_tile
+        rows = s.row_end - s.row_begin
+        flops += 2.0 * rows * s.n_valid * (2 if geglu else 1) * s.k_chunks * BK * taps
+        if mode == A_LINEAR:
+            m_bases = range(s.row_begin, s.row_end, BM)
+        else:
+            assert s.row_begin % hw == 0 and s.row_end % hw == 0, "conv segments must cover whole samples"
+            m_bases = [(img * Ho + oy) * Wo + ox
+                       for img in range(s.row_begin // hw, s.row_end // hw, bb)
+                       for oy in range(0, Ho, bh) for ox in range(0, Wo, bw)]
+        for m in m_bases:
+            for nt in range(n_tiles_n):
+                tiles.append((si, m, nt * bn, 0))
+    tl = np.asarray(tiles, dtype=np.int32).reshape(-1, 4) if tiles else np.zeros((0, 4), dtype=np.int32)
+    return Schedule(segs=torch.from_numpy(segs).to(device), tiles=torch.from_numpy(tl).to(device),
+                    n_segs=len(segments), n_tiles=len(tiles), bn=bn, box=box, flops=flops)
+
+
+def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Schedule, *, a_ld: int, a_k: int,
+                 a_rows: int, mode: int = A_LINEAR, batch: int = 1, H: int = 1, W: int = 1, k_tap_pitch: int = 0,
+                 out_ld: int, out_mode: int = OUT_BF16, bias: Optional[torch.Tensor] = None,
+                 rowvec: Optional[torch.Tensor] = None, rowvec_ld: int = 0, rows_per_sample: int = 1,
+                 residual: Optional[torch.Tensor] = None, res_ld: int = 0, gate: Optional[torch.Tensor] = None,
+                 gate_ld: int = 0, gate_group: int = 1, border_tab: Optional[torch.Tensor] = None, tab_ld: int = 0,
+                 flags: int = 0) -> None:
+    """out = epilogue(A @ W^T) through aptp_grouped_gemm_fwd. `a`, `w`, `out` may be views: only
+    data_ptr() and the explicit pitches are used."""
+    if sched.n_tiles == 0:
+        return
+    args = GemmArgs()
+    args.a, args.a_mode, args.a_ld, args.a_k, args.a_rows = a.data_ptr(), mode, a_ld, a_k, a_rows
+    args.batch, args.H, args.W = batch, H, W
+    args.w, args.w_rows, args.w_ld, args.k_tap_pitch = w.data_ptr(), w.shape[0], w.shape[1], k_tap_pitch
+    args.out, args.out_ld, args.out_mode = out.data_ptr(), out_ld, out_mode
+    args.bn = sched.bn
+    args.bw, args.bh, args.bb = sched.box
+    args.bias = _ptr(bias)
+    args.rowvec, args.rowvec_ld, args.rows_per_sample = _ptr(rowvec), rowvec_ld, rows_per_sample
+    args.residual, args.res_ld = _ptr(residual), res_ld
+    args.gate, args.gate_ld, args.gate_group = _ptr(gate), gate_ld, gate_group
+    args.border_tab, args.tab_ld = _ptr(border_tab), tab_ld
+    args.gn_stats, args.gn_group, args.gn_groups = None, 0, 0
+    args.flags = flags
+    args.segs, args.n_segs = sched.segs.data_ptr(), sched.n_segs
+    args.tiles, args.n_tiles = sched.tiles.data_ptr(), sched.n_tiles
+    check(load().aptp_grouped_gemm_fwd(C.byref(args), _stream()), "aptp_grouped_gemm_fwd")
+
+
+# --------------------------------------------------------------------------------------------
+# norms / elementwise
+# --------------------------------------------------------------------------------------------
+def groupnorm_stats(x0, c0, ld0, x1, c1, ld1, batch, hw, group_size, sample_channels, stats, stats_groups):
+    check(load().aptp_groupnorm_stats(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, batch, hw, group_size,
+                                      _ptr(sample_channels), _ptr(stats), stats_groups, _stream()),
+          "aptp_groupnorm_stats")
+
+
+def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps, stats, stats_groups, gamma, beta,
+                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu):
+    check(load().aptp_groupnorm_apply(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, _ptr(y), ldy, batch, hw, group_size,
+                                      float(eps), _ptr(stats), stats_groups, _ptr(gamma), _ptr(beta), affine_ld,
+                                      _ptr(sample_seg), _ptr(sample_channels), _ptr(gate), gate_ld, int(silu),
+                                      _stream()), "aptp_groupnorm_apply")
+
+
+def layernorm(x, ldx, y, ldy, rows, C_, eps, gamma, beta, sample_active=None, rows_per_sample=1):
+    check(load().aptp_layernorm(_ptr(x), ldx, _ptr(y), ldy, rows, C_, float(eps), _ptr(gamma), _ptr(beta),
+                                _ptr(sample_active), rows_per_sample, _stream()), "aptp_layernorm")
+
+
+def depth_lerp(x, ldx, y, ldy, out, ldo, rows, C_, d, rows_per_sample):
+    check(load().aptp_depth_lerp(_ptr(x), ldx, _ptr(y), ldy, _ptr(out), ldo, rows, C_, _ptr(d), rows_per_sample,
+                                 _stream()), "aptp_depth_lerp")
+
+
+def copy_rows(src, lds, dst, ldd, rows, C_, sample_mask=None, rows_per_sample=1):
+    check(load().aptp_copy_rows(_ptr(src), lds, _ptr(dst), ldd, rows, C_, _ptr(sample_mask), rows_per_sample,
+                                _stream()), "aptp_copy_rows")
+
+
+def upsample2x(src, dst, batch, H, W, C_):
+    check(load().aptp_upsample2x(_ptr(src), _ptr(dst), batch, H, W, C_, _stream()), "aptp_upsample2x")
+
+
+def im2col_input(sample_nchw, dst, batch, cin, H, W):
+    check(load().aptp_im2col_input(_ptr(sample_nchw), _ptr(dst), batch, cin, H, W, _stream()), "aptp_im2col_input")
+
+
+def timestep_embedding(t, dst, batch, dim):
+    check(load().aptp_timestep_embedding(_ptr(t), _ptr(dst), batch, dim, _stream()), "aptp_timestep_embedding")
+
+
+def cast_f32_bf16(src, dst, n):
+    check(load().aptp_cast_f32_bf16(_ptr(src), _ptr(dst), n, _stream()), "aptp_cast_f32_bf16")
+
+
+def silu_bf16(src, dst, n):
+    check(load().aptp_silu_bf16(_ptr(src), _ptr(dst), n, _stream()), "aptp_silu_bf16")
+
+
+def attention(q, ldq, k, ldk, v, ldv, out, ldo, batch, n_q, n_kv, sample_heads, max_heads, scale):
+    check(load().aptp_attention_fwd(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), ldo, batch, n_q, n_kv,
+                                    _ptr(sample_heads), max_heads, float(scale), _stream()), "aptp_attention_fwd")
+
+
+# --------------------------------------------------------------------------------------------
+# router
+# --------------------------------------------------------------------------------------------
+def gumbel_gate(z, u, out, batch, n_width, n_depth, width_starts, n_gates, depth_order, temperature, base,
+                non_zero_width):
+    check(load().aptp_gumbel_gate_fwd(_ptr(z), _ptr(u), _ptr(out), batch, n_width, n_depth, _ptr(width_starts),
+                                      n_gates, _ptr(depth_order), float(temperature), float(base),
+                                      int(non_zero_width), _stream()), "aptp_gumbel_gate_fwd")
+
+
+def arch_normalize(gates, out, batch, dim, col_depth, col_scale):
+    check(load().aptp_arch_normalize(_ptr(gates), _ptr(out), batch, dim, _ptr(col_depth), _ptr(col_scale), _stream()),
+          "aptp_arch_normalize")
+
+
+def route_cosine(a_norm, codes_norm, scores, indices, batch, dim, n_codes):
+    check(load().aptp_route_cosine(_ptr(a_norm), _ptr(codes_norm), _ptr(scores), _ptr(indices), batch, dim, n_codes,
+                                   _stream()), "aptp_route_cosine")
+
+
+def sinkhorn_phase(phase, Q, scores, partial, indices, batch_local, batch_global, n_codes, epsilon, first_iter):
+    check(load().aptp_sinkhorn_phase(phase, _ptr(Q), _ptr(scores), _ptr(partial), _ptr(indices), batch_local,
+                                     batch_global, n_codes, float(epsilon), int(first_iter), _stream()),
+          "aptp_sinkhorn_phase")
+
+
+def route_sinkhorn(scores, Q, partial, indices, batch, n_codes, epsilon, iterations):
+    check(load().aptp_route_sinkhorn(_ptr(scores), _ptr(Q), _ptr(partial), _ptr(indices), batch, n_codes,
+                                     float(epsilon), iterations, _stream()), "aptp_route_sinkhorn")

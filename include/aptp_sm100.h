@@ -1,0 +1,208 @@
+/*
+ * aptp_sm100.h -- C ABI of libaptp_sm100.so: the B200 (sm_100a) kernels behind the APTP gated
+ * SD-2.1 U-Net denoising step and its router (reference: rezashkv/diffusion_pruning).
+ *
+ * Conventions
+ *   - every entry point returns 0 (APTP_OK) or a negative status; aptp_last_error() gives the text;
+ *   - no allocation, no implicit synchronisation: all pointers are device pointers owned by the caller
+ *     (PyTorch), work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - activations are NHWC / token-major bf16: a [B,C,H,W] reference tensor is stored as rows
+ *     (b*H*W + y*W + x) of C contiguous channels, so conv-as-GEMM, Linear and the [B,HW,C] token
+ *     view used by the reference (pdm/models/unet/blocks.py:1235, :1306) are the same memory;
+ *   - samples are bucketed by architecture code ("expert"); a *segment* describes one bucket of a
+ *     layer: its row range, kept output columns, kept K chunks and where its compacted weights live.
+ *
+ * Each function cites the reference code it replaces (paths relative to the reference repo).
+ */
+#ifndef APTP_SM100_H
+#define APTP_SM100_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APTP_ABI_VERSION 1
+
+/* library / diagnostics */
+int aptp_version(void);
+const char* aptp_last_error(void);
+/* returns 1 if a pipelined kernel hit an mbarrier timeout since the last call (and clears it); syncs `stream`. */
+int aptp_check_abort(void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  grouped, expert-bucketed GEMM / implicit-GEMM conv on tcgen05 + TMEM fed by TMA.
+ *     out[rows, n] = epilogue( sum_k A[rows, k] * W[w_row_off + n, k] )
+ * replaces: F.conv2d / F.linear call sites of ResnetBlock2DWidth(Depth)Gated.forward
+ *   (pdm/models/unet/blocks.py:331,:337,:362,:366,:537,:568,:572), GatedAttention projections
+ *   (blocks.py:228-240,:266-268), GEGLUGated.forward (blocks.py:41-50), FeedForward.net[2],
+ *   Transformer2DModel.proj_in/out (blocks.py:1239-1243,:1301-1305), conv_in/conv_out and the
+ *   down/up-sampler convs (pdm/models/unet/unet_2d_conditional.py:1614,:1721), and -- through the
+ *   compacted per-expert weight blocks -- the prune() family (blocks.py:52-67,:121-129,:153-187,
+ *   :424-465).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct aptp_gemm_seg {
+  int32_t row_begin; /* first output row of this expert bucket                                   */
+  int32_t row_end;   /* one past its last output row (rows >= row_end are never written)          */
+  int32_t n_valid;   /* kept output columns (GEGLU: kept *output* columns, i.e. h columns)        */
+  int32_t n_store;   /* columns [n_valid, n_store) are written as zeros (K padding for consumer)  */
+  int32_t k_chunks;  /* 64-wide K chunks per tap that carry kept input channels                   */
+  int32_t w_row_off; /* first row of this bucket's block in the packed weight matrix              */
+  int32_t vec_off;   /* offset of this bucket's bias (floats) in `bias`                           */
+  int32_t tab_off;   /* offset of this bucket's 9 x n border table (floats) in `border_tab`       */
+} aptp_gemm_seg;
+
+typedef struct aptp_gemm_tile {
+  int32_t seg;    /* index into segs                                                              */
+  int32_t m_base; /* linear: first row; conv: linear index of the top-left output pixel of the box */
+  int32_t n0;     /* first packed weight row / accumulator column block of this tile              */
+  int32_t pad;
+} aptp_gemm_tile;
+
+enum { APTP_A_LINEAR = 0, APTP_A_CONV3X3 = 1, APTP_A_CONV3X3_S2 = 2 };
+enum { APTP_OUT_BF16 = 0, APTP_OUT_F32 = 1, APTP_OUT_F32_NCHW = 2 };
+enum {
+  APTP_EPI_GEGLU = 1,      /* tile columns are [bn/2 h | bn/2 g]; out = h * gelu_erf(g)            */
+  APTP_EPI_SILU = 2,       /* out = silu(out) (time-embedding MLP)                                 */
+  APTP_EPI_GN_STATS = 4    /* accumulate per-(sample,group) sum / sumsq of the stored values       */
+};
+
+typedef struct aptp_gemm_args {
+  /* A operand: bf16 activations */
+  const void* a;
+  int32_t a_mode;  /* APTP_A_*                                                                     */
+  int32_t a_ld;    /* elements between consecutive rows / pixels                                   */
+  int32_t a_k;     /* addressable channels per pixel (tensor-map extent; reads beyond are zero)    */
+  int64_t a_rows;  /* linear: rows; conv: batch*H*W input pixels                                   */
+  int32_t batch, H, W; /* conv: INPUT spatial size                                                 */
+  /* B operand: packed bf16 weights [w_rows, w_ld], K-major; conv K index = tap*k_tap_pitch + c    */
+  const void* w;
+  int64_t w_rows;
+  int32_t w_ld;
+  int32_t k_tap_pitch;
+  /* output */
+  void* out;
+  int32_t out_ld;
+  int32_t out_mode; /* APTP_OUT_*                                                                  */
+  /* tile shape: M tile is 128 rows = box bw x bh x bb output pixels (linear: 128 x 1 x 1)         */
+  int32_t bn;       /* accumulator columns per tile: multiple of 32, 32..256                       */
+  int32_t bw, bh, bb;
+  /* epilogue operands (any may be NULL) */
+  const float* bias;      /* [.. vec_off + col]                                                    */
+  const float* rowvec;    /* per-sample vector: rowvec[sample*rowvec_ld + col] (time embedding)    */
+  int32_t rowvec_ld;
+  int32_t rows_per_sample;
+  const void* residual;   /* bf16 [rows, res_ld], added after everything else                      */
+  int32_t res_ld;
+  const float* gate;      /* soft gates: out *= gate[sample*gate_ld + col/gate_group]              */
+  int32_t gate_ld, gate_group;
+  const float* border_tab; /* conv2 of a width-compacted ResNet: contribution of the pruned input
+                              channels, which the *gated* reference still feeds as silu(beta_c)
+                              (SURVEY Appendix D-1); [tab_off + (ycls*3+xcls)*tab_ld + col]        */
+  int32_t tab_ld;
+  float* gn_stats;        /* APTP_EPI_GN_STATS: [sample][group][2] fp32 (sum, sumsq), atomics      */
+  int32_t gn_group;       /* channels per group                                                   */
+  int32_t gn_groups;      /* groups per sample in gn_stats                                        */
+  int32_t flags;          /* APTP_EPI_*                                                            */
+  /* schedule (device memory) */
+  const aptp_gemm_seg* segs;
+  int32_t n_segs;
+  const aptp_gemm_tile* tiles;
+  int32_t n_tiles;
+} aptp_gemm_args;
+
+int aptp_grouped_gemm_fwd(const aptp_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  HBM-bound fused normalisation / gate / residual kernels.
+ * ---------------------------------------------------------------------------------------------- */
+/* GroupNorm statistics over NHWC bf16 (two sources = fused torch.cat of an up-block input).
+ * replaces: the reduction half of nn.GroupNorm at blocks.py:299,:353,:505,:559, Transformer2DModel.norm
+ * (blocks.py:1227) and conv_norm_out (unet_2d_conditional.py:1719).
+ * stats[sample][group] = (sum, sumsq) accumulated in fp32 (buffer must be zeroed by the caller). */
+int aptp_groupnorm_stats(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
+                         int32_t batch, int32_t hw, int32_t group_size, const int32_t* sample_channels,
+                         float* stats, int32_t stats_groups, void* stream);
+/* y = [silu]( (x*g - mean)*rstd*gamma + beta ) written bf16 with row pitch ldy; channels in
+ * [c_valid, c_store) are written as zeros. `sample_seg[b]` selects the per-expert compacted
+ * gamma/beta block (offset sample_seg[b]*affine_ld) and c_valid (sample_channels[b]).
+ * `gate` (optional, fp32 [batch, gate_ld]) is the soft width gate applied *before* the norm
+ * (blocks.py:345-353): with hard gates the engine compacts instead. */
+int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
+                         void* y, int32_t ldy, int32_t batch, int32_t hw, int32_t group_size, float eps,
+                         const float* stats, int32_t stats_groups, const float* gamma, const float* beta,
+                         int32_t affine_ld, const int32_t* sample_seg, const int32_t* sample_channels,
+                         const float* gate, int32_t gate_ld, int32_t silu, void* stream);
+/* LayerNorm over the channel dim of [rows, C] bf16 (eps 1e-5, affine); replaces
+ * BasicTransformerBlock.norm1/2/3 (blocks.py:782,:808-810,:821). row_active (optional, per sample)
+ * skips depth-dropped samples. */
+int aptp_layernorm(const void* x, int32_t ldx, void* y, int32_t ldy, int64_t rows, int32_t C, float eps,
+                   const float* gamma, const float* beta, const uint8_t* sample_active,
+                   int32_t rows_per_sample, void* stream);
+/* out = (1-d)*x + d*y per sample (DepthGate.forward, pdm/models/unet/gates.py:36-42), bf16 rows. */
+int aptp_depth_lerp(const void* x, int32_t ldx, const void* y, int32_t ldy, void* out, int32_t ldo,
+                    int64_t rows, int32_t C, const float* d, int32_t rows_per_sample, void* stream);
+/* dst[rows, :C] = src[rows, :C] for the samples with sample_mask[b] != 0 (NULL = all): identity path
+ * of depth-dropped blocks (blocks.py:497-498,:1190-1194) and torch.cat of up-block skips. */
+int aptp_copy_rows(const void* src, int32_t lds, void* dst, int32_t ldd, int64_t rows, int32_t C,
+                   const uint8_t* sample_mask, int32_t rows_per_sample, void* stream);
+/* nearest x2 upsample NHWC (diffusers Upsample2D: F.interpolate(scale_factor=2, mode="nearest")). */
+int aptp_upsample2x(const void* src, void* dst, int32_t batch, int32_t H, int32_t W, int32_t C, void* stream);
+/* NCHW fp32 sample -> im2col rows [B*H*W, 64] bf16 (K = 9*Cin zero-padded to 64) for conv_in. */
+int aptp_im2col_input(const float* sample_nchw, void* dst, int32_t batch, int32_t Cin, int32_t H, int32_t W,
+                      void* stream);
+/* Timesteps(320, flip_sin_to_cos=True, freq_shift=0): emb[b] = [cos(t f_k), sin(t f_k)] as bf16. */
+int aptp_timestep_embedding(const float* t, void* dst, int32_t batch, int32_t dim, void* stream);
+/* fp32 -> bf16 cast (text embeddings), plain elementwise silu over bf16. */
+int aptp_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int aptp_silu_bf16(const void* src, void* dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  flash-style attention on tcgen05 with per-sample kept-head lists.
+ * replaces: HeadGatedAttnProcessor2.__call__ head gating + F.scaled_dot_product_attention
+ * (blocks.py:245-262). q/k/v are bf16 [tokens, ld] with head h at columns [h*64, h*64+64) of the
+ * *compacted* projection; sample_heads[b] = kept heads of sample b (its bucket); samples with 0 heads
+ * are skipped. out has the same compacted layout.
+ * ---------------------------------------------------------------------------------------------- */
+int aptp_attention_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                       void* out, int32_t ldo, int32_t batch, int32_t n_q, int32_t n_kv,
+                       const int32_t* sample_heads, int32_t max_heads, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  router: fused Gumbel-sigmoid gate, width/depth normalisation, cosine scores, Sinkhorn, argmax.
+ * ---------------------------------------------------------------------------------------------- */
+/* gumbel_sigmoid_trick (pdm/models/vq/quantizer.py:196-215 + pdm/utils/estimation_utils.py:5-64):
+ * width slices sigma((z + G + base)/T) with the all-zero fix-up (estimation_utils.py:23-31), depth
+ * columns through softmax/cumsum/flip/logit (estimation_utils.py:49-64) scattered by depth_order.
+ * `u` are the uniforms the reference draws on the CPU (depth [B,n_depth] first, then the width
+ * slices in order), laid out [B, n_width + n_depth] in arch-vector column order. */
+int aptp_gumbel_gate_fwd(const float* z, const float* u, float* out, int32_t batch, int32_t n_width,
+                         int32_t n_depth, const int32_t* width_starts, int32_t n_width_gates,
+                         const int32_t* depth_order, float temperature, float base, int32_t non_zero_width,
+                         void* stream);
+/* width_depth_normalize (quantizer.py:233-250) + L2 normalise (quantizer.py:266-267,:326-327):
+ * out[b,:] = v/||v||, v = (width slices of depth-gated blocks * their depth gate, hard_concrete
+ * elsewhere) * sqrt(template) [* macs_template]. col_depth[c] = arch column of the depth gate that
+ * multiplies column c, or -1. */
+int aptp_arch_normalize(const float* gates, float* out, int32_t batch, int32_t dim, const int32_t* col_depth,
+                        const float* col_scale, void* stream);
+/* scores = A @ C^T  ([B,dim] x [K,dim]) in fp32 and argmax per row (quantizer.py:264-271). */
+int aptp_route_cosine(const float* a_norm, const float* codes_norm, float* scores, int64_t* indices,
+                      int32_t batch, int32_t dim, int32_t n_codes, void* stream);
+/* Sinkhorn OT assignment (quantizer.py:274-340). Phase API so that the 4 marginal all-reduces of
+ * distributed_sinkhorn (quantizer.py:285,:291) run as NCCL calls on the same stream between phases:
+ *   phase 0: Q = exp(S/eps); partial[0] = sum(Q)                       -> all-reduce partial[0:1]
+ *   phase 1 (x iters): Q /= total (first) ; row sums -> partial[0:K]   -> all-reduce partial[0:K]
+ *   phase 2: Q /= rowsum*K ; column-normalise ; /B
+ *   phase 3: argmax per sample.
+ * aptp_route_sinkhorn runs all phases for the single-process case. Marginals accumulate in fp64. */
+int aptp_sinkhorn_phase(int32_t phase, float* Q, const float* scores, double* partial, int64_t* indices,
+                        int32_t batch_local, int32_t batch_global, int32_t n_codes, float epsilon,
+                        int32_t first_iter, void* stream);
+int aptp_route_sinkhorn(const float* scores, float* Q, double* partial, int64_t* indices, int32_t batch,
+                        int32_t n_codes, float epsilon, int32_t iterations, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APTP_SM100_H */
