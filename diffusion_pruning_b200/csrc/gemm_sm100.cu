@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
         }
         if (!valid) continue;
         if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.res_ld + col0);
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.res_ld + seg.out_col_off + col0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (col0 + q * 8 < seg.n_valid) {  // n_valid is a multiple of 8 whenever a residual is used
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           if (col0 + j >= seg.n_valid) v[j] = 0.f;
 
         if (p.out_mode == APTP_OUT_BF16) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.out_ld + col0;
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.out_ld + seg.out_col_off + col0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (col0 + q * 8 < seg.n_store) {  // n_store is a multiple of 8
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
             }
           }
         } else if (p.out_mode == APTP_OUT_F32) {
-          float* op = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_ld + col0;
+          float* op = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_ld + seg.out_col_off + col0;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             if (col0 + q * 4 < seg.n_store) {  // n_store multiple of 4

@@ -47,12 +47,13 @@ class Segment:
     vec_off: int = 0
     tab_off: int = 0
     n_store: int = -1  # default: n_valid rounded up to 8
+    out_col_off: int = 0
     active: bool = True
 
 
 @dataclass
 class Schedule:
-    segs: torch.Tensor   # int32 [n_segs, 8] on device
+    segs: torch.Tensor   # int32 [n_segs, 12] on device
     tiles: torch.Tensor  # int32 [n_tiles, 4] on device
     n_segs: int
     n_tiles: int
@@ -75,7 +76,7 @@ def conv_box(W: int, H: int) -> tuple:
 def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_LINEAR, Ho: int = 1, Wo: int = 1,
                    geglu: bool = False, taps: Optional[int] = None) -> Schedule:
     """Enumerate tiles (m outer, n inner so concurrently running CTAs share the A tile in L2)."""
-    segs = np.zeros((max(len(segments), 1), 8), dtype=np.int32)
+    segs = np.zeros((max(len(segments), 1), 12), dtype=np.int32)
     tiles: List[tuple] = []
     box = (BM, 1, 1) if mode == A_LINEAR else conv_box(Wo, Ho)
     bw, bh, bb = box
@@ -86,7 +87,8 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
     flops = 0.0
     for si, s in enumerate(segments):
         n_store = s.n_store if s.n_store >= 0 else (s.n_valid + 7) // 8 * 8
-        segs[si] = (s.row_begin, s.row_end, s.n_valid, n_store, s.k_chunks, s.w_row_off, s.vec_off, s.tab_off)
+        segs[si, :9] = (s.row_begin, s.row_end, s.n_valid, n_store, s.k_chunks, s.w_row_off, s.vec_off, s.tab_off,
+                        s.out_col_off)
         if not s.active or s.row_end <= s.row_begin or s.n_valid <= 0 or s.k_chunks <= 0:
             continue
         n_tiles_n = (max(s.n_valid, n_store) + cols_per_tile - 1) // cols_per_tile

@@ -1,0 +1,1117 @@
+"""Drop-in `UNet2DConditionModelGated` whose forward runs on the hand-written sm_100a kernels.
+
+Mirrors the reference interface (pdm/models/unet/unet_2d_conditional.py:628): same constructor
+vocabulary for the shipped SD-2.1 layout, same module tree / state-dict keys as the diffusers SD-2.1
+U-Net (gates add no parameters, pdm/models/unet/gates.py:13), same `get_structure` /
+`set_structure` / `calc_macs` / `freeze` / `forward(sample, timestep, encoder_hidden_states)`.
+
+Execution model (B200-first, not a translation of the module-by-module eager reference):
+  * activations live in NHWC / token-major bf16, so 3x3 conv (implicit GEMM over shifted TMA boxes),
+    1x1 conv, Linear and the transformer's [B, HW, C] view share one layout -- no permute copies;
+  * hard (0/1) gates: samples are bucketed by architecture code and every prunable layer runs a
+    grouped tcgen05 GEMM over per-expert *compacted* weights -- pruned channels / heads / FF groups and
+    depth-dropped blocks are skipped, not multiplied by zero;
+  * soft gates (training-mode codes): dense weights, gate multipliers fused into the GroupNorm pass
+    and the GEMM epilogues, depth gate as one lerp kernel;
+  * the nn.Module tree below only owns parameters and fires forward hooks; arithmetic happens in
+    libaptp_sm100.so through diffusion_pruning_b200.kernels (no eager / CPU fallback exists).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from . import plan as P
+from ._lib import A_CONV3X3, A_CONV3X3_S2, A_LINEAR, EPI_GEGLU, EPI_SILU, OUT_BF16, OUT_F32, OUT_F32_NCHW
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class UNet2DConditionOutput:
+    sample: torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers (diffusers SD-2.1 names; their forward() is never used for arithmetic)
+# --------------------------------------------------------------------------------------------------
+class _Gate:
+    """VirtualGate state (gates.py:9-24): a plain tensor attribute, not a parameter."""
+
+    def __init__(self, width: int):
+        self.width = width
+        self.gate_f = torch.ones(1, width)
+
+    def set_structure_value(self, value: torch.Tensor) -> None:
+        self.gate_f = value
+
+
+class ResnetBlock2DWidthGated(nn.Module):
+    """Parameters of blocks.py:283 / :468 (depth_gated=True)."""
+
+    def __init__(self, cin, cout, temb, groups, eps, depth_gated=False, skip_dim=None):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+        self.cin, self.cout, self.groups, self.eps = cin, cout, groups, eps
+        self.gate = _Gate(groups)
+        self.depth_gate = _Gate(1) if depth_gated else None
+        self.skip_connection_dim = skip_dim
+        self.uid = ""
+
+    def gate_widths(self):
+        return [self.groups]
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, heads, ctx_dim=None):
+        super().__init__()
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_v = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+        self.heads, self.dim, self.ctx_dim = heads, dim, ctx_dim
+        self.gate = _Gate(heads)
+
+
+class _GEGLU(nn.Module):
+    def __init__(self, dim, inner, gate_width):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+        self.gate = _Gate(gate_width)
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim, gate_width):
+        super().__init__()
+        self.net = nn.ModuleList([_GEGLU(dim, dim * 4, gate_width), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+
+class _BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, ctx_dim, gate_width):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = _Attention(dim, heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = _Attention(dim, heads, ctx_dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = _FeedForward(dim, gate_width)
+
+
+class Transformer2DModelWidthGated(nn.Module):
+    """Parameters of blocks.py:941 / :1070 (depth_gated=True)."""
+
+    def __init__(self, dim, heads, ctx_dim, groups, gate_width, depth_gated=False):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
+        self.proj_in = nn.Linear(dim, dim)
+        self.transformer_blocks = nn.ModuleList([_BasicTransformerBlock(dim, heads, ctx_dim, gate_width)])
+        self.proj_out = nn.Linear(dim, dim)
+        self.dim, self.heads, self.ctx_dim, self.groups, self.gate_width = dim, heads, ctx_dim, groups, gate_width
+        self.depth_gate = _Gate(1) if depth_gated else None
+        self.uid = ""
+
+    def gate_widths(self):
+        return [self.heads, self.heads, self.gate_width]
+
+
+class _Sampler(nn.Module):
+    def __init__(self, c, stride):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=stride, padding=1)
+
+
+class _Block(nn.Module):
+    """Down / mid / up container. forward() runs the block on the engine so that forward hooks
+    registered by the trainer (pdm/training/trainer.py:496-511) fire with the block output."""
+    kind = "down"
+
+    def forward(self, eng, x, *rest):  # pragma: no cover - dispatched in subclasses
+        raise NotImplementedError
+
+
+class DownBlock2DHalfGated(_Block):
+    kind = "down"
+
+    def __init__(self, cfg, cin, cout, heads, has_attn, add_down):
+        super().__init__()
+        n = cfg["layers_per_block"]
+        self.resnets = nn.ModuleList([
+            ResnetBlock2DWidthGated(cin if i == 0 else cout, cout, cfg["temb"], cfg["groups"], cfg["eps"],
+                                    depth_gated=(i == n - 1)) for i in range(n)])
+        self.attentions = nn.ModuleList([
+            Transformer2DModelWidthGated(cout, heads, cfg["ctx_dim"], cfg["groups"], cfg["ff_gate_width"],
+                                         depth_gated=(i == n - 1)) for i in range(n)]) if has_attn else None
+        self.downsamplers = nn.ModuleList([_Sampler(cout, 2)]) if add_down else None
+        self.has_cross_attention = has_attn
+
+    def forward(self, eng, x):
+        outs = []
+        for i, r in enumerate(self.resnets):
+            x = eng.resnet(r, x)
+            if self.attentions is not None:
+                x = eng.transformer(self.attentions[i], x)
+            outs.append(x)
+        if self.downsamplers is not None:
+            x = eng.downsample(self.downsamplers[0], x)
+            outs.append(x)
+        return x, tuple(outs)
+
+
+class MidBlock2DCrossAttnWidthGated(_Block):
+    kind = "mid"
+
+    def __init__(self, cfg, c, heads):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2DWidthGated(c, c, cfg["temb"], cfg["groups"], cfg["eps"]) for _ in range(2)])
+        self.attentions = nn.ModuleList([Transformer2DModelWidthGated(c, heads, cfg["ctx_dim"], cfg["groups"], cfg["ff_gate_width"])])
+        self.has_cross_attention = True
+
+    def forward(self, eng, x):
+        x = eng.resnet(self.resnets[0], x)
+        x = eng.transformer(self.attentions[0], x)
+        x = eng.resnet(self.resnets[1], x)
+        return x
+
+
+class UpBlock2DHalfGated(_Block):
+    kind = "up"
+
+    def __init__(self, cfg, cin, cout, prev, heads, has_attn, add_up):
+        super().__init__()
+        n = cfg["layers_per_block"] + 1
+        res = []
+        for i in range(n):
+            skip = cin if i == n - 1 else cout
+            rin = prev if i == 0 else cout
+            res.append(ResnetBlock2DWidthGated(rin + skip, cout, cfg["temb"], cfg["groups"], cfg["eps"],
+                                               depth_gated=(i == n - 1), skip_dim=skip if i == n - 1 else None))
+        self.resnets = nn.ModuleList(res)
+        self.attentions = nn.ModuleList([
+            Transformer2DModelWidthGated(cout, heads, cfg["ctx_dim"], cfg["groups"], cfg["ff_gate_width"],
+                                         depth_gated=(i == n - 1)) for i in range(n)]) if has_attn else None
+        self.upsamplers = nn.ModuleList([_Sampler(cout, 1)]) if add_up else None
+        self.has_cross_attention = has_attn
+
+    def forward(self, eng, x, skips):
+        for i, r in enumerate(self.resnets):
+            x = eng.resnet(r, x, skip=skips.pop())
+            if self.attentions is not None:
+                x = eng.transformer(self.attentions[i], x)
+        if self.upsamplers is not None:
+            x = eng.upsample(self.upsamplers[0], x)
+        return x
+
+
+class _TimestepEmbedding(nn.Module):
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+
+# --------------------------------------------------------------------------------------------------
+# activations in engine layout
+# --------------------------------------------------------------------------------------------------
+class Act:
+    """[B*H*W, ld] bf16 rows of C valid channels (NHWC / token-major), samples in engine order."""
+    __slots__ = ("t", "B", "H", "W", "C", "ld")
+
+    def __init__(self, t, B, H, W, C, ld=None):
+        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.ld = ld if ld is not None else C
+
+    @property
+    def hw(self):
+        return self.H * self.W
+
+    @property
+    def rows(self):
+        return self.B * self.H * self.W
+
+    def nchw(self) -> torch.Tensor:
+        """Zero-copy [B, C, H, W] view (channels-last strides), as the reference's hooks see it."""
+        return self.t.view(self.B, self.H, self.W, self.ld)[..., : self.C].permute(0, 3, 1, 2)
+
+
+class UNet2DConditionModelGated(nn.Module):
+    """SD-2.1 gated U-Net (reference: unet_2d_conditional.py:628). Only the shipped block layout is
+    supported: CrossAttnDownBlock2DHalfGated x3 + DownBlock2DHalfGated, UNetMidBlock2DCrossAttnWidthGated,
+    UpBlock2DHalfGated + CrossAttnUpBlock2DHalfGated x3 (configs/pruning/sd-2-1_cc3m.yaml:11-26)."""
+
+    def __init__(self, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280),
+                 attention_head_dim=(5, 10, 20, 20), layers_per_block=2, cross_attention_dim=1024,
+                 norm_num_groups=32, norm_eps=1e-5, gated_ff=True, ff_gate_width=32,
+                 down_block_types=("CrossAttnDownBlock2DHalfGated", "CrossAttnDownBlock2DHalfGated",
+                                   "CrossAttnDownBlock2DHalfGated", "DownBlock2DHalfGated"),
+                 mid_block_type="UNetMidBlock2DCrossAttnWidthGated",
+                 up_block_types=("UpBlock2DHalfGated", "CrossAttnUpBlock2DHalfGated", "CrossAttnUpBlock2DHalfGated",
+                                 "CrossAttnUpBlock2DHalfGated"), sample_size=96, **unused):
+        super().__init__()
+        if not gated_ff:
+            raise NotImplementedError("only gated_ff=True (the shipped configs) is supported")
+        if mid_block_type != "UNetMidBlock2DCrossAttnWidthGated":
+            raise NotImplementedError(mid_block_type)
+        ch = tuple(block_out_channels)
+        heads = tuple(attention_head_dim) if not isinstance(attention_head_dim, int) else (attention_head_dim,) * len(ch)
+        for c, h in zip(ch, heads):
+            if c != h * 64:
+                raise NotImplementedError("attention head_dim must be 64 (SD-2.1); got C=%d heads=%d" % (c, h))
+            if c % 8 or c % norm_num_groups:
+                raise NotImplementedError("channels must be multiples of 8 and of norm_num_groups")
+        down_has_attn = tuple(t.startswith("CrossAttn") for t in down_block_types)
+        up_has_attn = tuple(t.startswith("CrossAttn") for t in up_block_types)
+        for t in tuple(down_block_types) + tuple(up_block_types):
+            if not t.endswith("HalfGated"):
+                raise NotImplementedError(f"block type {t}: only the *HalfGated blocks of the shipped configs exist")
+        self.config = dict(in_channels=in_channels, out_channels=out_channels, block_out_channels=ch,
+                           attention_head_dim=heads, layers_per_block=layers_per_block,
+                           cross_attention_dim=cross_attention_dim, norm_num_groups=norm_num_groups,
+                           norm_eps=norm_eps, ff_gate_width=ff_gate_width, sample_size=sample_size,
+                           down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types))
+        cfg = dict(layers_per_block=layers_per_block, temb=ch[0] * 4, groups=norm_num_groups, eps=norm_eps,
+                   ctx_dim=cross_attention_dim, ff_gate_width=ff_gate_width)
+        self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
+        self.time_embedding = _TimestepEmbedding(ch[0], ch[0] * 4)
+        downs, out_c = [], ch[0]
+        for i, c in enumerate(ch):
+            in_c, out_c = out_c, c
+            downs.append(DownBlock2DHalfGated(cfg, in_c, out_c, heads[i], down_has_attn[i], add_down=i < len(ch) - 1))
+        self.down_blocks = nn.ModuleList(downs)
+        self.mid_block = MidBlock2DCrossAttnWidthGated(cfg, ch[-1], heads[-1])
+        rev, rev_heads = list(reversed(ch)), list(reversed(heads))
+        ups, out_c = [], rev[0]
+        for i in range(len(ch)):
+            prev, out_c = out_c, rev[i]
+            in_c = rev[min(i + 1, len(ch) - 1)]
+            ups.append(UpBlock2DHalfGated(cfg, in_c, out_c, prev, rev_heads[i], up_has_attn[i], add_up=i < len(ch) - 1))
+        self.up_blocks = nn.ModuleList(ups)
+        self.conv_norm_out = nn.GroupNorm(norm_num_groups, ch[0], eps=norm_eps)
+        self.conv_out = nn.Conv2d(ch[0], out_channels, 3, padding=1)
+
+        # gate bookkeeping in get_structure() order
+        self._gated: List[nn.Module] = []
+        for bi, blk in enumerate(list(self.down_blocks) + [self.mid_block] + list(self.up_blocks)):
+            mods = list(blk.resnets) + (list(blk.attentions) if blk.attentions is not None else [])
+            for mi, m in enumerate(mods):
+                m.uid = f"b{bi}.m{mi}"
+            self._gated += mods
+        self._resnets = [m for m in self.modules() if isinstance(m, ResnetBlock2DWidthGated)]
+        off = 0
+        self._temb_off: Dict[str, int] = {}
+        for r in self._resnets:
+            self._temb_off[r.uid] = off
+            off += r.cout
+        self._temb_total = off
+        self.structure = {"width": [], "depth": []}
+        self.resource_info_dict = None
+        self.prunable_macs_list = None
+        self.total_macs = None
+        self._engine: Optional["_Engine"] = None
+        self._gate_state: Optional[Dict[str, Any]] = None
+        self.set_all_ones_structure()
+
+    # ---------------------------------------------------------------------------------------------
+    # reference API: structure
+    # ---------------------------------------------------------------------------------------------
+    def get_structure(self) -> Dict[str, List[List[int]]]:
+        """unet_2d_conditional.py:1332-1363 -- per block, resnets first then attentions."""
+        if len(self.structure["width"]) == 0:
+            self.structure = {"width": [m.gate_widths() for m in self._gated],
+                              "depth": [[1] if m.depth_gate is not None else [0] for m in self._gated]}
+        return self.structure
+
+    def set_structure(self, arch_vectors: Dict[str, List[torch.Tensor]]) -> None:
+        """unet_2d_conditional.py:1365-1413. Consumes (pops) the caller's lists like the reference."""
+        width, depth = arch_vectors["width"], arch_vectors["depth"]
+        flat_w, flat_d = [], []
+        for blk in list(self.down_blocks) + [self.mid_block] + list(self.up_blocks):
+            mods = list(blk.resnets) + (list(blk.attentions) if blk.attentions is not None else [])
+            w_take = []
+            for m in mods:
+                ws = []
+                for wd in m.gate_widths():
+                    assert wd == width[0].shape[1], f"width gate mismatch: expected {wd}, got {width[0].shape[1]}"
+                    ws.append(width.pop(0))
+                w_take.append(ws)
+            d_take = [depth.pop(0) if m.depth_gate is not None else None for m in mods]
+            for m, ws, d in zip(mods, w_take, d_take):
+                if isinstance(m, ResnetBlock2DWidthGated):
+                    m.gate.set_structure_value(ws[0])
+                else:
+                    tb = m.transformer_blocks[0]
+                    tb.attn1.gate.set_structure_value(ws[0])
+                    tb.attn2.gate.set_structure_value(ws[1])
+                    tb.ff.net[0].gate.set_structure_value(ws[2])
+                if d is not None:
+                    m.depth_gate.set_structure_value(d)
+                flat_w += ws
+                if d is not None:
+                    flat_d.append(d)
+        self._gate_state = None  # re-derived lazily on the next forward
+        self._flat_gates = (flat_w, flat_d)
+
+    def set_all_ones_structure(self, batch: int = 1, device=None) -> None:
+        st = self.get_structure()
+        self.set_structure({"width": [torch.ones(batch, w, device=device) for ws in st["width"] for w in ws],
+                            "depth": [torch.ones(batch, device=device) for d in st["depth"] if d == [1]]})
+
+    def freeze(self) -> None:
+        """unet_2d_conditional.py:2118-2122."""
+        for name, p in self.named_parameters():
+            if "gate_f" not in name:
+                p.requires_grad = False
+
+    # ---------------------------------------------------------------------------------------------
+    # reference API: MAC accounting (closed form of op_counter + calc_macs tree)
+    # ---------------------------------------------------------------------------------------------
+    def count_macs(self, H: int, W: int, n_ctx: int = 77) -> None:
+        """What Pruner.count_macs (trainer.py:1257-1296) measures with forward hooks at batch 1."""
+        from .macs import build_resource_info
+        self.resource_info_dict = build_resource_info(self, H, W, n_ctx)
+        d = self.calc_macs()
+        self.total_macs = d["total_macs"]
+        self.prunable_macs_list = self.get_prunable_macs()
+
+    def calc_macs(self) -> Dict[str, Any]:
+        from .macs import calc_macs
+        if self.resource_info_dict is None:
+            raise RuntimeError("call count_macs(H, W) first (the reference runs count_ops_and_params once)")
+        return calc_macs(self)
+
+    def get_prunable_macs(self):
+        from .macs import prunable_macs_list
+        return prunable_macs_list(self)
+
+    def get_block_utilization(self):
+        from .macs import block_utilization
+        return block_utilization(self)
+
+    # ---------------------------------------------------------------------------------------------
+    # forward
+    # ---------------------------------------------------------------------------------------------
+    def invalidate_weight_cache(self) -> None:
+        """Call after changing parameters (the pruning workflow keeps the U-Net frozen)."""
+        self._engine = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._engine = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def forward(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor,
+                class_labels=None, timestep_cond=None, attention_mask=None, cross_attention_kwargs=None,
+                added_cond_kwargs=None, down_block_additional_residuals=None, mid_block_additional_residual=None,
+                encoder_attention_mask=None, return_dict: bool = True):
+        """unet_2d_conditional.py:1415-1726 for the SD-2.1 configuration (no class / added conditioning,
+        no attention masks, no ControlNet residuals: those raise)."""
+        for name, v in (("class_labels", class_labels), ("timestep_cond", timestep_cond),
+                        ("attention_mask", attention_mask), ("added_cond_kwargs", added_cond_kwargs),
+                        ("down_block_additional_residuals", down_block_additional_residuals),
+                        ("mid_block_additional_residual", mid_block_additional_residual),
+                        ("encoder_attention_mask", encoder_attention_mask)):
+            if v is not None:
+                raise NotImplementedError(f"{name} is not part of the APTP hot path")
+        if not sample.is_cuda:
+            raise RuntimeError("UNet2DConditionModelGated runs on the sm_100a CUDA path only: move the model and "
+                               "inputs to a CUDA device (there is no CPU fallback)")
+        if self._engine is None or self._engine.device != sample.device:
+            self._engine = _Engine(self, sample.device)
+        out = self._engine.run(sample, timestep, encoder_hidden_states)
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(sample=out)
+
+
+# --------------------------------------------------------------------------------------------------
+# engine
+# --------------------------------------------------------------------------------------------------
+class _Engine:
+    def __init__(self, model: UNet2DConditionModelGated, device):
+        self.m = model
+        self.device = device
+        self.dense: Dict[str, Dict[str, torch.Tensor]] = {}
+        self.expert: Dict[Tuple[bytes, str], Dict[str, Any]] = {}
+        self.sched: Dict[Any, Any] = {}
+        self.arena: Dict[Any, torch.Tensor] = {}
+        self.flops = 0.0          # kept GEMM-class FLOPs of the last forward (roofline accounting)
+        self.launches = 0
+        self.count_flops = False
+        # per-forward state
+        self.B = 0
+        self.compact = False
+        self.eset: Optional[P.ExpertSet] = None
+        self.layout: Optional[P.BatchLayout] = None
+        self.soft: Dict[str, torch.Tensor] = {}
+
+    # ---- workspace -------------------------------------------------------------------------------
+    def buf(self, name: str, rows: int, cols: int, dtype=BF16) -> torch.Tensor:
+        key = (name, rows, cols, dtype)
+        t = self.arena.get(key)
+        if t is None:
+            t = torch.zeros(rows, cols, device=self.device, dtype=dtype)  # zero once: stale data stays finite
+            self.arena[key] = t
+        return t
+
+    # ---- gates -> mode / experts -------------------------------------------------------------------
+    def _prepare_gates(self, B: int):
+        m = self.m
+        st = m._gate_state
+        if st is None:
+            flat_w, flat_d = m._flat_gates
+            bg = flat_w[0].shape[0]
+            arch = torch.cat([w.detach().reshape(bg, -1).float() for w in flat_w] +
+                             [d.detach().reshape(bg, 1).float() for d in flat_d], dim=1).to(self.device)
+            hard = bool(((arch == 0) | (arch == 1)).all().item())  # one host sync per set_structure
+            st = {"arch": arch, "hard": hard, "bg": bg}
+            widths = [w for ws in m.get_structure()["width"] for w in ws]
+            st["width_starts"] = [0] + np.cumsum(widths).tolist()
+            st["n_width"] = int(sum(widths))
+            if hard:
+                codes = arch.to(torch.uint8).cpu().numpy()
+                uniq, inv = np.unique(codes, axis=0, return_inverse=True)
+                st["eset"] = P.ExpertSet(codes=uniq, sample_expert=inv.reshape(-1), width_starts=st["width_starts"],
+                                         n_width=st["n_width"])
+            m._gate_state = st
+        assert B % st["bg"] == 0, f"batch {B} is not a multiple of the gate batch {st['bg']}"
+        self.compact = st["hard"]
+        if self.compact:
+            self.eset = st["eset"]
+            lk = ("layout", self.eset.key(), st["eset"].sample_expert.tobytes(), B)
+            if lk not in self.sched:
+                self.sched[lk] = P.BatchLayout.build(self.eset.sample_expert, self.eset.n_experts, B)
+            self.layout = self.sched[lk]
+        else:
+            self.eset, self.layout = None, None
+            arch = st["arch"]
+            if B != st["bg"]:
+                arch = arch.repeat(B // st["bg"], 1)  # gates.py:18-19 (CFG batch doubling)
+            self.soft_arch = arch.contiguous()
+        self.gate_cols = {}
+        gi = 0
+        di = 0
+        ws = st["width_starts"]
+        for mod in m._gated:
+            n = len(mod.gate_widths())
+            self.gate_cols[mod.uid] = {"w": list(range(gi, gi + n)), "d": (di if mod.depth_gate is not None else None)}
+            gi += n
+            if mod.depth_gate is not None:
+                di += 1
+        self.width_starts = ws
+        self.n_width = st["n_width"]
+
+    # ---- small helpers -----------------------------------------------------------------------------
+    def _per_pos(self, per_expert: Sequence[int], dtype=torch.int32) -> torch.Tensor:
+        arr = np.asarray(per_expert)[self.layout.expert_of_pos]
+        return torch.as_tensor(arr, device=self.device).to(dtype)
+
+    def _soft_gate(self, gate_idx: int) -> torch.Tensor:
+        s, e = self.width_starts[gate_idx], self.width_starts[gate_idx + 1]
+        return self.soft_arch[:, s:e].contiguous()
+
+    def _soft_depth(self, depth_idx: int) -> torch.Tensor:
+        return self.soft_arch[:, self.n_width + depth_idx].contiguous()
+
+    def _expert_active(self, uid: str) -> np.ndarray:
+        """[E] bool: False where the block is depth-dropped for that expert."""
+        d = self.gate_cols[uid]["d"]
+        if d is None or not self.compact:
+            return np.ones(self.eset.n_experts if self.compact else 1, dtype=bool)
+        return self.eset.depth_bits(d).astype(bool)
+
+    def _segments(self, hw: int, n_valid, k_chunks, w_row_off, vec_off=None, tab_off=None, n_store=None,
+                  active=None, out_col_off=0) -> List[K.Segment]:
+        """One segment per expert bucket (adjacent identical buckets merged)."""
+        if not self.compact:
+            return [K.Segment(row_begin=0, row_end=self.B * hw, n_valid=int(n_valid[0]), k_chunks=int(k_chunks[0]),
+                              w_row_off=int(w_row_off[0]), vec_off=int(vec_off[0]) if vec_off is not None else 0,
+                              tab_off=int(tab_off[0]) if tab_off is not None else 0,
+                              n_store=int(n_store[0]) if n_store is not None else -1, active=True,
+                              out_col_off=out_col_off)]
+        segs: List[K.Segment] = []
+        st = self.layout.starts
+        for e in range(self.eset.n_experts):
+            if st[e + 1] == st[e]:
+                continue
+            s = K.Segment(row_begin=int(st[e]) * hw, row_end=int(st[e + 1]) * hw, n_valid=int(n_valid[e]),
+                          k_chunks=int(k_chunks[e]), w_row_off=int(w_row_off[e]),
+                          vec_off=int(vec_off[e]) if vec_off is not None else 0,
+                          tab_off=int(tab_off[e]) if tab_off is not None else 0,
+                          n_store=int(n_store[e]) if n_store is not None else -1,
+                          active=bool(active[e]) if active is not None else True, out_col_off=out_col_off)
+            if segs and segs[-1].row_end == s.row_begin and \
+                    (segs[-1].n_valid, segs[-1].k_chunks, segs[-1].w_row_off, segs[-1].vec_off, segs[-1].tab_off,
+                     segs[-1].n_store, segs[-1].active) == (s.n_valid, s.k_chunks, s.w_row_off, s.vec_off, s.tab_off,
+                                                           s.n_store, s.active):
+                segs[-1].row_end = s.row_end
+            else:
+                segs.append(s)
+        return segs
+
+    def _sched(self, key, builder):
+        full = (key, self.B, self.eset.key() if self.compact else b"soft",
+                self.layout.expert_of_pos.tobytes() if self.compact else b"")
+        s = self.sched.get(full)
+        if s is None:
+            s = builder()
+            self.sched[full] = s
+        return s
+
+    def _gemm(self, sched: K.Schedule, a, w, out, **kw):
+        K.grouped_gemm(a, w, out, sched, **kw)
+        self.launches += 1
+        self.flops += sched.flops
+
+    # ---- dense (unpruned) weights ---------------------------------------------------------------
+    def _dense_linear(self, name: str, lin: nn.Module, n_pad_to: int = 0) -> Dict[str, torch.Tensor]:
+        d = self.dense.get(name)
+        if d is None:
+            w = lin.weight.detach()
+            if w.ndim == 4:
+                w = P.pack_conv_weight(w) if w.shape[-1] == 3 else w.reshape(w.shape[0], w.shape[1])
+            w = w.to(self.device, BF16).contiguous()
+            if n_pad_to and w.shape[0] < n_pad_to:
+                w = torch.cat([w, torch.zeros(n_pad_to - w.shape[0], w.shape[1], device=self.device, dtype=BF16)], 0)
+            b = lin.bias.detach().to(self.device, torch.float32).contiguous() if lin.bias is not None else None
+            d = {"w": w, "b": b}
+            self.dense[name] = d
+        return d
+
+    def linear(self, name: str, lin: nn.Module, x: torch.Tensor, rows: int, k: int, ld: int, out: torch.Tensor,
+               out_ld: int, hw: int, *, residual=None, res_ld=0, flags=0, active=None, out_mode=OUT_BF16,
+               n_out: Optional[int] = None, out_col_off: int = 0):
+        """Unpruned Linear / 1x1 conv over token rows (depth-dropped buckets skipped via `active`)."""
+        d = self._dense_linear(name, lin)
+        n = n_out if n_out is not None else lin.weight.shape[0]
+        E = self.eset.n_experts if self.compact else 1
+
+        def build():
+            bn = P.choose_bn([n])
+            segs = self._segments(hw, [n] * E, [(k + 63) // 64] * E, [0] * E, active=active, out_col_off=out_col_off)
+            return K.build_schedule(segs, bn, self.device)
+        sched = self._sched(("lin", name, rows, hw), build)
+        self._gemm(sched, x, d["w"], out, a_ld=ld, a_k=k, a_rows=rows, out_ld=out_ld, out_mode=out_mode, bias=d["b"],
+                   rows_per_sample=hw, residual=residual, res_ld=res_ld, flags=flags)
+
+    def conv3x3(self, name: str, conv: nn.Module, x: Act, out: torch.Tensor, out_ld: int, *, stride=1, out_mode=OUT_BF16,
+                n_pad_to=0):
+        d = self._dense_linear(name, conv, n_pad_to=n_pad_to)
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        Ho, Wo = x.H // stride, x.W // stride
+        mode = A_CONV3X3 if stride == 1 else A_CONV3X3_S2
+        E = self.eset.n_experts if self.compact else 1
+
+        def build():
+            bn = P.choose_bn([max(cout, 32)])
+            segs = self._segments(Ho * Wo, [cout] * E, [(cin + 63) // 64] * E, [0] * E)
+            return K.build_schedule(segs, bn, self.device, mode=mode, Ho=Ho, Wo=Wo)
+        sched = self._sched(("conv", name, x.B, x.H, x.W), build)
+        self._gemm(sched, x.t, d["w"], out, a_ld=x.ld, a_k=x.C, a_rows=x.rows, mode=mode, batch=x.B, H=x.H, W=x.W,
+                   k_tap_pitch=cin, out_ld=out_ld, out_mode=out_mode, bias=d["b"], rows_per_sample=Ho * Wo)
+
+    # ---- group norm ------------------------------------------------------------------------------
+    def groupnorm(self, x: torch.Tensor, C: int, ld: int, B: int, hw: int, groups_full: int, gs: int, eps: float,
+                  gamma: torch.Tensor, beta: torch.Tensor, affine_ld: int, out: torch.Tensor, out_ld: int, silu: bool,
+                  sample_seg=None, sample_channels=None, gate=None):
+        stats = self.buf("gnstats", B, groups_full * 2, torch.float32)
+        stats.zero_()
+        K.groupnorm_stats(x, C, ld, None, 0, 0, B, hw, gs, sample_channels, stats, groups_full)
+        K.groupnorm_apply(x, C, ld, None, 0, 0, out, out_ld, B, hw, gs, eps, stats, groups_full, gamma, beta, affine_ld,
+                          sample_seg, sample_channels, gate, groups_full, silu)
+        self.launches += 3
+
+    # ---- time embedding --------------------------------------------------------------------------
+    def _temb_pack(self) -> Dict[str, Any]:
+        """All 22 time_emb_proj Linears in one packed matrix (+ their bias + conv1 bias folded in), per
+        distinct kept-set compacted in place inside each layer's block (blocks.py:442-449)."""
+        key = (self.eset.key() if self.compact else b"soft", "temb")
+        d = self.expert.get(key)
+        if d is not None:
+            return d
+        m = self.m
+        E = self.eset.n_experts if self.compact else 1
+        ntot = m._temb_total
+        tdim = m.time_embedding.linear_2.weight.shape[0]
+        w = torch.zeros(E * ntot, tdim, device=self.device, dtype=BF16)
+        b = torch.zeros(E * ntot, device=self.device, dtype=torch.float32)
+        for r in m._resnets:
+            off = m._temb_off[r.uid]
+            wt = r.time_emb_proj.weight.detach().to(self.device)
+            bt = (r.time_emb_proj.bias.detach() + r.conv1.bias.detach()).to(self.device, torch.float32)
+            gs = r.cout // r.groups
+            for e in range(E):
+                if self.compact:
+                    kept = np.nonzero(self.eset.width_bits(self.gate_cols[r.uid]["w"][0])[e])[0]
+                    rows = torch.as_tensor(P.expand_groups(kept, gs), device=self.device, dtype=torch.long)
+                else:
+                    rows = torch.arange(r.cout, device=self.device)
+                w[e * ntot + off: e * ntot + off + len(rows)] = wt.index_select(0, rows).to(BF16)
+                b[e * ntot + off: e * ntot + off + len(rows)] = bt.index_select(0, rows)
+        d = {"w": w, "b": b}
+        self.expert[key] = d
+        return d
+
+    def time_embed(self, timestep: torch.Tensor):
+        m = self.m
+        B = self.B
+        c0 = m.config["block_out_channels"][0]
+        tdim = c0 * 4
+        t = timestep.to(self.device, torch.float32).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(B)
+        t = t.contiguous()
+        if self.compact:
+            t = t[torch.as_tensor(self.layout.perm, device=self.device)].contiguous()
+        emb = self.buf("t_sin", B, c0)
+        K.timestep_embedding(t, emb, B, c0)
+        h = self.buf("t_h", B, tdim)
+        te = self.buf("t_e", B, tdim)
+        E = self.eset.n_experts if self.compact else 1
+        # linear_1 + SiLU, linear_2 + SiLU (every consumer applies nonlinearity(temb) first: blocks.py:333-340)
+        for name, lin, src, k, dst in (("te1", m.time_embedding.linear_1, emb, c0, h),
+                                       ("te2", m.time_embedding.linear_2, h, tdim, te)):
+            d = self._dense_linear(name, lin)
+            sched = self._sched(("te", name), lambda: K.build_schedule(
+                [K.Segment(0, B, tdim, (k + 63) // 64)], P.choose_bn([tdim]), self.device))
+            self._gemm(sched, src, d["w"], dst, a_ld=k, a_k=k, a_rows=B, out_ld=tdim, bias=d["b"], flags=EPI_SILU,
+                       rows_per_sample=1)
+        pack = self._temb_pack()
+        ntot = m._temb_total
+        rv = self.buf("t_rowvec", B, ntot, torch.float32)
+
+        def build():
+            segs = self._segments(1, [ntot] * E, [(tdim + 63) // 64] * E, [e * ntot for e in range(E)],
+                                  vec_off=[e * ntot for e in range(E)])
+            return K.build_schedule(segs, 256, self.device)
+        sched = self._sched(("temb_all",), build)
+        self._gemm(sched, te, pack["w"], rv, a_ld=tdim, a_k=tdim, a_rows=B, out_ld=ntot, out_mode=OUT_F32,
+                   bias=pack["b"], rows_per_sample=1)
+        self.temb_rowvec = rv
+
+    # ---- ResNet ------------------------------------------------------------------------------------
+    def _resnet_pack(self, r: ResnetBlock2DWidthGated) -> Dict[str, Any]:
+        key = (self.eset.key() if self.compact else b"soft", r.uid)
+        d = self.expert.get(key)
+        if d is not None:
+            return d
+        gs = r.cout // r.groups
+        w1 = P.pack_conv_weight(r.conv1.weight.detach().to(self.device))
+        w2 = P.pack_conv_weight(r.conv2.weight.detach().to(self.device))
+        g2 = r.norm2.weight.detach().to(self.device, torch.float32)
+        b2 = r.norm2.bias.detach().to(self.device, torch.float32)
+        if self.compact:
+            bits = self.eset.width_bits(self.gate_cols[r.uid]["w"][0])
+            kept_g, vid = P.kept_variants(bits)
+        else:
+            kept_g, vid = [np.arange(r.groups)], np.zeros(1, dtype=np.int64)
+        kept_c = [P.expand_groups(k, gs) for k in kept_g]
+        pruned_c = [np.setdiff1d(np.arange(r.cout), k) for k in kept_c]
+        V = len(kept_c)
+        d = {"vid": vid, "n1": np.asarray([len(k) for k in kept_c]), "V": V}
+        d["w1"] = P.pack_rows(w1, kept_c, r.cout)
+        d["w2"] = P.pack_cols(w2.to(BF16), kept_c, 9)
+        gam = torch.zeros(V, r.cout, device=self.device)
+        bet = torch.zeros(V, r.cout, device=self.device)
+        for v, k in enumerate(kept_c):
+            idx = torch.as_tensor(k, device=self.device, dtype=torch.long)
+            gam[v, :len(k)] = g2.index_select(0, idx)
+            bet[v, :len(k)] = b2.index_select(0, idx)
+        d["gamma2"], d["beta2"] = gam.contiguous(), bet.contiguous()
+        tab = P.border_table(r.conv2.weight.detach().to(self.device), b2, pruned_c)
+        d["tab"] = tab.contiguous() if bool((tab != 0).any().item()) else None
+        d["b2"] = r.conv2.bias.detach().to(self.device, torch.float32).contiguous()
+        d["g1"] = r.norm1.weight.detach().to(self.device, torch.float32).contiguous()
+        d["b1"] = r.norm1.bias.detach().to(self.device, torch.float32).contiguous()
+        self.expert[key] = d
+        return d
+
+    def resnet(self, r: ResnetBlock2DWidthGated, x: Act, skip: Optional[Act] = None) -> Act:
+        """ResnetBlock2DWidthGated / WidthDepthGated forward (blocks.py:293-371, :482-584)."""
+        B, H, W, hw = x.B, x.H, x.W, x.hw
+        M = x.rows
+        if skip is not None:  # up block: hidden_states = torch.cat([hidden_states, res_hidden_states], dim=1)
+            cat = self.buf("cat", M, x.C + skip.C)
+            K.copy_rows(x.t, x.ld, cat, x.C + skip.C, M, x.C)
+            K.copy_rows(skip.t, skip.ld, cat[:, x.C:], x.C + skip.C, M, skip.C)
+            self.launches += 2
+            xin = Act(cat, B, H, W, x.C + skip.C)
+        else:
+            xin = x
+        assert xin.C == r.cin, f"{r.uid}: expected {r.cin} input channels, got {xin.C}"
+        pk = self._resnet_pack(r)
+        E = self.eset.n_experts if self.compact else 1
+        vid = pk["vid"]
+        active = self._expert_active(r.uid)
+        gs_in, gs = r.cin // r.groups, r.cout // r.groups
+        n1_e = pk["n1"][vid]
+        cidx = self.gate_cols[r.uid]
+
+        def build_aux():
+            aux = {}
+            if self.compact:
+                aux["ch_in"] = self._per_pos(np.where(active, r.cin, 0))
+                aux["ch_mid"] = self._per_pos(np.where(active, n1_e, 0))
+                aux["seg_mid"] = self._per_pos(vid)
+                aux["drop_mask"] = self._per_pos((~active).astype(np.uint8), torch.uint8) if (~active).any() else None
+            return aux
+        aux = self._sched(("res_aux", r.uid), build_aux)
+
+        # norm1 + SiLU
+        a1 = self.buf("gn_a", M, r.cin)
+        self.groupnorm(xin.t, r.cin, xin.ld, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
+                       sample_channels=aux.get("ch_in"))
+        # conv1 (N-compacted) + time embedding (+ conv1/time biases, folded into the row vector)
+        h1 = self.buf("res_h1", M, r.cout)
+
+        def build_c1():
+            bn = P.choose_bn(list(pk["n1"]))
+            segs = self._segments(hw, n1_e, [(r.cin + 63) // 64] * E, vid * r.cout, active=active,
+                                  n_store=[min(P.round_up(int(n), 64), r.cout) for n in n1_e])
+            return K.build_schedule(segs, bn, self.device, mode=A_CONV3X3, Ho=H, Wo=W)
+        sched = self._sched(("res_c1", r.uid, H, W), build_c1)
+        rv = self.temb_rowvec[:, self.m._temb_off[r.uid]:]
+        self._gemm(sched, a1, pk["w1"], h1, a_ld=r.cin, a_k=r.cin, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W,
+                   k_tap_pitch=r.cin, out_ld=r.cout, rowvec=rv, rowvec_ld=self.m._temb_total, rows_per_sample=hw)
+        # width gate (soft: fused multiplier) + norm2 + SiLU on the compacted tensor
+        a2 = self.buf("gn_b", M, r.cout)
+        gate = self._soft_gate(cidx["w"][0]) if not self.compact else None
+        self.groupnorm(h1, r.cout, r.cout, B, hw, r.groups, gs, r.eps, pk["gamma2"], pk["beta2"], r.cout, a2, r.cout,
+                       True, sample_seg=aux.get("seg_mid"),
+                       sample_channels=aux.get("ch_mid"), gate=gate)
+        # shortcut
+        out = torch.empty(M, r.cout, device=self.device, dtype=BF16)
+        if r.conv_shortcut is not None:
+            self.linear("sc." + r.uid, r.conv_shortcut, xin.t, M, r.cin, xin.ld, out, r.cout, hw, active=active)
+            res, res_ld = out, r.cout
+        else:
+            res, res_ld = xin.t, xin.ld
+        # conv2 (K-compacted) + bias + border table + residual
+
+        def build_c2():
+            bn = P.choose_bn([r.cout])
+            tab_off = vid * 9 * r.cout
+            segs = self._segments(hw, [r.cout] * E, [(int(n) + 63) // 64 for n in n1_e], vid * r.cout,
+                                  tab_off=tab_off, active=active)
+            return K.build_schedule(segs, bn, self.device, mode=A_CONV3X3, Ho=H, Wo=W)
+        sched = self._sched(("res_c2", r.uid, H, W), build_c2)
+        self._gemm(sched, a2, pk["w2"], out, a_ld=r.cout, a_k=r.cout, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W,
+                   k_tap_pitch=r.cout, out_ld=r.cout, bias=pk["b2"], residual=res, res_ld=res_ld, rows_per_sample=hw,
+                   border_tab=pk["tab"], tab_ld=r.cout)
+        # depth gate
+        if r.depth_gate is not None:
+            keep_c = xin.C - (r.skip_connection_dim or 0)  # blocks.py:485-495
+            if self.compact:
+                if aux["drop_mask"] is not None:  # dropped experts: identity on the (non-skip) input
+                    K.copy_rows(xin.t, xin.ld, out, r.cout, M, keep_c, aux["drop_mask"], hw)
+                    self.launches += 1
+            else:
+                K.depth_lerp(xin.t, xin.ld, out, r.cout, out, r.cout, M, keep_c, self._soft_depth(cidx["d"]), hw)
+                self.launches += 1
+        return Act(out, B, H, W, r.cout)
+
+    # ---- transformer -------------------------------------------------------------------------------
+    def _attn_pack(self, uid: str, attn: _Attention, gate_idx: int) -> Dict[str, Any]:
+        key = (self.eset.key() if self.compact else b"soft", uid)
+        d = self.expert.get(key)
+        if d is not None:
+            return d
+        C = attn.dim
+        if self.compact:
+            kept_h, vid = P.kept_variants(self.eset.width_bits(gate_idx))
+        else:
+            kept_h, vid = [np.arange(attn.heads)], np.zeros(1, dtype=np.int64)
+        kept_c = [P.expand_groups(k, 64) for k in kept_h]
+        d = {"vid": vid, "nh": np.asarray([len(k) for k in kept_h]), "V": len(kept_h)}
+        for nm, lin in (("q", attn.to_q), ("k", attn.to_k), ("v", attn.to_v)):
+            d["w" + nm] = P.pack_rows(lin.weight.detach().to(self.device), kept_c, C)
+        d["wo"] = P.pack_cols(attn.to_out[0].weight.detach().to(self.device, BF16), kept_c, 1)
+        d["bo"] = attn.to_out[0].bias.detach().to(self.device, torch.float32).contiguous()
+        self.expert[key] = d
+        return d
+
+    def _ff_pack(self, uid: str, ff: _FeedForward, gate_idx: int) -> Dict[str, Any]:
+        key = (self.eset.key() if self.compact else b"soft", uid)
+        d = self.expert.get(key)
+        if d is not None:
+            return d
+        proj = ff.net[0].proj
+        inner = proj.weight.shape[0] // 2
+        C = proj.weight.shape[1]
+        gw = ff.net[0].gate.width
+        gs = inner // gw
+        if self.compact:
+            kept_g, vid = P.kept_variants(self.eset.width_bits(gate_idx))
+        else:
+            kept_g, vid = [np.arange(gw)], np.zeros(1, dtype=np.int64)
+        kept_c = [P.expand_groups(k, gs) for k in kept_g]
+        nf = np.asarray([len(k) for k in kept_c])
+        bn = P.choose_bn(list(nf), geglu=True)
+        half = bn // 2
+        rows_pad = ((inner + half - 1) // half) * bn
+        V = len(kept_c)
+        w = proj.weight.detach().to(self.device)
+        b = proj.bias.detach().to(self.device, torch.float32)
+        wp = torch.zeros(V * rows_pad, C, device=self.device, dtype=BF16)
+        bp = torch.zeros(V * rows_pad, device=self.device, dtype=torch.float32)
+        for v, cols in enumerate(kept_c):
+            idx = torch.as_tensor(cols, device=self.device, dtype=torch.long)
+            n = len(cols)
+            nt = (n + half - 1) // half
+            # tile t holds output columns [t*half, (t+1)*half): rows [t*bn, t*bn+half) = h, next half = g
+            hsel = torch.zeros(nt * half, C, device=self.device, dtype=BF16)
+            gsel = torch.zeros(nt * half, C, device=self.device, dtype=BF16)
+            hsel[:n] = w.index_select(0, idx).to(BF16)
+            gsel[:n] = w.index_select(0, idx + inner).to(BF16)
+            hb = torch.zeros(nt * half, device=self.device)
+            gb = torch.zeros(nt * half, device=self.device)
+            hb[:n] = b.index_select(0, idx)
+            gb[:n] = b.index_select(0, idx + inner)
+            blk = torch.stack([hsel.view(nt, half, C), gsel.view(nt, half, C)], dim=1).reshape(nt * bn, C)
+            bblk = torch.stack([hb.view(nt, half), gb.view(nt, half)], dim=1).reshape(nt * bn)
+            wp[v * rows_pad: v * rows_pad + nt * bn] = blk
+            bp[v * rows_pad: v * rows_pad + nt * bn] = bblk
+        d = {"vid": vid, "nf": nf, "V": V, "bn": bn, "rows_pad": rows_pad, "wp": wp, "bp": bp, "inner": inner,
+             "gs": gs}
+        d["w2"] = P.pack_cols(ff.net[2].weight.detach().to(self.device, BF16), kept_c, 1)
+        d["b2"] = ff.net[2].bias.detach().to(self.device, torch.float32).contiguous()
+        self.expert[key] = d
+        return d
+
+    def _attention(self, uid: str, attn: _Attention, gate_idx: int, xn: torch.Tensor, tok: torch.Tensor, B: int,
+                   hw: int, C: int, active: np.ndarray, ctx: Optional[torch.Tensor], n_ctx: int):
+        """GatedAttention + HeadGatedAttnProcessor2 (blocks.py:194-280); output accumulated into `tok`."""
+        pk = self._attn_pack(uid, attn, gate_idx)
+        E = self.eset.n_experts if self.compact else 1
+        vid, nh_e = pk["vid"], pk["nh"][pk["vid"]]
+        M = B * hw
+        is_cross = ctx is not None
+        n_kv = n_ctx if is_cross else hw
+        Mkv = B * n_kv
+        gate = self._soft_gate(gate_idx) if not self.compact else None
+        kq = C
+        kkv = attn.ctx_dim if is_cross else C
+        qkv = self.buf("qkv_q", M, C) if is_cross else self.buf("qkv", M, 3 * C)
+        kvb = self.buf("qkv_kv", Mkv, 2 * C) if is_cross else None
+
+        def build():
+            bn = P.choose_bn([int(n) * 64 for n in pk["nh"]])
+            s = {}
+            nv = [int(n) * 64 for n in nh_e]
+            if is_cross:
+                s["q"] = K.build_schedule(self._segments(hw, nv, [(kq + 63) // 64] * E, vid * C, active=active), bn,
+                                          self.device)
+                segs = []
+                for j in range(2):
+                    segs += self._segments(n_kv, nv, [(kkv + 63) // 64] * E, vid * C + j * pk["V"] * C, active=active,
+                                           out_col_off=j * C)
+                s["kv"] = K.build_schedule(segs, bn, self.device)
+            else:
+                segs = []
+                for j in range(3):
+                    segs += self._segments(hw, nv, [(kq + 63) // 64] * E, vid * C + j * pk["V"] * C, active=active,
+                                           out_col_off=j * C)
+                s["qkv"] = K.build_schedule(segs, bn, self.device)
+            s["o"] = K.build_schedule(self._segments(hw, [C] * E, [int(n) for n in nh_e], vid * C, active=active),
+                                      P.choose_bn([C]), self.device)
+            heads = np.where(active, nh_e, 0) if self.compact else np.asarray([attn.heads])
+            s["heads"] = self._per_pos(heads) if self.compact else torch.full((B,), attn.heads, device=self.device,
+                                                                             dtype=torch.int32)
+            s["max_heads"] = int(heads.max()) if len(heads) else 0
+            return s
+        s = self._sched(("attn", uid, hw, n_kv), build)
+        if "wqkv" not in pk:
+            pk["wqkv"] = torch.cat([pk["wq"], pk["wk"], pk["wv"]], 0).contiguous() if not is_cross else None
+            pk["wkv"] = torch.cat([pk["wk"], pk["wv"]], 0).contiguous() if is_cross else None
+        gkw = dict(gate=gate, gate_ld=attn.heads, gate_group=64) if gate is not None else {}
+        if is_cross:
+            self._gemm(s["q"], xn, pk["wq"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=C, rows_per_sample=hw, **gkw)
+            self._gemm(s["kv"], ctx, pk["wkv"], kvb, a_ld=kkv, a_k=kkv, a_rows=Mkv, out_ld=2 * C, rows_per_sample=n_kv,
+                       **gkw)
+            q, ldq, kk, vv, ldkv = qkv, C, kvb, kvb[:, C:], 2 * C
+        else:
+            self._gemm(s["qkv"], xn, pk["wqkv"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=3 * C, rows_per_sample=hw, **gkw)
+            q, ldq, kk, vv, ldkv = qkv, 3 * C, qkv[:, C:], qkv[:, 2 * C:], 3 * C
+        o = self.buf("attn_o", M, C)
+        if s["max_heads"] > 0:
+            K.attention(q, ldq, kk, ldkv, vv, ldkv, o, C, B, hw, n_kv, s["heads"], s["max_heads"], 1.0 / 8.0)
+            self.launches += 1
+            if self.count_flops:
+                self.flops += 4.0 * hw * n_kv * 64 * float(s["heads"].sum().item())
+        # to_out (K-compacted to the kept heads) + bias + residual, in place on the token stream
+        self._gemm(s["o"], o, pk["wo"], tok, a_ld=C, a_k=C, a_rows=M, out_ld=C, bias=pk["bo"], residual=tok, res_ld=C,
+                   rows_per_sample=hw)
+
+    def transformer(self, t: Transformer2DModelWidthGated, x: Act) -> Act:
+        """Transformer2DModelWidth(Depth)Gated.forward (blocks.py:1139-1355) incl. the
+        BasicTransformerBlockWidthGated body (blocks.py:763-851)."""
+        B, H, W, hw, C = x.B, x.H, x.W, x.hw, x.C
+        M = x.rows
+        tb = t.transformer_blocks[0]
+        cidx = self.gate_cols[t.uid]
+        active = self._expert_active(t.uid)
+        E = self.eset.n_experts if self.compact else 1
+        key = ("tr_dense", t.uid)
+        dn = self.dense.get(key)
+        if dn is None:
+            f32 = lambda p: p.detach().to(self.device, torch.float32).contiguous()
+            dn = {"g": f32(t.norm.weight), "b": f32(t.norm.bias)}
+            for i, ln in enumerate((tb.norm1, tb.norm2, tb.norm3)):
+                dn[f"lg{i}"], dn[f"lb{i}"] = f32(ln.weight), f32(ln.bias)
+            self.dense[key] = dn
+
+        def build_aux():
+            aux = {"ch": None, "act": None, "drop": None}
+            if self.compact and (~active).any():
+                aux["ch"] = self._per_pos(np.where(active, C, 0))
+                aux["act"] = self._per_pos(active.astype(np.uint8), torch.uint8)
+                aux["drop"] = self._per_pos((~active).astype(np.uint8), torch.uint8)
+            return aux
+        aux = self._sched(("tr_aux", t.uid), build_aux)
+        gs = C // t.groups
+        xn = self.buf("ln", M, C)
+        self.groupnorm(x.t, C, x.ld, B, hw, t.groups, gs, 1e-6, dn["g"], dn["b"], C, xn, C, False,
+                       sample_channels=aux["ch"])
+        tok = self.buf("tok", M, C)
+        self.linear("pi." + t.uid, t.proj_in, xn, M, C, C, tok, C, hw, active=active)
+        # self-attention
+        K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg0"], dn["lb0"], aux["act"], hw)
+        self._attention(t.uid + ".a1", tb.attn1, cidx["w"][0], xn, tok, B, hw, C, active, None, 0)
+        # cross-attention
+        K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg1"], dn["lb1"], aux["act"], hw)
+        self._attention(t.uid + ".a2", tb.attn2, cidx["w"][1], xn, tok, B, hw, C, active, self.ctx, self.n_ctx)
+        # feed-forward: GEGLU (N-compacted, gated) then Linear (K-compacted) + residual
+        K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg2"], dn["lb2"], aux["act"], hw)
+        self.launches += 3
+        fk = self._ff_pack(t.uid + ".ff", tb.ff, cidx["w"][2])
+        vid, nf_e = fk["vid"], fk["nf"][fk["vid"]]
+        inner = fk["inner"]
+        ffb = self.buf("ff", M, inner)
+
+        def build_ff():
+            s = {}
+            s["p"] = K.build_schedule(
+                self._segments(hw, nf_e, [(C + 63) // 64] * E, vid * fk["rows_pad"], vec_off=vid * fk["rows_pad"],
+                               n_store=[min(P.round_up(int(n), 64), inner) for n in nf_e], active=active),
+                fk["bn"], self.device, geglu=True)
+            s["o"] = K.build_schedule(
+                self._segments(hw, [C] * E, [(int(n) + 63) // 64 for n in nf_e], vid * C, active=active),
+                P.choose_bn([C]), self.device)
+            return s
+        s = self._sched(("ff", t.uid, hw), build_ff)
+        gate = self._soft_gate(cidx["w"][2]) if not self.compact else None
+        gkw = dict(gate=gate, gate_ld=t.gate_width, gate_group=fk["gs"]) if gate is not None else {}
+        self._gemm(s["p"], xn, fk["wp"], ffb, a_ld=C, a_k=C, a_rows=M, out_ld=inner, bias=fk["bp"], flags=EPI_GEGLU,
+                   rows_per_sample=hw, **gkw)
+        self._gemm(s["o"], ffb, fk["w2"], tok, a_ld=inner, a_k=inner, a_rows=M, out_ld=C, bias=fk["b2"], residual=tok,
+                   res_ld=C, rows_per_sample=hw)
+        # proj_out + residual
+        out = torch.empty(M, C, device=self.device, dtype=BF16)
+        self.linear("po." + t.uid, t.proj_out, tok, M, C, C, out, C, hw, residual=x.t, res_ld=x.ld, active=active)
+        if t.depth_gate is not None:
+            if self.compact:
+                if aux["drop"] is not None:
+                    K.copy_rows(x.t, x.ld, out, C, M, C, aux["drop"], hw)
+                    self.launches += 1
+            else:
+                K.depth_lerp(x.t, x.ld, out, C, out, C, M, C, self._soft_depth(cidx["d"]), hw)
+                self.launches += 1
+        return Act(out, B, H, W, C)
+
+    # ---- samplers ----------------------------------------------------------------------------------
+    def downsample(self, s: _Sampler, x: Act) -> Act:
+        out = torch.empty(x.rows // 4, x.C, device=self.device, dtype=BF16)
+        self.conv3x3("ds.%d" % id(s), s.conv, x, out, x.C, stride=2)
+        return Act(out, x.B, x.H // 2, x.W // 2, x.C)
+
+    def upsample(self, s: _Sampler, x: Act) -> Act:
+        up = self.buf("up", x.rows * 4, x.C)
+        K.upsample2x(x.t, up, x.B, x.H, x.W, x.C)
+        self.launches += 1
+        xu = Act(up, x.B, x.H * 2, x.W * 2, x.C)
+        out = torch.empty(xu.rows, x.C, device=self.device, dtype=BF16)
+        self.conv3x3("us.%d" % id(s), s.conv, xu, out, x.C)
+        return Act(out, xu.B, xu.H, xu.W, x.C)
+
+    # ---- whole forward -----------------------------------------------------------------------------
+    def run(self, sample: torch.Tensor, timestep, ctx: torch.Tensor) -> torch.Tensor:
+        m = self.m
+        B, cin, H, W = sample.shape
+        self.B = B
+        self.flops = 0.0
+        self.launches = 0
+        self._prepare_gates(B)
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([float(timestep)], device=self.device)
+        sample = sample.to(torch.float32)
+        ctx = ctx.to(self.device)
+        if self.compact:
+            perm = torch.as_tensor(self.layout.perm, device=self.device)
+            sample = sample.index_select(0, perm)
+            ctx = ctx.index_select(0, perm)
+        sample = sample.contiguous()
+        ctx = ctx.contiguous()
+        self.n_ctx = ctx.shape[1]
+        cdim = ctx.shape[2]
+        ctx16 = self.buf("ctx", B * self.n_ctx, cdim)
+        if ctx.dtype == BF16:
+            ctx16.copy_(ctx.reshape(B * self.n_ctx, cdim))
+        else:
+            K.cast_f32_bf16(ctx.to(torch.float32), ctx16, B * self.n_ctx * cdim)
+        self.launches += 1
+        self.ctx = ctx16
+        self.time_embed(timestep)
+        # conv_in as im2col (K = 36 -> 64) + GEMM
+        c0 = m.config["block_out_channels"][0]
+        col = self.buf("im2col", B * H * W, 64)
+        K.im2col_input(sample, col, B, cin, H, W)
+        self.launches += 1
+        d = self.dense.get("conv_in")
+        if d is None:
+            w = m.conv_in.weight.detach().to(self.device)
+            wp = torch.zeros(c0, 64, device=self.device, dtype=BF16)
+            wp[:, :9 * cin] = w.permute(0, 2, 3, 1).reshape(c0, 9 * cin).to(BF16)
+            d = {"w": wp, "b": m.conv_in.bias.detach().to(self.device, torch.float32).contiguous()}
+            self.dense["conv_in"] = d
+        x0 = torch.empty(B * H * W, c0, device=self.device, dtype=BF16)
+        sched = self._sched(("conv_in", H, W), lambda: K.build_schedule(
+            [K.Segment(0, B * H * W, c0, 1)], P.choose_bn([c0]), self.device))
+        self._gemm(sched, col, d["w"], x0, a_ld=64, a_k=64, a_rows=B * H * W, out_ld=c0, bias=d["b"],
+                   rows_per_sample=H * W)
+        x = Act(x0, B, H, W, c0)
+        skips = [x]
+        for blk in m.down_blocks:
+            x, outs = blk(self, x)
+            skips += list(outs)
+        x = m.mid_block(self, x)
+        for blk in m.up_blocks:
+            x = blk(self, x, skips)
+        # conv_norm_out + SiLU + conv_out (fp32 NCHW result)
+        key = "out_norm"
+        dn = self.dense.get(key)
+        if dn is None:
+            dn = {"g": m.conv_norm_out.weight.detach().to(self.device, torch.float32).contiguous(),
+                  "b": m.conv_norm_out.bias.detach().to(self.device, torch.float32).contiguous()}
+            self.dense[key] = dn
+        groups = m.config["norm_num_groups"]
+        a = self.buf("gn_a", x.rows, x.C)
+        self.groupnorm(x.t, x.C, x.ld, B, x.hw, groups, x.C // groups, m.config["norm_eps"], dn["g"], dn["b"], x.C, a,
+                       x.C, True)
+        cout = m.config["out_channels"]
+        y = torch.empty(B, cout, x.H, x.W, device=self.device, dtype=torch.float32)
+        dco = self._dense_linear("conv_out", m.conv_out, n_pad_to=32)
+        sched = self._sched(("conv_out", x.H, x.W), lambda: K.build_schedule(
+            [K.Segment(0, x.rows, cout, (x.C + 63) // 64)], 32, self.device, mode=A_CONV3X3, Ho=x.H, Wo=x.W))
+        self._gemm(sched, a, dco["w"], y, a_ld=x.C, a_k=x.C, a_rows=x.rows, mode=A_CONV3X3, batch=B, H=x.H, W=x.W,
+                   k_tap_pitch=x.C, out_ld=cout, out_mode=OUT_F32_NCHW, bias=dco["b"], rows_per_sample=x.hw)
+        if self.compact:
+            y = y.index_select(0, torch.as_tensor(self.layout.inv_perm, device=self.device))
+        return y

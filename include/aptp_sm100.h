@@ -50,6 +50,8 @@ typedef struct aptp_gemm_seg {
   int32_t w_row_off; /* first row of this bucket's block in the packed weight matrix              */
   int32_t vec_off;   /* offset of this bucket's bias (floats) in `bias`                           */
   int32_t tab_off;   /* offset of this bucket's 9 x n border table (floats) in `border_tab`       */
+  int32_t out_col_off; /* output / residual column of this bucket's column 0 (fused q|k|v blocks)   */
+  int32_t pad0, pad1, pad2;
 } aptp_gemm_seg;
 
 typedef struct aptp_gemm_tile {

@@ -1,0 +1,36 @@
+"""GPU parity: the CUDA U-Net path vs the fp32 CPU oracle on identical seeded weights and inputs."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert(res):
+    import unet_checks as U
+    max_abs, cos = res
+    assert max_abs <= U.MAX_ABS_TOL and cos >= U.COS_TOL, (max_abs, cos)
+
+
+def test_tiny_all_ones_equals_ungated():
+    import unet_checks as U
+    _assert(U.check_all_ones())
+
+
+@pytest.mark.parametrize("beta_std", [0.0, 0.1])
+def test_tiny_hard_mixed_experts(beta_std):
+    import unet_checks as U
+    _assert(U.check_hard(beta_std=beta_std))
+
+
+def test_tiny_soft_gates():
+    import unet_checks as U
+    _assert(U.check_soft())
+
+
+def test_tiny_cfg_batch_doubling():
+    import unet_checks as U
+    _assert(U.check_cfg_doubling())
+
+
+def test_full_sd21_hard_b2_h32():
+    import unet_checks as U
+    _assert(U.check_hard(tiny=False, B=2, H=32, code_ids=(0, 3)))
