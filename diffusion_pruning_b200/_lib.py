@@ -70,7 +70,10 @@ SIGNATURES = {
                                    c_int, c_void_p, c_int, c_float, c_void_p]),
     "aptp_gumbel_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                      c_float, c_float, c_int, c_void_p]),
-    "aptp_arch_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "aptp_gumbel_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float,
+                                     c_float, c_void_p]),
+    "aptp_arch_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "aptp_arch_normalize_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "aptp_route_cosine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "aptp_sinkhorn_phase": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                     c_int, c_void_p]),

@@ -70,6 +70,56 @@ __global__ void __launch_bounds__(GATE_THREADS)
   }
 }
 
+// Backward of gumbel_gate_kernel w.r.t. z (K5): width dz = dy * y(1-y)/T with y recomputed from (z, u)
+// (the non-zero-width fix-up adds a constant: estimation_utils.py:30); depth chains through
+// sigmoid -> logit -> flip -> cumsum -> softmax (estimation_utils.py:50-64) and the depth_order scatter.
+__global__ void __launch_bounds__(GATE_THREADS)
+    gumbel_gate_bwd_kernel(const float* __restrict__ z, const float* __restrict__ u, const float* __restrict__ dy,
+                           float* __restrict__ dz, int n_width, int n_depth, const int* __restrict__ depth_order,
+                           float inv_t, float base) {
+  const int row = blockIdx.x;
+  const int dim = n_width + n_depth;
+  const float* zr = z + (size_t)row * dim;
+  const float* ur = u + (size_t)row * dim;
+  const float* dyr = dy + (size_t)row * dim;
+  float* dzr = dz + (size_t)row * dim;
+  for (int c = threadIdx.x; c < n_width; c += GATE_THREADS) {
+    const float y = sigmoid_f((zr[c] + gumbel_from_uniform(ur[c]) + base) * inv_t);
+    dzr[c] = dyr[c] * y * (1.f - y) * inv_t;
+  }
+  if (threadIdx.x == 0 && n_depth > 0) {
+    float s[MAX_DEPTH], cs[MAX_DEPTH], dc[MAX_DEPTH];
+    float mx = -INFINITY;
+    for (int j = 0; j < n_depth; ++j) mx = fmaxf(mx, zr[n_width + j]);
+    float sum = 0.f;
+    for (int j = 0; j < n_depth; ++j) {
+      s[j] = expf(zr[n_width + j] - mx);
+      sum += s[j];
+    }
+    float run = 0.f;
+    for (int j = 0; j < n_depth; ++j) {
+      s[j] = s[j] / sum;
+      run += s[j];
+      cs[j] = run;
+    }
+    for (int j = 0; j < n_depth; ++j) {
+      const float x = cs[n_depth - 1 - j];
+      const float lg = logf(x + 1e-6f) - log1pf(-(x - 1e-6f));
+      const float y = sigmoid_f((lg + gumbel_from_uniform(ur[n_width + j]) + base) * inv_t);
+      const float dlg = dyr[n_width + depth_order[j]] * y * (1.f - y) * inv_t;
+      dc[n_depth - 1 - j] = dlg * (1.f / (x + 1e-6f) + 1.f / (1.f - (x - 1e-6f)));
+    }
+    // cumsum backward: ds_i = sum_{k >= i} dc_k ; softmax backward: dz_i = s_i (ds_i - sum_k s_k ds_k)
+    float acc = 0.f, dot = 0.f;
+    for (int i = n_depth - 1; i >= 0; --i) {
+      acc += dc[i];
+      dc[i] = acc;
+      dot += s[i] * acc;
+    }
+    for (int i = 0; i < n_depth; ++i) dzr[n_width + i] = s[i] * (dc[i] - dot);
+  }
+}
+
 constexpr int NORMZ_THREADS = 256;
 
 __device__ __forceinline__ double block_sum_d(double v, double* scratch) {
@@ -87,7 +137,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* scratch) {
 
 __global__ void __launch_bounds__(NORMZ_THREADS)
     arch_normalize_kernel(const float* __restrict__ gates, float* __restrict__ out, int dim,
-                          const int* __restrict__ col_depth, const float* __restrict__ col_scale) {
+                          const int* __restrict__ col_depth, const float* __restrict__ col_scale, int l2) {
   __shared__ double scratch[32];
   const int row = blockIdx.x;
   const float* g = gates + (size_t)row * dim;
@@ -101,9 +151,36 @@ __global__ void __launch_bounds__(NORMZ_THREADS)
     o[c] = v;
     ss += (double)v * (double)v;
   }
+  if (!l2) return;
   const double tot = block_sum_d(ss, scratch);
   const float nrm = (float)sqrt(tot);
   for (int c = threadIdx.x; c < dim; c += NORMZ_THREADS) o[c] = o[c] / nrm;
+}
+
+// Backward of width_depth_normalize (no L2): hard_concrete is straight-through (identity), the
+// depth-gated slices use the product rule.
+__global__ void __launch_bounds__(NORMZ_THREADS)
+    arch_normalize_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ dy, float* __restrict__ dx,
+                              int dim, const int* __restrict__ col_depth, const float* __restrict__ col_scale) {
+  extern __shared__ float dacc[];  // [dim] depth-column accumulators (only depth columns are used)
+  const int row = blockIdx.x;
+  const float* g = gates + (size_t)row * dim;
+  const float* d = dy + (size_t)row * dim;
+  float* o = dx + (size_t)row * dim;
+  for (int c = threadIdx.x; c < dim; c += NORMZ_THREADS) dacc[c] = 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < dim; c += NORMZ_THREADS) {
+    const int dc = col_depth[c];
+    const float gd = d[c] * col_scale[c];
+    if (dc >= 0) {
+      o[c] = gd * g[dc];
+      atomicAdd(&dacc[dc], gd * g[c]);
+    } else {
+      o[c] = gd;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < dim; c += NORMZ_THREADS) o[c] += dacc[c];
 }
 
 constexpr int MAX_CODES = 32;
@@ -253,12 +330,38 @@ extern "C" int aptp_gumbel_gate_fwd(const float* z, const float* u, float* out, 
   return APTP_OK;
 }
 
+extern "C" int aptp_gumbel_gate_bwd(const float* z, const float* u, const float* dy, float* dz, int32_t batch,
+                                    int32_t n_width, int32_t n_depth, const int32_t* depth_order, float temperature,
+                                    float base, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(z && u && dy && dz, "aptp_gumbel_gate_bwd: null pointer");
+  APTP_REQUIRE(n_depth <= MAX_DEPTH && (n_depth == 0 || depth_order), "aptp_gumbel_gate_bwd: n_depth=%d unsupported", n_depth);
+  APTP_REQUIRE(temperature > 0.f, "aptp_gumbel_gate_bwd: temperature must be > 0");
+  if (batch == 0) return APTP_OK;
+  gumbel_gate_bwd_kernel<<<batch, GATE_THREADS, 0, stream>>>(z, u, dy, dz, n_width, n_depth, depth_order,
+                                                            1.f / temperature, base);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_arch_normalize_bwd(const float* gates, const float* dy, float* dx, int32_t batch, int32_t dim,
+                                       const int32_t* col_depth, const float* col_scale, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(gates && dy && dx && col_depth && col_scale, "aptp_arch_normalize_bwd: null pointer");
+  APTP_REQUIRE((size_t)dim * sizeof(float) <= 48 * 1024, "aptp_arch_normalize_bwd: arch vector too wide");
+  if (batch == 0) return APTP_OK;
+  arch_normalize_bwd_kernel<<<batch, NORMZ_THREADS, dim * sizeof(float), stream>>>(gates, dy, dx, dim, col_depth,
+                                                                                   col_scale);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
 extern "C" int aptp_arch_normalize(const float* gates, float* out, int32_t batch, int32_t dim, const int32_t* col_depth,
-                                   const float* col_scale, void* stream_) {
+                                   const float* col_scale, int32_t l2, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   APTP_REQUIRE(gates && out && col_depth && col_scale, "aptp_arch_normalize: null pointer");
   if (batch == 0) return APTP_OK;
-  arch_normalize_kernel<<<batch, NORMZ_THREADS, 0, stream>>>(gates, out, dim, col_depth, col_scale);
+  arch_normalize_kernel<<<batch, NORMZ_THREADS, 0, stream>>>(gates, out, dim, col_depth, col_scale, l2);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

@@ -206,9 +206,19 @@ def gumbel_gate(z, u, out, batch, n_width, n_depth, width_starts, n_gates, depth
                                       int(non_zero_width), _stream()), "aptp_gumbel_gate_fwd")
 
 
-def arch_normalize(gates, out, batch, dim, col_depth, col_scale):
-    check(load().aptp_arch_normalize(_ptr(gates), _ptr(out), batch, dim, _ptr(col_depth), _ptr(col_scale), _stream()),
-          "aptp_arch_normalize")
+def gumbel_gate_bwd(z, u, dy, dz, batch, n_width, n_depth, depth_order, temperature, base):
+    check(load().aptp_gumbel_gate_bwd(_ptr(z), _ptr(u), _ptr(dy), _ptr(dz), batch, n_width, n_depth, _ptr(depth_order),
+                                      float(temperature), float(base), _stream()), "aptp_gumbel_gate_bwd")
+
+
+def arch_normalize(gates, out, batch, dim, col_depth, col_scale, l2=True):
+    check(load().aptp_arch_normalize(_ptr(gates), _ptr(out), batch, dim, _ptr(col_depth), _ptr(col_scale), int(l2),
+                                     _stream()), "aptp_arch_normalize")
+
+
+def arch_normalize_bwd(gates, dy, dx, batch, dim, col_depth, col_scale):
+    check(load().aptp_arch_normalize_bwd(_ptr(gates), _ptr(dy), _ptr(dx), batch, dim, _ptr(col_depth),
+                                         _ptr(col_scale), _stream()), "aptp_arch_normalize_bwd")
 
 
 def route_cosine(a_norm, codes_norm, scores, indices, batch, dim, n_codes):

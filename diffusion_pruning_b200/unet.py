@@ -446,6 +446,7 @@ class _Engine:
         self.flops = 0.0          # kept GEMM-class FLOPs of the last forward (roofline accounting)
         self.launches = 0
         self.count_flops = False
+        self.profile: Optional[list] = None  # set to [] to bracket every GEMM / attention launch with CUDA events
         # per-forward state
         self.B = 0
         self.compact = False
@@ -567,7 +568,14 @@ class _Engine:
         return s
 
     def _gemm(self, sched: K.Schedule, a, w, out, **kw):
-        K.grouped_gemm(a, w, out, sched, **kw)
+        if self.profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            K.grouped_gemm(a, w, out, sched, **kw)
+            e1.record()
+            self.profile.append(("gemm", e0, e1, sched.flops, sched.n_tiles))
+        else:
+            K.grouped_gemm(a, w, out, sched, **kw)
         self.launches += 1
         self.flops += sched.flops
 
@@ -926,6 +934,8 @@ class _Engine:
             s["heads"] = self._per_pos(heads) if self.compact else torch.full((B,), attn.heads, device=self.device,
                                                                              dtype=torch.int32)
             s["max_heads"] = int(heads.max()) if len(heads) else 0
+            s["heads_total"] = float(np.asarray(heads)[self.layout.expert_of_pos].sum()) if self.compact \
+                else float(attn.heads * B)
             return s
         s = self._sched(("attn", uid, hw, n_kv), build)
         if "wqkv" not in pk:
@@ -942,10 +952,16 @@ class _Engine:
             q, ldq, kk, vv, ldkv = qkv, 3 * C, qkv[:, C:], qkv[:, 2 * C:], 3 * C
         o = self.buf("attn_o", M, C)
         if s["max_heads"] > 0:
+            fl = 4.0 * hw * n_kv * 64 * s["heads_total"]
+            if self.profile is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             K.attention(q, ldq, kk, ldkv, vv, ldkv, o, C, B, hw, n_kv, s["heads"], s["max_heads"], 1.0 / 8.0)
+            if self.profile is not None:
+                e1.record()
+                self.profile.append(("attn", e0, e1, fl, 0))
             self.launches += 1
-            if self.count_flops:
-                self.flops += 4.0 * hw * n_kv * 64 * float(s["heads"].sum().item())
+            self.flops += fl
         # to_out (K-compacted to the kept heads) + bias + residual, in place on the token stream
         self._gemm(s["o"], o, pk["wo"], tok, a_ld=C, a_k=C, a_rows=M, out_ld=C, bias=pk["bo"], residual=tok, res_ld=C,
                    rows_per_sample=hw)

@@ -182,12 +182,19 @@ int aptp_gumbel_gate_fwd(const float* z, const float* u, float* out, int32_t bat
                          int32_t n_depth, const int32_t* width_starts, int32_t n_width_gates,
                          const int32_t* depth_order, float temperature, float base, int32_t non_zero_width,
                          void* stream);
+/* backward of aptp_gumbel_gate_fwd w.r.t. z (dl = dy*y(1-y)/T, estimation_utils.py:40-41; depth through
+ * logit/flip/cumsum/softmax, estimation_utils.py:50-56, and the depth_order scatter quantizer.py:205-206). */
+int aptp_gumbel_gate_bwd(const float* z, const float* u, const float* dy, float* dz, int32_t batch, int32_t n_width,
+                         int32_t n_depth, const int32_t* depth_order, float temperature, float base, void* stream);
 /* width_depth_normalize (quantizer.py:233-250) + L2 normalise (quantizer.py:266-267,:326-327):
- * out[b,:] = v/||v||, v = (width slices of depth-gated blocks * their depth gate, hard_concrete
+ * out[b,:] = v/||v|| (or v when l2_normalize = 0), v = (width slices of depth-gated blocks * their depth gate, hard_concrete
  * elsewhere) * sqrt(template) [* macs_template]. col_depth[c] = arch column of the depth gate that
  * multiplies column c, or -1. */
 int aptp_arch_normalize(const float* gates, float* out, int32_t batch, int32_t dim, const int32_t* col_depth,
-                        const float* col_scale, void* stream);
+                        const float* col_scale, int32_t l2_normalize, void* stream);
+/* backward of the l2_normalize=0 form (hard_concrete straight-through; product rule on depth-gated slices). */
+int aptp_arch_normalize_bwd(const float* gates, const float* dy, float* dx, int32_t batch, int32_t dim,
+                            const int32_t* col_depth, const float* col_scale, void* stream);
 /* scores = A @ C^T  ([B,dim] x [K,dim]) in fp32 and argmax per row (quantizer.py:264-271). */
 int aptp_route_cosine(const float* a_norm, const float* codes_norm, float* scores, int64_t* indices,
                       int32_t batch, int32_t dim, int32_t n_codes, void* stream);
