@@ -164,6 +164,11 @@ def run_ours(args):
     K.check_abort()
     clocks = ClockSampler(local)
     clocks.start()
+    if os.environ.get("APTP_CUDA_PROFILE"):  # ncu --profile-from-start off: capture exactly one step
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     ms_total = timed(step_resident, args.steps)
     clk = clocks.stop()
     eng = model._engine
@@ -181,6 +186,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     prof = eng.profile
     eng.profile = None
+    if os.environ.get("APTP_PROFILE_DUMP") and rank == 0:
+        with open(os.environ["APTP_PROFILE_DUMP"], "w") as f:
+            for kind, a, b, fl, label in prof:
+                ms = a.elapsed_time(b)
+                f.write(f"{kind}\t{ms:.4f}\t{fl / 1e9:.2f}\t{fl / max(ms, 1e-6) / 1e9:.1f}\t{label}\n")
     gemm = [(a.elapsed_time(b), fl) for kind, a, b, fl, _ in prof if kind == "gemm" and fl > 0]
     attn = [(a.elapsed_time(b), fl) for kind, a, b, fl, _ in prof if kind == "attn"]
     g_ms, g_fl = sum(x for x, _ in gemm), sum(f for _, f in gemm)

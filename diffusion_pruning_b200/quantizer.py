@@ -1,0 +1,276 @@
+"""Drop-in `StructureVectorQuantizer` (reference: pdm/models/vq/quantizer.py:15) -- the prompt router.
+
+Same constructor arguments, attributes (`n_e`, `vq_embed_dim`, `embedding`, `embedding_gs`, ...) and
+methods; the arithmetic runs in the fused sm_100a router kernels (csrc/router.cu):
+
+  gumbel_sigmoid_trick        -> aptp_gumbel_gate_fwd / _bwd   (71 slices in one pass, no host syncs)
+  width_depth_normalize       -> aptp_arch_normalize(_bwd)
+  cosine / Sinkhorn indices   -> aptp_route_cosine, aptp_route_sinkhorn / aptp_sinkhorn_phase with the
+                                 marginal all-reduces (quantizer.py:285,:291) issued as NCCL calls on the
+                                 same stream between phases (fp64 partial sums).
+
+The Gumbel uniforms are still drawn from the CPU generator in the reference's order (depth [B,14]
+first, then the 70 width slices; a fresh manual_seed(0) generator per slice in eval mode:
+pdm/utils/estimation_utils.py:5-10) so that gates and router assignments are reproducible bit-for-bit
+against the reference; they reach the GPU as ONE pinned H2D copy instead of 71.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import kernels as K
+from ._mixin import ConfigModelMixin
+
+
+def hard_concrete(out: torch.Tensor) -> torch.Tensor:
+    """pdm/utils/estimation_utils.py:67-75 without the CPU round trip: exact 0/1 forward value,
+    straight-through gradient."""
+    hard = (out >= 0.5).to(out.dtype)
+    return (hard - out).detach() + out
+
+
+class _GumbelGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, u, q):
+        out = torch.empty_like(z)
+        B = z.shape[0]
+        K.gumbel_gate(z, u, out, B, q.n_width, q.n_depth, q._dev("width_starts", z.device), len(q.width_list),
+                      q._dev("depth_order_t", z.device), q.temperature, q.base, q.non_zero_width)
+        ctx.save_for_backward(z, u)
+        ctx.q = q
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, u = ctx.saved_tensors
+        q = ctx.q
+        dz = torch.empty_like(z)
+        K.gumbel_gate_bwd(z, u, dy.contiguous(), dz, z.shape[0], q.n_width, q.n_depth,
+                          q._dev("depth_order_t", z.device), q.temperature, q.base)
+        return dz, None, None
+
+
+class _WidthDepthNormalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, q):
+        out = torch.empty_like(x)
+        K.arch_normalize(x, out, x.shape[0], x.shape[1], q._dev("col_depth", x.device), q._col_scale(x.device), l2=False)
+        ctx.save_for_backward(x)
+        ctx.q = q
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        q = ctx.q
+        dx = torch.empty_like(x)
+        K.arch_normalize_bwd(x, dy.contiguous(), dx, x.shape[0], x.shape[1], q._dev("col_depth", x.device),
+                             q._col_scale(x.device))
+        return dx, None
+
+
+class StructureVectorQuantizer(ConfigModelMixin, nn.Module):
+    def __init__(self, n_e: int, structure: dict, beta: float = 0.25, remap=None, unknown_index: str = "random",
+                 sane_index_shape: bool = True, temperature: float = 0.4, base: int = 2, depth_order: list = None,
+                 non_zero_width: bool = True, sinkhorn_epsilon: float = 0.05, sinkhorn_iterations: int = 3,
+                 resource_aware_normalization: bool = True, optimal_transport: bool = True):
+        super().__init__()
+        self.register_to_config(n_e=n_e, structure=structure, beta=beta, remap=remap, unknown_index=unknown_index,
+                                sane_index_shape=sane_index_shape, temperature=temperature, base=base,
+                                depth_order=depth_order, non_zero_width=non_zero_width,
+                                sinkhorn_epsilon=sinkhorn_epsilon, sinkhorn_iterations=sinkhorn_iterations,
+                                resource_aware_normalization=resource_aware_normalization,
+                                optimal_transport=optimal_transport)
+        if remap is not None:
+            raise NotImplementedError("remap is never used by the reference configs (remap=None always)")
+        vq_embed_dim = 0
+        for w_config, d_config in zip(structure["width"], structure["depth"]):  # quantizer.py:44-49
+            vq_embed_dim += sum(w_config)
+            if d_config == [1]:
+                vq_embed_dim += 1
+        self.n_e, self.vq_embed_dim, self.beta, self.structure = n_e, vq_embed_dim, beta, structure
+        self.width_list = [w for sub in structure["width"] for w in sub]
+        self.width_list_sum = [sum(sub) for sub in structure["width"]]
+        idx = [0] + np.cumsum(self.width_list_sum).tolist()
+        self.width_intervals = [(idx[i], idx[i + 1]) for i in range(len(idx) - 1)]
+        self.depth_list = [d for sub in structure["depth"] for d in sub]
+        self.n_width, self.n_depth = sum(self.width_list), sum(self.depth_list)
+        self.depth_indices = (self.n_width - 1 + np.cumsum(self.depth_list)).tolist()
+        if depth_order is None:
+            depth_order = list(range(self.n_depth))
+        self.input_depth_order = depth_order
+        self.depth_order = [i % self.n_depth for i in depth_order]
+        template = torch.tensor(self.width_list + [d for d in self.depth_list if d != 0])
+        self.template = (1.0 / torch.repeat_interleave(template, template).type(torch.float32)).requires_grad_(False)
+        self.prunable_macs_template = None
+        if resource_aware_normalization is None:
+            resource_aware_normalization = True
+        self.resource_effect_normalization = resource_aware_normalization
+        self.embedding = nn.Embedding(self.n_e, self.vq_embed_dim)
+        nn.init.orthogonal_(self.embedding.weight)
+        self.embedding_gs = nn.Parameter(self.embedding.weight.detach().clone(), requires_grad=False)
+        self.remap, self.re_embed, self.sane_index_shape = None, n_e, sane_index_shape
+        self.temperature, self.base, self.non_zero_width = temperature, base, non_zero_width
+        self.optimal_transport = optimal_transport
+        self.sinkhorn_epsilon, self.sinkhorn_iterations = sinkhorn_epsilon, sinkhorn_iterations
+        # device-side layout tables
+        col_depth = -np.ones(self.vq_embed_dim, dtype=np.int32)
+        for i, d in enumerate(self.depth_list):
+            if d != 0:
+                lo, hi = self.width_intervals[i]
+                col_depth[lo:hi] = self.depth_indices[i]
+        self._host = {"width_starts": torch.tensor([0] + np.cumsum(self.width_list).tolist(), dtype=torch.int32),
+                      "depth_order_t": torch.tensor(self.depth_order, dtype=torch.int32),
+                      "col_depth": torch.from_numpy(col_depth)}
+        self._devcache: Dict[Tuple[str, str], torch.Tensor] = {}
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    def _dev(self, name: str, device) -> torch.Tensor:
+        key = (name, str(device))
+        t = self._devcache.get(key)
+        if t is None:
+            t = self._host[name].to(device)
+            self._devcache[key] = t
+        return t
+
+    def _col_scale(self, device) -> torch.Tensor:
+        s = torch.sqrt(self.template)
+        if self.resource_effect_normalization:
+            if self.prunable_macs_template is None:
+                raise RuntimeError("resource_aware_normalization=True needs set_prunable_macs_template() first")
+            s = s * self.prunable_macs_template.to(torch.float32)
+        return s.to(device).contiguous()
+
+    def _draw_uniforms(self, batch: int) -> torch.Tensor:
+        """CPU draws in the reference's order (quantizer.py:203-212 -> estimation_utils.py:5-10), laid out in
+        arch-vector column order [width | depth]."""
+        fixed = not self.training
+
+        def one(shape):
+            if fixed:
+                return torch.rand(shape, generator=torch.Generator().manual_seed(0))
+            return torch.rand(shape)
+        ud = one((batch, self.n_depth))
+        uw = [one((batch, w)) for w in self.width_list]
+        return torch.cat(uw + [ud], dim=1)
+
+    @staticmethod
+    def _require_cuda(t: torch.Tensor, what: str):
+        if not t.is_cuda:
+            raise RuntimeError(f"{what}: the router runs on the sm_100a CUDA kernels only (no CPU fallback)")
+
+    # ---- reference API -----------------------------------------------------------------------------
+    def gumbel_sigmoid_trick(self, z_q: torch.Tensor, uniforms: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """quantizer.py:196-215. `uniforms` (optional, [B, dim] in column order) overrides the CPU draw."""
+        self._require_cuda(z_q, "gumbel_sigmoid_trick")
+        z = z_q.contiguous().float()
+        u = uniforms if uniforms is not None else self._draw_uniforms(z.shape[0])
+        u = u.pin_memory().to(z.device, non_blocking=True) if not u.is_cuda else u
+        return _GumbelGate.apply(z, u.contiguous(), self)
+
+    def width_depth_normalize(self, inputs: torch.Tensor) -> torch.Tensor:
+        """quantizer.py:233-250."""
+        self._require_cuda(inputs, "width_depth_normalize")
+        return _WidthDepthNormalize.apply(inputs.contiguous().float(), self)
+
+    def set_prunable_macs_template(self, prunable_macs_list):
+        """quantizer.py:252-261."""
+        depth_template = []
+        for i, elem in enumerate(self.depth_list):
+            if elem == 1:
+                depth_template.append([sum(prunable_macs_list[i])])
+        prunable_macs_list = list(prunable_macs_list) + depth_template
+        flat = [item for sub in prunable_macs_list for item in sub]
+        self.prunable_macs_template = torch.repeat_interleave(
+            torch.tensor(flat), torch.tensor(self.width_list + [1 for _ in range(len(depth_template))]))
+
+    def _normalized(self, gates: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(gates)
+        K.arch_normalize(gates, out, gates.shape[0], gates.shape[1], self._dev("col_depth", gates.device),
+                         self._col_scale(gates.device), l2=True)
+        return out
+
+    @torch.no_grad()
+    def _scores(self, z: torch.Tensor):
+        a = self._normalized(self.gumbel_sigmoid_trick(z).detach())
+        c = self._normalized(self.embedding_gs.detach().to(z.device).float().contiguous())
+        B = a.shape[0]
+        scores = torch.empty(B, self.n_e, device=z.device, dtype=torch.float32)
+        idx = torch.empty(B, device=z.device, dtype=torch.int64)
+        K.route_cosine(a, c, scores, idx, B, self.vq_embed_dim, self.n_e)
+        return scores, idx
+
+    @torch.no_grad()
+    def get_cosine_sim_min_encoding_indices(self, z: torch.Tensor) -> torch.Tensor:
+        """quantizer.py:264-271."""
+        return self._scores(z)[1]
+
+    @torch.no_grad()
+    def get_optimal_transport_min_encoding_indices(self, a: torch.Tensor) -> torch.Tensor:
+        """quantizer.py:274-340 (Sinkhorn; distributed variant when torch.distributed is initialised)."""
+        scores, _ = self._scores(a)
+        B = scores.shape[0]
+        Q = torch.empty_like(scores)
+        partial = torch.zeros(1 + self.n_e, device=scores.device, dtype=torch.float64)
+        idx = torch.empty(B, device=scores.device, dtype=torch.int64)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            Bg = B * world
+            K.sinkhorn_phase(0, Q, scores, partial, idx, B, Bg, self.n_e, self.sinkhorn_epsilon, 0)
+            dist.all_reduce(partial[:1])
+            for it in range(self.sinkhorn_iterations):
+                K.sinkhorn_phase(1, Q, scores, partial, idx, B, Bg, self.n_e, self.sinkhorn_epsilon, it == 0)
+                dist.all_reduce(partial[1:])
+                K.sinkhorn_phase(2, Q, scores, partial, idx, B, Bg, self.n_e, self.sinkhorn_epsilon, 0)
+            K.sinkhorn_phase(3, Q, scores, partial, idx, B, Bg, self.n_e, self.sinkhorn_epsilon, 0)
+        else:
+            K.route_sinkhorn(scores, Q, partial, idx, B, self.n_e, self.sinkhorn_epsilon, self.sinkhorn_iterations)
+        self.last_assignment = Q
+        return idx
+
+    def forward(self, z: torch.Tensor):
+        """quantizer.py:136-169."""
+        self._require_cuda(z, "StructureVectorQuantizer.forward")
+        z = z.contiguous()
+        z_flat = z.view(-1, self.vq_embed_dim)
+        if self.training:
+            embedding_gs = self.gumbel_sigmoid_trick(self.embedding.weight)
+            self.embedding_gs.data = embedding_gs.detach()
+            if self.optimal_transport:
+                idx = self.get_optimal_transport_min_encoding_indices(z_flat)
+            else:
+                idx = self.get_cosine_sim_min_encoding_indices(z_flat)
+        else:
+            embedding_gs = self.embedding_gs.detach()
+            idx = self.get_cosine_sim_min_encoding_indices(z_flat)
+        z_q = embedding_gs[idx].view(z.shape)
+        z_q_out = z_q.contiguous()
+        if self.sane_index_shape:
+            idx = idx.reshape(z_q.shape[0])
+        if not self.training:
+            z_q_out = hard_concrete(z_q)
+        return z_q_out, (None, None, idx)
+
+    def get_codebook_entry(self, indices: torch.LongTensor, shape: Tuple[int, ...] = None) -> torch.Tensor:
+        z_q = self.embedding(indices)
+        if shape is not None:
+            z_q = z_q.view(shape).contiguous()
+        return z_q
+
+    def get_codebook_entry_gumbel_sigmoid(self, indices, shape=None, hard=False) -> torch.Tensor:
+        z_q = self.get_codebook_entry(indices, shape).contiguous()
+        gs = self.gumbel_sigmoid_trick(z_q)
+        return hard_concrete(gs) if hard else gs
+
+    def _transform_width_vector(self, inputs):
+        assert inputs.shape[1] == sum(self.width_list)
+        out, s = [], 0
+        for w in self.width_list:
+            out.append(inputs[:, s:s + w])
+            s += w
+        return out

@@ -446,6 +446,7 @@ class _Engine:
         self.flops = 0.0          # kept GEMM-class FLOPs of the last forward (roofline accounting)
         self.launches = 0
         self.count_flops = False
+        self._label = ""
         self.profile: Optional[list] = None  # set to [] to bracket every GEMM / attention launch with CUDA events
         # per-forward state
         self.B = 0
@@ -559,6 +560,7 @@ class _Engine:
         return segs
 
     def _sched(self, key, builder):
+        self._label = str(key[:2])
         full = (key, self.B, self.eset.key() if self.compact else b"soft",
                 self.layout.expert_of_pos.tobytes() if self.compact else b"")
         s = self.sched.get(full)
@@ -573,7 +575,7 @@ class _Engine:
             e0.record()
             K.grouped_gemm(a, w, out, sched, **kw)
             e1.record()
-            self.profile.append(("gemm", e0, e1, sched.flops, sched.n_tiles))
+            self.profile.append(("gemm", e0, e1, sched.flops, f"{self._label} bn{sched.bn} tiles{sched.n_tiles} mode{kw.get('mode', 0)}"))
         else:
             K.grouped_gemm(a, w, out, sched, **kw)
         self.launches += 1
@@ -959,7 +961,7 @@ class _Engine:
             K.attention(q, ldq, kk, ldkv, vv, ldkv, o, C, B, hw, n_kv, s["heads"], s["max_heads"], 1.0 / 8.0)
             if self.profile is not None:
                 e1.record()
-                self.profile.append(("attn", e0, e1, fl, 0))
+                self.profile.append(("attn", e0, e1, fl, f"{uid} nq{hw} nkv{n_kv}"))
             self.launches += 1
             self.flops += fl
         # to_out (K-compacted to the kept heads) + bias + residual, in place on the token stream
