@@ -5,8 +5,9 @@
 // One persistent CTA per SM walks a host-built tile list. Warp roles:
 //   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
 //   warp 1      MMA issuer    (one thread, tcgen05.mma cta_group::1 kind::f16, M=128 x N=bn x K=16)
-//   warps 2..5  epilogue      (tcgen05.ld 32x32b from the double-buffered TMEM accumulator,
-//                              bias / time-embedding / border table / gate / GEGLU / residual, bf16 store)
+//   warps 2..9  epilogue      (tcgen05.ld 32x32b from the double-buffered TMEM accumulator,
+//                              bias / time-embedding / border table / gate / GEGLU / residual; the bf16
+//                              tile is transposed through swizzled smem so global traffic is coalesced)
 // The 3x3 conv is an implicit GEMM: for every tap the A tile is a shifted 4-D TMA box over the NHWC
 // activation (out-of-bounds rows/cols are zero-filled by the TMA unit = the conv padding); the
 // stride-2 down-sampler conv uses a 5-D view that splits H and W into (index, parity).
@@ -21,8 +22,11 @@ namespace aptp {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                       // 2 per TMEM lane quadrant, alternating 32-column chunks
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TMEM_COLS = 512;
+constexpr int STG_WARP_BYTES = 32 * 64;            // per-warp staging: 32 rows x 32 bf16 columns
+constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 
 struct GemmParams {
   CUtensorMap tmap_a;
@@ -33,6 +37,7 @@ struct GemmParams {
   int a_mode;
   int batch, Ho, Wo;  // OUTPUT spatial size (conv modes)
   int bn, bw, bh, bb;
+  int lbw, lbh;       // log2 of the (power-of-two) box extents
   int stages;
   int k_tap_pitch;
   void* out;
@@ -57,12 +62,71 @@ __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int stages)
   }
 }
 
+// Exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16
+// resolution): two MUFU ops (rcp, ex2) + 9 FMA-pipe ops, branch-free.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float half_erf = fmaf(-0.5f * poly, e, 0.5f);  // 0.5 * erf(|x|/sqrt2)
+  return x * (0.5f + copysignf(half_erf, x));
+}
+
+// tile-local row r (0..127) -> global output row; conv tiles are bw x bh x bb pixel boxes.
+struct TileGeom {
+  int linear;
+  int m_base;
+  int img0, oy0, ox0;
+};
+__device__ __forceinline__ long long map_row(const GemmParams& p, const TileGeom& g, int r, bool& valid, int& oy,
+                                             int& ox) {
+  if (g.linear) {
+    valid = true;
+    oy = ox = 1;
+    return (long long)g.m_base + r;
+  }
+  const int ix = r & (p.bw - 1);
+  const int iy = (r >> p.lbw) & (p.bh - 1);
+  const int ib = r >> (p.lbw + p.lbh);
+  oy = g.oy0 + iy;
+  ox = g.ox0 + ix;
+  const int img = g.img0 + ib;
+  valid = (img < p.batch) && (oy < p.Ho) && (ox < p.Wo);
+  return ((long long)img * p.Ho + oy) * p.Wo + ox;
+}
+
+// 32 floats starting at src (all lanes read the same addresses -> L1 broadcast); float4 when aligned.
+__device__ __forceinline__ void add32(float* v, const float* __restrict__ src, int n_ok) {
+  if (n_ok >= 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(src) + q);
+      v[q * 4 + 0] += f.x;
+      v[q * 4 + 1] += f.y;
+      v[q * 4 + 2] += f.z;
+      v[q * 4 + 3] += f.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_ok) v[j] += __ldg(src + j);
+  }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
   const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.bn * 128u;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint8_t* stg_base = smem + (size_t)stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -83,7 +147,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], 4);
+        mbar_init(&tempty_bar[a], EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -181,49 +245,83 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
     }
   } else {
     // ------------------------------- epilogue -----------------------------------
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
-    const int r = quad * 32 + lane;
+    // Thread = one accumulator row (TMEM lane). Results are transposed through a per-warp swizzled
+    // smem tile so that every global store / residual load instruction covers 8 rows x 64 contiguous
+    // bytes (full sectors) instead of 32 rows x 16 bytes.
+    const int ew = warp - 2;
+    const int quad = warp & 3;       // TMEM lane quadrant this warp may touch
+    const int cpar = ew >> 2;        // this warp handles chunks cpar, cpar+2, ...
+    const int r_own = quad * 32 + lane;
+    uint8_t* stg = stg_base + ew * STG_WARP_BYTES;
+    // staging addresses: own row (write side) and the coalesced (8 rows x 4 x 16 B) side
+    const uint32_t stg_own = smem_u32(stg) + lane * 64;
+    const int own_sw = (lane >> 1) & 3;
+    const int co_q = lane & 3;  // 16-byte column unit handled by this lane on the coalesced side
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool geglu = (p.flags & APTP_EPI_GEGLU) != 0;
     const int out_cols_per_tile = geglu ? p.bn / 2 : p.bn;
+    const bool bf16_out = (p.out_mode == APTP_OUT_BF16);
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       const aptp_gemm_tile tile = p.tiles[t];
       const aptp_gemm_seg seg = p.segs[tile.seg];
-      // ---- which output row does this thread own? ----
-      long long row;
-      bool valid = true;
-      int ycls = 1, xcls = 1;
-      if (p.a_mode == APTP_A_LINEAR) {
-        row = (long long)tile.m_base + r;
-      } else {
+      TileGeom g;
+      g.linear = (p.a_mode == APTP_A_LINEAR);
+      g.m_base = tile.m_base;
+      g.img0 = g.oy0 = g.ox0 = 0;
+      if (!g.linear) {
         const int hw = p.Ho * p.Wo;
-        const int img0 = tile.m_base / hw;
-        const int rem = tile.m_base - img0 * hw;
-        const int oy0 = rem / p.Wo, ox0 = rem - oy0 * p.Wo;
-        const int ix = r % p.bw;
-        const int iy = (r / p.bw) % p.bh;
-        const int ib = r / (p.bw * p.bh);
-        const int oy = oy0 + iy, ox = ox0 + ix, img = img0 + ib;
-        valid = (img < p.batch) && (oy < p.Ho) && (ox < p.Wo);
-        row = ((long long)img * p.Ho + oy) * p.Wo + ox;
-        ycls = (oy == 0) ? 0 : ((oy == p.Ho - 1) ? 2 : 1);
-        xcls = (ox == 0) ? 0 : ((ox == p.Wo - 1) ? 2 : 1);
+        g.img0 = tile.m_base / hw;
+        const int rem = tile.m_base - g.img0 * hw;
+        g.oy0 = rem / p.Wo;
+        g.ox0 = rem - g.oy0 * p.Wo;
       }
+      // ---- own row ----
+      bool valid;
+      int oy, ox;
+      const long long row = map_row(p, g, r_own, valid, oy, ox);
       valid = valid && (row < (long long)seg.row_end) && (row >= (long long)seg.row_begin);
-      const int sample = valid ? (int)(row / p.rows_per_sample) : 0;
-      const int ocol_base = geglu ? tile.n0 / 2 : tile.n0;  // first OUTPUT column of this tile
+      const int sample = valid ? (int)row / p.rows_per_sample : 0;
+      const int ycls = g.linear ? 1 : ((oy == 0) ? 0 : ((oy == p.Ho - 1) ? 2 : 1));
+      const int xcls = g.linear ? 1 : ((ox == 0) ? 0 : ((ox == p.Wo - 1) ? 2 : 1));
       const float* tabp =
           p.border_tab ? p.border_tab + seg.tab_off + (size_t)(ycls * 3 + xcls) * p.tab_ld : nullptr;
+      // ---- the 4 rows this lane moves on the coalesced side ----
+      long long co_row[4];
+      bool co_ok[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        int a, b;
+        bool v;
+        const long long rr = map_row(p, g, quad * 32 + it * 8 + (lane >> 2), v, a, b);
+        co_ok[it] = v && (rr < (long long)seg.row_end) && (rr >= (long long)seg.row_begin);
+        co_row[it] = rr;
+      }
+      const int ocol_base = geglu ? tile.n0 / 2 : tile.n0;  // first OUTPUT column of this tile
+
+      // residual of the first chunk goes in flight before we wait for the accumulator
+      uint4 rres[4];
+      const bool use_res = (p.residual != nullptr) && bf16_out;
+      auto load_res = [&](int col0) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          rres[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (co_ok[it] && col0 + co_q * 8 < seg.n_valid)
+            rres[it] = *reinterpret_cast<const uint4*>(p.residual + (size_t)co_row[it] * p.res_ld +
+                                                       seg.out_col_off + col0 + co_q * 8);  // may alias `out`
+        }
+      };
+      if (use_res && ocol_base + cpar * 32 < seg.n_store) load_res(ocol_base + cpar * 32);
 
       const bool got = mbar_wait(&tfull_bar[acc], acc_phase, p.abort_flag);
       if (!got) break;
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
 
-      for (int c = 0; c * 32 < out_cols_per_tile; ++c) {
+      for (int c = cpar; c * 32 < out_cols_per_tile; c += 2) {
         const int col0 = ocol_base + c * 32;
         if (col0 >= seg.n_store) break;  // warp-uniform
+        const int n_ok = seg.n_valid - col0;  // columns of this chunk that carry data (may be <= 0)
         uint32_t ra[32];
         float v[32];
         tmem_ld_32x32(t_addr + c * 32, ra);
@@ -231,103 +329,130 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           uint32_t rb[32];
           tmem_ld_32x32(t_addr + p.bn / 2 + c * 32, rb);
           tmem_ld_wait();
+          float gv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float h = __uint_as_float(ra[j]);
-            float g = __uint_as_float(rb[j]);
-            const int col = col0 + j;
-            if (p.bias && col < seg.n_valid) {
-              // packed bias follows the packed (interleaved) weight rows
-              h += __ldg(p.bias + seg.vec_off + tile.n0 + c * 32 + j);
-              g += __ldg(p.bias + seg.vec_off + tile.n0 + p.bn / 2 + c * 32 + j);
-            }
-            if (p.gate && valid && col < seg.n_valid) {
-              const float gs = __ldg(p.gate + (size_t)sample * p.gate_ld + col / p.gate_group);
-              h *= gs;
-              g *= gs;
-            }
-            v[j] = h * gelu_erf_f(g);
+            v[j] = __uint_as_float(ra[j]);
+            gv[j] = __uint_as_float(rb[j]);
           }
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < seg.n_valid) v[j] += __ldg(p.bias + seg.vec_off + col0 + j);
-          }
-          if (p.rowvec && valid) {
-            const float* rv = p.rowvec + (size_t)sample * p.rowvec_ld + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < seg.n_valid) v[j] += __ldg(rv + j);
-          }
-          if (tabp) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < seg.n_valid) v[j] += __ldg(tabp + col0 + j);
+          if (p.bias) {  // packed bias follows the packed (interleaved) weight rows
+            add32(v, p.bias + seg.vec_off + tile.n0 + c * 32, n_ok);
+            add32(gv, p.bias + seg.vec_off + tile.n0 + p.bn / 2 + c * 32, n_ok);
           }
           if (p.gate && valid) {
             const float* gp = p.gate + (size_t)sample * p.gate_ld;
 #pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < n_ok) {
+                const float gs = __ldg(gp + (col0 + j) / p.gate_group);
+                v[j] *= gs;
+                gv[j] *= gs;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_fast(gv[j]);
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+          if (p.bias) add32(v, p.bias + seg.vec_off + col0, n_ok);
+          if (p.rowvec && valid) add32(v, p.rowvec + (size_t)sample * p.rowvec_ld + col0, n_ok);
+          if (tabp) add32(v, tabp + col0, n_ok);
+          if (p.gate && valid) {
+            const float* gp = p.gate + (size_t)sample * p.gate_ld;
+#pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < seg.n_valid) v[j] *= __ldg(gp + (col0 + j) / p.gate_group);
+              if (j < n_ok) v[j] *= __ldg(gp + (col0 + j) / p.gate_group);
           }
           if (p.flags & APTP_EPI_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
           }
         }
-        if (!valid) continue;
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.res_ld + seg.out_col_off + col0);
+
+        if (bf16_out) {
+          if (use_res) {
+            // residual: coalesced registers -> swizzled smem -> own row
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rl = it * 8 + (lane >> 2);
+              const uint32_t a = smem_u32(stg) + rl * 64 + ((co_q ^ ((rl >> 1) & 3)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(rres[it].x), "r"(rres[it].y),
+                           "r"(rres[it].z), "r"(rres[it].w)
+                           : "memory");
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                           : "r"(stg_own + ((q ^ own_sw) << 4))
+                           : "memory");
+              v[q * 8 + 0] += bf16_lo(w0);
+              v[q * 8 + 1] += bf16_hi(w0);
+              v[q * 8 + 2] += bf16_lo(w1);
+              v[q * 8 + 3] += bf16_hi(w1);
+              v[q * 8 + 4] += bf16_lo(w2);
+              v[q * 8 + 5] += bf16_hi(w2);
+              v[q * 8 + 6] += bf16_lo(w3);
+              v[q * 8 + 7] += bf16_hi(w3);
+            }
+            __syncwarp();
+            // prefetch the residual of this warp's next chunk
+            if (col0 + 64 < seg.n_store && (c + 2) * 32 < out_cols_per_tile) load_res(col0 + 64);
+          }
+          if (n_ok < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j >= n_ok) v[j] = 0.f;
+          }
+          // own row -> swizzled smem
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (col0 + q * 8 < seg.n_valid) {  // n_valid is a multiple of 8 whenever a residual is used
-              const uint4 rr = __ldg(rp + q);
-              const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + ((q ^ own_sw) << 4)),
+                         "r"(pack_bf16(v[q * 8 + 0], v[q * 8 + 1])), "r"(pack_bf16(v[q * 8 + 2], v[q * 8 + 3])),
+                         "r"(pack_bf16(v[q * 8 + 4], v[q * 8 + 5])), "r"(pack_bf16(v[q * 8 + 6], v[q * 8 + 7]))
+                         : "memory");
+          }
+          __syncwarp();
+          // coalesced side: 8 rows x 64 B per instruction
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + seg.out_col_off + col0 + co_q * 8;
+          const bool col_ok = col0 + co_q * 8 < seg.n_store;  // n_store is a multiple of 8
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[q * 8 + 2 * e] += bf16_lo(w4[e]);
-                v[q * 8 + 2 * e + 1] += bf16_hi(w4[e]);
+          for (int it = 0; it < 4; ++it) {
+            const int rl = it * 8 + (lane >> 2);
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(smem_u32(stg) + rl * 64 + ((co_q ^ ((rl >> 1) & 3)) << 4))
+                         : "memory");
+            if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o;
+          }
+          __syncwarp();
+        } else if (valid) {
+          if (n_ok < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j >= n_ok) v[j] = 0.f;
+          }
+          if (p.out_mode == APTP_OUT_F32) {
+            float* op = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_ld + seg.out_col_off + col0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (col0 + q * 4 < seg.n_store) {  // n_store multiple of 4
+                *reinterpret_cast<float4*>(op + q * 4) =
+                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
               }
             }
+          } else {  // fp32 NCHW: out[(sample*out_ld + col) * rows_per_sample + pixel]
+            float* op = reinterpret_cast<float*>(p.out);
+            const long long pix = row - (long long)sample * p.rows_per_sample;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < n_ok) op[((size_t)sample * p.out_ld + col0 + j) * p.rows_per_sample + pix] = v[j];
           }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j >= seg.n_valid) v[j] = 0.f;
-
-        if (p.out_mode == APTP_OUT_BF16) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.out_ld + seg.out_col_off + col0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (col0 + q * 8 < seg.n_store) {  // n_store is a multiple of 8
-              uint4 o;
-              o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(op + q * 8) = o;
-            }
-          }
-        } else if (p.out_mode == APTP_OUT_F32) {
-          float* op = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_ld + seg.out_col_off + col0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (col0 + q * 4 < seg.n_store) {  // n_store multiple of 4
-              *reinterpret_cast<float4*>(op + q * 4) =
-                  make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            }
-          }
-        } else {  // fp32 NCHW: out[(sample*out_ld + col) * rows_per_sample + pixel]
-          float* op = reinterpret_cast<float*>(p.out);
-          const long long pix = row - (long long)sample * p.rows_per_sample;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < seg.n_valid)
-              op[((size_t)sample * p.out_ld + col0 + j) * p.rows_per_sample + pix] = v[j];
         }
       }
       tc_fence_before();
@@ -364,6 +489,9 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
                    (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
                "aptp_grouped_gemm_fwd: operands must be 16-byte aligned");
   APTP_REQUIRE(a->rows_per_sample > 0, "aptp_grouped_gemm_fwd: rows_per_sample must be > 0");
+  APTP_REQUIRE(a->residual == nullptr || (a->out_mode == APTP_OUT_BF16 && a->res_ld % 8 == 0),
+               "aptp_grouped_gemm_fwd: residual needs a bf16 output and res_ld %% 8 == 0");
+  APTP_REQUIRE(a->a_rows < (1ll << 31), "aptp_grouped_gemm_fwd: too many rows");
   APTP_REQUIRE(!(a->flags & APTP_EPI_GN_STATS), "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS not implemented yet");
   if (a->flags & APTP_EPI_GEGLU) APTP_REQUIRE(a->bn % 64 == 0, "aptp_grouped_gemm_fwd: GEGLU needs bn %% 64 == 0");
 
@@ -421,6 +549,11 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   p.bw = a->a_mode == APTP_A_LINEAR ? BM : a->bw;
   p.bh = a->a_mode == APTP_A_LINEAR ? 1 : a->bh;
   p.bb = a->a_mode == APTP_A_LINEAR ? 1 : a->bb;
+  APTP_REQUIRE((p.bw & (p.bw - 1)) == 0 && (p.bh & (p.bh - 1)) == 0, "aptp_grouped_gemm_fwd: box extents must be powers of two");
+  p.lbw = 0;
+  while ((1 << p.lbw) < p.bw) ++p.lbw;
+  p.lbh = 0;
+  while ((1 << p.lbh) < p.bh) ++p.lbh;
   p.k_tap_pitch = a->k_tap_pitch;
   p.out = a->out;
   p.out_ld = a->out_ld;
@@ -441,12 +574,12 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   APTP_REQUIRE(p.abort_flag != nullptr, "aptp_grouped_gemm_fwd: could not allocate abort flag");
 
   const int stage_bytes = A_STAGE_BYTES + a->bn * 128;
-  const int budget = 225 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  const int budget = 225 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - STG_BYTES /*epilogue staging*/;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   APTP_REQUIRE(stages >= 2, "aptp_grouped_gemm_fwd: tile too large for shared memory");
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + STG_BYTES + 1024 + 256;
   if (!g_gemm_smem_set) {
     APTP_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_gemm_smem_set = 1;

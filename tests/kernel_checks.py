@@ -157,6 +157,70 @@ def check_geglu(M=512, Kd=320, inner=1280, n_keep=1000, bn=256, seed=0):
     assert (out[:, n_keep:].float() == 0).all(), "geglu: padding must be zero"
 
 
+
+def check_gemm_epilogue_mix(seed=0):
+    """Soft-gate multiplier, column offset into a fused [q|k|v]-style output, residual aliasing the output
+    (in-place token stream update), ragged last tile."""
+    M, Kd, N, HW, gg = 1000, 320, 320, 250, 64
+    B = M // HW
+    a = _rand(M, Kd, seed=seed).bfloat16()
+    w = _rand(N, Kd, scale=Kd ** -0.5, seed=seed + 1).bfloat16()
+    b = _rand(N, seed=seed + 2)
+    gate = torch.rand(B, N // gg, device=DEV) * 0.8 + 0.1
+    out = torch.full((M, 3 * N), 3.0, device=DEV, dtype=torch.bfloat16)
+    sched = K.build_schedule([K.Segment(0, M, N, (Kd + 63) // 64, out_col_off=N)], 160, DEV)
+    K.grouped_gemm(a, w, out, sched, a_ld=Kd, a_k=Kd, a_rows=M, out_ld=3 * N, bias=b, rows_per_sample=HW, gate=gate,
+                   gate_ld=N // gg, gate_group=gg)
+    K.check_abort()
+    ref = (a.float() @ w.float().t() + b) * gate.repeat_interleave(HW, 0).repeat_interleave(gg, 1)
+    _close(out[:, N:2 * N], ref, 2e-2, 1e-2, "epilogue gate + out_col_off")
+    assert (out[:, :N].float() == 3.0).all() and (out[:, 2 * N:].float() == 3.0).all(), "neighbour columns touched"
+    tok = _rand(M, N, seed=seed + 5).bfloat16()
+    tok0 = tok.clone()
+    sched = K.build_schedule([K.Segment(0, M, N, (Kd + 63) // 64)], 128, DEV)
+    K.grouped_gemm(a, w, tok, sched, a_ld=Kd, a_k=Kd, a_rows=M, out_ld=N, bias=b, residual=tok, res_ld=N)
+    K.check_abort()
+    _close(tok, a.float() @ w.float().t() + b + tok0.float(), 2e-2, 1e-2, "in-place residual")
+
+
+def check_conv_residual(B=3, H=16, W=16, Cin=128, Cout=128, bn=128, seed=0):
+    """conv2 of a ResNet: bias + border table + residual read through a different row pitch."""
+    x = _rand(B, Cin, H, W, seed=seed).bfloat16()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=seed + 1).bfloat16()
+    b = _rand(Cout, seed=seed + 2)
+    res = _rand(B * H * W, Cout + 64, seed=seed + 3).bfloat16()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_packed = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = torch.full((B * H * W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    sched = K.build_schedule([K.Segment(0, B * H * W, Cout, (Cin + 63) // 64)], bn, DEV, mode=A_CONV3X3, Ho=H, Wo=W)
+    K.grouped_gemm(x_nhwc, w_packed, out, sched, a_ld=Cin, a_k=Cin, a_rows=B * H * W, mode=A_CONV3X3, batch=B, H=H,
+                   W=W, k_tap_pitch=Cin, out_ld=Cout, bias=b, rows_per_sample=H * W, residual=res, res_ld=Cout + 64)
+    K.check_abort()
+    ref = _conv_ref(x.float(), w.float(), b, 1).permute(0, 2, 3, 1).reshape(B * H * W, Cout) + res[:, :Cout].float()
+    _close(out, ref, 2e-2, 1e-2, "conv3x3 + residual")
+
+
+def check_geglu_gate(seed=0):
+    M, Kd, inner, HW, gw = 512, 320, 1280, 256, 32
+    a = _rand(M, Kd, seed=seed).bfloat16()
+    w = _rand(2 * inner, Kd, scale=Kd ** -0.5, seed=seed + 1).bfloat16()
+    b = _rand(2 * inner, seed=seed + 2)
+    gate = torch.rand(M // HW, gw, device=DEV) * 0.9 + 0.05
+    bn, half = 256, 128
+    nt = inner // half
+    wp = torch.stack([w[:inner].view(nt, half, Kd), w[inner:].view(nt, half, Kd)], 1).reshape(nt * bn, Kd).contiguous()
+    bp = torch.stack([b[:inner].view(nt, half), b[inner:].view(nt, half)], 1).reshape(nt * bn).contiguous()
+    out = torch.full((M, inner), float("nan"), device=DEV, dtype=torch.bfloat16)
+    sched = K.build_schedule([K.Segment(0, M, inner, (Kd + 63) // 64)], bn, DEV, geglu=True)
+    K.grouped_gemm(a, wp, out, sched, a_ld=Kd, a_k=Kd, a_rows=M, out_ld=inner, bias=bp, flags=EPI_GEGLU,
+                   rows_per_sample=HW, gate=gate, gate_ld=gw, gate_group=inner // gw)
+    K.check_abort()
+    proj = a.float() @ w.float().t() + b
+    gfull = gate.repeat_interleave(HW, 0).repeat_interleave(inner // gw, 1)
+    ref = (proj[:, :inner] * gfull) * F.gelu(proj[:, inner:] * gfull)
+    _close(out, ref, 2e-2, 1e-2, "geglu + soft gate")
+
+
 def check_out_modes(seed=0):
     B, HW, Kd, N = 2, 256, 320, 4
     a = _rand(B * HW, Kd, seed=seed).bfloat16()
@@ -288,6 +352,10 @@ ALL = [
     ("conv3x3_s2_16", lambda: check_conv3x3(stride=2, temb=False)),
     ("conv3x3_s2_64", lambda: check_conv3x3(B=2, H=64, W=64, Cin=64, Cout=64, bn=64, stride=2, temb=False)),
     ("geglu", check_geglu),
+    ("geglu_gate", check_geglu_gate),
+    ("gemm_epilogue_mix", check_gemm_epilogue_mix),
+    ("conv_residual", check_conv_residual),
+    ("conv_residual_8", lambda: check_conv_residual(B=5, H=8, W=8, Cin=192, Cout=320, bn=160)),
     ("out_modes", check_out_modes),
     ("groupnorm", lambda: check_groupnorm()),
     ("groupnorm_two_src", lambda: check_groupnorm(C0=640, C1=320, silu=False)),

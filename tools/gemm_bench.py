@@ -23,15 +23,22 @@ def timeit(fn, iters=10):
     return s.elapsed_time(e) / iters
 
 
-def bench_linear(M, Kd, N, bn):
+def bench_linear(M, Kd, N, bn, residual=False, geglu=False):
+    from diffusion_pruning_b200._lib import EPI_GEGLU
     a = torch.randn(M, Kd, device="cuda").bfloat16()
     w = torch.randn(N, Kd, device="cuda").bfloat16()
-    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    sched = K.build_schedule([K.Segment(0, M, N, Kd // 64)], bn, "cuda")
-    ms = timeit(lambda: K.grouped_gemm(a, w, out, sched, a_ld=Kd, a_k=Kd, a_rows=M, out_ld=N))
+    n_out = N // 2 if geglu else N
+    out = torch.empty(M, n_out, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, n_out, device="cuda").bfloat16() if residual else None
+    sched = K.build_schedule([K.Segment(0, M, n_out, Kd // 64)], bn, "cuda", geglu=geglu)
+    ms = timeit(lambda: K.grouped_gemm(a, w, out, sched, a_ld=Kd, a_k=Kd, a_rows=M, out_ld=n_out, bias=bias,
+                                       residual=res, res_ld=n_out, flags=EPI_GEGLU if geglu else 0))
     ms_t = timeit(lambda: torch.matmul(a, w.t()))
     fl = 2.0 * M * Kd * N
-    print(f"linear M{M} K{Kd} N{N} bn{bn}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s | torch {ms_t:.3f} ms {fl/ms_t/1e9:.0f} TFLOP/s", flush=True)
+    gb = (M * Kd + M * n_out * (2 if residual else 1) + N * Kd) * 2 / 1e9
+    print(f"linear M{M} K{Kd} N{N} bn{bn} res={int(residual)} geglu={int(geglu)}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s "
+          f"{gb/ms*1e3:.0f} GB/s | torch.matmul {ms_t:.3f} ms {fl/ms_t/1e9:.0f} TFLOP/s", flush=True)
 
 
 def bench_conv(B, H, C, Cout, bn):
@@ -60,7 +67,11 @@ def bench_attn(B, heads, N, Nkv):
 if __name__ == "__main__":
     bench_linear(8192, 8192, 8192, 256)
     bench_linear(262144, 320, 320, 160)
+    bench_linear(262144, 320, 320, 160, residual=True)
     bench_linear(262144, 320, 2560, 256)
+    bench_linear(262144, 320, 2560, 256, geglu=True)
+    bench_linear(262144, 320, 2560, 192, geglu=True)
+    bench_linear(262144, 1280, 320, 160, residual=True)
     bench_linear(65536, 640, 640, 160)
     bench_linear(16384, 1280, 1280, 256)
     bench_conv(64, 64, 320, 320, 160)
