@@ -9,13 +9,14 @@
 //                                                consumed MN-major straight from its [keys, d] layout)
 //   warps 4..7  softmax of Q tile 0, warps 8..11 softmax of Q tile 1 (setmaxnreg moves the registers of
 //               the producer warpgroup to them): one thread per query row; the
-//               whole S row is read once (tcgen05.ld), exp2 runs on ex2.approx with the softmax scale
-//               folded into one FFMA, P is written back bf16 over S (tcgen05.st). O stays in TMEM for
-//               the whole KV loop and is only rescaled when the running max grows by more than 2^8
-//               (lazy rescaling), so the steady state is: TMEM read S, 128 x (FFMA + EX2), TMEM write P.
-// The two Q tiles ping-pong on the tensor pipe: while one tile's softmax runs, the other tile's MMAs
-// execute. With short KV (cross-attention, 77 keys) a CTA loops over several query pairs to amortise
-// TMEM allocation and barrier setup.
+//               whole S row is read once (tcgen05.ld) into registers and S is handed straight back to
+//               the tensor pipe (s_free), so QK^T of the NEXT key tile runs underneath this tile's
+//               exponentials; exp2 runs on ex2.approx with the softmax scale folded into one FFMA; P is
+//               written bf16 to its own TMEM columns (tcgen05.st). O stays in TMEM for the whole KV
+//               loop and is only rescaled when the running max grows by more than 2^8 (lazy
+//               rescaling), so the steady state is: TMEM read S, 128 x (FFMA + EX2), TMEM write P.
+// With short KV (cross-attention, 77 keys) a CTA loops over several query pairs to amortise TMEM
+// allocation and barrier setup.
 #include "common.cuh"
 #include "../../include/aptp_sm100.h"
 
@@ -33,8 +34,9 @@ constexpr int ATT_SMEM_KV = 2 * ATT_TILE_BYTES;
 constexpr int ATT_SMEM_BAR = ATT_SMEM_KV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;
 constexpr int ATT_SMEM_BYTES = ATT_SMEM_BAR + 256 + 1024;
 constexpr int ATT_TMEM_COLS = 512;
-constexpr int ATT_TMEM_S = 0;      // S0 at cols [0,128), S1 at [128,256); P_w aliases the first 64 columns of S_w
-constexpr int ATT_TMEM_O = 256;    // O0 at [256,320), O1 at [320,384)
+constexpr int ATT_TMEM_S = 0;      // S0 at cols [0,128), S1 at [128,256)
+constexpr int ATT_TMEM_P = 256;    // P0 at [256,320), P1 at [320,384): 128 keys x bf16 = 64 packed columns
+constexpr int ATT_TMEM_O = 384;    // O0 at [384,448), O1 at [448,512)
 constexpr float ATT_RESCALE_LOG2 = 8.f;
 
 struct AttnParams {
@@ -60,9 +62,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   uint64_t* kv_full = bars + 2;                  // stages
   uint64_t* kv_empty = kv_full + ATT_KV_STAGES;  // stages
   uint64_t* s_full = kv_empty + ATT_KV_STAGES;   // 2
-  uint64_t* p_full = s_full + 2;                 // 2
-  uint64_t* o_full = p_full + 2;                 // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = s_full + 2;                 // 2: softmax holds S in registers, S columns reusable
+  uint64_t* p_full = s_free + 2;                 // 2
+  uint64_t* pv_done = p_full + 2;                // 2: PV MMA of a tile complete (P reusable, O current)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -83,8 +86,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
+        mbar_init(&s_free[i], 4);
         mbar_init(&p_full[i], 4);
-        mbar_init(&o_full[i], 1);
+        mbar_init(&pv_done[i], 1);
       }
       fence_barrier_init();
     }
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
-      uint32_t gp[2] = {0, 0};  // P tiles consumed per Q tile (phase of p_full)
+      uint32_t gp[2] = {0, 0};  // tiles consumed per Q tile (phase of s_free / p_full)
       bool ok = true;
       auto issue_s = [&](int w, int kv_stage) {
         const uint32_t q_addr = smem_u32(smem + ATT_SMEM_Q + w * ATT_TILE_BYTES);
@@ -164,16 +168,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             nphase ^= 1;
           }
           const bool more = j + 1 < n_tiles;
+          if (more && !mbar_wait(&kv_full[ns], nphase, p.abort_flag)) {
+            ok = false;
+            break;
+          }
+          // S_w of the next key tile as soon as the softmax warps hold the current S in registers
+          for (int w = 0; w < n_w && ok; ++w) {
+            ok = mbar_wait(&s_free[w], gp[w] & 1, p.abort_flag);
+            if (ok && more) {
+              tc_fence_after();
+              issue_s(w, ns);
+            }
+          }
+          if (!ok) break;
+          // O_w (+)= P_w V_j once P_w is in tensor memory
           const uint32_t v_addr = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
           for (int w = 0; w < n_w; ++w) {
-            // O_w (+)= P_w V_j
             if (!mbar_wait(&p_full[w], gp[w] & 1, p.abort_flag)) {
               ok = false;
               break;
             }
             ++gp[w];
             tc_fence_after();
-            const uint32_t p_tmem = tmem_base + ATT_TMEM_S + w * ATT_BN;
+            const uint32_t p_tmem = tmem_base + ATT_TMEM_P + w * (ATT_BN / 2);
             const uint32_t o_tmem = tmem_base + ATT_TMEM_O + w * ATT_D;
 #pragma unroll
             for (int k = 0; k < ATT_BN / 16; ++k) {
@@ -181,18 +198,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
               umma_bf16_ts(o_tmem, p_tmem + k * 8, make_desc_mnmajor_sw128(v_addr + k * 2048, ATT_TILE_BYTES), idesc_o,
                            (j | k) != 0);
             }
-            if (more) {
-              if (w == 0) {
-                if (!mbar_wait(&kv_full[ns], nphase, p.abort_flag)) {
-                  ok = false;
-                  break;
-                }
-                tc_fence_after();
-              }
-              issue_s(w, ns);  // S_w of the next KV tile overwrites P_w only after the PV above (in-order pipe)
-            } else {
-              umma_commit(&o_full[w]);
-            }
+            umma_commit(&pv_done[w]);
           }
           if (!ok) break;
           umma_commit(&kv_empty[stage]);
@@ -205,15 +211,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   }
   } else {
     // ------------------------------- softmax ------------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int w = (warp - 4) >> 2;   // Q tile of this warpgroup
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t s_addr = lane_addr + ATT_TMEM_S + w * ATT_BN;
+    const uint32_t p_addr = lane_addr + ATT_TMEM_P + w * (ATT_BN / 2);
     const uint32_t o_addr = lane_addr + ATT_TMEM_O + w * ATT_D;
-    uint32_t g = 0;    // KV tiles processed (phase of s_full)
-    uint32_t itw = 0;  // items processed by this warpgroup (phase of o_full)
+    uint32_t g = 0;   // key tiles processed (phase of s_full)
+    uint32_t gd = 0;  // pv_done phases consumed
     bool ok = true;
     for (int qp = blockIdx.x; qp < p.n_qpairs && ok; qp += gridDim.x) {
       const int q0 = qp * 2 * ATT_BM + w * ATT_BM;
@@ -229,6 +236,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         tmem_ld_32x32(s_addr + 64, s + 64);
         tmem_ld_32x32(s_addr + 96, s + 96);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[w]);  // the tensor pipe may overwrite S with the next tile now
         const int kv_left = p.n_kv - j * ATT_BN;  // keys valid in this tile (>= 1)
         float mx = -INFINITY;
         if (kv_left >= ATT_BN) {
@@ -241,12 +251,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             else s[i] = 0xff800000u;  // -inf -> p = 0
           }
         }
+        if (j > 0) {  // PV of the previous tile must be complete before P is overwritten / O rescaled
+          ok = mbar_wait(&pv_done[w], gd & 1, p.abort_flag);
+          ++gd;
+          if (!ok) break;
+          tc_fence_after();
+        }
         const float m_cand = mx * p.scale_log2;
         const bool need = m_cand > m_used + ATT_RESCALE_LOG2;  // first tile: m_used = -inf
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? m_cand : m_used;
           if (j > 0) {
-            // PV of the previous tile has completed (s_full of this tile was committed after it)
             const float factor = need ? ex2_approx(m_used - m_new) : 1.f;
             uint32_t o[ATT_D];
             tmem_ld_32x32(o_addr, o);
@@ -260,27 +275,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           }
           m_used = m_new;
         }
-        uint32_t pk[ATT_BN / 2];
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < ATT_BN; i += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_used));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_used));
-          l0 += p0;
-          l1 += p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i]), p.scale_log2, -m_used));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 1]), p.scale_log2, -m_used));
+            l0 += p0;
+            l1 += p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st_32x16(p_addr + c * 16, pk);
         }
         l_run += l0 + l1;
-        tmem_st_32x32(s_addr, pk);
-        tmem_st_32x32(s_addr + 32, pk + 32);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[w]);
       }
       if (!ok) break;
-      ok = mbar_wait(&o_full[w], itw & 1, p.abort_flag);
-      ++itw;
+      ok = mbar_wait(&pv_done[w], gd & 1, p.abort_flag);
+      ++gd;
       if (!ok) break;
       tc_fence_after();
       {
