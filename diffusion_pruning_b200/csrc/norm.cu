@@ -85,13 +85,23 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(Src2 s, int hw, 
     const int v = threadIdx.x % cv;
     const int prow = threadIdx.x / cv;
     if (prow < rows_per_iter) {
-      for (int p = p_begin + prow; p < p_end; p += rows_per_iter) {
-        float f[8];
-        unpack8(load_vec(s, (long long)b * hw + p, v * 8), f);
+      // 4 independent 16-byte loads in flight per thread
+      for (int p = p_begin + prow; p < p_end; p += 4 * rows_per_iter) {
+        uint4 raw[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          sum[0][e] += f[e];
-          sq[0][e] += f[e] * f[e];
+        for (int u = 0; u < 4; ++u) {
+          const int pp = p + u * rows_per_iter;
+          raw[u] = (pp < p_end) ? load_vec(s, (long long)b * hw + pp, v * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            sum[0][e] += f[e];
+            sq[0][e] += f[e] * f[e];
+          }
         }
       }
       flush_runs(bins, sum[0], sq[0], v * 8, ctot, gs);
@@ -173,34 +183,43 @@ __global__ void __launch_bounds__(NORM_THREADS)
         sft[e] = 0.f;
       }
     }
-    for (int p = p_begin + prow; p < p_end; p += rows_per_iter) {
-      const long long pix = (long long)b * hw + p;
-      float f[8];
-      if (v * 8 < ctot) {
-        unpack8(load_vec(s, pix, v * 8), f);
-      } else {
+    const bool has_data = v * 8 < ctot;
+    for (int p = p_begin + prow; p < p_end; p += 4 * rows_per_iter) {
+      uint4 raw[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int pp = p + u * rows_per_iter;
+        raw[u] = (has_data && pp < p_end) ? load_vec(s, (long long)b * hw + pp, v * 8) : make_uint4(0u, 0u, 0u, 0u);
       }
-      float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float t = f[e] * a[e] + sft[e];
-        if (silu) t = silu_f(t);
-        o[e] = (v * 8 + e < ctot) ? t : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int pp = p + u * rows_per_iter;
+        if (pp >= p_end) break;
+        float f[8];
+        unpack8(raw[u], f);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float t = f[e] * a[e] + sft[e];
+          if (silu) t = __fdividef(t, 1.f + __expf(-t));
+          o[e] = (v * 8 + e < ctot) ? t : 0.f;  // zero K padding even if stale memory holds inf/nan
+        }
+        uint4 out;
+        out.x = pack_bf16(o[0], o[1]);
+        out.y = pack_bf16(o[2], o[3]);
+        out.z = pack_bf16(o[4], o[5]);
+        out.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(y + ((long long)b * hw + pp) * ldy + v * 8) = out;
       }
-      uint4 out;
-      out.x = pack_bf16(o[0], o[1]);
-      out.y = pack_bf16(o[2], o[3]);
-      out.z = pack_bf16(o[4], o[5]);
-      out.w = pack_bf16(o[6], o[7]);
-      *reinterpret_cast<uint4*>(y + pix * ldy + v * 8) = out;
     }
   }
 }
 
-// One warp per row; C <= 32*8*MAXV.
+// One warp per token row, SLOTS 16-byte vectors per lane held in registers (exact two-pass). SLOTS is a
+// template parameter so narrow rows (C = 320: 2 slots) keep the register count -- and with it the
+// number of resident warps and loads in flight -- where an HBM-bound kernel needs them.
 constexpr int LN_MAXV = 8;
+template <int SLOTS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                         __nv_bfloat16* __restrict__ y, int ldy, long long rows, int C,
                                                         float eps, const float* __restrict__ gamma,
@@ -212,21 +231,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   if (row >= rows) return;
   if (sample_active && !sample_active[row / rows_per_sample]) return;
   const int cv = C / 8;
-  float f[LN_MAXV][8];
+  uint4 raw[SLOTS];
+#pragma unroll
+  for (int q = 0; q < SLOTS; ++q) {
+    const int v = lane + q * 32;
+    raw[q] = (v < cv) ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx + v * 8)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float f[SLOTS][8];
   float s = 0.f;
 #pragma unroll
-  for (int q = 0; q < LN_MAXV; ++q) {
-    const int v = lane + q * 32;
-    if (v < cv) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * ldx + v * 8)), f[q]);
+  for (int q = 0; q < SLOTS; ++q) {
+    unpack8(raw[q], f[q]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s += f[q][e];
-    }
+    for (int e = 0; e < 8; ++e) s += f[q][e];  // padded vectors are zero
   }
   const float mean = warp_sum(s) / (float)C;
   float ss = 0.f;
 #pragma unroll
-  for (int q = 0; q < LN_MAXV; ++q) {
+  for (int q = 0; q < SLOTS; ++q) {
     const int v = lane + q * 32;
     if (v < cv) {
 #pragma unroll
@@ -238,7 +260,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
   const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
 #pragma unroll
-  for (int q = 0; q < LN_MAXV; ++q) {
+  for (int q = 0; q < SLOTS; ++q) {
     const int v = lane + q * 32;
     if (v < cv) {
       float o[8];
@@ -328,9 +350,17 @@ extern "C" int aptp_layernorm(const void* x, int32_t ldx, void* y, int32_t ldy, 
   APTP_REQUIRE(rows_per_sample > 0, "aptp_layernorm: rows_per_sample must be > 0");
   if (rows == 0) return APTP_OK;
   const long long blocks = (rows + 7) / 8;
-  layernorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
-                                                        reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, eps, gamma,
-                                                        beta, sample_active, rows_per_sample);
+  const int slots = (C / 8 + 31) / 32;
+#define APTP_LN_LAUNCH(S)                                                                                          \
+  layernorm_kernel<S><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,       \
+                                                            reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, eps, \
+                                                            gamma, beta, sample_active, rows_per_sample)
+  if (slots <= 1) APTP_LN_LAUNCH(1);
+  else if (slots == 2) APTP_LN_LAUNCH(2);
+  else if (slots == 3) APTP_LN_LAUNCH(3);
+  else if (slots <= 5) APTP_LN_LAUNCH(5);
+  else APTP_LN_LAUNCH(8);
+#undef APTP_LN_LAUNCH
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }
