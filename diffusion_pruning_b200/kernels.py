@@ -197,6 +197,60 @@ def attention(q, ldq, k, ldk, v, ldv, out, ldo, batch, n_q, n_kv, sample_heads, 
 
 
 # --------------------------------------------------------------------------------------------
+# backward of the gated ops (K5)
+# --------------------------------------------------------------------------------------------
+def scale_cols(u, ldu, y, ldy, batch, hw, C_, gate, gate_ld, group):
+    check(load().aptp_scale_cols_fwd(_ptr(u), ldu, _ptr(y), ldy, batch, hw, C_, _ptr(gate), gate_ld, group, _stream()),
+          "aptp_scale_cols_fwd")
+
+
+def scale_cols_bwd(u, ldu, dy, lddy, du, lddu, batch, hw, C_, gate, gate_ld, group, dgate):
+    check(load().aptp_scale_cols_bwd(_ptr(u), ldu, _ptr(dy), lddy, _ptr(du), lddu, batch, hw, C_, _ptr(gate), gate_ld,
+                                     group, _ptr(dgate), _stream()), "aptp_scale_cols_bwd")
+
+
+def geglu(hg, ld, out, ldo, batch, hw, inner, gate, gate_ld, group):
+    check(load().aptp_geglu_fwd(_ptr(hg), ld, _ptr(out), ldo, batch, hw, inner, _ptr(gate), gate_ld, group, _stream()),
+          "aptp_geglu_fwd")
+
+
+def geglu_bwd(hg, ld, df, lddf, dhg, lddhg, batch, hw, inner, gate, gate_ld, group, dgate):
+    check(load().aptp_geglu_bwd(_ptr(hg), ld, _ptr(df), lddf, _ptr(dhg), lddhg, batch, hw, inner, _ptr(gate), gate_ld,
+                                group, _ptr(dgate), _stream()), "aptp_geglu_bwd")
+
+
+def groupnorm_bwd(x, ldx, da, ldda, dx, lddx, accumulate, batch, hw, C_, group_size, eps, stats, stats_groups, gamma,
+                  beta, gate, gate_ld, silu, bstats, dgate):
+    check(load().aptp_groupnorm_bwd(_ptr(x), ldx, _ptr(da), ldda, _ptr(dx), lddx, int(accumulate), batch, hw, C_,
+                                    group_size, float(eps), _ptr(stats), stats_groups, _ptr(gamma), _ptr(beta),
+                                    _ptr(gate), gate_ld, int(silu), _ptr(bstats), _ptr(dgate), _stream()),
+          "aptp_groupnorm_bwd")
+
+
+def layernorm_bwd(x, ldx, dy, lddy, dx, lddx, accumulate, rows, C_, eps, gamma):
+    check(load().aptp_layernorm_bwd(_ptr(x), ldx, _ptr(dy), lddy, _ptr(dx), lddx, int(accumulate), rows, C_,
+                                    float(eps), _ptr(gamma), _stream()), "aptp_layernorm_bwd")
+
+
+def depth_lerp_bwd(dout, lddo, x, ldx, y, ldy, dy, lddy, dx, lddx, accumulate, batch, hw, C_, d, dd):
+    check(load().aptp_depth_lerp_bwd(_ptr(dout), lddo, _ptr(x), ldx, _ptr(y), ldy, _ptr(dy), lddy, _ptr(dx), lddx,
+                                     int(accumulate), batch, hw, C_, _ptr(d), _ptr(dd), _stream()),
+          "aptp_depth_lerp_bwd")
+
+
+def add_rows(src, lds, dst, ldd, rows, C_):
+    check(load().aptp_add_rows(_ptr(src), lds, _ptr(dst), ldd, rows, C_, _stream()), "aptp_add_rows")
+
+
+def upsample2x_bwd(dy, dx, batch, H, W, C_):
+    check(load().aptp_upsample2x_bwd(_ptr(dy), _ptr(dx), batch, H, W, C_, _stream()), "aptp_upsample2x_bwd")
+
+
+def zero_insert2x(src, dst, batch, H, W, C_):
+    check(load().aptp_zero_insert2x(_ptr(src), _ptr(dst), batch, H, W, C_, _stream()), "aptp_zero_insert2x")
+
+
+# --------------------------------------------------------------------------------------------
 # router
 # --------------------------------------------------------------------------------------------
 def gumbel_gate(z, u, out, batch, n_width, n_depth, width_starts, n_gates, depth_order, temperature, base,

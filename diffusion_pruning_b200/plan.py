@@ -118,6 +118,14 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
 
 
+def pack_conv_weight_dgrad(w: torch.Tensor) -> torch.Tensor:
+    """Weights of the conv dgrad expressed as a forward 3x3 conv of the output gradient:
+    dX[y,x,c] = sum_{tap,n} dY[y+1-dy, x+1-dx, n] W[n,c,dy,dx]  ->  [Cin, 9*Cout] with K index =
+    (tap')*Cout + n and tap' = 8 - tap (taps flipped, channels transposed)."""
+    cout, cin = w.shape[0], w.shape[1]
+    return w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, 9 * cout).contiguous()
+
+
 def pack_rows(w2d: torch.Tensor, kept_rows: List[np.ndarray], n_pad: int) -> torch.Tensor:
     """N compaction: one [n_pad, K] block per variant, kept rows first, zero rows after."""
     out = torch.zeros(len(kept_rows) * n_pad, w2d.shape[1], device=w2d.device, dtype=torch.bfloat16)

@@ -211,6 +211,47 @@ int aptp_sinkhorn_phase(int32_t phase, float* Q, const float* scores, double* pa
 int aptp_route_sinkhorn(const float* scores, float* Q, double* partial, int64_t* indices, int32_t batch,
                         int32_t n_codes, float epsilon, int32_t iterations, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K5  backward of the gated ops. The U-Net is frozen during pruning
+ * (pdm/models/unet/unet_2d_conditional.py:2118-2122): only activation gradients (bf16) and
+ * per-(sample, gate) reductions (fp32, accumulated with atomics into caller-zeroed buffers) exist.
+ * dgrad GEMMs / convs reuse aptp_grouped_gemm_fwd with transposed (conv: tap-flipped) packed weights.
+ * ---------------------------------------------------------------------------------------------- */
+/* y = gate[b, c/group] * u over [batch*hw, C] (WidthGate on q,k,v: blocks.py:250-255; gates.py:15-21) */
+int aptp_scale_cols_fwd(const void* u, int32_t ldu, void* y, int32_t ldy, int32_t batch, int32_t hw, int32_t C,
+                        const float* gate, int32_t gate_ld, int32_t group, void* stream);
+/* du = gate * dy ; dgate[b,k] += sum_{pixels, c in k} dy * u */
+int aptp_scale_cols_bwd(const void* u, int32_t ldu, const void* dy, int32_t lddy, void* du, int32_t lddu, int32_t batch,
+                        int32_t hw, int32_t C, const float* gate, int32_t gate_ld, int32_t group, float* dgate,
+                        void* stream);
+/* GEGLUGated.forward (blocks.py:41-50) on the un-packed projection hg = [h | gate] (training form):
+ * out = (g h) * gelu_erf(g gate); backward writes d(hg) and accumulates dgate. gate may be NULL. */
+int aptp_geglu_fwd(const void* hg, int32_t ld, void* out, int32_t ldo, int32_t batch, int32_t hw, int32_t inner,
+                   const float* gate, int32_t gate_ld, int32_t group, void* stream);
+int aptp_geglu_bwd(const void* hg, int32_t ld, const void* df, int32_t lddf, void* dhg, int32_t lddhg, int32_t batch,
+                   int32_t hw, int32_t inner, const float* gate, int32_t gate_ld, int32_t group, float* dgate,
+                   void* stream);
+/* backward of aptp_groupnorm_apply (GroupNorm [+ width gate before, + SiLU after]; blocks.py:345-359):
+ * dx (+)= ..., dgate[b, group] += sum dxg * x. `stats` are the forward (sum, sumsq); bstats is scratch
+ * [batch, stats_groups, 2] (zeroed here). */
+int aptp_groupnorm_bwd(const void* x, int32_t ldx, const void* da, int32_t ldda, void* dx, int32_t lddx,
+                       int32_t accumulate, int32_t batch, int32_t hw, int32_t C, int32_t group_size, float eps,
+                       const float* stats, int32_t stats_groups, const float* gamma, const float* beta,
+                       const float* gate, int32_t gate_ld, int32_t silu, float* bstats, float* dgate, void* stream);
+/* backward of aptp_layernorm w.r.t. x: dx (+)= rstd (dy gamma - mean(.) - xh mean(. xh)) */
+int aptp_layernorm_bwd(const void* x, int32_t ldx, const void* dy, int32_t lddy, void* dx, int32_t lddx,
+                       int32_t accumulate, int64_t rows, int32_t C, float eps, const float* gamma, void* stream);
+/* DepthGate backward (gates.py:36-42): dy = d dout ; dx (+)= (1-d) dout ; dd[b] += sum dout (y - x) */
+int aptp_depth_lerp_bwd(const void* dout, int32_t lddo, const void* x, int32_t ldx, const void* y, int32_t ldy,
+                        void* dy, int32_t lddy, void* dx, int32_t lddx, int32_t accumulate, int32_t batch, int32_t hw,
+                        int32_t C, const float* d, float* dd, void* stream);
+/* dst += src (gradient fan-in of skips / residual branches) */
+int aptp_add_rows(const void* src, int32_t lds, void* dst, int32_t ldd, int64_t rows, int32_t C, void* stream);
+/* backward of aptp_upsample2x; and the zero-insertion that turns the stride-2 conv dgrad into a stride-1 conv
+ * of the tap-flipped weights (H, W = output size of the forward conv). */
+int aptp_upsample2x_bwd(const void* dy, void* dx, int32_t batch, int32_t H, int32_t W, int32_t C, void* stream);
+int aptp_zero_insert2x(const void* src, void* dst, int32_t batch, int32_t H, int32_t W, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,168 @@
+"""Backward-kernel numerics (K5): each kernel against torch autograd of the plain fp32 op on the same
+(bf16-rounded) inputs. Used by tests/test_backward_gpu.py and tools/kernel_check.py."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from diffusion_pruning_b200 import kernels as K
+from kernel_checks import DEV, _close, _rand
+
+
+def check_scale_cols(B=3, hw=200, C=384, group=64, seed=0):
+    u = _rand(B * hw, C, seed=seed).bfloat16()
+    dy = _rand(B * hw, C, seed=seed + 1).bfloat16()
+    gate = torch.rand(B, C // group, device=DEV) * 0.9 + 0.05
+    y = torch.empty_like(u)
+    K.scale_cols(u, C, y, C, B, hw, C, gate, C // group, group)
+    gfull = gate.repeat_interleave(hw, 0).repeat_interleave(group, 1)
+    _close(y, u.float() * gfull, 1e-2, 1e-2, "scale_cols fwd")
+    du = torch.empty_like(u)
+    dg = torch.zeros(B, C // group, device=DEV)
+    K.scale_cols_bwd(u, C, dy, C, du, C, B, hw, C, gate, C // group, group, dg)
+    _close(du, dy.float() * gfull, 1e-2, 1e-2, "scale_cols du")
+    ref = (dy.float() * u.float()).reshape(B, hw, C // group, group).sum(dim=(1, 3))
+    _close(dg, ref, 5e-2, 2e-3, "scale_cols dgate")
+
+
+def check_geglu_train(B=2, hw=130, inner=2560, gw=32, use_gate=True, seed=0):
+    hg = _rand(B * hw, 2 * inner, seed=seed).bfloat16()
+    df = _rand(B * hw, inner, seed=seed + 1).bfloat16()
+    gate = (torch.rand(B, gw, device=DEV) * 0.9 + 0.05) if use_gate else None
+    grp = inner // gw
+    out = torch.empty(B * hw, inner, device=DEV, dtype=torch.bfloat16)
+    K.geglu(hg, 2 * inner, out, inner, B, hw, inner, gate, gw, grp)
+    x = hg.float().requires_grad_(True)
+    g = gate.clone().requires_grad_(True) if use_gate else None
+    gfull = g.repeat_interleave(hw, 0).repeat_interleave(grp, 1) if use_gate else 1.0
+    ref = (gfull * x[:, :inner]) * F.gelu(gfull * x[:, inner:])
+    _close(out, ref.detach(), 2e-2, 1e-2, "geglu_train fwd")
+    ref.backward(df.float())
+    dhg = torch.empty_like(hg)
+    dg = torch.zeros(B, gw, device=DEV)
+    K.geglu_bwd(hg, 2 * inner, df, inner, dhg, 2 * inner, B, hw, inner, gate, gw, grp, dg if use_gate else None)
+    _close(dhg, x.grad, 2e-2, 1e-2, "geglu_train dhg")
+    if use_gate:
+        _close(dg, g.grad, 0.5, 5e-3, "geglu_train dgate")
+
+
+def check_groupnorm_bwd(B=3, hw=256, C=320, groups=32, silu=True, use_gate=True, accumulate=False, seed=0):
+    gs = C // groups
+    x = (_rand(B * hw, C, seed=seed) * 2 + 0.5).bfloat16()
+    da = _rand(B * hw, C, seed=seed + 1).bfloat16()
+    gamma = _rand(C, seed=seed + 2) * 0.2 + 1
+    beta = _rand(C, seed=seed + 3) * 0.2
+    gate = (torch.rand(B, groups, device=DEV) * 0.9 + 0.05) if use_gate else None
+    stats = torch.zeros(B, groups, 2, device=DEV)
+    K.groupnorm_stats(x, C, C, None, 0, 0, B, hw, gs, None, stats, groups)
+    dx0 = _rand(B * hw, C, seed=seed + 4).bfloat16()
+    dx = dx0.clone() if accumulate else torch.full_like(x, float("nan"))
+    bstats = torch.empty(B, groups, 2, device=DEV)
+    dg = torch.zeros(B, groups, device=DEV)
+    K.groupnorm_bwd(x, C, da, C, dx, C, accumulate, B, hw, C, gs, 1e-5, stats, groups, gamma, beta, gate, groups, silu,
+                    bstats, dg if use_gate else None)
+    xr = x.float().requires_grad_(True)
+    g = gate.clone().requires_grad_(True) if use_gate else None
+    xin = xr.reshape(B, hw, C).permute(0, 2, 1)
+    if use_gate:
+        xin = xin * g.repeat_interleave(gs, 1)[:, :, None]
+    y = F.group_norm(xin, groups, gamma, beta, 1e-5)
+    if silu:
+        y = F.silu(y)
+    y.backward(da.float().reshape(B, hw, C).permute(0, 2, 1))
+    ref = xr.grad + (dx0.float() if accumulate else 0)
+    _close(dx, ref, 3e-2, 2e-2, f"groupnorm_bwd dx silu={silu} gate={use_gate}")
+    if use_gate:
+        _close(dg, g.grad, 0.3, 2e-2, "groupnorm_bwd dgate")
+
+
+def check_layernorm_bwd(rows=777, C=640, accumulate=True, seed=0):
+    x = (_rand(rows, C, seed=seed) * 3 + 1).bfloat16()
+    dy = _rand(rows, C, seed=seed + 1).bfloat16()
+    gamma = _rand(C, seed=seed + 2) * 0.2 + 1
+    dx0 = _rand(rows, C, seed=seed + 3).bfloat16()
+    dx = dx0.clone() if accumulate else torch.full_like(x, float("nan"))
+    K.layernorm_bwd(x, C, dy, C, dx, C, accumulate, rows, C, 1e-5, gamma)
+    xr = x.float().requires_grad_(True)
+    F.layer_norm(xr, (C,), gamma, torch.zeros_like(gamma), 1e-5).backward(dy.float())
+    _close(dx, xr.grad + (dx0.float() if accumulate else 0), 3e-2, 2e-2, "layernorm_bwd")
+
+
+def check_depth_lerp_bwd(B=3, hw=100, C=128, seed=0):
+    x = _rand(B * hw, C + 64, seed=seed).bfloat16()
+    y = _rand(B * hw, C, seed=seed + 1).bfloat16()
+    dout = _rand(B * hw, C, seed=seed + 2).bfloat16()
+    d = torch.tensor([0.25, 1.0, 0.6], device=DEV)[:B]
+    dy = torch.empty_like(y)
+    dx0 = _rand(B * hw, C + 64, seed=seed + 3).bfloat16()
+    dx = dx0.clone()
+    dd = torch.zeros(B, device=DEV)
+    K.depth_lerp_bwd(dout, C, x, C + 64, y, C, dy, C, dx, C + 64, True, B, hw, C, d, dd)
+    df = d.repeat_interleave(hw)[:, None]
+    _close(dy, df * dout.float(), 1e-2, 1e-2, "depth_lerp_bwd dy")
+    _close(dx[:, :C], dx0[:, :C].float() + (1 - df) * dout.float(), 2e-2, 1e-2, "depth_lerp_bwd dx")
+    assert torch.equal(dx[:, C:], dx0[:, C:]), "depth_lerp_bwd touched columns beyond C"
+    ref = (dout.float() * (y.float() - x[:, :C].float())).reshape(B, -1).sum(1)
+    _close(dd, ref, 0.5, 5e-3, "depth_lerp_bwd dd")
+
+
+def check_resample_bwd(B=2, H=8, W=8, C=64, seed=0):
+    dy = _rand(B * 4 * H * W, C, seed=seed).bfloat16()
+    dx = torch.empty(B * H * W, C, device=DEV, dtype=torch.bfloat16)
+    K.upsample2x_bwd(dy, dx, B, H, W, C)
+    ref = dy.float().reshape(B, H, 2, W, 2, C).sum(dim=(2, 4)).reshape(B * H * W, C)
+    _close(dx, ref, 2e-2, 1e-2, "upsample2x_bwd")
+    src = _rand(B * H * W, C, seed=seed + 1).bfloat16()
+    dst = torch.full((B * 4 * H * W, C), 7.0, device=DEV, dtype=torch.bfloat16)
+    K.zero_insert2x(src, dst, B, H, W, C)
+    r = torch.zeros(B, 2 * H, 2 * W, C, device=DEV)
+    r[:, ::2, ::2] = src.float().reshape(B, H, W, C)
+    _close(dst, r.reshape(-1, C), 0, 0, "zero_insert2x")
+    a = _rand(B * H * W, C, seed=seed + 2).bfloat16()
+    b = _rand(B * H * W, C + 8, seed=seed + 3).bfloat16()
+    b0 = b.clone()
+    K.add_rows(a, C, b, C + 8, B * H * W, C)
+    _close(b[:, :C], a.float() + b0[:, :C].float(), 2e-2, 1e-2, "add_rows")
+    assert torch.equal(b[:, C:], b0[:, C:])
+
+
+def check_conv_dgrad(B=2, H=16, W=16, Cin=128, Cout=192, stride=1, seed=0):
+    """dgrad of the 3x3 conv through the SAME grouped GEMM kernel: transposed, tap-flipped packed weights
+    (stride 2: zero-inserted output gradient first)."""
+    from diffusion_pruning_b200._lib import A_CONV3X3
+    from diffusion_pruning_b200.plan import pack_conv_weight_dgrad
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=seed).bfloat16()
+    Ho, Wo = H // stride, W // stride
+    dy = _rand(B, Cout, Ho, Wo, seed=seed + 1).bfloat16()
+    x = torch.zeros(B, Cin, H, W, device=DEV, requires_grad=True)
+    F.conv2d(x, w.float(), None, stride=stride, padding=1).backward(dy.float())
+    wt = pack_conv_weight_dgrad(w)  # [Cin, 9*Cout]
+    dy_rows = dy.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Cout).contiguous()
+    if stride == 2:
+        up = torch.empty(B * H * W, Cout, device=DEV, dtype=torch.bfloat16)
+        K.zero_insert2x(dy_rows, up, B, Ho, Wo, Cout)
+        dy_rows = up
+    dx = torch.full((B * H * W, Cin), float("nan"), device=DEV, dtype=torch.bfloat16)
+    sched = K.build_schedule([K.Segment(0, B * H * W, Cin, (Cout + 63) // 64)], 128, DEV, mode=A_CONV3X3, Ho=H, Wo=W)
+    K.grouped_gemm(dy_rows, wt, dx, sched, a_ld=Cout, a_k=Cout, a_rows=B * H * W, mode=A_CONV3X3, batch=B, H=H, W=W,
+                   k_tap_pitch=Cout, out_ld=Cin, rows_per_sample=H * W)
+    K.check_abort()
+    _close(dx, x.grad.permute(0, 2, 3, 1).reshape(B * H * W, Cin), 3e-2, 2e-2, f"conv dgrad stride {stride}")
+
+
+ALL = [
+    ("bwd_scale_cols", check_scale_cols),
+    ("bwd_scale_cols_wide", lambda: check_scale_cols(B=2, hw=64, C=3840, group=64)),
+    ("bwd_geglu", check_geglu_train),
+    ("bwd_geglu_nogate", lambda: check_geglu_train(use_gate=False, inner=1280)),
+    ("bwd_groupnorm", check_groupnorm_bwd),
+    ("bwd_groupnorm_plain_acc", lambda: check_groupnorm_bwd(silu=False, use_gate=False, accumulate=True)),
+    ("bwd_groupnorm_wide", lambda: check_groupnorm_bwd(B=2, hw=64, C=2560, use_gate=False)),
+    ("bwd_layernorm", check_layernorm_bwd),
+    ("bwd_layernorm_320", lambda: check_layernorm_bwd(rows=100, C=320, accumulate=False)),
+    ("bwd_layernorm_1280", lambda: check_layernorm_bwd(rows=64, C=1280)),
+    ("bwd_depth_lerp", check_depth_lerp_bwd),
+    ("bwd_resample", check_resample_bwd),
+    ("bwd_conv_dgrad", check_conv_dgrad),
+    ("bwd_conv_dgrad_s2", lambda: check_conv_dgrad(stride=2)),
+]

@@ -16,7 +16,8 @@ import kernel_checks  # noqa: E402
 def main():
     pats = sys.argv[1:]
     n_fail = 0
-    for name, fn in kernel_checks.ALL:
+    import backward_checks
+    for name, fn in kernel_checks.ALL + backward_checks.ALL:
         if pats and not any(p in name for p in pats):
             continue
         t0 = time.time()
