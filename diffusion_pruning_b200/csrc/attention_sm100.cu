@@ -47,6 +47,8 @@ struct AttnParams {
   int n_qpairs;
   const int* sample_heads;
   float scale_log2;  // softmax scale * log2(e)
+  float* lse2;       // optional [batch, max_heads, n_q]: log2-domain log-sum-exp (for the backward)
+  int max_heads;
   int* abort_flag;
 };
 
@@ -303,6 +305,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       {
         const float inv_l = 1.f / l_run;
         const int qrow = q0 + r;
+        if (p.lse2 && qrow < p.n_q) p.lse2[((size_t)b * p.max_heads + head) * p.n_q + qrow] = m_used + log2f(l_run);
         __nv_bfloat16* op = p.out + ((size_t)b * p.n_q + qrow) * p.ldo + head * ATT_D;
         uint32_t o[ATT_D];
         tmem_ld_32x32(o_addr, o);
@@ -337,7 +340,8 @@ using namespace aptp;
 
 extern "C" int aptp_attention_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                                   void* out, int32_t ldo, int32_t batch, int32_t n_q, int32_t n_kv,
-                                  const int32_t* sample_heads, int32_t max_heads, float scale, void* stream_) {
+                                  const int32_t* sample_heads, int32_t max_heads, float scale, float* lse2,
+                                  void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   APTP_REQUIRE(q && k && v && out && sample_heads, "aptp_attention_fwd: null pointer");
   APTP_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "aptp_attention_fwd: pitches must be multiples of 8");
@@ -371,6 +375,8 @@ extern "C" int aptp_attention_fwd(const void* q, int32_t ldq, const void* k, int
   p.n_qpairs = (n_q + 2 * ATT_BM - 1) / (2 * ATT_BM);
   p.sample_heads = sample_heads;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse2 = lse2;
+  p.max_heads = max_heads;
   p.abort_flag = device_abort_flag();
   APTP_REQUIRE(p.abort_flag != nullptr, "aptp_attention_fwd: could not allocate abort flag");
   if (!g_attn_smem_set) {

@@ -191,9 +191,18 @@ def silu_bf16(src, dst, n):
     check(load().aptp_silu_bf16(_ptr(src), _ptr(dst), n, _stream()), "aptp_silu_bf16")
 
 
-def attention(q, ldq, k, ldk, v, ldv, out, ldo, batch, n_q, n_kv, sample_heads, max_heads, scale):
+def attention(q, ldq, k, ldk, v, ldv, out, ldo, batch, n_q, n_kv, sample_heads, max_heads, scale, lse2=None):
     check(load().aptp_attention_fwd(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), ldo, batch, n_q, n_kv,
-                                    _ptr(sample_heads), max_heads, float(scale), _stream()), "aptp_attention_fwd")
+                                    _ptr(sample_heads), max_heads, float(scale), _ptr(lse2), _stream()),
+          "aptp_attention_fwd")
+
+
+def attention_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, lse2, delta, dq, lddq, dk, lddk, dv, lddv, batch, n_q,
+                  n_kv, sample_heads, max_heads, scale):
+    check(load().aptp_attention_bwd(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(o), ldo, _ptr(dout), lddo,
+                                    _ptr(lse2), _ptr(delta), _ptr(dq), lddq, _ptr(dk), lddk, _ptr(dv), lddv, batch,
+                                    n_q, n_kv, _ptr(sample_heads), max_heads, float(scale), _stream()),
+          "aptp_attention_bwd")
 
 
 # --------------------------------------------------------------------------------------------

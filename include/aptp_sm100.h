@@ -168,7 +168,17 @@ int aptp_silu_bf16(const void* src, void* dst, int64_t n, void* stream);
  * ---------------------------------------------------------------------------------------------- */
 int aptp_attention_fwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
                        void* out, int32_t ldo, int32_t batch, int32_t n_q, int32_t n_kv,
-                       const int32_t* sample_heads, int32_t max_heads, float scale, void* stream);
+                       const int32_t* sample_heads, int32_t max_heads, float scale, float* lse2, void* stream);
+/* lse2 (optional, may be NULL): [batch, max_heads, n_q] fp32, log2-domain log-sum-exp of the scaled scores,
+ * consumed by aptp_attention_bwd. */
+/* Backward (K5): dq, dk, dv of the same attention (compacted head layout as the forward); `o` is the forward
+ * output, `dout` its gradient, delta is scratch [batch, max_heads, n_q] (rowsum(dout*o), written here).
+ * Two tcgen05 kernels: Q-stationary (dq) and KV-stationary (dk, dv). */
+int aptp_attention_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                       const void* o, int32_t ldo, const void* dout, int32_t lddo, const float* lse2, float* delta,
+                       void* dq, int32_t lddq, void* dk, int32_t lddk, void* dv, int32_t lddv, int32_t batch,
+                       int32_t n_q, int32_t n_kv, const int32_t* sample_heads, int32_t max_heads, float scale,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  router: fused Gumbel-sigmoid gate, width/depth normalisation, cosine scores, Sinkhorn, argmax.

@@ -150,7 +150,45 @@ def check_conv_dgrad(B=2, H=16, W=16, Cin=128, Cout=192, stride=1, seed=0):
     _close(dx, x.grad.permute(0, 2, 3, 1).reshape(B * H * W, Cin), 3e-2, 2e-2, f"conv dgrad stride {stride}")
 
 
+def check_attention_bwd(B=2, heads=3, kept=(3, 1), Nq=256, Nkv=256, seed=0):
+    C = heads * 64
+    q = _rand(B * Nq, C, seed=seed).bfloat16()
+    k = _rand(B * Nkv, C, seed=seed + 1).bfloat16()
+    v = _rand(B * Nkv, C, seed=seed + 2).bfloat16()
+    do = _rand(B * Nq, C, seed=seed + 3).bfloat16()
+    out = torch.zeros(B * Nq, C, device=DEV, dtype=torch.bfloat16)
+    sh = torch.tensor(list(kept), device=DEV, dtype=torch.int32)
+    lse = torch.zeros(B, heads, Nq, device=DEV)
+    K.attention(q, C, k, C, v, C, out, C, B, Nq, Nkv, sh, heads, 0.125, lse)
+    delta = torch.empty(B, heads, Nq, device=DEV)
+    dq = torch.full_like(q, 9.0)
+    dk = torch.full_like(k, 9.0)
+    dv = torch.full_like(v, 9.0)
+    K.attention_bwd(q, C, k, C, v, C, out, C, do, C, lse, delta, dq, C, dk, C, dv, C, B, Nq, Nkv, sh, heads, 0.125)
+    K.check_abort()
+    qf = q.float().reshape(B, Nq, heads, 64).transpose(1, 2).requires_grad_(True)
+    kf = k.float().reshape(B, Nkv, heads, 64).transpose(1, 2).requires_grad_(True)
+    vf = v.float().reshape(B, Nkv, heads, 64).transpose(1, 2).requires_grad_(True)
+    sc = (qf @ kf.transpose(-1, -2)) * 0.125
+    ref = torch.softmax(sc, -1) @ vf
+    ref.backward(do.float().reshape(B, Nq, heads, 64).transpose(1, 2))
+    lse_ref = torch.logsumexp(sc.detach(), -1) * 1.4426950408889634
+    for b in range(B):
+        kb = kept[b]
+        _close(lse[b, :kb], lse_ref[b, :kb], 2e-2, 1e-3, f"attention lse sample {b}")
+        for name, got, r, n in (("dq", dq, qf.grad, Nq), ("dk", dk, kf.grad, Nkv), ("dv", dv, vf.grad, Nkv)):
+            g = got.reshape(B, n, heads, 64).float()[b]
+            rr = r[b].transpose(0, 1)
+            scale = rr[:, :kb].abs().max().item() if kb else 1.0
+            _close(g[:, :kb], rr[:, :kb], 3e-2 * max(scale, 1e-3), 3e-2, f"attention_bwd {name} sample {b} Nq{Nq} Nkv{Nkv}")
+            assert (g[:, kb:] == 9.0).all(), f"attention_bwd {name}: pruned heads must not be written"
+
+
 ALL = [
+    ("bwd_attention", check_attention_bwd),
+    ("bwd_attention_cross77", lambda: check_attention_bwd(Nkv=77)),
+    ("bwd_attention_small", lambda: check_attention_bwd(B=3, heads=2, kept=(2, 0, 1), Nq=64, Nkv=64)),
+    ("bwd_attention_long", lambda: check_attention_bwd(B=1, heads=1, kept=(1,), Nq=1024, Nkv=640)),
     ("bwd_scale_cols", check_scale_cols),
     ("bwd_scale_cols_wide", lambda: check_scale_cols(B=2, hw=64, C=3840, group=64)),
     ("bwd_geglu", check_geglu_train),
