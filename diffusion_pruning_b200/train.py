@@ -1,0 +1,645 @@
+"""Training-mode (soft-gate, differentiable) execution of the gated U-Net: the student forward of the
+pruning step (pdm/training/trainer.py:1192-1195) and its backward w.r.t. the 84 gate tensors.
+
+All U-Net weights are frozen during pruning (pdm/models/unet/unet_2d_conditional.py:2118-2122) and the
+inputs are detached, so the backward produces only activation gradients (bf16) and per-(sample, gate)
+reductions (fp32): dgrad GEMMs / convs run on the same tcgen05 grouped GEMM with transposed (conv:
+tap-flipped) weights, attention backward on its two tcgen05 kernels, and the gated elementwise /
+normalisation ops on the K5 kernels of csrc/backward.cu. There is no autograd graph
+inside the U-Net: the forward records a tape, `UNetTrainFunction` exposes the whole step to PyTorch as
+ONE autograd node whose differentiable inputs are the gate tensors handed to `set_structure` and whose
+outputs are the prediction plus the nine hooked block activations (trainer.py:496-511, :1220-1225).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from . import plan as P
+from ._lib import A_CONV3X3, A_LINEAR, EPI_SILU, OUT_BF16, OUT_F32, OUT_F32_NCHW
+from .unet import BF16, Act, ResnetBlock2DWidthGated, Transformer2DModelWidthGated, _Engine
+
+
+class _G:
+    """A gradient in engine layout: bf16 rows [M, C] behind an explicit pitch (may be a column slice)."""
+    __slots__ = ("t", "ld", "C")
+
+    def __init__(self, t: torch.Tensor, ld: int, C: int):
+        self.t, self.ld, self.C = t, ld, C
+
+
+class TrainEngine(_Engine):
+    """Soft-gate forward with a tape + explicit backward. Sample order is the caller's (no bucketing:
+    with soft gates nothing can be skipped)."""
+
+    # ------------------------------------------------------------------------------------------
+    # small helpers
+    # ------------------------------------------------------------------------------------------
+    def _new(self, rows: int, cols: int, dtype=BF16, zero: bool = False) -> torch.Tensor:
+        f = torch.zeros if zero else torch.empty
+        return f(rows, cols, device=self.device, dtype=dtype)
+
+    def _mm(self, key, a: torch.Tensor, a_ld: int, a_k: int, M: int, w: torch.Tensor, N: int, out: torch.Tensor,
+            out_ld: int, *, bias=None, residual=None, res_ld=0, rows_per_sample=1, flags=0, out_col_off=0,
+            conv: Optional[Tuple[int, int, int]] = None, k_tap_pitch=0, rowvec=None, rowvec_ld=0, out_mode=OUT_BF16):
+        """Single-segment dense GEMM / 3x3 conv (stride 1) on the grouped tcgen05 kernel."""
+        mode = A_LINEAR if conv is None else A_CONV3X3
+        sk = ("tr", key, M, N, a_k, conv, out_col_off)
+        sched = self.sched.get(sk)
+        if sched is None:
+            seg = K.Segment(0, M, N, (a_k + 63) // 64, out_col_off=out_col_off)
+            bn = P.choose_bn([max(N, 32)])
+            if conv is None:
+                sched = K.build_schedule([seg], bn, self.device)
+            else:
+                sched = K.build_schedule([seg], bn, self.device, mode=A_CONV3X3, Ho=conv[1], Wo=conv[2])
+            self.sched[sk] = sched
+        kw: Dict[str, Any] = {}
+        if conv is not None:
+            kw = dict(mode=A_CONV3X3, batch=conv[0], H=conv[1], W=conv[2], k_tap_pitch=k_tap_pitch)
+        K.grouped_gemm(a, w, out, sched, a_ld=a_ld, a_k=a_k, a_rows=M, out_ld=out_ld, out_mode=out_mode, bias=bias,
+                       rows_per_sample=rows_per_sample, residual=residual, res_ld=res_ld, flags=flags, rowvec=rowvec,
+                       rowvec_ld=rowvec_ld, **kw)
+        self.launches += 1
+        self.flops += sched.flops
+
+    def _wT(self, name: str, mod: nn.Module, pad_out_to: int = 0) -> torch.Tensor:
+        """Transposed weight for the dgrad: Linear / 1x1 conv -> [K, N]; 3x3 conv -> [Cin, 9*Cout] tap-flipped."""
+        key = name + ".T"
+        d = self.dense.get(key)
+        if d is None:
+            w = mod.weight.detach().to(self.device)
+            if w.ndim == 4 and w.shape[-1] == 3:
+                if pad_out_to and w.shape[0] < pad_out_to:
+                    w = torch.cat([w, torch.zeros(pad_out_to - w.shape[0], *w.shape[1:], device=self.device,
+                                                  dtype=w.dtype)], 0)
+                d = P.pack_conv_weight_dgrad(w).to(BF16).contiguous()
+            else:
+                d = w.reshape(w.shape[0], -1).t().to(BF16).contiguous()
+            self.dense[key] = d
+        return d
+
+    def _w(self, name: str, mod: nn.Module) -> Dict[str, torch.Tensor]:
+        return self._dense_linear(name, mod)
+
+    def _gn_fwd(self, x: torch.Tensor, ld: int, C: int, B: int, hw: int, groups: int, eps: float, gamma, beta,
+                out: torch.Tensor, silu: bool, gate=None) -> torch.Tensor:
+        stats = torch.zeros(B, groups, 2, device=self.device, dtype=torch.float32)
+        gs = C // groups
+        K.groupnorm_stats(x, C, ld, None, 0, 0, B, hw, gs, None, stats, groups)
+        K.groupnorm_apply(x, C, ld, None, 0, 0, out, C, B, hw, gs, eps, stats, groups, gamma, beta, C, None, None, gate,
+                          groups, silu)
+        self.launches += 2
+        return stats
+
+    def _gn_bwd(self, x, ld, C, B, hw, groups, eps, stats, gamma, beta, da, dx: torch.Tensor, lddx: int,
+                accumulate: bool, silu: bool, gate=None, dgate=None):
+        bstats = self.buf("gn_bstats", B, groups * 2, torch.float32)
+        K.groupnorm_bwd(x, ld, da, C, dx, lddx, accumulate, B, hw, C, C // groups, eps, stats, groups, gamma, beta, gate,
+                        groups, silu, bstats, dgate)
+        self.launches += 2
+
+    # ------------------------------------------------------------------------------------------
+    # forward with tape
+    # ------------------------------------------------------------------------------------------
+    def run_train(self, sample: torch.Tensor, timestep, ctx: torch.Tensor, gate_list: List[torch.Tensor]):
+        m = self.m
+        B, cin, H, W = sample.shape
+        self.B = B
+        self.flops, self.launches = 0.0, 0
+        self.compact, self.eset, self.layout = False, None, None
+        # gates: [B, 1620] fp32 in get_structure order (widths then depths), as the caller supplied them
+        widths = [w for ws in m.get_structure()["width"] for w in ws]
+        n_w = len(widths)
+        arch = torch.cat([g.detach().reshape(g.shape[0], -1).float() for g in gate_list[:n_w]] +
+                         [g.detach().reshape(-1, 1).float() for g in gate_list[n_w:]], dim=1).to(self.device)
+        if arch.shape[0] != B:
+            assert B % arch.shape[0] == 0
+            arch = arch.repeat(B // arch.shape[0], 1)
+        self.soft_arch = arch.contiguous()
+        self.gate_rows = gate_list[0].shape[0]
+        self.width_starts = [0]
+        for w in widths:
+            self.width_starts.append(self.width_starts[-1] + w)
+        self.n_width = self.width_starts[-1]
+        self.gate_cols = {}
+        gi = di = 0
+        for mod in m._gated:
+            n = len(mod.gate_widths())
+            self.gate_cols[mod.uid] = {"w": list(range(gi, gi + n)), "d": (di if mod.depth_gate is not None else None)}
+            gi += n
+            di += int(mod.depth_gate is not None)
+        self.darch = torch.zeros_like(self.soft_arch)  # gradient accumulator, same column layout
+        self.tape: List[Tuple] = []
+        self.first_uid = m._gated[0].uid  # nothing upstream of it needs a gradient
+
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([float(timestep)], device=self.device)
+        sample = sample.detach().to(self.device, torch.float32).contiguous()
+        ctx = ctx.detach().to(self.device).contiguous()
+        self.n_ctx = ctx.shape[1]
+        cdim = ctx.shape[2]
+        ctx16 = self.buf("ctx", B * self.n_ctx, cdim)
+        if ctx.dtype == BF16:
+            ctx16.copy_(ctx.reshape(B * self.n_ctx, cdim))
+        else:
+            K.cast_f32_bf16(ctx.to(torch.float32), ctx16, B * self.n_ctx * cdim)
+        self.ctx = ctx16
+        self.time_embed(timestep)
+        c0 = m.config["block_out_channels"][0]
+        col = self.buf("im2col", B * H * W, 64)
+        K.im2col_input(sample, col, B, cin, H, W)
+        d = self.dense.get("conv_in")
+        if d is None:
+            w = m.conv_in.weight.detach().to(self.device)
+            wp = torch.zeros(c0, 64, device=self.device, dtype=BF16)
+            wp[:, :9 * cin] = w.permute(0, 2, 3, 1).reshape(c0, 9 * cin).to(BF16)
+            d = {"w": wp, "b": m.conv_in.bias.detach().to(self.device, torch.float32).contiguous()}
+            self.dense["conv_in"] = d
+        x0 = self._new(B * H * W, c0)
+        self._mm("conv_in", col, 64, 64, B * H * W, d["w"], c0, x0, c0, bias=d["b"], rows_per_sample=H * W)
+        x = Act(x0, B, H, W, c0)
+        taps: List[Act] = []
+        skips = [x]
+        for blk in m.down_blocks:
+            for i, r in enumerate(blk.resnets):
+                x = self.t_resnet(r, x)
+                if blk.attentions is not None:
+                    x = self.t_transformer(blk.attentions[i], x)
+                skips.append(x)
+            if blk.downsamplers is not None:
+                x = self.t_downsample(blk.downsamplers[0], x)
+                skips.append(x)
+            taps.append(x)
+        mb = m.mid_block
+        x = self.t_resnet(mb.resnets[0], x)
+        x = self.t_transformer(mb.attentions[0], x)
+        x = self.t_resnet(mb.resnets[1], x)
+        taps.append(x)
+        for blk in m.up_blocks:
+            for i, r in enumerate(blk.resnets):
+                x = self.t_resnet(r, x, skip=skips.pop())
+                if blk.attentions is not None:
+                    x = self.t_transformer(blk.attentions[i], x)
+            if blk.upsamplers is not None:
+                x = self.t_upsample(blk.upsamplers[0], x)
+            taps.append(x)
+        # conv_norm_out + SiLU + conv_out
+        dn = self.dense.get("out_norm")
+        if dn is None:
+            dn = {"g": m.conv_norm_out.weight.detach().to(self.device, torch.float32).contiguous(),
+                  "b": m.conv_norm_out.bias.detach().to(self.device, torch.float32).contiguous()}
+            self.dense["out_norm"] = dn
+        groups = m.config["norm_num_groups"]
+        a = self.buf("gn_a", x.rows, x.C)
+        stats = self._gn_fwd(x.t, x.ld, x.C, B, x.hw, groups, m.config["norm_eps"], dn["g"], dn["b"], a, True)
+        cout = m.config["out_channels"]
+        y = torch.empty(B, cout, x.H, x.W, device=self.device, dtype=torch.float32)
+        dco = self._dense_linear("conv_out", m.conv_out, n_pad_to=32)
+        sk = ("conv_out_tr", x.H, x.W, B)
+        sched = self.sched.get(sk)
+        if sched is None:
+            sched = K.build_schedule([K.Segment(0, x.rows, cout, (x.C + 63) // 64)], 32, self.device, mode=A_CONV3X3,
+                                     Ho=x.H, Wo=x.W)
+            self.sched[sk] = sched
+        K.grouped_gemm(a, dco["w"], y, sched, a_ld=x.C, a_k=x.C, a_rows=x.rows, mode=A_CONV3X3, batch=B, H=x.H, W=x.W,
+                       k_tap_pitch=x.C, out_ld=cout, out_mode=OUT_F32_NCHW, bias=dco["b"], rows_per_sample=x.hw)
+        self.final = (x, stats, dn)
+        self.tap_acts = taps
+        return y, taps
+
+    # ---- ResNet ----------------------------------------------------------------------------------
+    def t_resnet(self, r: ResnetBlock2DWidthGated, x: Act, skip: Optional[Act] = None) -> Act:
+        B, H, W, hw, M = x.B, x.H, x.W, x.hw, x.rows
+        if skip is not None:
+            cat = self._new(M, x.C + skip.C)
+            K.copy_rows(x.t, x.ld, cat, x.C + skip.C, M, x.C)
+            K.copy_rows(skip.t, skip.ld, cat[:, x.C:], x.C + skip.C, M, skip.C)
+            xin = Act(cat, B, H, W, x.C + skip.C)
+        else:
+            xin = x
+        assert xin.C == r.cin
+        pk = self._resnet_pack(r)
+        cidx = self.gate_cols[r.uid]
+        gate = self._soft_gate(cidx["w"][0])
+        a1 = self.buf("gn_a", M, r.cin)
+        st1 = self._gn_fwd(xin.t, xin.ld, r.cin, B, hw, r.groups, r.eps, pk["g1"], pk["b1"], a1, True)
+        h1 = self._new(M, r.cout)
+        rv = self.temb_rowvec[:, self.m._temb_off[r.uid]:]
+        self._mm(("c1", r.uid), a1, r.cin, r.cin, M, pk["w1"], r.cout, h1, r.cout, conv=(B, H, W), k_tap_pitch=r.cin,
+                 rowvec=rv, rowvec_ld=self.m._temb_total, rows_per_sample=hw)
+        a2 = self.buf("gn_b", M, r.cout)
+        st2 = self._gn_fwd(h1, r.cout, r.cout, B, hw, r.groups, r.eps, pk["gamma2"], pk["beta2"], a2, True, gate=gate)
+        y = self._new(M, r.cout)
+        if r.conv_shortcut is not None:
+            sc = self._w("sc." + r.uid, r.conv_shortcut)
+            self._mm(("sc", r.uid), xin.t, xin.ld, r.cin, M, sc["w"], r.cout, y, r.cout, bias=sc["b"], rows_per_sample=hw)
+            res, res_ld = y, r.cout
+        else:
+            res, res_ld = xin.t, xin.ld
+        self._mm(("c2", r.uid), a2, r.cout, r.cout, M, pk["w2"], r.cout, y, r.cout, conv=(B, H, W), k_tap_pitch=r.cout,
+                 bias=pk["b2"], residual=res, res_ld=res_ld, rows_per_sample=hw)
+        out, dgate_d = y, None
+        keep_c = xin.C - (r.skip_connection_dim or 0)
+        if r.depth_gate is not None:
+            out = self._new(M, r.cout)
+            dgate_d = self._soft_depth(cidx["d"])
+            K.depth_lerp(xin.t, xin.ld, y, r.cout, out, r.cout, M, keep_c, dgate_d, hw)
+        o = Act(out, B, H, W, r.cout)
+        self.tape.append(("res", r, dict(x=x, skip=skip, xin=xin, st1=st1, h1=h1, st2=st2, y=y, gate=gate, d=dgate_d,
+                                         keep=keep_c, out=o)))
+        return o
+
+    def b_resnet(self, r: ResnetBlock2DWidthGated, s: Dict[str, Any], dout: _G):
+        xin: Act = s["xin"]
+        B, H, W, hw, M = xin.B, xin.H, xin.W, xin.hw, xin.rows
+        pk = self._resnet_pack(r)
+        cidx = self.gate_cols[r.uid]
+        need_in = r.uid != self.first_uid
+        dxin = None
+        if r.depth_gate is not None:
+            dxin = self._new(M, r.cin, zero=(s["keep"] != r.cin))
+            dy = self._new(M, r.cout)
+            dd = self.darch[:, self.n_width + cidx["d"]]
+            ddc = torch.zeros(B, device=self.device, dtype=torch.float32)
+            K.depth_lerp_bwd(dout.t, dout.ld, xin.t, xin.ld, s["y"], r.cout, dy, r.cout, dxin, r.cin, False, B, hw,
+                             s["keep"], s["d"], ddc)
+            dd.add_(ddc)
+            dyg = _G(dy, r.cout, r.cout)
+            have = True
+        else:
+            dyg = dout
+            have = False
+        if need_in:
+            if r.conv_shortcut is not None:
+                wt = self._wT("sc." + r.uid, r.conv_shortcut)
+                if dxin is None:
+                    dxin = self._new(M, r.cin)
+                self._mm(("sc.T", r.uid), dyg.t, dyg.ld, r.cout, M, wt, r.cin, dxin, r.cin,
+                         residual=dxin if have else None, res_ld=r.cin, rows_per_sample=hw)
+            else:
+                if have:
+                    K.add_rows(dyg.t, dyg.ld, dxin, r.cin, M, r.cout)
+                elif dyg.ld == r.cin and dyg.C == r.cin:
+                    dxin = dyg.t  # identity skip: take ownership of the incoming gradient buffer
+                else:
+                    dxin = self._new(M, r.cin)
+                    K.copy_rows(dyg.t, dyg.ld, dxin, r.cin, M, r.cin)
+        # conv2 dgrad -> GN2(+gate,+SiLU) backward
+        da2 = self.buf("bw_a", M, r.cout)
+        self._mm(("c2.T", r.uid), dyg.t, dyg.ld, r.cout, M, self._wT("c2." + r.uid, r.conv2), r.cout, da2, r.cout,
+                 conv=(B, H, W), k_tap_pitch=r.cout, rows_per_sample=hw)
+        dh1 = self.buf("bw_b", M, r.cout)
+        gcol = self.width_starts[cidx["w"][0]]
+        dg = torch.zeros(B, r.groups, device=self.device, dtype=torch.float32)
+        self._gn_bwd(s["h1"], r.cout, r.cout, B, hw, r.groups, r.eps, s["st2"], pk["gamma2"], pk["beta2"], da2, dh1,
+                     r.cout, False, True, gate=s["gate"], dgate=dg)
+        self.darch[:, gcol:gcol + r.groups].add_(dg)
+        if not need_in:
+            return None
+        da1 = self.buf("bw_c", M, r.cin)
+        self._mm(("c1.T", r.uid), dh1, r.cout, r.cout, M, self._wT("c1." + r.uid, r.conv1), r.cin, da1, r.cin,
+                 conv=(B, H, W), k_tap_pitch=r.cout, rows_per_sample=hw)
+        self._gn_bwd(xin.t, xin.ld, r.cin, B, hw, r.groups, r.eps, s["st1"], pk["g1"], pk["b1"], da1, dxin, r.cin, True,
+                     True)
+        return _G(dxin, r.cin, r.cin)
+
+    # ---- transformer -----------------------------------------------------------------------------
+    def _t_attn(self, uid: str, attn, gate_idx: int, xn: torch.Tensor, tok_in: torch.Tensor, tok_out: torch.Tensor,
+                B: int, hw: int, C: int, cross: bool) -> Dict[str, Any]:
+        M = B * hw
+        heads = attn.heads
+        gate = self._soft_gate(gate_idx)
+        n_kv = self.n_ctx if cross else hw
+        Mkv = B * n_kv
+        wq, wk, wv = self._w("q." + uid, attn.to_q), self._w("k." + uid, attn.to_k), self._w("v." + uid, attn.to_v)
+        key = "wqkv." + uid
+        if key not in self.dense:
+            if cross:
+                self.dense[key] = torch.cat([wk["w"], wv["w"]], 0).contiguous()
+            else:
+                self.dense[key] = torch.cat([wq["w"], wk["w"], wv["w"]], 0).contiguous()
+        wcat = self.dense[key]
+        if cross:
+            uq = self._new(M, C)
+            ukv = self._new(Mkv, 2 * C)
+            self._mm(("q", uid), xn, C, C, M, wq["w"], C, uq, C, rows_per_sample=hw)
+            self._mm(("kv", uid), self.ctx, attn.ctx_dim, attn.ctx_dim, Mkv, wcat, 2 * C, ukv, 2 * C,
+                     rows_per_sample=n_kv)
+            gq = self._new(M, C)
+            gkv = self._new(Mkv, 2 * C)
+            K.scale_cols(uq, C, gq, C, B, hw, C, gate, heads, 64)
+            K.scale_cols(ukv, 2 * C, gkv, 2 * C, B, n_kv, C, gate, heads, 64)
+            K.scale_cols(ukv[:, C:], 2 * C, gkv[:, C:], 2 * C, B, n_kv, C, gate, heads, 64)
+            q, ldq, kk, vv, ldkv = gq, C, gkv, gkv[:, C:], 2 * C
+            saved = dict(uq=uq, ukv=ukv, gq=gq, gkv=gkv)
+        else:
+            u = self._new(M, 3 * C)
+            self._mm(("qkv", uid), xn, C, C, M, wcat, 3 * C, u, 3 * C, rows_per_sample=hw)
+            g = self._new(M, 3 * C)
+            for j in range(3):
+                K.scale_cols(u[:, j * C:], 3 * C, g[:, j * C:], 3 * C, B, hw, C, gate, heads, 64)
+            q, ldq, kk, vv, ldkv = g, 3 * C, g[:, C:], g[:, 2 * C:], 3 * C
+            saved = dict(u=u, g=g)
+        o = self._new(M, C)
+        lse = torch.empty(B, heads, hw, device=self.device, dtype=torch.float32)
+        sh = self.sched.get(("heads_full", B, heads))
+        if sh is None:
+            sh = torch.full((B,), heads, device=self.device, dtype=torch.int32)
+            self.sched[("heads_full", B, heads)] = sh
+        K.attention(q, ldq, kk, ldkv, vv, ldkv, o, C, B, hw, n_kv, sh, heads, 0.125, lse)
+        wo = self._w("o." + uid, attn.to_out[0])
+        self._mm(("o", uid), o, C, C, M, wo["w"], C, tok_out, C, bias=wo["b"], residual=tok_in, res_ld=C,
+                 rows_per_sample=hw)
+        self.launches += 8
+        self.flops += 4.0 * hw * n_kv * 64 * heads * B
+        saved.update(o=o, lse=lse, gate=gate, sh=sh, n_kv=n_kv, cross=cross)
+        return saved
+
+    def _b_attn(self, uid: str, attn, gate_idx: int, s: Dict[str, Any], dtok: torch.Tensor, B: int, hw: int, C: int):
+        """dtok is d(tok_out); returns d(ln) [M, C] (gradient of the LayerNorm output feeding q / qkv)."""
+        M = B * hw
+        heads = attn.heads
+        n_kv, cross = s["n_kv"], s["cross"]
+        Mkv = B * n_kv
+        do = self.buf("bw_do", M, C)
+        self._mm(("o.T", uid), dtok, C, C, M, self._wT("o." + uid, attn.to_out[0]), C, do, C, rows_per_sample=hw)
+        delta = self.buf("bw_delta", B * heads, hw, torch.float32)
+        dg = torch.zeros(B, heads, device=self.device, dtype=torch.float32)
+        if cross:
+            dq = self.buf("bw_dq", M, C)
+            dkv = self.buf("bw_dkv", Mkv, 2 * C)
+            gq, gkv = s["gq"], s["gkv"]
+            K.attention_bwd(gq, C, gkv, 2 * C, gkv[:, C:], 2 * C, s["o"], C, do, C, s["lse"], delta, dq, C, dkv, 2 * C,
+                            dkv[:, C:], 2 * C, B, hw, n_kv, s["sh"], heads, 0.125)
+            duq = self.buf("bw_duq", M, C)
+            dukv = self.buf("bw_dukv", Mkv, 2 * C)  # dk, dv only feed the gate gradient (ctx needs none)
+            K.scale_cols_bwd(s["uq"], C, dq, C, duq, C, B, hw, C, s["gate"], heads, 64, dg)
+            K.scale_cols_bwd(s["ukv"], 2 * C, dkv, 2 * C, dukv, 2 * C, B, n_kv, C, s["gate"], heads, 64, dg)
+            K.scale_cols_bwd(s["ukv"][:, C:], 2 * C, dkv[:, C:], 2 * C, dukv[:, C:], 2 * C, B, n_kv, C, s["gate"], heads,
+                             64, dg)
+            dln = self.buf("bw_dln", M, C)
+            self._mm(("q.T", uid), duq, C, C, M, self._wT("q." + uid, attn.to_q), C, dln, C, rows_per_sample=hw)
+        else:
+            g = s["g"]
+            dqkv = self.buf("bw_dqkv", M, 3 * C)
+            K.attention_bwd(g, 3 * C, g[:, C:], 3 * C, g[:, 2 * C:], 3 * C, s["o"], C, do, C, s["lse"], delta, dqkv, 3 * C,
+                            dqkv[:, C:], 3 * C, dqkv[:, 2 * C:], 3 * C, B, hw, n_kv, s["sh"], heads, 0.125)
+            du = self.buf("bw_du", M, 3 * C)
+            for j in range(3):
+                K.scale_cols_bwd(s["u"][:, j * C:], 3 * C, dqkv[:, j * C:], 3 * C, du[:, j * C:], 3 * C, B, hw, C,
+                                 s["gate"], heads, 64, dg)
+            key = "wqkv.T." + uid
+            if key not in self.dense:
+                self.dense[key] = self.dense["wqkv." + uid].t().contiguous()  # [C, 3C]
+            dln = self.buf("bw_dln", M, C)
+            self._mm(("qkv.T", uid), du, 3 * C, 3 * C, M, self.dense[key], C, dln, C, rows_per_sample=hw)
+        gcol = self.width_starts[gate_idx]
+        self.darch[:, gcol:gcol + heads].add_(dg)
+        self.launches += 8
+        return dln
+
+    def t_transformer(self, t: Transformer2DModelWidthGated, x: Act) -> Act:
+        B, H, W, hw, C, M = x.B, x.H, x.W, x.hw, x.C, x.rows
+        tb = t.transformer_blocks[0]
+        cidx = self.gate_cols[t.uid]
+        key = ("tr_dense", t.uid)
+        dn = self.dense.get(key)
+        if dn is None:
+            f32 = lambda p: p.detach().to(self.device, torch.float32).contiguous()
+            dn = {"g": f32(t.norm.weight), "b": f32(t.norm.bias)}
+            for i, ln in enumerate((tb.norm1, tb.norm2, tb.norm3)):
+                dn[f"lg{i}"], dn[f"lb{i}"] = f32(ln.weight), f32(ln.bias)
+            self.dense[key] = dn
+        xn = self.buf("ln", M, C)
+        st = self._gn_fwd(x.t, x.ld, C, B, hw, t.groups, 1e-6, dn["g"], dn["b"], xn, False)
+        pi = self._w("pi." + t.uid, t.proj_in)
+        tok0 = self._new(M, C)
+        self._mm(("pi", t.uid), xn, C, C, M, pi["w"], C, tok0, C, bias=pi["b"], rows_per_sample=hw)
+        K.layernorm(tok0, C, xn, C, M, C, 1e-5, dn["lg0"], dn["lb0"])
+        tok1 = self._new(M, C)
+        s1 = self._t_attn(t.uid + ".a1", tb.attn1, cidx["w"][0], xn, tok0, tok1, B, hw, C, cross=False)
+        K.layernorm(tok1, C, xn, C, M, C, 1e-5, dn["lg1"], dn["lb1"])
+        tok2 = self._new(M, C)
+        s2 = self._t_attn(t.uid + ".a2", tb.attn2, cidx["w"][1], xn, tok1, tok2, B, hw, C, cross=True)
+        K.layernorm(tok2, C, xn, C, M, C, 1e-5, dn["lg2"], dn["lb2"])
+        proj = tb.ff.net[0].proj
+        inner = proj.weight.shape[0] // 2
+        wp = self._w("ffp." + t.uid, proj)
+        hg = self._new(M, 2 * inner)
+        self._mm(("ffp", t.uid), xn, C, C, M, wp["w"], 2 * inner, hg, 2 * inner, bias=wp["b"], rows_per_sample=hw)
+        fgate = self._soft_gate(cidx["w"][2])
+        f = self.buf("ff", M, inner)
+        K.geglu(hg, 2 * inner, f, inner, B, hw, inner, fgate, t.gate_width, inner // t.gate_width)
+        w2 = self._w("ff2." + t.uid, tb.ff.net[2])
+        tok3 = self.buf("tok3", M, C)
+        self._mm(("ff2", t.uid), f, inner, inner, M, w2["w"], C, tok3, C, bias=w2["b"], residual=tok2, res_ld=C,
+                 rows_per_sample=hw)
+        po = self._w("po." + t.uid, t.proj_out)
+        y = self._new(M, C)
+        self._mm(("po", t.uid), tok3, C, C, M, po["w"], C, y, C, bias=po["b"], residual=x.t, res_ld=x.ld,
+                 rows_per_sample=hw)
+        out, d = y, None
+        if t.depth_gate is not None:
+            out = self._new(M, C)
+            d = self._soft_depth(cidx["d"])
+            K.depth_lerp(x.t, x.ld, y, C, out, C, M, C, d, hw)
+        self.launches += 6
+        o = Act(out, B, H, W, C)
+        self.tape.append(("tr", t, dict(x=x, st=st, tok0=tok0, tok1=tok1, tok2=tok2, s1=s1, s2=s2, hg=hg, fgate=fgate,
+                                        inner=inner, y=y, d=d, out=o, dn=dn)))
+        return o
+
+    def b_transformer(self, t: Transformer2DModelWidthGated, s: Dict[str, Any], dout: _G) -> _G:
+        x: Act = s["x"]
+        B, H, W, hw, C, M = x.B, x.H, x.W, x.hw, x.C, x.rows
+        tb = t.transformer_blocks[0]
+        cidx = self.gate_cols[t.uid]
+        dn = s["dn"]
+        if t.depth_gate is not None:
+            dy = self._new(M, C)
+            dx = self._new(M, C)
+            ddc = torch.zeros(B, device=self.device, dtype=torch.float32)
+            K.depth_lerp_bwd(dout.t, dout.ld, x.t, x.ld, s["y"], C, dy, C, dx, C, False, B, hw, C, s["d"], ddc)
+            self.darch[:, self.n_width + cidx["d"]].add_(ddc)
+            K.add_rows(dy, C, dx, C, M, C)  # residual x of proj_out
+        else:
+            if dout.ld == C:
+                dy = dout.t
+            else:
+                dy = self._new(M, C)
+                K.copy_rows(dout.t, dout.ld, dy, C, M, C)
+            dx = dy  # out = proj_out(.) + x: the incoming buffer becomes dx after its last read as dy
+        dtok = self._new(M, C)
+        self._mm(("po.T", t.uid), dy, C, C, M, self._wT("po." + t.uid, t.proj_out), C, dtok, C, rows_per_sample=hw)
+        # feed-forward
+        inner = s["inner"]
+        df = self.buf("bw_df", M, inner)
+        self._mm(("ff2.T", t.uid), dtok, C, C, M, self._wT("ff2." + t.uid, tb.ff.net[2]), inner, df, inner,
+                 rows_per_sample=hw)
+        dhg = self.buf("bw_dhg", M, 2 * inner)
+        dgf = torch.zeros(B, t.gate_width, device=self.device, dtype=torch.float32)
+        K.geglu_bwd(s["hg"], 2 * inner, df, inner, dhg, 2 * inner, B, hw, inner, s["fgate"], t.gate_width,
+                    inner // t.gate_width, dgf)
+        gcol = self.width_starts[cidx["w"][2]]
+        self.darch[:, gcol:gcol + t.gate_width].add_(dgf)
+        dln = self.buf("bw_dln", M, C)
+        self._mm(("ffp.T", t.uid), dhg, 2 * inner, 2 * inner, M, self._wT("ffp." + t.uid, tb.ff.net[0].proj), C, dln, C,
+                 rows_per_sample=hw)
+        K.layernorm_bwd(s["tok2"], C, dln, C, dtok, C, True, M, C, 1e-5, dn["lg2"])
+        # cross-attention, self-attention
+        dln = self._b_attn(t.uid + ".a2", tb.attn2, cidx["w"][1], s["s2"], dtok, B, hw, C)
+        K.layernorm_bwd(s["tok1"], C, dln, C, dtok, C, True, M, C, 1e-5, dn["lg1"])
+        dln = self._b_attn(t.uid + ".a1", tb.attn1, cidx["w"][0], s["s1"], dtok, B, hw, C)
+        K.layernorm_bwd(s["tok0"], C, dln, C, dtok, C, True, M, C, 1e-5, dn["lg0"])
+        # proj_in, GroupNorm
+        dxn = self.buf("bw_dxn", M, C)
+        self._mm(("pi.T", t.uid), dtok, C, C, M, self._wT("pi." + t.uid, t.proj_in), C, dxn, C, rows_per_sample=hw)
+        self._gn_bwd(x.t, x.ld, C, B, hw, t.groups, 1e-6, s["st"], dn["g"], dn["b"], dxn, dx, C, True, False)
+        self.launches += 8
+        return _G(dx, C, C)
+
+    # ---- samplers ----------------------------------------------------------------------------------
+    def t_downsample(self, smp, x: Act) -> Act:
+        out = self._new(x.rows // 4, x.C)
+        self.conv3x3("ds.%d" % id(smp), smp.conv, x, out, x.C, stride=2)
+        o = Act(out, x.B, x.H // 2, x.W // 2, x.C)
+        self.tape.append(("down", smp, dict(x=x, out=o)))
+        return o
+
+    def b_downsample(self, smp, s, dout: _G) -> _G:
+        x: Act = s["x"]
+        o: Act = s["out"]
+        dyc = dout.t
+        if dout.ld != x.C:
+            dyc = self._new(o.rows, x.C)
+            K.copy_rows(dout.t, dout.ld, dyc, x.C, o.rows, x.C)
+        up = self.buf("bw_zi", x.rows, x.C)
+        K.zero_insert2x(dyc, up, x.B, o.H, o.W, x.C)
+        dx = self._new(x.rows, x.C)
+        self._mm(("ds.T", id(smp)), up, x.C, x.C, x.rows, self._wT("ds.%d" % id(smp), smp.conv), x.C, dx, x.C,
+                 conv=(x.B, x.H, x.W), k_tap_pitch=x.C, rows_per_sample=x.hw)
+        return _G(dx, x.C, x.C)
+
+    def t_upsample(self, smp, x: Act) -> Act:
+        up = self.buf("up", x.rows * 4, x.C)
+        K.upsample2x(x.t, up, x.B, x.H, x.W, x.C)
+        xu = Act(up, x.B, x.H * 2, x.W * 2, x.C)
+        out = self._new(xu.rows, x.C)
+        self.conv3x3("us.%d" % id(smp), smp.conv, xu, out, x.C)
+        o = Act(out, xu.B, xu.H, xu.W, x.C)
+        self.tape.append(("up", smp, dict(x=x, out=o)))
+        return o
+
+    def b_upsample(self, smp, s, dout: _G) -> _G:
+        x: Act = s["x"]
+        o: Act = s["out"]
+        dup = self.buf("bw_zi", o.rows, x.C)
+        self._mm(("us.T", id(smp)), dout.t, dout.ld, x.C, o.rows, self._wT("us.%d" % id(smp), smp.conv), x.C, dup, x.C,
+                 conv=(o.B, o.H, o.W), k_tap_pitch=x.C, rows_per_sample=o.hw)
+        dx = self._new(x.rows, x.C)
+        K.upsample2x_bwd(dup, dx, x.B, x.H, x.W, x.C)
+        return _G(dx, x.C, x.C)
+
+    # ------------------------------------------------------------------------------------------
+    # backward over the tape
+    # ------------------------------------------------------------------------------------------
+    def _to_rows(self, g_nchw: torch.Tensor, C: int) -> _G:
+        Bn, Cn, Hn, Wn = g_nchw.shape
+        t = g_nchw.permute(0, 2, 3, 1).reshape(Bn * Hn * Wn, Cn).to(BF16).contiguous()
+        return _G(t, C, C)
+
+    def _acc(self, grads: Dict[int, _G], act: Act, g: Optional[_G]):
+        if g is None:
+            return
+        k = id(act)
+        cur = grads.get(k)
+        if cur is None:
+            grads[k] = g
+        else:
+            if cur.ld != cur.C:  # accumulate into an owned, dense buffer
+                own = self._new(act.rows, cur.C)
+                K.copy_rows(cur.t, cur.ld, own, cur.C, act.rows, cur.C)
+                cur = _G(own, cur.C, cur.C)
+                grads[k] = cur
+            K.add_rows(g.t, g.ld, cur.t, cur.ld, act.rows, cur.C)
+
+    def backward(self, dpred: Optional[torch.Tensor], dtaps: List[Optional[torch.Tensor]]) -> torch.Tensor:
+        """Returns d(loss)/d(arch) [gate_rows, 1620] in fp32."""
+        m = self.m
+        grads: Dict[int, _G] = {}
+        x, stats, dn = self.final
+        B = self.B
+        groups = m.config["norm_num_groups"]
+        if dpred is not None:
+            cout = m.config["out_channels"]
+            dp = torch.zeros(x.rows, 64, device=self.device, dtype=BF16)
+            dp[:, :cout] = dpred.permute(0, 2, 3, 1).reshape(x.rows, cout).to(BF16)
+            da = self.buf("bw_a", x.rows, x.C)
+            self._mm(("conv_out.T",), dp, 64, 64, x.rows, self._wT("conv_out", m.conv_out, pad_out_to=64), x.C, da, x.C,
+                     conv=(x.B, x.H, x.W), k_tap_pitch=64, rows_per_sample=x.hw)
+            dxl = self._new(x.rows, x.C)
+            self._gn_bwd(x.t, x.ld, x.C, B, x.hw, groups, m.config["norm_eps"], stats, dn["g"], dn["b"], da, dxl, x.C,
+                         False, True)
+            self._acc(grads, x, _G(dxl, x.C, x.C))
+        for act, dt in zip(self.tap_acts, dtaps):
+            if dt is not None:
+                self._acc(grads, act, self._to_rows(dt, act.C))
+        for kind, mod, s in reversed(self.tape):
+            out: Act = s["out"]
+            g = grads.pop(id(out), None)
+            if g is None:
+                continue
+            if kind == "res":
+                dxin = self.b_resnet(mod, s, g)
+                if dxin is None:
+                    continue
+                if s["skip"] is not None:
+                    xC = s["x"].C
+                    self._acc(grads, s["x"], _G(dxin.t, dxin.ld, xC))
+                    self._acc(grads, s["skip"], _G(dxin.t[:, xC:], dxin.ld, s["skip"].C))
+                else:
+                    self._acc(grads, s["x"], dxin)
+            elif kind == "tr":
+                self._acc(grads, s["x"], self.b_transformer(mod, s, g))
+            elif kind == "down":
+                self._acc(grads, s["x"], self.b_downsample(mod, s, g))
+            elif kind == "up":
+                self._acc(grads, s["x"], self.b_upsample(mod, s, g))
+        d = self.darch
+        if self.gate_rows != B:  # gates were tiled along the batch (gates.py:18-19): fold the copies back
+            d = d.reshape(B // self.gate_rows, self.gate_rows, -1).sum(0)
+        self.tape = []
+        self.final = None
+        return d
+
+
+class UNetTrainFunction(torch.autograd.Function):
+    """(prediction, 9 block activations) = U-Net(sample, t, ctx; gates) with gradients to the gates only."""
+
+    @staticmethod
+    def forward(ctx, model, sample, timestep, enc, n_taps_out, *gates):
+        eng = model._get_train_engine(sample.device)
+        y, taps = eng.run_train(sample, timestep, enc, list(gates))
+        ctx.eng = eng
+        ctx.gate_shapes = [g.shape for g in gates]
+        ctx.n_width_gates = len(eng.width_starts) - 1
+        outs = [y] + [t.nchw().float() for t in taps]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dy, *dtaps):
+        eng = ctx.eng
+        darch = eng.backward(dy, list(dtaps))
+        grads = []
+        ws = eng.width_starts
+        for i, shp in enumerate(ctx.gate_shapes):
+            if i < ctx.n_width_gates:
+                g = darch[:, ws[i]:ws[i + 1]]
+            else:
+                g = darch[:, eng.n_width + (i - ctx.n_width_gates)]
+            grads.append(g.reshape(shp).contiguous())
+        return (None, None, None, None, None, *grads)

@@ -424,12 +424,40 @@ class UNet2DConditionModelGated(nn.Module):
         if not sample.is_cuda:
             raise RuntimeError("UNet2DConditionModelGated runs on the sm_100a CUDA path only: move the model and "
                                "inputs to a CUDA device (there is no CPU fallback)")
-        if self._engine is None or self._engine.device != sample.device:
-            self._engine = _Engine(self, sample.device)
-        out = self._engine.run(sample, timestep, encoder_hidden_states)
+        blocks = list(self.down_blocks) + [self.mid_block] + list(self.up_blocks)
+        want_taps = any(len(b._forward_hooks) > 0 for b in blocks)
+        flat_w, flat_d = self._flat_gates
+        gates = list(flat_w) + list(flat_d)
+        if torch.is_grad_enabled() and any(g.requires_grad for g in gates):
+            # differentiable student forward of the pruning step (trainer.py:1192-1195): one autograd node
+            from .train import UNetTrainFunction
+            outs = UNetTrainFunction.apply(self, sample, timestep, encoder_hidden_states, len(blocks), *gates)
+            out, taps = outs[0], list(outs[1:])
+        else:
+            if self._engine is None or self._engine.device != sample.device:
+                self._engine = _Engine(self, sample.device)
+            out, taps = self._engine.run(sample, timestep, encoder_hidden_states, want_taps=want_taps)
+        if want_taps:
+            # fire the hooks the trainer registers on down_blocks[i] / mid_block / up_blocks[i]
+            # (trainer.py:496-511) with tensors shaped like the reference's outputs: down blocks return
+            # (hidden_states, residuals) and the hook reads output[0]
+            for blk, tap in zip(blocks, taps):
+                o = (tap, ()) if blk.kind == "down" else tap
+                for hook in list(blk._forward_hooks.values()):
+                    hook(blk, (), o)
         if not return_dict:
             return (out,)
         return UNet2DConditionOutput(sample=out)
+
+    def _get_train_engine(self, device):
+        from .train import TrainEngine
+        te = getattr(self, "_train_engine", None)
+        if te is None or te.device != device:
+            te = TrainEngine(self, device)
+            if self._engine is not None and self._engine.device == device:
+                te.dense = self._engine.dense  # share the packed frozen weights
+            self._train_engine = te
+        return te
 
 
 # --------------------------------------------------------------------------------------------------
@@ -1060,7 +1088,7 @@ class _Engine:
         return Act(out, xu.B, xu.H, xu.W, x.C)
 
     # ---- whole forward -----------------------------------------------------------------------------
-    def run(self, sample: torch.Tensor, timestep, ctx: torch.Tensor) -> torch.Tensor:
+    def run(self, sample: torch.Tensor, timestep, ctx: torch.Tensor, want_taps: bool = False):
         m = self.m
         B, cin, H, W = sample.shape
         self.B = B
@@ -1106,12 +1134,16 @@ class _Engine:
                    rows_per_sample=H * W)
         x = Act(x0, B, H, W, c0)
         skips = [x]
+        tap_acts = []
         for blk in m.down_blocks:
-            x, outs = blk(self, x)
+            x, outs = blk.forward(self, x)
             skips += list(outs)
-        x = m.mid_block(self, x)
+            tap_acts.append(x)
+        x = m.mid_block.forward(self, x)
+        tap_acts.append(x)
         for blk in m.up_blocks:
-            x = blk(self, x, skips)
+            x = blk.forward(self, x, skips)
+            tap_acts.append(x)
         # conv_norm_out + SiLU + conv_out (fp32 NCHW result)
         key = "out_norm"
         dn = self.dense.get(key)
@@ -1130,6 +1162,12 @@ class _Engine:
             [K.Segment(0, x.rows, cout, (x.C + 63) // 64)], 32, self.device, mode=A_CONV3X3, Ho=x.H, Wo=x.W))
         self._gemm(sched, a, dco["w"], y, a_ld=x.C, a_k=x.C, a_rows=x.rows, mode=A_CONV3X3, batch=B, H=x.H, W=x.W,
                    k_tap_pitch=x.C, out_ld=cout, out_mode=OUT_F32_NCHW, bias=dco["b"], rows_per_sample=x.hw)
+        taps = []
         if self.compact:
-            y = y.index_select(0, torch.as_tensor(self.layout.inv_perm, device=self.device))
-        return y
+            inv = torch.as_tensor(self.layout.inv_perm, device=self.device)
+            y = y.index_select(0, inv)
+            if want_taps:
+                taps = [t.nchw().index_select(0, inv) for t in tap_acts]
+        elif want_taps:
+            taps = [t.nchw().clone() for t in tap_acts]  # block outputs live in reused buffers
+        return y, taps

@@ -238,7 +238,7 @@ def silu_bf16(src, dst, n):
     dst.view(-1)[:n] = F.silu(src.reshape(-1)[:n].float()).to(torch.bfloat16)
 
 
-def attention(q, ldq, k, ldk, v, ldv, out, ldo, batch, n_q, n_kv, sample_heads, max_heads, scale):
+def attention(q, ldq, k, ldk, v, ldv, out, ldo, batch, n_q, n_kv, sample_heads, max_heads, scale, lse2=None):
     for b in range(batch):
         nh = int(sample_heads[b])
         if nh == 0:

@@ -35,7 +35,7 @@ def _run(model, oracle, arch, B, H=16):
     with torch.no_grad():
         ref = oracle(sample, t, ctx)
         eng = _Engine(model, torch.device("cpu"))
-        got = eng.run(sample, t, ctx)
+        got, _ = eng.run(sample, t, ctx)
     cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
     err = (got - ref).abs().max().item() / max(1.0, ref.abs().max().item())
     return err, cos, eng

@@ -1,0 +1,14 @@
+"""GPU parity of the differentiable U-Net step (forward with soft gates + explicit backward to the gates)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_grads_tiny_with_block_taps():
+    import train_checks as T
+    T.assert_train(T.check_train_grads())
+
+
+def test_train_grads_tiny_prediction_only():
+    import train_checks as T
+    T.assert_train(T.check_train_grads(B=3, use_taps=False))
