@@ -101,7 +101,7 @@ def _ratio(g: torch.Tensor) -> torch.Tensor:
 
 
 def calc_macs(model) -> Dict[str, Any]:
-    ri = model.resource_info_dict
+    ri = model._macs_table
     total, prunable = ri["fixed"], 0.0
     cur_p, cur_t = 0.0, ri["fixed"]
     for kind, m, mm in ri["layers"]:
@@ -136,7 +136,7 @@ def prunable_macs_list(model) -> List[List[float]]:
     """get_prunable_macs (unet_2d_conditional.py:2165-2172): one list per gated sub-block, in
     get_structure order (consumed by StructureVectorQuantizer.set_prunable_macs_template)."""
     out = []
-    for kind, m, mm in model.resource_info_dict["layers"]:
+    for kind, m, mm in model._macs_table["layers"]:
         if kind == "res":
             out.append([mm[0]])
         else:
@@ -147,7 +147,7 @@ def prunable_macs_list(model) -> List[List[float]]:
 def block_utilization(model):
     """get_block_utilization (unet_2d_conditional.py:2174-2181) flattened per gated sub-block."""
     util = []
-    for kind, m, mm in model.resource_info_dict["layers"]:
+    for kind, m, mm in model._macs_table["layers"]:
         if kind == "res":
             u = hard_concrete(m.gate.gate_f).mean(dim=1)
         else:

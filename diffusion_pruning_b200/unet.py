@@ -315,6 +315,7 @@ class UNet2DConditionModelGated(nn.Module):
         self._temb_total = off
         self.structure = {"width": [], "depth": []}
         self.resource_info_dict = None
+        self._macs_table = None
         self.prunable_macs_list = None
         self.total_macs = None
         self._engine: Optional["_Engine"] = None
@@ -376,16 +377,22 @@ class UNet2DConditionModelGated(nn.Module):
     # reference API: MAC accounting (closed form of op_counter + calc_macs tree)
     # ---------------------------------------------------------------------------------------------
     def count_macs(self, H: int, W: int, n_ctx: int = 77) -> None:
-        """What Pruner.count_macs (trainer.py:1257-1296) measures with forward hooks at batch 1."""
+        """What Pruner.count_macs (trainer.py:1257-1296) measures with forward hooks at batch 1 through
+        op_counter.count_ops_and_params, as a closed form; afterwards the attributes
+        the trainer sets (`resource_info_dict` = calc_macs() at all-ones gates, `prunable_macs_list`
+        normalised by the prunable total, `total_macs`) are filled in the same way (trainer.py:1281-1286)."""
         from .macs import build_resource_info
-        self.resource_info_dict = build_resource_info(self, H, W, n_ctx)
+        self._macs_table = build_resource_info(self, H, W, n_ctx)
+        dev = next(self.parameters()).device
+        self.set_all_ones_structure(1, device=dev)
         d = self.calc_macs()
+        self.resource_info_dict = d
         self.total_macs = d["total_macs"]
-        self.prunable_macs_list = self.get_prunable_macs()
+        self.prunable_macs_list = [[e / d["prunable_macs"] for e in elem] for elem in self.get_prunable_macs()]
 
     def calc_macs(self) -> Dict[str, Any]:
         from .macs import calc_macs
-        if self.resource_info_dict is None:
+        if self._macs_table is None:
             raise RuntimeError("call count_macs(H, W) first (the reference runs count_ops_and_params once)")
         return calc_macs(self)
 

@@ -12,3 +12,10 @@ def test_train_grads_tiny_with_block_taps():
 def test_train_grads_tiny_prediction_only():
     import train_checks as T
     T.assert_train(T.check_train_grads(B=3, use_taps=False))
+
+
+def test_pruning_step_losses_and_grads_vs_oracle():
+    """BASELINE config 3 at test size: six loss scalars within rel 2e-2, d loss/d codebook and d loss/d hypernet
+    vs oracle autograd."""
+    import train_checks as T
+    T.assert_step(*T.check_pruning_step())
