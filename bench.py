@@ -233,6 +233,123 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[2]: pruning train step (DDPM + distillation + block + resource + contrastive losses, gate
+    backward, Sinkhorn router, AdamW on hypernet + codebook), 32 samples per GPU at 64x64, data parallel with a
+    gradient all-reduce. Secondary workload (`--workload train`); the default bench line stays configs[1]."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from diffusion_pruning_b200 import HyperStructure, StructureVectorQuantizer
+    from diffusion_pruning_b200 import kernels as K
+    from diffusion_pruning_b200 import pruning_step as PS
+    from diffusion_pruning_b200.synthetic import DEPTH_ORDER
+    from diffusion_pruning_b200.unet import UNet2DConditionModelGated
+    Bt = args.train_batch
+    torch.manual_seed(1234)
+    with torch.device(device):
+        unet = UNet2DConditionModelGated()
+    unet.eval()
+    unet.freeze()
+    st = unet.get_structure()
+    torch.manual_seed(7)
+    hyper = HyperStructure(structure=st, input_dim=768, wn_flag=False, linear_bias=True).to(device)
+    quant = StructureVectorQuantizer(n_e=N_CODES, structure=st, beta=0.25, temperature=0.4, base=3,
+                                     depth_order=list(DEPTH_ORDER), non_zero_width=True,
+                                     resource_aware_normalization=False, optimal_transport=True).to(device)
+    quant.train()
+    hyper.train()
+    unet.count_macs(LATENT, LATENT)
+    cfg = PS.PruningLossConfig()
+    p_actual = PS.actual_pruning_target(unet, cfg.pruning_target)
+    taps = PS.BlockTaps(unet)
+    params = [p for p in list(hyper.parameters()) + list(quant.parameters()) if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=2e-4)
+    g = torch.Generator().manual_seed(100 + rank)
+    host = {"noisy_latents": torch.randn(Bt, 4, LATENT, LATENT, generator=g).pin_memory(),
+            "timesteps": torch.randint(0, 1000, (Bt,), generator=g).pin_memory(),
+            "target": torch.randn(Bt, 4, LATENT, LATENT, generator=g).pin_memory(),
+            "encoder_hidden_states": torch.randn(Bt, N_CTX, CTX_DIM, generator=g).pin_memory(),
+            "mpnet_embeddings": torch.randn(Bt, 768, generator=g).pin_memory()}
+    acp = PS.alphas_cumprod().to(device)
+    flat = torch.zeros(sum(p.numel() for p in params), device=device)
+
+    def step():
+        batch = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        out = PS.pruning_step(unet, hyper, quant, batch, cfg, taps, p_actual, acp=acp)
+        opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
+        if world > 1:  # DDP semantics: mean of the 1.26 M trainable gradients, one NCCL all-reduce
+            off = 0
+            for p in params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.grad.reshape(-1) if p.grad is not None else torch.zeros(n, device=device))
+                off += n
+            dist.all_reduce(flat)
+            flat.div_(world)
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad = flat[off:off + n].view_as(p).clone()
+                off += n
+        opt.step()
+        return out["loss"].detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step()
+    K.check_abort()
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+        loss_h = float(loss)  # the trainer reads the loss every step (D2H)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    clk = clocks.stop()
+    K.check_abort()
+    peaks = load_peaks()
+    value = Bt * world * args.steps / (ms / 1e3)
+    tflop_per_sample = 2.52  # SURVEY 8(d): two forwards + dgrad-only backward at 64x64
+    out = {"metric": "pruning_train_samples_steps_per_s", "value": round(value, 2), "unit": UNIT, "n_gpus": world,
+           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "configs[2]: pruning train step (teacher + student forward, backward to the gates, "
+                                  "Sinkhorn router, 7 losses, AdamW on hypernet + codebook), 64x64 latent",
+                      "batch_per_gpu": Bt, "latent": LATENT, "codes": N_CODES, "parallelism": f"dp{world} + grad all-reduce",
+                      "l2": "activations exceed L2"},
+           "e2e": {"value": round(value, 2), "unit": UNIT,
+                   "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
+                   "d2h_bytes_per_step": 4},
+           "gpu_launches": None, "clocks": clk, "final_loss": loss_h,
+           "roofline": {"bound": "tensor", "achieved": round(Bt * tflop_per_sample / (ms / args.steps / 1e3), 1),
+                        "peak": peaks["tflops"], "unit": "TFLOP/s",
+                        "frac": round(Bt * tflop_per_sample / (ms / args.steps / 1e3) / peaks["tflops"], 4),
+                        "note": "whole-step dense-equivalent FLOPs (2.52 TFLOP/sample) / step time", "traffic": None}}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def build_oracle_fast():
     """Full-size fp32 oracle with cheap deterministic init (fan-in scaled uniform)."""
     import math
@@ -305,9 +422,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="forward", choices=["forward", "train"])
+    ap.add_argument("--train-batch", type=int, default=32)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)
 
