@@ -260,3 +260,74 @@ def install(monkeypatch):
                  "upsample2x", "im2col_input", "timestep_embedding", "cast_f32_bf16", "silu_bf16", "attention",
                  "check_abort"):
         monkeypatch.setattr(K, name, globals()[name])
+
+
+# ------------------------------------------------------------------------------------------------
+# router kernels (contract of csrc/router.cu), so the quantizer's HOST logic -- uniform draw order, phase
+# protocol of the sharded Sinkhorn with its all-reduces -- can run under gloo in the GPU-less container
+# ------------------------------------------------------------------------------------------------
+def gumbel_gate(z, u, out, batch, n_width, n_depth, width_starts, n_gates, depth_order, temperature, base,
+                non_zero_width):
+    g = -torch.log(-torch.log(u + 1e-20) + 1e-20)
+    y = torch.sigmoid((z[:, :n_width] + g[:, :n_width] + base) / temperature)
+    ws = width_starts.tolist()
+    if non_zero_width:
+        y = y.clone()
+        for i in range(n_gates):
+            s, e = ws[i], ws[i + 1]
+            dead = (y[:, s:e] >= 0.5).sum(1) == 0
+            y[dead, s] += 0.5
+    out[:, :n_width] = y
+    if n_depth:
+        x = torch.flip(torch.cumsum(torch.softmax(z[:, n_width:], 1), 1), dims=[1])
+        x = torch.log(x + 1e-6) - torch.log1p(-(x - 1e-6))
+        yd = torch.sigmoid((x + g[:, n_width:] + base) / temperature)
+        out[:, n_width + depth_order.long()] = yd
+
+
+def arch_normalize(gates, out, batch, dim, col_depth, col_scale, l2=True):
+    cd = col_depth.long()
+    hard = (gates >= 0.5).float()
+    dep = gates[:, cd.clamp_min(0)]
+    v = torch.where(cd[None, :] >= 0, gates * dep, hard) * col_scale[None, :]
+    out.copy_(v / v.norm(dim=1, keepdim=True) if l2 else v)
+
+
+def route_cosine(a_norm, codes_norm, scores, indices, batch, dim, n_codes):
+    s = (a_norm.double() @ codes_norm.double().t()).float()
+    scores.copy_(s)
+    indices.copy_(torch.argmax(s, dim=1))
+
+
+def sinkhorn_phase(phase, Q, scores, partial, indices, batch_local, batch_global, n_codes, epsilon, first_iter):
+    if phase == 0:
+        Q.copy_(torch.exp(scores / epsilon))
+        partial[0] = Q.double().sum()
+    elif phase == 1:
+        if first_iter:
+            Q.div_(partial[0].float())
+        partial[1:1 + n_codes] = Q.double().sum(0)
+    elif phase == 2:
+        Q.div_(partial[1:1 + n_codes].float()[None, :])
+        Q.div_(float(n_codes))
+        Q.div_(Q.sum(1, keepdim=True))
+        Q.div_(float(batch_global))
+    else:
+        Q.mul_(float(batch_global))
+        indices.copy_(torch.argmax(Q, dim=1))
+
+
+def route_sinkhorn(scores, Q, partial, indices, batch, n_codes, epsilon, iterations):
+    sinkhorn_phase(0, Q, scores, partial, indices, batch, batch, n_codes, epsilon, 0)
+    for it in range(iterations):
+        sinkhorn_phase(1, Q, scores, partial, indices, batch, batch, n_codes, epsilon, it == 0)
+        sinkhorn_phase(2, Q, scores, partial, indices, batch, batch, n_codes, epsilon, 0)
+    sinkhorn_phase(3, Q, scores, partial, indices, batch, batch, n_codes, epsilon, 0)
+
+
+def install_router(setattr_fn):
+    """setattr_fn(obj, name, value): monkeypatch.setattr or plain setattr (spawned workers)."""
+    from diffusion_pruning_b200.quantizer import StructureVectorQuantizer
+    for name in ("gumbel_gate", "arch_normalize", "route_cosine", "sinkhorn_phase", "route_sinkhorn"):
+        setattr_fn(K, name, globals()[name])
+    setattr_fn(StructureVectorQuantizer, "_require_cuda", staticmethod(lambda t, what: None))
