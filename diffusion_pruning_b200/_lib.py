@@ -66,6 +66,7 @@ SIGNATURES = {
     "aptp_timestep_embedding": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "aptp_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "aptp_silu_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "aptp_cfg_ddim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_int, c_void_p]),
     "aptp_attention_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                    c_int, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "aptp_attention_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,

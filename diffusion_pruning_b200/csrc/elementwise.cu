@@ -115,6 +115,30 @@ __global__ void __launch_bounds__(256) silu_bf16_kernel(const __nv_bfloat16* __r
     dst[i] = __float2bfloat16(silu_f(__bfloat162float(src[i])));
 }
 
+// Classifier-free-guidance combine + one DDIM step (eta = 0, v-prediction or epsilon), fused:
+//   v = v_u + g (v_c - v_u)                                  pruning_pipelines.py:805-807
+//   x0 = sa x - sb v ; eps = sa v + sb x   (v-prediction)     diffusers DDIMScheduler.step
+//   x_prev = sa_prev x0 + sb_prev eps
+// pred holds [uncond batch | cond batch] (pruning_pipelines.py:765, :792), all fp32 NCHW.
+__global__ void __launch_bounds__(256) cfg_ddim_kernel(const float* __restrict__ pred, const float* __restrict__ x,
+                                                       float* __restrict__ x_out, long long n, float guidance, float sa,
+                                                       float sb, float sa_prev, float sb_prev, int v_prediction) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pu = pred[i], pc = pred[n + i];
+    const float m = pu + guidance * (pc - pu);
+    const float xv = x[i];
+    float x0, eps;
+    if (v_prediction) {
+      x0 = sa * xv - sb * m;
+      eps = sa * m + sb * xv;
+    } else {
+      eps = m;
+      x0 = (xv - sb * m) / sa;
+    }
+    x_out[i] = sa_prev * x0 + sb_prev * eps;
+  }
+}
+
 static unsigned grid_for(long long total) {
   long long blocks = (total + 255) / 256;
   long long cap = (long long)sm_count() * 16;
@@ -204,6 +228,19 @@ extern "C" int aptp_silu_bf16(const void* src, void* dst, int64_t n, void* strea
   if (n == 0) return APTP_OK;
   silu_bf16_kernel<<<grid_for(n), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src),
                                                    reinterpret_cast<__nv_bfloat16*>(dst), n);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_cfg_ddim_step(const float* pred, const float* x, float* x_out, int64_t n, float guidance,
+                                  float alpha_t, float alpha_prev, int32_t v_prediction, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(pred && x && x_out, "aptp_cfg_ddim_step: null pointer");
+  APTP_REQUIRE(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f,
+               "aptp_cfg_ddim_step: alphas_cumprod must be in (0, 1]");
+  if (n == 0) return APTP_OK;
+  cfg_ddim_kernel<<<grid_for(n), 256, 0, stream>>>(pred, x, x_out, n, guidance, sqrtf(alpha_t), sqrtf(1.f - alpha_t),
+                                                  sqrtf(alpha_prev), sqrtf(1.f - alpha_prev), v_prediction);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

@@ -191,6 +191,11 @@ def silu_bf16(src, dst, n):
     check(load().aptp_silu_bf16(_ptr(src), _ptr(dst), n, _stream()), "aptp_silu_bf16")
 
 
+def cfg_ddim_step(pred, x, x_out, n, guidance, alpha_t, alpha_prev, v_prediction=True):
+    check(load().aptp_cfg_ddim_step(_ptr(pred), _ptr(x), _ptr(x_out), n, float(guidance), float(alpha_t),
+                                    float(alpha_prev), int(v_prediction), _stream()), "aptp_cfg_ddim_step")
+
+
 def attention(q, ldq, k, ldk, v, ldv, out, ldo, batch, n_q, n_kv, sample_heads, max_heads, scale, lse2=None):
     check(load().aptp_attention_fwd(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out), ldo, batch, n_q, n_kv,
                                     _ptr(sample_heads), max_heads, float(scale), _ptr(lse2), _stream()),

@@ -158,6 +158,12 @@ int aptp_timestep_embedding(const float* t, void* dst, int32_t batch, int32_t di
 /* fp32 -> bf16 cast (text embeddings), plain elementwise silu over bf16. */
 int aptp_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int aptp_silu_bf16(const void* src, void* dst, int64_t n, void* stream);
+/* Fused classifier-free-guidance combine + DDIM update (eta 0) of the sampling loop
+ * (pdm/pipelines/pruning_pipelines.py:805-814; diffusers DDIMScheduler.step):
+ * pred = [uncond | cond] noise predictions (2n floats), x / x_out = latents (n floats); alpha_* are
+ * alphas_cumprod at the current / previous timestep. */
+int aptp_cfg_ddim_step(const float* pred, const float* x, float* x_out, int64_t n, float guidance, float alpha_t,
+                       float alpha_prev, int32_t v_prediction, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3  flash-style attention on tcgen05 with per-sample kept-head lists.
