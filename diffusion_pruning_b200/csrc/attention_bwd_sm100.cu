@@ -120,12 +120,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // stationary: Q_w at tiles 0,1 ; dO_w at tiles 2,3
-      mbar_expect_tx(B.st_full, n_w * 2 * AB_BIG);
+      mbar_expect_tx_e(B.st_full, n_w * 2 * AB_BIG);
       for (int w = 0; w < n_w; ++w) {
-        tma_load_2d(smem + AB_SMEM_ST + w * AB_BIG, &p.tmap_q128, B.st_full, head * AB_D, b * p.n_q + q0 + w * 128);
-        tma_load_2d(smem + AB_SMEM_ST + (2 + w) * AB_BIG, &p.tmap_do128, B.st_full, head * AB_D,
+        tma_load_2d_e(smem + AB_SMEM_ST + w * AB_BIG, &p.tmap_q128, B.st_full, head * AB_D, b * p.n_q + q0 + w * 128);
+        tma_load_2d_e(smem + AB_SMEM_ST + (2 + w) * AB_BIG, &p.tmap_do128, B.st_full, head * AB_D,
                     b * p.n_q + q0 + w * 128);
       }
       int stage = 0;
@@ -133,15 +133,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
       for (int j = 0; j < n_tiles; ++j) {
         if (!mbar_wait(&B.ring_empty[stage], phase ^ 1, p.abort_flag)) break;
         uint8_t* sk = smem + AB_SMEM_RING + stage * 2 * AB_SMALL;
-        mbar_expect_tx(&B.ring_full[stage], 2 * AB_SMALL);
-        tma_load_2d(sk, &p.tmap_k64, &B.ring_full[stage], head * AB_D, b * p.n_kv + j * 64);
-        tma_load_2d(sk + AB_SMALL, &p.tmap_v64, &B.ring_full[stage], head * AB_D, b * p.n_kv + j * 64);
+        mbar_expect_tx_e(&B.ring_full[stage], 2 * AB_SMALL);
+        tma_load_2d_e(sk, &p.tmap_k64, &B.ring_full[stage], head * AB_D, b * p.n_kv + j * 64);
+        tma_load_2d_e(sk + AB_SMALL, &p.tmap_v64, &B.ring_full[stage], head * AB_D, b * p.n_kv + j * 64);
         if (++stage == AB_STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);  // A from TMEM (K-major), B MN-major
       auto issue_sp = [&](int w, int stg) {
@@ -152,13 +152,13 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
         const uint32_t t = tmem_base + w * TW;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(t, make_desc_kmajor_sw128(q_addr + k * 32), make_desc_kmajor_sw128(k_addr + k * 32), idesc_s,
+          umma_bf16_ss_e(t, make_desc_kmajor_sw128(q_addr + k * 32), make_desc_kmajor_sw128(k_addr + k * 32), idesc_s,
                        k != 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(t + 64, make_desc_kmajor_sw128(do_addr + k * 32), make_desc_kmajor_sw128(v_addr + k * 32), idesc_s,
+          umma_bf16_ss_e(t + 64, make_desc_kmajor_sw128(do_addr + k * 32), make_desc_kmajor_sw128(v_addr + k * 32), idesc_s,
                        k != 0);
-        umma_commit(&B.s_full[w]);
+        umma_commit_e(&B.s_full[w]);
       };
       int stage = 0;
       uint32_t phase = 0;
@@ -194,12 +194,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
           const uint32_t t = tmem_base + w * TW;
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 16 keys per step: 8 packed TMEM columns of dS, 2 swizzle atoms of K
-            umma_bf16_ts(t + 160, t + 128 + k * 8, make_desc_mnmajor_sw128(k_addr + k * 2048, AB_SMALL), idesc_acc,
+            umma_bf16_ts_e(t + 160, t + 128 + k * 8, make_desc_mnmajor_sw128(k_addr + k * 2048, AB_SMALL), idesc_acc,
                          (j | k) != 0);
-          umma_commit(&B.acc_done[w]);
+          umma_commit_e(&B.acc_done[w]);
         }
         if (!ok) break;
-        umma_commit(&B.ring_empty[stage]);
+        umma_commit_e(&B.ring_empty[stage]);
         stage = ns;
         phase = nphase;
       }
@@ -290,12 +290,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // stationary: K_w at tiles 0,1 ; V_w at tiles 2,3
-      mbar_expect_tx(B.st_full, n_w * 2 * AB_BIG);
+      mbar_expect_tx_e(B.st_full, n_w * 2 * AB_BIG);
       for (int w = 0; w < n_w; ++w) {
-        tma_load_2d(smem + AB_SMEM_ST + w * AB_BIG, &p.tmap_k128, B.st_full, head * AB_D, b * p.n_kv + k0 + w * 128);
-        tma_load_2d(smem + AB_SMEM_ST + (2 + w) * AB_BIG, &p.tmap_v128, B.st_full, head * AB_D,
+        tma_load_2d_e(smem + AB_SMEM_ST + w * AB_BIG, &p.tmap_k128, B.st_full, head * AB_D, b * p.n_kv + k0 + w * 128);
+        tma_load_2d_e(smem + AB_SMEM_ST + (2 + w) * AB_BIG, &p.tmap_v128, B.st_full, head * AB_D,
                     b * p.n_kv + k0 + w * 128);
       }
       int stage = 0;
@@ -303,15 +303,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
       for (int j = 0; j < n_tiles; ++j) {
         if (!mbar_wait(&B.ring_empty[stage], phase ^ 1, p.abort_flag)) break;
         uint8_t* sq = smem + AB_SMEM_RING + stage * 2 * AB_SMALL;
-        mbar_expect_tx(&B.ring_full[stage], 2 * AB_SMALL);
-        tma_load_2d(sq, &p.tmap_q64, &B.ring_full[stage], head * AB_D, b * p.n_q + j * 64);
-        tma_load_2d(sq + AB_SMALL, &p.tmap_do64, &B.ring_full[stage], head * AB_D, b * p.n_q + j * 64);
+        mbar_expect_tx_e(&B.ring_full[stage], 2 * AB_SMALL);
+        tma_load_2d_e(sq, &p.tmap_q64, &B.ring_full[stage], head * AB_D, b * p.n_q + j * 64);
+        tma_load_2d_e(sq + AB_SMALL, &p.tmap_do64, &B.ring_full[stage], head * AB_D, b * p.n_q + j * 64);
         if (++stage == AB_STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
       const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
       auto issue_sp = [&](int w, int stg) {
@@ -322,13 +322,13 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         const uint32_t t = tmem_base + w * TW;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(t, make_desc_kmajor_sw128(k_addr + k * 32), make_desc_kmajor_sw128(q_addr + k * 32), idesc_s,
+          umma_bf16_ss_e(t, make_desc_kmajor_sw128(k_addr + k * 32), make_desc_kmajor_sw128(q_addr + k * 32), idesc_s,
                        k != 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(t + 64, make_desc_kmajor_sw128(v_addr + k * 32), make_desc_kmajor_sw128(do_addr + k * 32), idesc_s,
+          umma_bf16_ss_e(t + 64, make_desc_kmajor_sw128(v_addr + k * 32), make_desc_kmajor_sw128(do_addr + k * 32), idesc_s,
                        k != 0);
-        umma_commit(&B.s_full[w]);
+        umma_commit_e(&B.s_full[w]);
       };
       int stage = 0;
       uint32_t phase = 0;
@@ -356,11 +356,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
           const uint32_t t = tmem_base + w * TW;
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dV += P^T dO_j
-            umma_bf16_ts(t + 128, t + k * 8, make_desc_mnmajor_sw128(do_addr + k * 2048, AB_SMALL), idesc_acc,
+            umma_bf16_ts_e(t + 128, t + k * 8, make_desc_mnmajor_sw128(do_addr + k * 2048, AB_SMALL), idesc_acc,
                          (j | k) != 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dK += dS^T Q_j
-            umma_bf16_ts(t + 192, t + 64 + k * 8, make_desc_mnmajor_sw128(q_addr + k * 2048, AB_SMALL), idesc_acc,
+            umma_bf16_ts_e(t + 192, t + 64 + k * 8, make_desc_mnmajor_sw128(q_addr + k * 2048, AB_SMALL), idesc_acc,
                          (j | k) != 0);
           if (more) {
             if (w == 0 && !mbar_wait(&B.ring_full[ns], nphase, p.abort_flag)) {
@@ -370,11 +370,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
             tc_fence_after();
             issue_sp(w, ns);  // overwrites S^T / dP^T (and the aliased bf16 operands) after the MMAs above: in-order pipe
           } else {
-            umma_commit(&B.acc_done[w]);
+            umma_commit_e(&B.acc_done[w]);
           }
         }
         if (!ok) break;
-        umma_commit(&B.ring_empty[stage]);
+        umma_commit_e(&B.ring_empty[stage]);
         stage = ns;
         phase = nphase;
       }

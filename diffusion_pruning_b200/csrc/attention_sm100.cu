@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    // Whole warp in uniform control flow; one elected lane issues (a loop nested under `lane == 0` makes
+    // ptxas wrap every UTMALDG / UTCHMMA in an R2UR waterfall loop, ~140 cycles per instruction).
+    {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
@@ -116,18 +118,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         const int q0 = qp * 2 * ATT_BM;
         const bool act1 = q0 + ATT_BM < p.n_q;
         if (!mbar_wait(q_empty, (it & 1) ^ 1, p.abort_flag)) break;
-        mbar_expect_tx(q_full, act1 ? 2 * ATT_TILE_BYTES : ATT_TILE_BYTES);
-        tma_load_2d(smem + ATT_SMEM_Q, &p.tmap_q, q_full, head * ATT_D, b * p.n_q + q0);
-        if (act1) tma_load_2d(smem + ATT_SMEM_Q + ATT_TILE_BYTES, &p.tmap_q, q_full, head * ATT_D, b * p.n_q + q0 + ATT_BM);
+        if (elect_one()) {
+          mbar_expect_tx(q_full, act1 ? 2 * ATT_TILE_BYTES : ATT_TILE_BYTES);
+          tma_load_2d(smem + ATT_SMEM_Q, &p.tmap_q, q_full, head * ATT_D, b * p.n_q + q0);
+          if (act1)
+            tma_load_2d(smem + ATT_SMEM_Q + ATT_TILE_BYTES, &p.tmap_q, q_full, head * ATT_D, b * p.n_q + q0 + ATT_BM);
+        }
+        __syncwarp();
         for (int j = 0; j < n_tiles; ++j) {
           if (!mbar_wait(&kv_empty[stage], phase ^ 1, p.abort_flag)) {
             ok = false;
             break;
           }
-          uint8_t* sk = smem + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES;
-          mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-          tma_load_2d(sk, &p.tmap_k, &kv_full[stage], head * ATT_D, b * p.n_kv + j * ATT_BN);
-          tma_load_2d(sk + ATT_TILE_BYTES, &p.tmap_v, &kv_full[stage], head * ATT_D, b * p.n_kv + j * ATT_BN);
+          if (elect_one()) {
+            uint8_t* sk = smem + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES;
+            mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+            tma_load_2d(sk, &p.tmap_k, &kv_full[stage], head * ATT_D, b * p.n_kv + j * ATT_BN);
+            tma_load_2d(sk + ATT_TILE_BYTES, &p.tmap_v, &kv_full[stage], head * ATT_D, b * p.n_kv + j * ATT_BN);
+          }
+          __syncwarp();
           if (++stage == ATT_KV_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -137,23 +146,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    {
       const uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // A (=P) K-major from TMEM, B (=V) MN-major
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;
       uint32_t gp[2] = {0, 0};  // tiles consumed per Q tile (phase of s_free / p_full)
       bool ok = true;
       auto issue_s = [&](int w, int kv_stage) {
-        const uint32_t q_addr = smem_u32(smem + ATT_SMEM_Q + w * ATT_TILE_BYTES);
-        const uint32_t k_addr = smem_u32(smem + ATT_SMEM_KV + kv_stage * 2 * ATT_TILE_BYTES);
+        const uint64_t dq = make_desc_kmajor_sw128(smem_base + ATT_SMEM_Q + w * ATT_TILE_BYTES);
+        const uint64_t dk = make_desc_kmajor_sw128(smem_base + ATT_SMEM_KV + kv_stage * 2 * ATT_TILE_BYTES);
         const uint32_t s_tmem = tmem_base + ATT_TMEM_S + w * ATT_BN;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          umma_bf16_ss(s_tmem, make_desc_kmajor_sw128(q_addr + k * 32), make_desc_kmajor_sw128(k_addr + k * 32),
-                       idesc_s, k != 0);
-        umma_commit(&s_full[w]);
+          for (int k = 0; k < ATT_D / 16; ++k)  // +32 B per K=16 step = +2 in the descriptor address field
+            umma_bf16_ss(s_tmem, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k != 0);
+          umma_commit(&s_full[w]);
+        }
+        __syncwarp();
       };
       for (int qp = blockIdx.x; qp < p.n_qpairs && ok; qp += gridDim.x, ++it) {
         const int q0 = qp * 2 * ATT_BM;
@@ -184,7 +196,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           }
           if (!ok) break;
           // O_w (+)= P_w V_j once P_w is in tensor memory
-          const uint32_t v_addr = smem_u32(smem + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
+          // V: 16 keys = 2 swizzle atoms (2048 B) per step = +128 in the descriptor address field
+          const uint64_t dv = make_desc_mnmajor_sw128(
+              smem_base + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, ATT_TILE_BYTES);
           for (int w = 0; w < n_w; ++w) {
             if (!mbar_wait(&p_full[w], gp[w] & 1, p.abort_flag)) {
               ok = false;
@@ -194,20 +208,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             tc_fence_after();
             const uint32_t p_tmem = tmem_base + ATT_TMEM_P + w * (ATT_BN / 2);
             const uint32_t o_tmem = tmem_base + ATT_TMEM_O + w * ATT_D;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < ATT_BN / 16; ++k) {
-              // P: 16 keys = 8 packed 32-bit TMEM columns per step; V: 16 keys = 2 swizzle atoms (2048 B)
-              umma_bf16_ts(o_tmem, p_tmem + k * 8, make_desc_mnmajor_sw128(v_addr + k * 2048, ATT_TILE_BYTES), idesc_o,
-                           (j | k) != 0);
+              for (int k = 0; k < ATT_BN / 16; ++k)  // P: 16 keys = 8 packed 32-bit TMEM columns per step
+                umma_bf16_ts(o_tmem, p_tmem + k * 8, dv + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
+              umma_commit(&pv_done[w]);
             }
-            umma_commit(&pv_done[w]);
+            __syncwarp();
           }
           if (!ok) break;
-          umma_commit(&kv_empty[stage]);
+          if (elect_one()) umma_commit(&kv_empty[stage]);
+          __syncwarp();
           stage = ns;
           phase = nphase;
         }
-        umma_commit(q_empty);
+        if (elect_one()) umma_commit(q_empty);
+        __syncwarp();
       }
     }
   }

@@ -271,6 +271,29 @@ __device__ __host__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
   return d;
 }
 
+// ---- warp-collective ("elected") issue ----
+// Called by ALL 32 lanes of a converged warp; one elected lane issues the instruction. Keeping the issuing
+// warp in uniform control flow lets ptxas hold descriptors / barrier addresses in uniform registers; a loop
+// nested under `if (lane == 0)` instead wraps every UTCHMMA / UTMALDG in an R2UR waterfall loop (measured:
+// ~140 cycles per MMA instruction, the limiter of the round-1 GEMM and attention kernels).
+__device__ __forceinline__ void umma_bf16_ss_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if (elect_one()) umma_bf16_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_bf16_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if (elect_one()) umma_bf16_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
+}
+__device__ __forceinline__ void tma_load_2d_e(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  if (elect_one()) tma_load_2d(smem, map, bar, c0, c1);
+}
+__device__ __forceinline__ void mbar_expect_tx_e(uint64_t* bar, uint32_t bytes) {
+  if (elect_one()) mbar_expect_tx(bar, bytes);
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -162,14 +162,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    // Whole warp in uniform control flow, one elected lane issues (see the MMA issuer for why).
+    {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
+      const int taps = (p.a_mode == APTP_A_LINEAR) ? 1 : 9;
       for (int t = blockIdx.x; t < p.n_tiles && ok; t += gridDim.x) {
         const aptp_gemm_tile tile = p.tiles[t];
         const aptp_gemm_seg seg = p.segs[tile.seg];
-        const int taps = (p.a_mode == APTP_A_LINEAR) ? 1 : 9;
         int img = 0, oy0 = 0, ox0 = 0;
         if (p.a_mode != APTP_A_LINEAR) {
           const int hw = p.Ho * p.Wo;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           oy0 = rem / p.Wo;
           ox0 = rem - oy0 * p.Wo;
         }
+        const int b_row = seg.w_row_off + tile.n0;
         for (int tap = 0; tap < taps && ok; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
           for (int kc = 0; kc < seg.k_chunks; ++kc) {
@@ -185,21 +187,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
               ok = false;
               break;
             }
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            uint8_t* sb = sa + A_STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
-            if (p.a_mode == APTP_A_LINEAR) {
-              tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kc * BK, tile.m_base);
-            } else if (p.a_mode == APTP_A_CONV3X3) {
-              tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * BK, ox0 + dx - 1, oy0 + dy - 1, img);
-            } else {
-              // input y = 2*oy + dy - 1: dy=0 -> (parity 1, shift -1); dy=1 -> (0, 0); dy=2 -> (1, 0)
-              const int py = (dy == 1) ? 0 : 1, sy = (dy == 0) ? -1 : 0;
-              const int px = (dx == 1) ? 0 : 1, sx = (dx == 0) ? -1 : 0;
-              tma_load_5d(sa, &p.tmap_a, &full_bar[stage], px * p.k_tap_pitch + kc * BK, ox0 + sx, py, oy0 + sy,
-                          img);
+            if (elect_one()) {
+              uint8_t* sa = smem + (size_t)stage * stage_bytes;
+              uint8_t* sb = sa + A_STAGE_BYTES;
+              mbar_expect_tx(&full_bar[stage], stage_bytes);
+              if (p.a_mode == APTP_A_LINEAR) {
+                tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kc * BK, tile.m_base);
+              } else if (p.a_mode == APTP_A_CONV3X3) {
+                tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * BK, ox0 + dx - 1, oy0 + dy - 1, img);
+              } else {
+                // input y = 2*oy + dy - 1: dy=0 -> (parity 1, shift -1); dy=1 -> (0, 0); dy=2 -> (1, 0)
+                const int py = (dy == 1) ? 0 : 1, sy = (dy == 0) ? -1 : 0;
+                const int px = (dx == 1) ? 0 : 1, sx = (dx == 0) ? -1 : 0;
+                tma_load_5d(sa, &p.tmap_a, &full_bar[stage], px * p.k_tap_pitch + kc * BK, ox0 + sx, py, oy0 + sy,
+                            img);
+              }
+              tma_load_2d(sb, &p.tmap_b, &full_bar[stage], tap * p.k_tap_pitch + kc * BK, b_row);
             }
-            tma_load_2d(sb, &p.tmap_b, &full_bar[stage], tap * p.k_tap_pitch + kc * BK, seg.w_row_off + tile.n0);
+            __syncwarp();
             advance(stage, phase, stages);
           }
         }
@@ -207,17 +212,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    // The WHOLE warp walks the tile list in uniform control flow (so descriptors, barrier addresses and
+    // loop counters live in uniform registers) and one elected lane issues the tcgen05 instructions.
+    // A loop nested under `if (lane == 0)` instead makes ptxas wrap every UTCHMMA in a per-lane
+    // R2UR "waterfall" loop, which capped the issue rate at ~140 cycles per MMA (ncu, round 1).
+    {
       const uint32_t idesc = make_idesc_bf16(BM, (uint32_t)p.bn, 0, 0);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       bool ok = true;
       for (int t = blockIdx.x; t < p.n_tiles && ok; t += gridDim.x) {
-        const aptp_gemm_tile tile = p.tiles[t];
-        const aptp_gemm_seg seg = p.segs[tile.seg];
-        const int kblocks = ((p.a_mode == APTP_A_LINEAR) ? 1 : 9) * seg.k_chunks;
+        const int seg_id = __shfl_sync(0xffffffffu, p.tiles[t].seg, 0);
+        const int k_chunks = __shfl_sync(0xffffffffu, p.segs[seg_id].k_chunks, 0);
+        const int kblocks = ((p.a_mode == APTP_A_LINEAR) ? 1 : 9) * k_chunks;
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
@@ -227,18 +237,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
             break;
           }
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+          const uint64_t da = make_desc_kmajor_sw128(a_addr);
+          const uint64_t db = make_desc_kmajor_sw128(a_addr + A_STAGE_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16_ss(d_tmem, make_desc_kmajor_sw128(a_addr + k * 32), make_desc_kmajor_sw128(b_addr + k * 32),
-                         idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // +32 bytes per K=16 step inside the 128B-swizzled row: +2 in the (addr >> 4) field
+              umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           advance(stage, phase, stages);
         }
         if (!ok) break;
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
