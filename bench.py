@@ -174,6 +174,7 @@ def run_ours(args):
     eng = model._engine
     launches_per_step = eng.launches
     kept_flops = eng.flops
+    gemm_alg_bytes = eng.gemm_bytes
     # end-to-end through the public API with host buffers
     for _ in range(2):
         step_e2e()
@@ -197,6 +198,11 @@ def run_ours(args):
     a_ms, a_fl = sum(x for x, _ in attn), sum(f for _, f in attn)
     K.check_abort()
     peaks = load_peaks()
+    traffic, traffic_src = {}, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):  # ncu DRAM bytes of the same command (tools/gpu_ncu.sh), per launch
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("grouped_gemm_kernel", {}), tj.get("source")
     ms_step = ms_total / args.steps
     value = BATCH * world * args.steps / (ms_total / 1e3)
     e2e_value = BATCH * world * args.steps / (ms_e2e / 1e3)
@@ -218,7 +224,10 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "grouped_gemm_kernel (tcgen05 grouped GEMM / implicit conv)",
                      "achieved": round(g_fl / (g_ms / 1e3) / 1e12, 1) if g_ms else None, "peak": peaks["tflops"],
                      "unit": "TFLOP/s", "frac": round(g_fl / (g_ms / 1e3) / 1e12 / peaks["tflops"], 4) if g_ms else None,
-                     "traffic": None, "peak_source": peaks["source"], "peak_sustained": peaks["tflops_sustained"],
+                     "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": round(gemm_alg_bytes / max(len(gemm), 1)),
+                     "algorithmic_flop_per_launch": round(g_fl / max(len(gemm), 1)),
+                     "peak_source": peaks["source"], "peak_sustained": peaks["tflops_sustained"],
                      "launches": len(gemm), "kernel_ms_per_step": round(g_ms, 3),
                      "attention": {"achieved": round(a_fl / (a_ms / 1e3) / 1e12, 1) if a_ms else None,
                                    "kernel_ms_per_step": round(a_ms, 3), "launches": len(attn)},

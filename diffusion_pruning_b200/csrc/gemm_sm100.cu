@@ -22,11 +22,13 @@ namespace aptp {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 8;                       // 2 per TMEM lane quadrant, alternating 32-column chunks
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_PER_QUAD = 3;                    // epilogue warps per TMEM lane quadrant (32-column chunks dealt round-robin)
+constexpr int EPI_WARPS = 4 * EPI_PER_QUAD;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..13 epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int STG_WARP_BYTES = 32 * 64;            // per-warp staging: 32 rows x 32 bf16 columns
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
+constexpr int SBIAS_BYTES = EPI_WARPS * 64 * 4;     // per epilogue warp: the bias slice of its current chunk (32, or 2 x 32 for GEGLU)
 
 struct GemmParams {
   CUtensorMap tmap_a;
@@ -120,13 +122,26 @@ __device__ __forceinline__ void add32(float* v, const float* __restrict__ src, i
   }
 }
 
+// 32 floats from shared memory (same address in all lanes: broadcast)
+__device__ __forceinline__ void add32_smem(float* v, const float* src) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = *(reinterpret_cast<const float4*>(src) + q);
+    v[q * 4 + 0] += f.x;
+    v[q * 4 + 1] += f.y;
+    v[q * 4 + 2] += f.z;
+    v[q * 4 + 3] += f.w;
+  }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
   const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.bn * 128u;
   uint8_t* stg_base = smem + (size_t)stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES);
+  float* sbias = reinterpret_cast<float*>(stg_base + STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES + SBIAS_BYTES);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -265,7 +280,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
     // bytes (full sectors) instead of 32 rows x 16 bytes.
     const int ew = warp - 2;
     const int quad = warp & 3;       // TMEM lane quadrant this warp may touch
-    const int cpar = ew >> 2;        // this warp handles chunks cpar, cpar+2, ...
+    const int cpar = ew >> 2;        // position of this warp among the EPI_PER_QUAD warps of its quadrant
+    float* wbias = sbias + ew * 64;
+    uint32_t chunk_rot = 0;          // chunks dealt so far (mod EPI_PER_QUAD): keeps the deal balanced across tiles
     const int r_own = quad * 32 + lane;
     uint8_t* stg = stg_base + ew * STG_WARP_BYTES;
     // staging addresses: own row (write side) and the coalesced (8 rows x 4 x 16 B) side
@@ -326,17 +343,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
                                                        seg.out_col_off + col0 + co_q * 8);  // may alias `out`
         }
       };
-      if (use_res && ocol_base + cpar * 32 < seg.n_store) load_res(ocol_base + cpar * 32);
+      // this tile's chunks are dealt round-robin to the EPI_PER_QUAD warps of the quadrant, continuing where the
+      // previous tile stopped, so tiles whose chunk count is not a multiple of EPI_PER_QUAD still balance
+      const int n_chunks = (out_cols_per_tile + 31) >> 5;
+      const int c_first = (cpar + EPI_PER_QUAD - (int)(chunk_rot % EPI_PER_QUAD)) % EPI_PER_QUAD;
+      chunk_rot += (uint32_t)n_chunks;
+      // bias slice of a chunk: one coalesced load per lane, issued early; broadcast through smem at use
+      float bias_h = 0.f, bias_g = 0.f;
+      auto load_bias = [&](int c) {
+        const int col0 = ocol_base + c * 32;
+        bias_h = bias_g = 0.f;
+        if (p.bias && col0 + lane < seg.n_valid) {
+          if (geglu) {  // packed bias follows the packed (interleaved [h | g]) weight rows
+            bias_h = __ldg(p.bias + seg.vec_off + tile.n0 + c * 32 + lane);
+            bias_g = __ldg(p.bias + seg.vec_off + tile.n0 + p.bn / 2 + c * 32 + lane);
+          } else {
+            bias_h = __ldg(p.bias + seg.vec_off + col0 + lane);
+          }
+        }
+      };
+      if (c_first < n_chunks) {
+        if (use_res && ocol_base + c_first * 32 < seg.n_store) load_res(ocol_base + c_first * 32);
+        load_bias(c_first);
+      }
 
       const bool got = mbar_wait(&tfull_bar[acc], acc_phase, p.abort_flag);
       if (!got) break;
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
 
-      for (int c = cpar; c * 32 < out_cols_per_tile; c += 2) {
+      for (int c = c_first; c < n_chunks; c += EPI_PER_QUAD) {
         const int col0 = ocol_base + c * 32;
         if (col0 >= seg.n_store) break;  // warp-uniform
         const int n_ok = seg.n_valid - col0;  // columns of this chunk that carry data (may be <= 0)
+        if (p.bias) {
+          wbias[lane] = bias_h;
+          if (geglu) wbias[32 + lane] = bias_g;
+          __syncwarp();
+        }
+        const bool more = (c + EPI_PER_QUAD < n_chunks) && (col0 + 32 * EPI_PER_QUAD < seg.n_store);
         uint32_t ra[32];
         float v[32];
         tmem_ld_32x32(t_addr + c * 32, ra);
@@ -350,9 +395,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
             v[j] = __uint_as_float(ra[j]);
             gv[j] = __uint_as_float(rb[j]);
           }
-          if (p.bias) {  // packed bias follows the packed (interleaved) weight rows
-            add32(v, p.bias + seg.vec_off + tile.n0 + c * 32, n_ok);
-            add32(gv, p.bias + seg.vec_off + tile.n0 + p.bn / 2 + c * 32, n_ok);
+          if (p.bias) {
+            add32_smem(v, wbias);
+            add32_smem(gv, wbias + 32);
+            __syncwarp();
+            if (more) load_bias(c + EPI_PER_QUAD);
           }
           if (p.gate && valid) {
             const float* gp = p.gate + (size_t)sample * p.gate_ld;
@@ -371,7 +418,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-          if (p.bias) add32(v, p.bias + seg.vec_off + col0, n_ok);
+          if (p.bias) {
+            add32_smem(v, wbias);
+            __syncwarp();
+            if (more) load_bias(c + EPI_PER_QUAD);
+          }
           if (p.rowvec && valid) add32(v, p.rowvec + (size_t)sample * p.rowvec_ld + col0, n_ok);
           if (tabp) add32(v, tabp + col0, n_ok);
           if (p.gate && valid) {
@@ -416,7 +467,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
             }
             __syncwarp();
             // prefetch the residual of this warp's next chunk
-            if (col0 + 64 < seg.n_store && (c + 2) * 32 < out_cols_per_tile) load_res(col0 + 64);
+            if (more) load_res(col0 + 32 * EPI_PER_QUAD);
           }
           if (n_ok < 32) {
 #pragma unroll
@@ -589,12 +640,12 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   APTP_REQUIRE(p.abort_flag != nullptr, "aptp_grouped_gemm_fwd: could not allocate abort flag");
 
   const int stage_bytes = A_STAGE_BYTES + a->bn * 128;
-  const int budget = 225 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - STG_BYTES /*epilogue staging*/;
+  const int budget = 225 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - STG_BYTES /*epilogue staging*/ - SBIAS_BYTES;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   APTP_REQUIRE(stages >= 2, "aptp_grouped_gemm_fwd: tile too large for shared memory");
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + STG_BYTES + 1024 + 256;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + STG_BYTES + SBIAS_BYTES + 1024 + 256;
   if (!g_gemm_smem_set) {
     APTP_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_gemm_smem_set = 1;

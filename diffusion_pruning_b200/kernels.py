@@ -60,6 +60,8 @@ class Schedule:
     bn: int
     box: tuple           # (bw, bh, bb)
     flops: float = 0.0   # 2 * kept MACs of this launch (for roofline accounting)
+    bytes_in: float = 0.0   # algorithmic operand bytes: kept A rows x kept K + kept weight block (bf16), read once
+    out_elems: float = 0.0  # output elements written (x2 / x4 bytes by output type; same count for a residual read)
 
 
 def conv_box(W: int, H: int) -> tuple:
@@ -85,6 +87,8 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
     if taps is None:
         taps = 1 if mode == A_LINEAR else 9
     flops = 0.0
+    bytes_in = 0.0
+    out_elems = 0.0
     for si, s in enumerate(segments):
         n_store = s.n_store if s.n_store >= 0 else (s.n_valid + 7) // 8 * 8
         segs[si, :9] = (s.row_begin, s.row_end, s.n_valid, n_store, s.k_chunks, s.w_row_off, s.vec_off, s.tab_off,
@@ -94,6 +98,8 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
         n_tiles_n = (max(s.n_valid, n_store) + cols_per_tile - 1) // cols_per_tile
         rows = s.row_end - s.row_begin
         flops += 2.0 * rows * s.n_valid * (2 if geglu else 1) * s.k_chunks * BK * taps
+        bytes_in += 2.0 * rows * s.k_chunks * BK + 2.0 * s.n_valid * (2 if geglu else 1) * s.k_chunks * BK * taps
+        out_elems += float(rows) * n_store
         if mode == A_LINEAR:
             m_bases = range(s.row_begin, s.row_end, BM)
         else:
@@ -106,7 +112,8 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
                 tiles.append((si, m, nt * bn, 0))
     tl = np.asarray(tiles, dtype=np.int32).reshape(-1, 4) if tiles else np.zeros((0, 4), dtype=np.int32)
     return Schedule(segs=torch.from_numpy(segs).to(device), tiles=torch.from_numpy(tl).to(device),
-                    n_segs=len(segments), n_tiles=len(tiles), bn=bn, box=box, flops=flops)
+                    n_segs=len(segments), n_tiles=len(tiles), bn=bn, box=box, flops=flops, bytes_in=bytes_in,
+                    out_elems=out_elems)
 
 
 def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Schedule, *, a_ld: int, a_k: int,

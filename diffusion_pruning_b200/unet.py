@@ -479,6 +479,7 @@ class _Engine:
         self.sched: Dict[Any, Any] = {}
         self.arena: Dict[Any, torch.Tensor] = {}
         self.flops = 0.0          # kept GEMM-class FLOPs of the last forward (roofline accounting)
+        self.gemm_bytes = 0.0     # algorithmic HBM bytes of the grouped-GEMM launches of the last forward
         self.launches = 0
         self.count_flops = False
         self._label = ""
@@ -615,6 +616,8 @@ class _Engine:
             K.grouped_gemm(a, w, out, sched, **kw)
         self.launches += 1
         self.flops += sched.flops
+        self.gemm_bytes += sched.bytes_in + sched.out_elems * ((2 if kw.get('out_mode', OUT_BF16) == OUT_BF16 else 4)
+                                                               + (2 if kw.get('residual') is not None else 0))
 
     # ---- dense (unpruned) weights ---------------------------------------------------------------
     def _dense_linear(self, name: str, lin: nn.Module, n_pad_to: int = 0) -> Dict[str, torch.Tensor]:
@@ -1100,6 +1103,7 @@ class _Engine:
         B, cin, H, W = sample.shape
         self.B = B
         self.flops = 0.0
+        self.gemm_bytes = 0.0
         self.launches = 0
         self._prepare_gates(B)
         if not torch.is_tensor(timestep):
