@@ -21,7 +21,7 @@ class GemmSeg(C.Structure):
 
 
 class GemmTile(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("seg", "m_base", "n0", "pad")]
+    _fields_ = [(n, C.c_int32) for n in ("seg", "m_base", "n0", "flags")]
 
 
 class GemmArgs(C.Structure):
@@ -113,11 +113,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = Path(os.environ.get("APTP_LIB") or LIB_PATH)  # APTP_LIB: kernel-tuning builds of the same library (tools/)
+    if not path.exists():
         raise AptpError(
-            f"{LIB_PATH} is missing: build it with `python -m diffusion_pruning_b200.build` "
+            f"{path} is missing: build it with `python -m diffusion_pruning_b200.build` "
             "(the product path has no fallback implementation)")
-    lib = C.CDLL(os.fspath(LIB_PATH))
+    lib = C.CDLL(os.fspath(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res

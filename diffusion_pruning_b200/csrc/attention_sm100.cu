@@ -38,6 +38,14 @@ constexpr int ATT_TMEM_S = 0;      // S0 at cols [0,128), S1 at [128,256)
 constexpr int ATT_TMEM_P = 256;    // P0 at [256,320), P1 at [320,384): 128 keys x bf16 = 64 packed columns
 constexpr int ATT_TMEM_O = 384;    // O0 at [384,448), O1 at [448,512)
 constexpr float ATT_RESCALE_LOG2 = 8.f;
+// share of the exponentials computed on the FMA/ALU pipes instead of the XU pipe: ATT_POLY_PAIRS of every
+// ATT_POLY_PERIOD column pairs
+#ifndef ATT_POLY_PAIRS
+#define ATT_POLY_PAIRS 0
+#endif
+#ifndef ATT_POLY_PERIOD
+#define ATT_POLY_PERIOD 4
+#endif
 
 struct AttnParams {
   CUtensorMap tmap_q, tmap_k, tmap_v;
@@ -250,34 +258,86 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         tc_fence_after();
         uint32_t s[ATT_BN];
         tmem_ld_32x32(s_addr, s);
-        tmem_ld_32x32(s_addr + 32, s + 32);
+        tmem_ld_wait();
+        tmem_ld_32x32(s_addr + 32, s + 32);  // the rest of the row arrives under the first chunk's exponentials
         tmem_ld_32x32(s_addr + 64, s + 64);
         tmem_ld_32x32(s_addr + 96, s + 96);
+        const int kv_left = p.n_kv - j * ATT_BN;  // keys valid in this tile (>= 1)
+        const bool optimistic = (j > 0);          // exponentials against the STALE max (checked afterwards)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        uint64_t lsum = 0ull;                     // packed (l0, l1) partial row sums of this tile
+        const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        uint64_t negm2 = pack_f32x2(-m_used, -m_used);
+        // x = s * scale - m  ->  p = 2^x for 32 columns, packed to bf16. ATT_POLY_PAIRS of every ATT_POLY_PERIOD
+        // column pairs may run 2^x on the FMA/ALU pipes (Cody-Waite + degree-3 minimax) instead of MUFU.EX2;
+        // measured on B200 (profiles/r01_attention_notes.md) the kernel is not XU-bound at head_dim 64 with two
+        // softmax warps per scheduler, so the default keeps every exponential on the XU pipe.
+        auto exp_chunk = [&](int c, uint32_t* pk) {
+          const float lo_clamp = (m_used - 125.f) / p.scale_log2;  // s below this gives p < 2^-125
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int pair = (c * 32 + i) >> 1;
+            float p0, p1;
+            if ((pair % ATT_POLY_PERIOD) < ATT_POLY_PAIRS) {
+              const float s0 = fmaxf(__uint_as_float(s[c * 32 + i]), lo_clamp);
+              const float s1 = fmaxf(__uint_as_float(s[c * 32 + i + 1]), lo_clamp);
+              exp2_poly_x2(pack_f32x2(s0, s1), scale2, negm2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])),
+                                     scale2, negm2), x0, x1);
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
+            lsum = add_f32x2(lsum, pack_f32x2(p0, p1));
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+        };
+        auto max_chunk = [&](int c) {
+          if (kv_left < ATT_BN) {  // ragged last key tile: -inf -> p = 0
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= kv_left) s[c * 32 + i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(s[c * 32 + i]));
+            mx1 = fmaxf(mx1, __uint_as_float(s[c * 32 + i + 1]));
+          }
+        };
+        uint32_t pk0[16], pk1[16];
+        max_chunk(0);
+        if (optimistic) exp_chunk(0, pk0);
         tmem_ld_wait();
+        // the whole S row is in registers: hand S back so QK^T of the next key tile runs under the rest
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[w]);  // the tensor pipe may overwrite S with the next tile now
-        const int kv_left = p.n_kv - j * ATT_BN;  // keys valid in this tile (>= 1)
-        float mx = -INFINITY;
-        if (kv_left >= ATT_BN) {
-#pragma unroll
-          for (int i = 0; i < ATT_BN; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < ATT_BN; ++i) {
-            if (i < kv_left) mx = fmaxf(mx, __uint_as_float(s[i]));
-            else s[i] = 0xff800000u;  // -inf -> p = 0
-          }
-        }
+        if (lane == 0) mbar_arrive(&s_free[w]);
+        max_chunk(1);
+        if (optimistic) exp_chunk(1, pk1);
         if (j > 0) {  // PV of the previous tile must be complete before P is overwritten / O rescaled
           ok = mbar_wait(&pv_done[w], gd & 1, p.abort_flag);
           ++gd;
           if (!ok) break;
           tc_fence_after();
         }
-        const float m_cand = mx * p.scale_log2;
+        if (optimistic) {
+          tmem_st_32x16(p_addr, pk0);
+          tmem_st_32x16(p_addr + 16, pk1);
+        }
+#pragma unroll
+        for (int c = 2; c < ATT_BN / 32; ++c) {
+          max_chunk(c);
+          if (optimistic) {
+            exp_chunk(c, pk0);
+            tmem_st_32x16(p_addr + c * 16, pk0);
+          }
+        }
+        const float m_cand = fmaxf(mx0, mx1) * p.scale_log2;
         const bool need = m_cand > m_used + ATT_RESCALE_LOG2;  // first tile: m_used = -inf
         if (__any_sync(0xffffffffu, need)) {
+          // rare after the first tile: the running max grew by more than 2^8. Rescale O and redo this tile's
+          // exponentials against the new max (S is still in registers, P has not been handed to the MMA yet).
           const float m_new = need ? m_cand : m_used;
           if (j > 0) {
             const float factor = need ? ex2_approx(m_used - m_new) : 1.f;
@@ -292,22 +352,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             l_run *= factor;
           }
           m_used = m_new;
-        }
-        float l0 = 0.f, l1 = 0.f;
+          negm2 = pack_f32x2(-m_used, -m_used);
+          lsum = 0ull;
 #pragma unroll
-        for (int c = 0; c < ATT_BN / 32; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i]), p.scale_log2, -m_used));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 1]), p.scale_log2, -m_used));
-            l0 += p0;
-            l1 += p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
+          for (int c = 0; c < ATT_BN / 32; ++c) {
+            exp_chunk(c, pk0);
+            tmem_st_32x16(p_addr + c * 16, pk0);
           }
-          tmem_st_32x16(p_addr + c * 16, pk);
         }
-        l_run += l0 + l1;
+        {
+          float l0, l1;
+          unpack_f32x2(lsum, l0, l1);
+          l_run += l0 + l1;
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

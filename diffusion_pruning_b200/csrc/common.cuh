@@ -139,6 +139,34 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- thread-block clusters ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster (also orders shared-memory / mbarrier initialisation cluster-wide)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load delivered to the same shared-memory offset (and mbarrier) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // ---- tcgen05 / TMEM ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -292,6 +320,46 @@ __device__ __forceinline__ void tma_load_2d_e(void* smem, const CUtensorMap* map
 }
 __device__ __forceinline__ void mbar_expect_tx_e(uint64_t* bar, uint32_t bytes) {
   if (elect_one()) mbar_expect_tx(bar, bytes);
+}
+
+// ---- packed fp32x2 math (FFMA2 / FADD2 on sm_100: two lanes per issue slot) ----
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^(s*scale + negm) for two values without the XU pipe. x is formed twice: once plain, once with the
+// 1.5*2^23 magic constant added so the rounded integer part n lands in the low mantissa bits; r = x - n is in
+// [-0.5, 0.5]; 2^r by a degree-3 minimax polynomial (relative error 7.5e-5, far below bf16 rounding 2^-9 = 2e-3);
+// 2^n by adding n to the exponent field. The caller clamps s so that x >= -125.
+__device__ __forceinline__ void exp2_poly_x2(uint64_t s2, uint64_t scale2, uint64_t negm2, float& p0, float& p1) {
+  const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f);
+  const uint64_t nmagic2 = pack_f32x2(-12582912.f, -12582912.f);
+  const uint64_t x2 = fma_f32x2(s2, scale2, negm2);
+  const uint64_t xf2 = add_f32x2(x2, magic2);           // mantissa low bits = round(x)
+  const uint64_t nr2 = add_f32x2(xf2, nmagic2);         // round(x) as float
+  const uint64_t r2 = fma_f32x2(nr2, pack_f32x2(-1.f, -1.f), x2);  // r = x - round(x)
+  uint64_t q2 = fma_f32x2(r2, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.242611125f, 0.242611125f));
+  q2 = fma_f32x2(q2, r2, pack_f32x2(0.693260968f, 0.693260968f));
+  q2 = fma_f32x2(q2, r2, pack_f32x2(0.999928057f, 0.999928057f));
+  float q0, q1, f0, f1;
+  unpack_f32x2(q2, q0, q1);
+  unpack_f32x2(xf2, f0, f1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(f0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(f1) << 23));
 }
 
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }

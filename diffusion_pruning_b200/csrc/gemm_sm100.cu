@@ -24,10 +24,15 @@ constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int EPI_PER_QUAD = 3;                    // epilogue warps per TMEM lane quadrant (32-column chunks dealt round-robin)
 constexpr int EPI_WARPS = 4 * EPI_PER_QUAD;
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..13 epilogue
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;  // warpgroup 0: warp 0 TMA, warp 1 MMA, 2 idle; warps 4..15 epilogue
+// registers move from the control warpgroup to the epilogue warpgroups (setmaxnreg): 128 x 56 + 384 x 152 = 64K
+#define GEMM_CTRL_REGS "56"
+#define GEMM_EPI_REGS "152"
 constexpr int TMEM_COLS = 512;
 constexpr int STG_WARP_BYTES = 32 * 64;            // per-warp staging: 32 rows x 32 bf16 columns
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
+constexpr int MAX_SMEM_SEGS = 96;                   // expert-bucket records cached in shared memory (else read from global)
+constexpr int SSEG_BYTES = MAX_SMEM_SEGS * 48;
 constexpr int SBIAS_BYTES = EPI_WARPS * 64 * 4;     // per epilogue warp: the bias slice of its current chunk (32, or 2 x 32 for GEGLU)
 
 struct GemmParams {
@@ -36,6 +41,7 @@ struct GemmParams {
   const aptp_gemm_seg* segs;
   const aptp_gemm_tile* tiles;
   int n_tiles;
+  int n_segs;
   int a_mode;
   int batch, Ho, Wo;  // OUTPUT spatial size (conv modes)
   int bn, bw, bh, bb;
@@ -87,12 +93,12 @@ struct TileGeom {
   int m_base;
   int img0, oy0, ox0;
 };
-__device__ __forceinline__ long long map_row(const GemmParams& p, const TileGeom& g, int r, bool& valid, int& oy,
+__device__ __forceinline__ int map_row(const GemmParams& p, const TileGeom& g, int r, bool& valid, int& oy,
                                              int& ox) {
   if (g.linear) {
     valid = true;
     oy = ox = 1;
-    return (long long)g.m_base + r;
+    return g.m_base + r;
   }
   const int ix = r & (p.bw - 1);
   const int iy = (r >> p.lbw) & (p.bh - 1);
@@ -101,7 +107,7 @@ __device__ __forceinline__ long long map_row(const GemmParams& p, const TileGeom
   ox = g.ox0 + ix;
   const int img = g.img0 + ib;
   valid = (img < p.batch) && (oy < p.Ho) && (ox < p.Wo);
-  return ((long long)img * p.Ho + oy) * p.Wo + ox;
+  return (img * p.Ho + oy) * p.Wo + ox;  // output rows < 2^31 (checked on the host)
 }
 
 // 32 floats starting at src (all lanes read the same addresses -> L1 broadcast); float4 when aligned.
@@ -134,14 +140,20 @@ __device__ __forceinline__ void add32_smem(float* v, const float* src) {
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
+// kGeglu selects the GEGLU epilogue (two accumulator halves per output column, erf-GELU) and compiles out the
+// residual / row-vector / border-table / fp32 paths it never uses, so neither instantiation pays for the other's
+// registers.
+template <bool kGeglu>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
   const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.bn * 128u;
   uint8_t* stg_base = smem + (size_t)stages * stage_bytes;
   float* sbias = reinterpret_cast<float*>(stg_base + STG_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES + SBIAS_BYTES);
+  aptp_gemm_seg* ssegs = reinterpret_cast<aptp_gemm_seg*>(stg_base + STG_BYTES + SBIAS_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES + SBIAS_BYTES + SSEG_BYTES);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -149,6 +161,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  // CTA pair (cluster of 2): the pair works on tiles (2i, 2i+1) of the list, which share the expert bucket and
+  // the weight rows (n0) and differ in their 128 output rows; each CTA fetches HALF of the weight tile of every
+  // stage and multicasts it to both, so the L2 -> shared-memory traffic for B is halved.
+  // (rank / pair bookkeeping is recomputed inside each role: values kept live across the setmaxnreg split are
+  // spilled to local memory by ptxas and reloaded in the hot loops)
+#define GEMM_ROLE_PROLOGUE()                                                                        \
+  const uint32_t cta_rank = cluster_ctarank();                                                      \
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1, n_pairs = p.n_tiles >> 1;        \
+  const aptp_gemm_seg* segs = (p.n_segs <= MAX_SMEM_SEGS) ? ssegs : p.segs;                         \
+  const uint32_t tmem_base = *tmem_slot;                                                            \
+  (void)cta_rank; (void)pair0; (void)pair_stride; (void)n_pairs; (void)segs; (void)tmem_base;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
@@ -158,7 +181,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 1);
+        mbar_init(&empty_bar[s], 2);  // one tcgen05.commit from each CTA of the pair
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
@@ -170,22 +193,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  // expert-bucket records -> shared memory (every role reads one per tile; a dependent global load per tile
+  // is a ~1 us bubble on the short K=320 tiles)
+  const bool segs_in_smem = p.n_segs <= MAX_SMEM_SEGS;
+  if (segs_in_smem) {
+    const int4* src = reinterpret_cast<const int4*>(p.segs);
+    int4* dst = reinterpret_cast<int4*>(ssegs);
+    for (int i = threadIdx.x; i < p.n_segs * 3; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any multicast load / remote arrive
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 " GEMM_CTRL_REGS ";");
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
     // Whole warp in uniform control flow, one elected lane issues (see the MMA issuer for why).
     {
+      GEMM_ROLE_PROLOGUE();
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
       const int taps = (p.a_mode == APTP_A_LINEAR) ? 1 : 9;
-      for (int t = blockIdx.x; t < p.n_tiles && ok; t += gridDim.x) {
-        const aptp_gemm_tile tile = p.tiles[t];
-        const aptp_gemm_seg seg = p.segs[tile.seg];
+      aptp_gemm_tile tile_next = p.tiles[2 * pair0 + cta_rank];  // grid/2 <= n_pairs
+      const uint32_t b_half_bytes = (uint32_t)p.bn * 64u;          // bn/2 weight rows x 128 B
+      for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride) {
+        const aptp_gemm_tile tile = tile_next;
+        if (pr + pair_stride < n_pairs) tile_next = p.tiles[2 * (pr + pair_stride) + cta_rank];  // in flight
+        const aptp_gemm_seg seg = segs[tile.seg];
         int img = 0, oy0 = 0, ox0 = 0;
         if (p.a_mode != APTP_A_LINEAR) {
           const int hw = p.Ho * p.Wo;
@@ -194,7 +230,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           oy0 = rem / p.Wo;
           ox0 = rem - oy0 * p.Wo;
         }
-        const int b_row = seg.w_row_off + tile.n0;
+        const int b_row = seg.w_row_off + tile.n0 + (int)cta_rank * (p.bn >> 1);  // this CTA's half of the weight tile
         for (int tap = 0; tap < taps && ok; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
           for (int kc = 0; kc < seg.k_chunks; ++kc) {
@@ -217,7 +253,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
                 tma_load_5d(sa, &p.tmap_a, &full_bar[stage], px * p.k_tap_pitch + kc * BK, ox0 + sx, py, oy0 + sy,
                             img);
               }
-              tma_load_2d(sb, &p.tmap_b, &full_bar[stage], tap * p.k_tap_pitch + kc * BK, b_row);
+              tma_load_2d_mc(sb + cta_rank * b_half_bytes, &p.tmap_b, &full_bar[stage], tap * p.k_tap_pitch + kc * BK,
+                             b_row, (uint16_t)0x3);
             }
             __syncwarp();
             advance(stage, phase, stages);
@@ -232,6 +269,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
     // A loop nested under `if (lane == 0)` instead makes ptxas wrap every UTCHMMA in a per-lane
     // R2UR "waterfall" loop, which capped the issue rate at ~140 cycles per MMA (ncu, round 1).
     {
+      GEMM_ROLE_PROLOGUE();
       const uint32_t idesc = make_idesc_bf16(BM, (uint32_t)p.bn, 0, 0);
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
@@ -239,9 +277,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
       int acc = 0;
       uint32_t acc_phase = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < p.n_tiles && ok; t += gridDim.x) {
-        const int seg_id = __shfl_sync(0xffffffffu, p.tiles[t].seg, 0);
-        const int k_chunks = __shfl_sync(0xffffffffu, p.segs[seg_id].k_chunks, 0);
+      int seg_next = p.tiles[2 * pair0 + cta_rank].seg;
+      for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride) {
+        const int seg_id = __shfl_sync(0xffffffffu, seg_next, 0);
+        if (pr + pair_stride < n_pairs) seg_next = p.tiles[2 * (pr + pair_stride) + cta_rank].seg;
+        const int k_chunks = __shfl_sync(0xffffffffu, segs[seg_id].k_chunks, 0);
         const int kblocks = ((p.a_mode == APTP_A_LINEAR) ? 1 : 9) * k_chunks;
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.abort_flag)) break;
         tc_fence_after();
@@ -261,7 +301,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
               // +32 bytes per K=16 step inside the 128B-swizzled row: +2 in the (addr >> 4) field
               umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);
+            umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // the stage is free once BOTH CTAs have read it
           }
           __syncwarp();
           advance(stage, phase, stages);
@@ -273,12 +313,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  }
   } else {
     // ------------------------------- epilogue -----------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " GEMM_EPI_REGS ";");
+    GEMM_ROLE_PROLOGUE();
     // Thread = one accumulator row (TMEM lane). Results are transposed through a per-warp swizzled
     // smem tile so that every global store / residual load instruction covers 8 rows x 64 contiguous
     // bytes (full sectors) instead of 32 rows x 16 bytes.
-    const int ew = warp - 2;
+    const int ew = warp - 4;
     const int quad = warp & 3;       // TMEM lane quadrant this warp may touch
     const int cpar = ew >> 2;        // position of this warp among the EPI_PER_QUAD warps of its quadrant
     float* wbias = sbias + ew * 64;
@@ -291,12 +334,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
     const int co_q = lane & 3;  // 16-byte column unit handled by this lane on the coalesced side
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool geglu = (p.flags & APTP_EPI_GEGLU) != 0;
+    constexpr bool geglu = kGeglu;
     const int out_cols_per_tile = geglu ? p.bn / 2 : p.bn;
-    const bool bf16_out = (p.out_mode == APTP_OUT_BF16);
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const aptp_gemm_tile tile = p.tiles[t];
-      const aptp_gemm_seg seg = p.segs[tile.seg];
+    const bool bf16_out = kGeglu || (p.out_mode == APTP_OUT_BF16);
+    aptp_gemm_tile tile_next = p.tiles[2 * pair0 + cta_rank];
+    for (int pr = pair0; pr < n_pairs; pr += pair_stride) {
+      const aptp_gemm_tile tile = tile_next;
+      if (pr + pair_stride < n_pairs) tile_next = p.tiles[2 * (pr + pair_stride) + cta_rank];
+      const aptp_gemm_seg seg = segs[tile.seg];
+      const bool placeholder = (tile.flags & APTP_TILE_PLACEHOLDER) != 0;  // odd tile count of a bucket: no stores
       TileGeom g;
       g.linear = (p.a_mode == APTP_A_LINEAR);
       g.m_base = tile.m_base;
@@ -311,29 +357,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
       // ---- own row ----
       bool valid;
       int oy, ox;
-      const long long row = map_row(p, g, r_own, valid, oy, ox);
-      valid = valid && (row < (long long)seg.row_end) && (row >= (long long)seg.row_begin);
-      const int sample = valid ? (int)row / p.rows_per_sample : 0;
+      const int row = map_row(p, g, r_own, valid, oy, ox);
+      valid = valid && !placeholder && (row < seg.row_end) && (row >= seg.row_begin);
+      const int sample = valid ? row / p.rows_per_sample : 0;
       const int ycls = g.linear ? 1 : ((oy == 0) ? 0 : ((oy == p.Ho - 1) ? 2 : 1));
       const int xcls = g.linear ? 1 : ((ox == 0) ? 0 : ((ox == p.Wo - 1) ? 2 : 1));
       const float* tabp =
-          p.border_tab ? p.border_tab + seg.tab_off + (size_t)(ycls * 3 + xcls) * p.tab_ld : nullptr;
+          (!kGeglu && p.border_tab) ? p.border_tab + seg.tab_off + (size_t)(ycls * 3 + xcls) * p.tab_ld : nullptr;
       // ---- the 4 rows this lane moves on the coalesced side ----
-      long long co_row[4];
+      int co_row[4];
       bool co_ok[4];
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         int a, b;
         bool v;
-        const long long rr = map_row(p, g, quad * 32 + it * 8 + (lane >> 2), v, a, b);
-        co_ok[it] = v && (rr < (long long)seg.row_end) && (rr >= (long long)seg.row_begin);
+        const int rr = map_row(p, g, quad * 32 + it * 8 + (lane >> 2), v, a, b);
+        co_ok[it] = v && !placeholder && (rr < seg.row_end) && (rr >= seg.row_begin);
         co_row[it] = rr;
       }
       const int ocol_base = geglu ? tile.n0 / 2 : tile.n0;  // first OUTPUT column of this tile
 
       // residual of the first chunk goes in flight before we wait for the accumulator
       uint4 rres[4];
-      const bool use_res = (p.residual != nullptr) && bf16_out;
+      const bool use_res = !kGeglu && (p.residual != nullptr) && bf16_out;
       auto load_res = [&](int col0) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -382,11 +428,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           __syncwarp();
         }
         const bool more = (c + EPI_PER_QUAD < n_chunks) && (col0 + 32 * EPI_PER_QUAD < seg.n_store);
-        uint32_t ra[32];
         float v[32];
-        tmem_ld_32x32(t_addr + c * 32, ra);
-        if (geglu) {
-          uint32_t rb[32];
+        if constexpr (kGeglu) {
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32(t_addr + c * 32, ra);
           tmem_ld_32x32(t_addr + p.bn / 2 + c * 32, rb);
           tmem_ld_wait();
           float gv[32];
@@ -398,8 +443,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           if (p.bias) {
             add32_smem(v, wbias);
             add32_smem(gv, wbias + 32);
-            __syncwarp();
-            if (more) load_bias(c + EPI_PER_QUAD);
           }
           if (p.gate && valid) {
             const float* gp = p.gate + (size_t)sample * p.gate_ld;
@@ -414,7 +457,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_fast(gv[j]);
+          if (p.bias) {
+            __syncwarp();
+            if (more) load_bias(c + EPI_PER_QUAD);
+          }
         } else {
+          uint32_t ra[32];
+          tmem_ld_32x32(t_addr + c * 32, ra);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
@@ -438,32 +487,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
         }
 
         if (bf16_out) {
+          // per-warp staging tile: 32 rows x 64 B, 16-byte units XOR-swizzled by (row >> 1) & 3. Plain C++ accesses
+          // (ordered by __syncwarp) so the compiler can batch the four loads / stores of each phase.
+          uint4* stg4 = reinterpret_cast<uint4*>(stg);
           if (use_res) {
             // residual: coalesced registers -> swizzled smem -> own row
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int rl = it * 8 + (lane >> 2);
-              const uint32_t a = smem_u32(stg) + rl * 64 + ((co_q ^ ((rl >> 1) & 3)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(rres[it].x), "r"(rres[it].y),
-                           "r"(rres[it].z), "r"(rres[it].w)
-                           : "memory");
+              stg4[rl * 4 + (co_q ^ ((rl >> 1) & 3))] = rres[it];
             }
             __syncwarp();
+            uint4 w4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w4[q] = stg4[lane * 4 + (q ^ own_sw)];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint32_t w0, w1, w2, w3;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                           : "r"(stg_own + ((q ^ own_sw) << 4))
-                           : "memory");
-              v[q * 8 + 0] += bf16_lo(w0);
-              v[q * 8 + 1] += bf16_hi(w0);
-              v[q * 8 + 2] += bf16_lo(w1);
-              v[q * 8 + 3] += bf16_hi(w1);
-              v[q * 8 + 4] += bf16_lo(w2);
-              v[q * 8 + 5] += bf16_hi(w2);
-              v[q * 8 + 6] += bf16_lo(w3);
-              v[q * 8 + 7] += bf16_hi(w3);
+              v[q * 8 + 0] += bf16_lo(w4[q].x);
+              v[q * 8 + 1] += bf16_hi(w4[q].x);
+              v[q * 8 + 2] += bf16_lo(w4[q].y);
+              v[q * 8 + 3] += bf16_hi(w4[q].y);
+              v[q * 8 + 4] += bf16_lo(w4[q].z);
+              v[q * 8 + 5] += bf16_hi(w4[q].z);
+              v[q * 8 + 6] += bf16_lo(w4[q].w);
+              v[q * 8 + 7] += bf16_hi(w4[q].w);
             }
             __syncwarp();
             // prefetch the residual of this warp's next chunk
@@ -476,26 +523,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
           }
           // own row -> swizzled smem
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_own + ((q ^ own_sw) << 4)),
-                         "r"(pack_bf16(v[q * 8 + 0], v[q * 8 + 1])), "r"(pack_bf16(v[q * 8 + 2], v[q * 8 + 3])),
-                         "r"(pack_bf16(v[q * 8 + 4], v[q * 8 + 5])), "r"(pack_bf16(v[q * 8 + 6], v[q * 8 + 7]))
-                         : "memory");
-          }
+          for (int q = 0; q < 4; ++q)
+            stg4[lane * 4 + (q ^ own_sw)] =
+                make_uint4(pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                           pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
           __syncwarp();
           // coalesced side: 8 rows x 64 B per instruction
           __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + seg.out_col_off + col0 + co_q * 8;
           const bool col_ok = col0 + co_q * 8 < seg.n_store;  // n_store is a multiple of 8
+          uint4 o4[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rl = it * 8 + (lane >> 2);
-            uint4 o;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
-                         : "r"(smem_u32(stg) + rl * 64 + ((co_q ^ ((rl >> 1) & 3)) << 4))
-                         : "memory");
-            if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o;
+            o4[it] = stg4[rl * 4 + (co_q ^ ((rl >> 1) & 3))];
           }
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o4[it];
           __syncwarp();
         } else if (valid) {
           if (n_ok < 32) {
@@ -514,7 +558,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
             }
           } else {  // fp32 NCHW: out[(sample*out_ld + col) * rows_per_sample + pixel]
             float* op = reinterpret_cast<float*>(p.out);
-            const long long pix = row - (long long)sample * p.rows_per_sample;
+            const int pix = row - sample * p.rows_per_sample;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j < n_ok) op[((size_t)sample * p.out_ld + col0 + j) * p.rows_per_sample + pix] = v[j];
@@ -530,14 +574,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) grouped_gemm_kernel(const __g
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(*tmem_slot, TMEM_COLS);
   }
 }
 
 static int g_gemm_smem_set = 0;
+static int g_gemm_max_clusters = 0;
 
 }  // namespace aptp
 
@@ -548,6 +593,7 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   APTP_REQUIRE(a != nullptr, "aptp_grouped_gemm_fwd: null args");
   APTP_REQUIRE(a->a && a->w && a->out && a->segs && a->tiles, "aptp_grouped_gemm_fwd: null pointer");
   if (a->n_tiles == 0) return APTP_OK;
+  APTP_REQUIRE(a->n_tiles % 2 == 0, "aptp_grouped_gemm_fwd: tiles must come in pairs (n_tiles=%d is odd)", a->n_tiles);
   APTP_REQUIRE(a->bn >= 32 && a->bn <= 256 && a->bn % 32 == 0, "aptp_grouped_gemm_fwd: bn=%d must be a multiple of 32 in [32,256]", a->bn);
   APTP_REQUIRE(a->a_ld % 8 == 0 && a->w_ld % 8 == 0, "aptp_grouped_gemm_fwd: a_ld/w_ld must be multiples of 8 (16-byte rows)");
   APTP_REQUIRE(a->out_mode == APTP_OUT_F32_NCHW || a->out_ld % 8 == 0, "aptp_grouped_gemm_fwd: out_ld must be a multiple of 8");
@@ -559,7 +605,11 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
                "aptp_grouped_gemm_fwd: residual needs a bf16 output and res_ld %% 8 == 0");
   APTP_REQUIRE(a->a_rows < (1ll << 31), "aptp_grouped_gemm_fwd: too many rows");
   APTP_REQUIRE(!(a->flags & APTP_EPI_GN_STATS), "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS not implemented yet");
-  if (a->flags & APTP_EPI_GEGLU) APTP_REQUIRE(a->bn % 64 == 0, "aptp_grouped_gemm_fwd: GEGLU needs bn %% 64 == 0");
+  if (a->flags & APTP_EPI_GEGLU) {
+    APTP_REQUIRE(a->bn % 64 == 0, "aptp_grouped_gemm_fwd: GEGLU needs bn %% 64 == 0");
+    APTP_REQUIRE(a->out_mode == APTP_OUT_BF16 && !a->residual && !a->rowvec && !a->border_tab && !(a->flags & APTP_EPI_SILU),
+                 "aptp_grouped_gemm_fwd: the GEGLU epilogue takes bias and gate only and writes bf16");
+  }
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -600,13 +650,14 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   {
     uint64_t dims[2] = {(uint64_t)a->w_ld, (uint64_t)a->w_rows};
     uint64_t strides[1] = {(uint64_t)a->w_ld * 2};
-    uint32_t box[2] = {BK, (uint32_t)a->bn};
+    uint32_t box[2] = {BK, (uint32_t)a->bn / 2};  // each CTA of a pair loads (and multicasts) half of the weight tile
     int rc = make_tmap_bf16(&p.tmap_b, a->w, 2, dims, strides, box);
     if (rc) return rc;
   }
   p.segs = a->segs;
   p.tiles = a->tiles;
   p.n_tiles = a->n_tiles;
+  p.n_segs = a->n_segs;
   p.a_mode = a->a_mode;
   p.batch = a->batch;
   p.Ho = Ho;
@@ -640,18 +691,42 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   APTP_REQUIRE(p.abort_flag != nullptr, "aptp_grouped_gemm_fwd: could not allocate abort flag");
 
   const int stage_bytes = A_STAGE_BYTES + a->bn * 128;
-  const int budget = 225 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - STG_BYTES /*epilogue staging*/ - SBIAS_BYTES;
+  const int budget = 225 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - STG_BYTES /*epilogue staging*/ - SBIAS_BYTES - SSEG_BYTES;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   APTP_REQUIRE(stages >= 2, "aptp_grouped_gemm_fwd: tile too large for shared memory");
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + STG_BYTES + SBIAS_BYTES + 1024 + 256;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + STG_BYTES + SBIAS_BYTES + SSEG_BYTES + 1024 + 256;
   if (!g_gemm_smem_set) {
-    APTP_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    APTP_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    APTP_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_gemm_smem_set = 1;
   }
-  int grid = a->n_tiles < sm_count() ? a->n_tiles : sm_count();
-  grouped_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+  if (!g_gemm_max_clusters) {
+    // CTA pairs must land on one GPC: the number of co-resident pairs can be below sm_count()/2
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(sm_count() & ~1, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 227 * 1024;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    APTP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, grouped_gemm_kernel<false>, &cfg));
+    APTP_REQUIRE(n > 0, "aptp_grouped_gemm_fwd: no CTA pair fits on this device");
+    g_gemm_max_clusters = n;
+  }
+  const int n_pairs = a->n_tiles / 2;
+  const int grid = 2 * (n_pairs < g_gemm_max_clusters ? n_pairs : g_gemm_max_clusters);
+  if (a->flags & APTP_EPI_GEGLU)
+    grouped_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+  else
+    grouped_gemm_kernel<false><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

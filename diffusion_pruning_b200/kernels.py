@@ -18,6 +18,7 @@ from ._lib import (A_CONV3X3, A_CONV3X3_S2, A_LINEAR, EPI_GEGLU, EPI_SILU, OUT_B
 
 BM = 128
 BK = 64
+TILE_PLACEHOLDER = 1  # APTP_TILE_PLACEHOLDER
 
 
 def _stream() -> int:
@@ -107,9 +108,16 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
             m_bases = [(img * Ho + oy) * Wo + ox
                        for img in range(s.row_begin // hw, s.row_end // hw, bb)
                        for oy in range(0, Ho, bh) for ox in range(0, Wo, bw)]
-        for m in m_bases:
+        # tiles go in PAIRS (2i, 2i+1) = two row tiles that share the weight tile: a cluster of two CTAs
+        # multicasts it. An odd row-tile count is padded with a placeholder that repeats its partner.
+        m_bases = list(m_bases)
+        for i in range(0, len(m_bases), 2):
+            m0 = m_bases[i]
+            has1 = i + 1 < len(m_bases)
+            m1 = m_bases[i + 1] if has1 else m0
             for nt in range(n_tiles_n):
-                tiles.append((si, m, nt * bn, 0))
+                tiles.append((si, m0, nt * bn, 0))
+                tiles.append((si, m1, nt * bn, 0 if has1 else TILE_PLACEHOLDER))
     tl = np.asarray(tiles, dtype=np.int32).reshape(-1, 4) if tiles else np.zeros((0, 4), dtype=np.int32)
     return Schedule(segs=torch.from_numpy(segs).to(device), tiles=torch.from_numpy(tl).to(device),
                     n_segs=len(segments), n_tiles=len(tiles), bn=bn, box=box, flops=flops, bytes_in=bytes_in,

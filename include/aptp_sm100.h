@@ -58,8 +58,12 @@ typedef struct aptp_gemm_tile {
   int32_t seg;    /* index into segs                                                              */
   int32_t m_base; /* linear: first row; conv: linear index of the top-left output pixel of the box */
   int32_t n0;     /* first packed weight row / accumulator column block of this tile              */
-  int32_t pad;
+  int32_t flags;  /* APTP_TILE_*                                                                   */
 } aptp_gemm_tile;
+/* Tiles are consumed in PAIRS by a cluster of two CTAs that share (multicast) the weight tile: n_tiles is
+ * even and tiles[2i], tiles[2i+1] have the same seg and n0 and different m_base. A bucket with an odd
+ * number of row tiles is padded with a placeholder that repeats its partner's m_base and stores nothing. */
+enum { APTP_TILE_PLACEHOLDER = 1 };
 
 enum { APTP_A_LINEAR = 0, APTP_A_CONV3X3 = 1, APTP_A_CONV3X3_S2 = 2 };
 enum { APTP_OUT_BF16 = 0, APTP_OUT_F32 = 1, APTP_OUT_F32_NCHW = 2 };

@@ -339,6 +339,29 @@ def check_attention(B=2, heads=3, kept=(3, 1), Nq=256, Nkv=256, seed=0):
         assert (got[b, :, kept[b]:] == 9.0).all(), "pruned heads must not be written"
 
 
+def check_attention_rescale(B=2, heads=2, Nq=256, Nkv=640, seed=3):
+    """Scores whose row maximum keeps growing from key tile to key tile (and jumps by far more than the 2^8
+    lazy-rescale window), plus a ragged last key tile: exercises the optimistic-exponential redo path and the
+    polynomial exp2 clamp of the softmax."""
+    C = heads * 64
+    q = (_rand(B * Nq, C, seed=seed) * 3.0).bfloat16()
+    k = _rand(B * Nkv, C, seed=seed + 1)
+    ramp = torch.linspace(0.2, 6.0, Nkv, device=DEV).repeat(B).unsqueeze(1)   # later keys score (much) higher
+    k = (k * ramp).bfloat16()
+    v = _rand(B * Nkv, C, seed=seed + 2).bfloat16()
+    out = torch.zeros(B * Nq, C, device=DEV, dtype=torch.bfloat16)
+    sh = torch.full((B,), heads, device=DEV, dtype=torch.int32)
+    K.attention(q, C, k, C, v, C, out, C, B, Nq, Nkv, sh, heads, 0.125)
+    K.check_abort()
+    qf = q.float().reshape(B, Nq, heads, 64).transpose(1, 2)
+    kf = k.float().reshape(B, Nkv, heads, 64).transpose(1, 2)
+    vf = v.float().reshape(B, Nkv, heads, 64).transpose(1, 2)
+    ref = _sdpa_ref(qf, kf, vf, 0.125).transpose(1, 2).reshape(B, Nq, heads, 64)
+    got = out.reshape(B, Nq, heads, 64).float()
+    assert torch.isfinite(got).all(), "attention produced non-finite values"
+    _close(got, ref, 3e-2, 3e-2, f"attention rescale Nq{Nq} Nkv{Nkv}")
+
+
 ALL = [
     ("gemm_linear_small", lambda: check_gemm_linear()),
     ("gemm_linear_bn256", lambda: check_gemm_linear(M=4096, Kd=1280, N=1280, bn=256)),
@@ -366,6 +389,8 @@ ALL = [
     ("layernorm_1280", lambda: check_layernorm(rows=77, C=1280)),
     ("elementwise", check_elementwise),
     ("attention_self", lambda: check_attention()),
+    ("attention_rescale", lambda: check_attention_rescale()),
+    ("attention_rescale_ragged", lambda: check_attention_rescale(Nq=384, Nkv=600, seed=5)),
     ("attention_cross77", lambda: check_attention(Nkv=77)),
     ("attention_small_q", lambda: check_attention(B=3, heads=2, kept=(2, 0, 1), Nq=64, Nkv=64)),
     ("attention_long", lambda: check_attention(B=1, heads=1, kept=(1,), Nq=1024, Nkv=1024)),
