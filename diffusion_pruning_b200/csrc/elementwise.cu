@@ -42,12 +42,27 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const __nv_bfloat16* __r
                                                         int cv, const uint8_t* __restrict__ mask,
                                                         int rows_per_sample) {
   const long long total = rows * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / cv;
-    const int v = (int)(i - row * cv);
-    if (mask && !mask[row / rows_per_sample]) continue;
-    *reinterpret_cast<uint4*>(dst + row * ldd + v * 8) = __ldg(reinterpret_cast<const uint4*>(src + row * lds + v * 8));
+  const long long T = (long long)gridDim.x * blockDim.x;
+  // 4 independent 16-byte loads in flight per thread before the first store
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * T) {
+    uint4 val[4];
+    long long off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * T;
+      off[u] = -1;
+      if (i < total) {
+        const long long row = i / cv;
+        const int v = (int)(i - row * cv);
+        if (!mask || mask[row / rows_per_sample]) {
+          val[u] = __ldg(reinterpret_cast<const uint4*>(src + row * lds + v * 8));
+          off[u] = row * ldd + v * 8;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (off[u] >= 0) *reinterpret_cast<uint4*>(dst + off[u]) = val[u];
   }
 }
 

@@ -85,24 +85,31 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(Src2 s, int hw, 
     const int v = threadIdx.x % cv;
     const int prow = threadIdx.x / cv;
     if (prow < rows_per_iter) {
-      // 4 independent 16-byte loads in flight per thread
-      for (int p = p_begin + prow; p < p_end; p += 4 * rows_per_iter) {
-        uint4 raw[4];
+      // software pipeline: the 4 loads of the NEXT step are in flight while this step's values are reduced
+      const int step = 4 * rows_per_iter;
+      uint4 cur[4], nxt[4];
+      auto load4 = [&](uint4* dst, int p) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int pp = p + u * rows_per_iter;
-          raw[u] = (pp < p_end) ? load_vec(s, (long long)b * hw + pp, v * 8) : make_uint4(0u, 0u, 0u, 0u);
+          dst[u] = (pp < p_end) ? load_vec(s, (long long)b * hw + pp, v * 8) : make_uint4(0u, 0u, 0u, 0u);
         }
+      };
+      load4(cur, p_begin + prow);
+      for (int p = p_begin + prow; p < p_end; p += step) {
+        load4(nxt, p + step);  // past the end: zeros, no memory access
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
-          unpack8(raw[u], f);
+          unpack8(cur[u], f);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             sum[0][e] += f[e];
             sq[0][e] += f[e] * f[e];
           }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
       }
       flush_runs(bins, sum[0], sq[0], v * 8, ctot, gs);
     }
@@ -184,24 +191,29 @@ __global__ void __launch_bounds__(NORM_THREADS)
       }
     }
     const bool has_data = v * 8 < ctot;
-    for (int p = p_begin + prow; p < p_end; p += 4 * rows_per_iter) {
-      uint4 raw[4];
+    const int step = 4 * rows_per_iter;
+    uint4 cur[4], nxt[4];
+    auto load4 = [&](uint4* dst, int p) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int pp = p + u * rows_per_iter;
-        raw[u] = (has_data && pp < p_end) ? load_vec(s, (long long)b * hw + pp, v * 8) : make_uint4(0u, 0u, 0u, 0u);
+        dst[u] = (has_data && pp < p_end) ? load_vec(s, (long long)b * hw + pp, v * 8) : make_uint4(0u, 0u, 0u, 0u);
       }
+    };
+    load4(cur, p_begin + prow);
+    for (int p = p_begin + prow; p < p_end; p += step) {
+      load4(nxt, p + step);  // next step's loads in flight under this step's math and stores
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int pp = p + u * rows_per_iter;
         if (pp >= p_end) break;
         float f[8];
-        unpack8(raw[u], f);
+        unpack8(cur[u], f);
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float t = f[e] * a[e] + sft[e];
-          if (silu) t = __fdividef(t, 1.f + __expf(-t));
+          if (silu) t = silu_tanh_f(t);
           o[e] = (v * 8 + e < ctot) ? t : 0.f;  // zero K padding even if stale memory holds inf/nan
         }
         uint4 out;
@@ -211,13 +223,16 @@ __global__ void __launch_bounds__(NORM_THREADS)
         out.w = pack_bf16(o[6], o[7]);
         *reinterpret_cast<uint4*>(y + ((long long)b * hw + pp) * ldy + v * 8) = out;
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
     }
   }
 }
 
-// One warp per token row, SLOTS 16-byte vectors per lane held in registers (exact two-pass). SLOTS is a
-// template parameter so narrow rows (C = 320: 2 slots) keep the register count -- and with it the
-// number of resident warps and loads in flight -- where an HBM-bound kernel needs them.
+// One warp per token row at a time, SLOTS 16-byte vectors per lane held in registers (exact two-pass). Warps are
+// persistent (grid-stride over rows) and the NEXT row's vectors are already in flight while the current row is
+// reduced, normalised and stored: with C = 320 a lane only has 1-2 loads of its own row to keep in flight, far
+// too few to cover HBM latency. SLOTS is a template parameter so narrow rows keep the register count low.
 constexpr int LN_MAXV = 8;
 template <int SLOTS>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
@@ -227,64 +242,172 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         const uint8_t* __restrict__ sample_active,
                                                         int rows_per_sample) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= rows) return;
-  if (sample_active && !sample_active[row / rows_per_sample]) return;
+  const long long stride = (long long)gridDim.x * 8;
   const int cv = C / 8;
-  uint4 raw[SLOTS];
+  const float inv_c = 1.f / (float)C;
+  auto load_row = [&](uint4* dst, long long row) {
+    const bool on = row < rows && (!sample_active || sample_active[row / rows_per_sample]);
 #pragma unroll
-  for (int q = 0; q < SLOTS; ++q) {
-    const int v = lane + q * 32;
-    raw[q] = (v < cv) ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx + v * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    for (int q = 0; q < SLOTS; ++q) {
+      const int v = lane + q * 32;
+      dst[q] = (on && v < cv) ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx + v * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  // narrow rows: the affine parameters of this lane's channels stay in registers for all rows; wide rows
+  // re-read them (L1-resident) to keep the register count, and with it the resident warps, where HBM needs them
+  constexpr bool kAffineInRegs = SLOTS <= 2;
+  float gg[kAffineInRegs ? SLOTS : 1][8], bb[kAffineInRegs ? SLOTS : 1][8];
+  if constexpr (kAffineInRegs) {
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      const int v = lane + q * 32;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        gg[q][e] = (v < cv) ? __ldg(gamma + v * 8 + e) : 0.f;
+        bb[q][e] = (v < cv) ? __ldg(beta + v * 8 + e) : 0.f;
+      }
+    }
   }
-  float f[SLOTS][8];
-  float s = 0.f;
+  long long row = (long long)blockIdx.x * 8 + warp;
+  uint4 cur[SLOTS], nxt[SLOTS];
+  load_row(cur, row);
+  for (; row < rows; row += stride) {
+    load_row(nxt, row + stride);
+    const bool on = !sample_active || sample_active[row / rows_per_sample];
+    if (on) {
+      float f[SLOTS][8];
+      float sm = 0.f;
 #pragma unroll
-  for (int q = 0; q < SLOTS; ++q) {
-    unpack8(raw[q], f[q]);
+      for (int q = 0; q < SLOTS; ++q) {
+        unpack8(cur[q], f[q]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s += f[q][e];  // padded vectors are zero
+        for (int e = 0; e < 8; ++e) sm += f[q][e];  // padded vectors are zero
+      }
+      const float mean = warp_sum(sm) * inv_c;
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < SLOTS; ++q) {
+        const int v = lane + q * 32;
+        if (v < cv) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float d = f[q][e] - mean;
+            ss += d * d;
+          }
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(ss) * inv_c + eps);
+#pragma unroll
+      for (int q = 0; q < SLOTS; ++q) {
+        const int v = lane + q * 32;
+        if (v < cv) {
+          float o[8];
+          if constexpr (kAffineInRegs) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (f[q][e] - mean) * rstd * gg[q][e] + bb[q][e];
+          } else {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+            const float gl[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bl[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (f[q][e] - mean) * rstd * gl[e] + bl[e];
+          }
+          uint4 out;
+          out.x = pack_bf16(o[0], o[1]);
+          out.y = pack_bf16(o[2], o[3]);
+          out.z = pack_bf16(o[4], o[5]);
+          out.w = pack_bf16(o[6], o[7]);
+          *reinterpret_cast<uint4*>(y + row * ldy + v * 8) = out;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) cur[q] = nxt[q];
   }
-  const float mean = warp_sum(s) / (float)C;
-  float ss = 0.f;
+}
+
+// LayerNorm for the SD-2.1 widths: C / 8 = 5 * LPR 16-byte vectors per row with LPR in {8, 16, 32}
+// (C = 320, 640, 1280): LPR lanes share a row with exactly 5 vectors each (no idle lane slots, unlike the
+// 32-lanes-per-row mapping above where C = 320 fills 40 of 64 slots), so a warp works on 32 / LPR rows at once and
+// keeps 5 useful loads per lane in flight; warps are persistent and the next row group is prefetched.
+template <int LPR>
+__global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                         __nv_bfloat16* __restrict__ y, int ldy, long long rows, int C,
+                                                         float eps, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta,
+                                                         const uint8_t* __restrict__ sample_active,
+                                                         int rows_per_sample) {
+  constexpr int RPW = 32 / LPR;  // rows per warp per step
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long stride = (long long)gridDim.x * 8 * RPW;
+  const float inv_c = 1.f / (float)C;
+  auto load_row = [&](uint4* dst, long long row) {
+    const bool on = row < rows && (!sample_active || sample_active[row / rows_per_sample]);
 #pragma unroll
-  for (int q = 0; q < SLOTS; ++q) {
-    const int v = lane + q * 32;
-    if (v < cv) {
+    for (int q = 0; q < 5; ++q)
+      dst[q] = on ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx + (l + q * LPR) * 8)) : make_uint4(0u, 0u, 0u, 0u);
+  };
+  long long row = ((long long)blockIdx.x * 8 + warp) * RPW + sub;
+  uint4 cur[5], nxt[5];
+  load_row(cur, row);
+  for (; row - sub < rows; row += stride) {  // warp-uniform trip count (row - sub is the warp's first row)
+    load_row(nxt, row + stride);
+    const bool on = row < rows && (!sample_active || sample_active[row / rows_per_sample]);
+    float f[5][8];
+    float sm = 0.f;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      unpack8(cur[q], f[q]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sm += f[q][e];
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+    const float mean = sm * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float d = f[q][e] - mean;
         ss += d * d;
       }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
 #pragma unroll
-  for (int q = 0; q < SLOTS; ++q) {
-    const int v = lane + q * 32;
-    if (v < cv) {
-      float o[8];
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * inv_c + eps);
+    if (on) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (f[q][e] - mean) * rstd * gg[e] + bb[e];
-      uint4 out;
-      out.x = pack_bf16(o[0], o[1]);
-      out.y = pack_bf16(o[2], o[3]);
-      out.z = pack_bf16(o[4], o[5]);
-      out.w = pack_bf16(o[6], o[7]);
-      *reinterpret_cast<uint4*>(y + row * ldy + v * 8) = out;
+      for (int q = 0; q < 5; ++q) {
+        const int c = (l + q * LPR) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        const float gl[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bl[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (f[q][e] - mean) * rstd * gl[e] + bl[e];
+        uint4 out;
+        out.x = pack_bf16(o[0], o[1]);
+        out.y = pack_bf16(o[2], o[3]);
+        out.z = pack_bf16(o[4], o[5]);
+        out.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(y + row * ldy + c) = out;
+      }
     }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) cur[q] = nxt[q];
   }
 }
 
 static int pick_pix_per_cta(int hw, int batch) {
-  // aim for ~4 CTAs per SM across the grid, at least 16 pixels per CTA
-  int target_ctas = 4 * sm_count();
+  // ~8 CTAs per SM across the grid (two waves at the register-limited occupancy), at least 16 pixels per CTA
+  int target_ctas = 8 * sm_count();
   int chunks = (target_ctas + batch - 1) / batch;
   if (chunks < 1) chunks = 1;
   int ppc = (hw + chunks - 1) / chunks;
@@ -349,7 +472,23 @@ extern "C" int aptp_layernorm(const void* x, int32_t ldx, void* y, int32_t ldy, 
   APTP_REQUIRE(C % 8 == 0 && C <= 32 * 8 * LN_MAXV && ldx % 8 == 0 && ldy % 8 == 0, "aptp_layernorm: unsupported C=%d", C);
   APTP_REQUIRE(rows_per_sample > 0, "aptp_layernorm: rows_per_sample must be > 0");
   if (rows == 0) return APTP_OK;
-  const long long blocks = (rows + 7) / 8;
+  const long long max_blocks = 8LL * sm_count();  // persistent warps: each walks rows with the next one prefetched
+  const int lpr = (C % 40 == 0) ? C / 40 : 0;
+  if (lpr == 8) {  // C = 320 (measured: wider rows are as fast on the 32-lanes-per-row kernel)
+    const int rpw = 32 / lpr;
+    long long blocks = (rows + 8 * rpw - 1) / (8 * rpw);
+    if (blocks > max_blocks) blocks = max_blocks;
+#define APTP_LN5_LAUNCH(L)                                                                                          \
+  layernorm5_kernel<L><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,       \
+                                                             reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, eps, \
+                                                             gamma, beta, sample_active, rows_per_sample)
+    APTP_LN5_LAUNCH(8);
+#undef APTP_LN5_LAUNCH
+    APTP_CUDA_CHECK(cudaGetLastError());
+    return APTP_OK;
+  }
+  long long blocks = (rows + 7) / 8;
+  if (blocks > max_blocks) blocks = max_blocks;
   const int slots = (C / 8 + 31) / 32;
 #define APTP_LN_LAUNCH(S)                                                                                          \
   layernorm_kernel<S><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,       \
