@@ -318,6 +318,12 @@ def run_train(args):
     for _ in range(max(args.warmup, 3)):
         loss = step()
     K.check_abort()
+    if os.environ.get("APTP_CUDA_PROFILE"):  # ncu --profile-from-start off: capture exactly one train step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     clocks = ClockSampler(local)
     clocks.start()
     barrier()
