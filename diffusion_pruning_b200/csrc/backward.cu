@@ -257,7 +257,9 @@ __device__ __forceinline__ void gn_coeffs(const GnB& a, int b, int c0, float* me
   }
 }
 __device__ __forceinline__ float silu_grad(float y) {
-  const float s = 1.f / (1.f + __expf(-y));
+  float t;  // sigmoid(y) = 0.5 + 0.5 tanh(y / 2): one XU op (matches the forward's silu_tanh_f)
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  const float s = fmaf(0.5f, t, 0.5f);
   return s * (1.f + y * (1.f - s));
 }
 
@@ -270,19 +272,34 @@ __global__ void __launch_bounds__(BW_THREADS) gn_bwd_stats_kernel(GnB a, float* 
   if (g.v_ok) {
     float mean[8], rstd[8], gm[8], bt[8], gt[8];
     gn_coeffs(a, g.b, g.c0, mean, rstd, gm, bt, gt);
-    for (int p = g.p_first; p < g.p_end; p += g.p_step) {
-      const long long row = (long long)g.b * a.hw + p;
-      float fx[8], fd[8];
-      unpack8b(ldv(a.x + row * a.ldx + g.c0), fx);
-      unpack8b(ldv(a.da + row * a.ldda + g.c0), fd);
+    // 4 pixels per step: 8 independent 16-byte loads in flight per thread before any math
+    for (int p = g.p_first; p < g.p_end; p += 4 * g.p_step) {
+      uint4 rx[4], rd[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float xh = gt[e] * (fx[e] - mean[e]) * rstd[e];
-        float dy = fd[e];
-        if (a.silu) dy *= silu_grad(xh * gm[e] + bt[e]);
-        const float dxh = dy * gm[e];
-        acc[0][e] += dxh;
-        acc[1][e] += dxh * xh;
+      for (int u = 0; u < 4; ++u) {
+        const int pp = p + u * g.p_step;
+        const long long row = (long long)g.b * a.hw + pp;
+        rx[u] = rd[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (pp < g.p_end) {
+          rx[u] = ldv(a.x + row * a.ldx + g.c0);
+          rd[u] = ldv(a.da + row * a.ldda + g.c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p + u * g.p_step >= g.p_end) break;
+        float fx[8], fd[8];
+        unpack8b(rx[u], fx);
+        unpack8b(rd[u], fd);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = gt[e] * (fx[e] - mean[e]) * rstd[e];
+          float dy = fd[e];
+          if (a.silu) dy *= silu_grad(xh * gm[e] + bt[e]);
+          const float dxh = dy * gm[e];
+          acc[0][e] += dxh;
+          acc[1][e] += dxh * xh;
+        }
       }
     }
   }
@@ -308,27 +325,40 @@ __global__ void __launch_bounds__(BW_THREADS)
       s1[e] = bstats[((size_t)g.b * a.stats_groups + grp) * 2] * inv_n;
       s2[e] = bstats[((size_t)g.b * a.stats_groups + grp) * 2 + 1] * inv_n;
     }
-    for (int p = g.p_first; p < g.p_end; p += g.p_step) {
-      const long long row = (long long)g.b * a.hw + p;
-      float fx[8], fd[8], o[8];
-      unpack8b(ldv(a.x + row * a.ldx + g.c0), fx);
-      unpack8b(ldv(a.da + row * a.ldda + g.c0), fd);
-      if (accumulate) unpack8b(*reinterpret_cast<const uint4*>(dx + row * lddx + g.c0), o);
-      else {
+    for (int p = g.p_first; p < g.p_end; p += 2 * g.p_step) {
+      uint4 rx[2], rd[2], ro[2];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      for (int u = 0; u < 2; ++u) {
+        const int pp = p + u * g.p_step;
+        const long long row = (long long)g.b * a.hw + pp;
+        rx[u] = rd[u] = ro[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (pp < g.p_end) {
+          rx[u] = ldv(a.x + row * a.ldx + g.c0);
+          rd[u] = ldv(a.da + row * a.ldda + g.c0);
+          if (accumulate) ro[u] = *reinterpret_cast<const uint4*>(dx + row * lddx + g.c0);
+        }
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float xh = gt[e] * (fx[e] - mean[e]) * rstd[e];
-        float dy = fd[e];
-        if (a.silu) dy *= silu_grad(xh * gm[e] + bt[e]);
-        const float dxh = dy * gm[e];
-        const float dxg = rstd[e] * (dxh - s1[e] - xh * s2[e]);
-        acc[0][e] += dxg * fx[e];
-        o[e] += gt[e] * dxg;
+      for (int u = 0; u < 2; ++u) {
+        const int pp = p + u * g.p_step;
+        if (pp >= g.p_end) break;
+        const long long row = (long long)g.b * a.hw + pp;
+        float fx[8], fd[8], o[8];
+        unpack8b(rx[u], fx);
+        unpack8b(rd[u], fd);
+        unpack8b(ro[u], o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = gt[e] * (fx[e] - mean[e]) * rstd[e];
+          float dy = fd[e];
+          if (a.silu) dy *= silu_grad(xh * gm[e] + bt[e]);
+          const float dxh = dy * gm[e];
+          const float dxg = rstd[e] * (dxh - s1[e] - xh * s2[e]);
+          acc[0][e] += dxg * fx[e];
+          o[e] += gt[e] * dxg;
+        }
+        stv(dx + row * lddx + g.c0, pack8b(o));
       }
-      stv(dx + row * lddx + g.c0, pack8b(o));
     }
   }
   if (dgate) reduce_groups<1>(bins, acc, g.c0, a.C, a.gs, g.v_ok, dgate, a.gate_ld, g.b);

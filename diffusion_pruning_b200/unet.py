@@ -1175,10 +1175,18 @@ class _Engine:
                    k_tap_pitch=x.C, out_ld=cout, out_mode=OUT_F32_NCHW, bias=dco["b"], rows_per_sample=x.hw)
         taps = []
         if self.compact:
+            identity = bool((self.layout.inv_perm == np.arange(B)).all())
             inv = torch.as_tensor(self.layout.inv_perm, device=self.device)
-            y = y.index_select(0, inv)
+            if not identity:
+                y = y.index_select(0, inv)
             if want_taps:
-                taps = [t.nchw().index_select(0, inv) for t in tap_acts]
+                # block outputs as the reference's hooks see them ([B, C, H, W]), kept channels-last: the gather back
+                # to the caller's sample order runs over whole NHWC samples (contiguous chunks), and losses computed
+                # on these tensors stay on PyTorch's dense vectorised kernels
+                for t in tap_acts:
+                    v = t.t.view(t.B, t.H, t.W, t.ld)[..., : t.C]
+                    v = v.clone() if identity else v.index_select(0, inv)
+                    taps.append(v.permute(0, 3, 1, 2))
         elif want_taps:
             taps = [t.nchw().clone() for t in tap_acts]  # block outputs live in reused buffers
         return y, taps
