@@ -378,7 +378,7 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // silu(x) = x * sigmoid(x) = 0.5 x (1 + tanh(x/2)): ONE XU op (tanh.approx, |rel err| ~ 2^-11, below bf16
 // rounding) instead of ex2 + rcp -- the GroupNorm+SiLU pass would otherwise need ~70 % of the XU pipe at HBM speed
 __device__ __forceinline__ float silu_tanh_f(float x) {

@@ -10,6 +10,9 @@
 
 namespace aptp {
 
+#ifndef APTP_GN_SILU
+#define APTP_GN_SILU silu_f
+#endif
 constexpr int NORM_THREADS = 256;
 constexpr int MAX_SLOTS = 2;  // 8-channel vectors per thread: supports up to 256*2*8 = 4096 channels
 
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(NORM_THREADS)
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float t = f[e] * a[e] + sft[e];
-          if (silu) t = silu_tanh_f(t);
+          if (silu) t = APTP_GN_SILU(t);
           o[e] = (v * 8 + e < ctot) ? t : 0.f;  // zero K padding even if stale memory holds inf/nan
         }
         uint4 out;

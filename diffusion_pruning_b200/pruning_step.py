@@ -107,6 +107,17 @@ def pruning_step(unet, hyper_net, quantizer, batch: Dict[str, torch.Tensor], cfg
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
 
+    # The teacher forward (trainer.py:1185-1190) depends on the batch only, not on the architecture vector, so it is
+    # ENQUEUED FIRST: its ~500 kernels (one CUDA-graph replay) keep the GPU busy while the host walks through the
+    # hyper-network / quantizer / contrastive-loss code below, whose small kernels and host<->device handshakes would
+    # otherwise leave the GPU idle between two steps. Results are identical (the teacher consumes no random numbers).
+    with torch.no_grad():
+        full = hyper_net.transform_structure_vector(
+            torch.ones(text.shape[0], quantizer.vq_embed_dim, device=text.device, dtype=torch.float32))
+        unet.set_structure(full)
+        full_pred = unet(noisy, timesteps, enc).sample.detach()
+        teacher_acts = dict(taps.acts)
+
     arch_vector = hyper_net(text)                                      # trainer.py:1129
     arch_vector_quantized, _ = quantizer(arch_vector)                  # :1130
     arch_vector = quantizer.gumbel_sigmoid_trick(arch_vector)          # :1132
@@ -127,11 +138,6 @@ def pruning_step(unet, hyper_net, quantizer, batch: Dict[str, torch.Tensor], cfg
     separated = hyper_net.transform_structure_vector(arch_vector if pretrain else arch_vector_quantized)
     c_loss, _ = contrastive_loss(text_all, arch_all, cfg.arch_vector_temperature, cfg.prompt_embedding_temperature)
 
-    with torch.no_grad():                                              # teacher, :1185-1190
-        full = hyper_net.transform_structure_vector(torch.ones_like(arch_vector))
-        unet.set_structure(full)
-        full_pred = unet(noisy, timesteps, enc).sample.detach()
-        teacher_acts = dict(taps.acts)
     unet.set_structure(separated)                                      # student, :1192-1195
     model_pred = unet(noisy, timesteps, enc).sample
     student_acts = dict(taps.acts)

@@ -35,13 +35,13 @@ def main():
     def step():
         out = PS.pruning_step(unet, hyper, quant, batch, cfg, taps, p_actual, acp=acp)
         out["loss"].backward()
-    for _ in range(2):
+    for _ in range(5):
         step()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
         step()
         torch.cuda.synchronize()
     print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=50, max_shapes_column_width=70))
-    print(prof.key_averages(group_by_stack_n=6).table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=40))
+    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=60))
 
 main()
