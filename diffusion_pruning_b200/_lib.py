@@ -99,6 +99,18 @@ SIGNATURES = {
     "aptp_upsample2x_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "aptp_zero_insert2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "aptp_route_sinkhorn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
+    "aptp_add_noise_velocity": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                        c_int, c_int, c_void_p]),
+    "aptp_mse_rows_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "aptp_mse_rows_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_float,
+                                  c_void_p]),
+    "aptp_pred_losses_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aptp_macs_ratio_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, C.c_double, c_void_p,
+                                    c_void_p, c_void_p]),
+    "aptp_macs_ratio_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                    c_int, c_void_p]),
+    "aptp_pred_losses_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_void_p]),
 }
 
 _lib = None

@@ -54,8 +54,8 @@ struct AbBars {
   uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ AbBars ab_setup(uint8_t* smem, int warp, int lane) {
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_SMEM_BAR);
+__device__ __forceinline__ AbBars ab_setup(uint8_t* smem, int warp, int lane, int bar_offset = AB_SMEM_BAR) {
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + bar_offset);
   AbBars b;
   b.st_full = bars;
   b.ring_full = bars + 1;
@@ -271,9 +271,21 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
 
 // =====================================================================================================
 // dK, dV: one CTA = 256 keys (two 128-row tiles) of one (sample, kept head); loop over 64-query tiles.
-// TMEM per tile w (256 columns): S^T [0,64) (P^T bf16 aliases [0,32)) | dP^T [64,128) (dS^T bf16 aliases
-// [64,96)) | dV [128,192) | dK [192,256)
+// TMEM per tile w (256 columns): S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256).
+// TMEM reads pace this kernel (64 B/clk/SM: S^T + dP^T of both tiles = 2048 clk per query tile), so the
+// accumulators are handed back to the tensor pipe as soon as they sit in registers (s_free) and S^T/dP^T of the
+// next query tile are computed under this tile's exponentials. P^T and dS^T therefore cannot alias the
+// accumulator columns: they go to shared memory as K-major 128B-swizzled A operands (the layout TMA would
+// have produced for a [128 x 64] bf16 tile) and the accumulate MMAs are SS. The per-query LSE / delta of the
+// NEXT tile are fetched one tile ahead into a per-warp shared-memory slot (coalesced, bounds folded into
+// +inf / 0), so the hot loop has no global loads.
 // =====================================================================================================
+constexpr int AK_SMEM_OP = AB_SMEM_RING + AB_STAGES * 2 * AB_SMALL;  // P^T, dS^T per tile w: 4 x 16 KB
+constexpr int AK_SMEM_LD = AK_SMEM_OP + 4 * AB_BIG;                  // 8 warps x 2 slots x (L[64] | D[64]) fp32
+constexpr int AK_SMEM_BAR = AK_SMEM_LD + 8 * 2 * 128 * 4;
+constexpr int AK_SMEM_BYTES = AK_SMEM_BAR + 256 + 1024;
+static_assert(AK_SMEM_BYTES <= 227 * 1024, "dkv kernel shared memory");
+
 __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnBwdParams p) {
   const int head = blockIdx.y, b = blockIdx.z;
   if (head >= p.sample_heads[b]) return;
@@ -281,7 +293,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const AbBars B = ab_setup(smem, warp, lane);
+  const AbBars B = ab_setup(smem, warp, lane, AK_SMEM_BAR);
   const uint32_t tmem_base = *B.tmem_slot;
   const int n_tiles = (p.n_q + 63) / 64;
   const int k0 = blockIdx.x * 256;
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
       }
     } else if (warp == 1) {
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-      const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);  // A K-major (P^T / dS^T in smem), B MN-major
       auto issue_sp = [&](int w, int stg) {
         const uint32_t k_addr = smem_u32(smem + AB_SMEM_ST + w * AB_BIG);
         const uint32_t v_addr = smem_u32(smem + AB_SMEM_ST + (2 + w) * AB_BIG);
@@ -345,6 +357,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
           nphase ^= 1;
         }
         const bool more = j + 1 < n_tiles;
+        if (more && !mbar_wait(&B.ring_full[ns], nphase, p.abort_flag)) break;
+        for (int w = 0; w < n_w && ok; ++w) {  // S^T / dP^T of tile j are in registers: compute tile j+1 over them
+          ok = mbar_wait(&B.s_free[w], j & 1, p.abort_flag);
+          if (ok && more) {
+            tc_fence_after();
+            issue_sp(w, ns);
+          }
+        }
+        if (!ok) break;
         const uint32_t q_addr = smem_u32(smem + AB_SMEM_RING + stage * 2 * AB_SMALL);
         const uint32_t do_addr = q_addr + AB_SMALL;
         for (int w = 0; w < n_w; ++w) {
@@ -354,24 +375,17 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
           }
           tc_fence_after();
           const uint32_t t = tmem_base + w * TW;
+          const uint32_t p_addr = smem_u32(smem + AK_SMEM_OP + w * 2 * AB_BIG);
+          const uint32_t ds_addr = p_addr + AB_BIG;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // dV += P^T dO_j
-            umma_bf16_ts_e(t + 128, t + k * 8, make_desc_mnmajor_sw128(do_addr + k * 2048, AB_SMALL), idesc_acc,
-                         (j | k) != 0);
+          for (int k = 0; k < 4; ++k)  // dV += P^T dO_j   (16 queries per step)
+            umma_bf16_ss_e(t + 128, make_desc_kmajor_sw128(p_addr + k * 32),
+                           make_desc_mnmajor_sw128(do_addr + k * 2048, AB_SMALL), idesc_acc, (j | k) != 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dK += dS^T Q_j
-            umma_bf16_ts_e(t + 192, t + 64 + k * 8, make_desc_mnmajor_sw128(q_addr + k * 2048, AB_SMALL), idesc_acc,
-                         (j | k) != 0);
-          if (more) {
-            if (w == 0 && !mbar_wait(&B.ring_full[ns], nphase, p.abort_flag)) {
-              ok = false;
-              break;
-            }
-            tc_fence_after();
-            issue_sp(w, ns);  // overwrites S^T / dP^T (and the aliased bf16 operands) after the MMAs above: in-order pipe
-          } else {
-            umma_commit_e(&B.acc_done[w]);
-          }
+            umma_bf16_ss_e(t + 192, make_desc_kmajor_sw128(ds_addr + k * 32),
+                           make_desc_mnmajor_sw128(q_addr + k * 2048, AB_SMALL), idesc_acc, (j | k) != 0);
+          umma_commit_e(&B.acc_done[w]);
         }
         if (!ok) break;
         umma_commit_e(&B.ring_empty[stage]);
@@ -389,8 +403,32 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
       const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + w * TW;
       const float* Lp = p.lse2 + ((size_t)b * p.max_heads + head) * p.n_q;
       const float* Dp = p.delta + ((size_t)b * p.max_heads + head) * p.n_q;
+      float* ld_slot = reinterpret_cast<float*>(smem + AK_SMEM_LD) + (warp - 4) * 256;  // [2][L 64 | D 64]
+      uint8_t* op_p = smem + AK_SMEM_OP + w * 2 * AB_BIG + r * 128;  // this key's 128-byte row of P^T
+      uint8_t* op_ds = op_p + AB_BIG;
+      const int swz = r & 7;
+      // out-of-range queries: L = +inf makes P^T = 0 and dS^T = 0 * finite = 0
+      auto fetch = [&](int j, float& l0, float& l1, float& d0, float& d1) {
+        const int qa = j * 64 + lane, qc = qa + 32;
+        l0 = (qa < p.n_q) ? __ldg(Lp + qa) : INFINITY;
+        l1 = (qc < p.n_q) ? __ldg(Lp + qc) : INFINITY;
+        d0 = (qa < p.n_q) ? __ldg(Dp + qa) : 0.f;
+        d1 = (qc < p.n_q) ? __ldg(Dp + qc) : 0.f;
+      };
+      {
+        float l0, l1, d0, d1;
+        fetch(0, l0, l1, d0, d1);
+        ld_slot[lane] = l0;
+        ld_slot[32 + lane] = l1;
+        ld_slot[64 + lane] = d0;
+        ld_slot[96 + lane] = d1;
+        __syncwarp();
+      }
       bool ok = true;
       for (int j = 0; j < n_tiles; ++j) {
+        float nl0 = INFINITY, nl1 = INFINITY, nd0 = 0.f, nd1 = 0.f;
+        const bool more = j + 1 < n_tiles;
+        if (more) fetch(j + 1, nl0, nl1, nd0, nd1);
         ok = mbar_wait(&B.s_full[w], j & 1, p.abort_flag);
         if (!ok) break;
         tc_fence_after();
@@ -400,25 +438,16 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         tmem_ld_32x32(t + 64, dp);
         tmem_ld_32x32(t + 96, dp + 32);
         tmem_ld_wait();
-        const int qb = j * 64;
-        const int q_left = p.n_q - qb;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&B.s_free[w]);
+        const float* Ls = ld_slot + (j & 1) * 128;
+        const float* Ds = Ls + 64;
         uint32_t pp[32], ds[32];
 #pragma unroll
         for (int i = 0; i < 64; i += 4) {
-          float4 L4, D4;
-          if (i + 4 <= q_left && ((qb + i) & 3) == 0 && (p.n_q & 3) == 0) {
-            L4 = __ldg(reinterpret_cast<const float4*>(Lp + qb + i));
-            D4 = __ldg(reinterpret_cast<const float4*>(Dp + qb + i));
-          } else {
-            L4.x = (i + 0 < q_left) ? __ldg(Lp + qb + i + 0) : INFINITY;
-            L4.y = (i + 1 < q_left) ? __ldg(Lp + qb + i + 1) : INFINITY;
-            L4.z = (i + 2 < q_left) ? __ldg(Lp + qb + i + 2) : INFINITY;
-            L4.w = (i + 3 < q_left) ? __ldg(Lp + qb + i + 3) : INFINITY;
-            D4.x = (i + 0 < q_left) ? __ldg(Dp + qb + i + 0) : 0.f;
-            D4.y = (i + 1 < q_left) ? __ldg(Dp + qb + i + 1) : 0.f;
-            D4.z = (i + 2 < q_left) ? __ldg(Dp + qb + i + 2) : 0.f;
-            D4.w = (i + 3 < q_left) ? __ldg(Dp + qb + i + 3) : 0.f;
-          }
+          const float4 L4 = *reinterpret_cast<const float4*>(Ls + i);
+          const float4 D4 = *reinterpret_cast<const float4*>(Ds + i);
           const float p0 = ex2_approx(fmaf(__uint_as_float(s[i + 0]), p.scale_log2, -L4.x));
           const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -L4.y));
           const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), p.scale_log2, -L4.z));
@@ -428,14 +457,28 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
           ds[(i >> 1)] = pack_bf16(p0 * (__uint_as_float(dp[i + 0]) - D4.x), p1 * (__uint_as_float(dp[i + 1]) - D4.y));
           ds[(i >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(dp[i + 2]) - D4.z), p3 * (__uint_as_float(dp[i + 3]) - D4.w));
         }
-        tmem_st_32x32(t, pp);        // P^T over S^T (already in registers)
-        tmem_st_32x32(t + 64, ds);   // dS^T over dP^T
-        tmem_st_wait();
-        tc_fence_before();
+        if (j > 0) {  // the accumulate MMAs of the previous tile must have finished reading P^T / dS^T
+          ok = mbar_wait(&B.acc_done[w], (j - 1) & 1, p.abort_flag);
+          if (!ok) break;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {  // 16-byte chunk c of row r sits at chunk (c ^ (r & 7)): the TMA 128B swizzle
+          const int off = (c ^ swz) << 4;
+          *reinterpret_cast<uint4*>(op_p + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+          *reinterpret_cast<uint4*>(op_ds + off) = make_uint4(ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]);
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor pipe's async-proxy reads
+        if (more) {
+          float* nx = ld_slot + ((j + 1) & 1) * 128;
+          nx[lane] = nl0;
+          nx[32 + lane] = nl1;
+          nx[64 + lane] = nd0;
+          nx[96 + lane] = nd1;
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&B.p_full[w]);
       }
-      if (ok) ok = mbar_wait(&B.acc_done[w], 0, p.abort_flag);
+      if (ok) ok = mbar_wait(&B.acc_done[w], (n_tiles - 1) & 1, p.abort_flag);
       if (ok) {
         tc_fence_after();
         uint32_t o[AB_D];
@@ -536,7 +579,7 @@ extern "C" int aptp_attention_bwd(const void* q, int32_t ldq, const void* k, int
   APTP_REQUIRE(p.abort_flag != nullptr, "aptp_attention_bwd: could not allocate abort flag");
   if (!g_ab_smem_set) {
     APTP_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
-    APTP_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES));
+    APTP_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AK_SMEM_BYTES));
     g_ab_smem_set = 1;
   }
   const long long nd = (long long)batch * n_q * max_heads;
@@ -548,7 +591,7 @@ extern "C" int aptp_attention_bwd(const void* q, int32_t ldq, const void* k, int
   attn_bwd_dq_kernel<<<gq, AB_THREADS, AB_SMEM_BYTES, stream>>>(p);
   APTP_CUDA_CHECK(cudaGetLastError());
   dim3 gk((n_kv + 255) / 256, max_heads, batch);
-  attn_bwd_dkv_kernel<<<gk, AB_THREADS, AB_SMEM_BYTES, stream>>>(p);
+  attn_bwd_dkv_kernel<<<gk, AB_THREADS, AK_SMEM_BYTES, stream>>>(p);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

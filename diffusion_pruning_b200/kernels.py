@@ -318,3 +318,53 @@ def sinkhorn_phase(phase, Q, scores, partial, indices, batch_local, batch_global
 def route_sinkhorn(scores, Q, partial, indices, batch, n_codes, epsilon, iterations):
     check(load().aptp_route_sinkhorn(_ptr(scores), _ptr(Q), _ptr(partial), _ptr(indices), batch, n_codes,
                                      float(epsilon), iterations, _stream()), "aptp_route_sinkhorn")
+
+
+# --------------------------------------------------------------------------------------------
+# K6: loss front/back end of the pruning train step
+# --------------------------------------------------------------------------------------------
+def add_noise_velocity(latents, noise, timesteps, sqrt_acp, sqrt_1m_acp, noisy, target, batch, per_sample,
+                       v_prediction=True):
+    check(load().aptp_add_noise_velocity(_ptr(latents), _ptr(noise), _ptr(timesteps), _ptr(sqrt_acp), _ptr(sqrt_1m_acp),
+                                         _ptr(noisy), _ptr(target), batch, per_sample, int(v_prediction), _stream()),
+          "aptp_add_noise_velocity")
+
+
+def mse_rows_fwd(a, lda, b, ldb, rows, C_, partial):
+    check(load().aptp_mse_rows_fwd(_ptr(a), lda, _ptr(b), ldb, rows, C_, _ptr(partial), partial.numel(), _stream()),
+          "aptp_mse_rows_fwd")
+
+
+def mse_rows_bwd(a, lda, b, ldb, da, ldda, rows, C_, coef, scale):
+    check(load().aptp_mse_rows_bwd(_ptr(a), lda, _ptr(b), ldb, _ptr(da), ldda, rows, C_, _ptr(coef), float(scale),
+                                   _stream()), "aptp_mse_rows_bwd")
+
+
+def pred_losses_fwd(pred, target, teacher, batch, per_sample, chunks, partial):
+    check(load().aptp_pred_losses_fwd(_ptr(pred), _ptr(target), _ptr(teacher), batch, per_sample, chunks, _ptr(partial),
+                                      _stream()), "aptp_pred_losses_fwd")
+
+
+def pred_losses_bwd(pred, target, teacher, weight, g, dpred, batch, per_sample):
+    check(load().aptp_pred_losses_bwd(_ptr(pred), _ptr(target), _ptr(teacher), _ptr(weight), _ptr(g), _ptr(dpred), batch,
+                                      per_sample, _stream()), "aptp_pred_losses_bwd")
+
+
+# --------------------------------------------------------------------------------------------
+# K7: closed-form MAC accounting
+# --------------------------------------------------------------------------------------------
+MACS_GATE_DTYPE = np.dtype([("col", np.int32), ("width", np.int32), ("macs", np.float64)])
+MACS_SUB_DTYPE = np.dtype([("first_gate", np.int32), ("n_gates", np.int32), ("depth_col", np.int32),
+                           ("reserved", np.int32), ("fixed", np.float64)])
+
+
+def macs_ratio_fwd(arch, gates_dev, n_gates, subs_dev, n_subs, fixed_total, cur_prunable, cur_total):
+    check(load().aptp_macs_ratio_fwd(_ptr(arch), arch.stride(0), arch.shape[0], _ptr(gates_dev), n_gates, _ptr(subs_dev),
+                                     n_subs, float(fixed_total), _ptr(cur_prunable), _ptr(cur_total), _stream()),
+          "aptp_macs_ratio_fwd")
+
+
+def macs_ratio_bwd(arch, gates_dev, n_gates, subs_dev, n_subs, dcur, darch):
+    check(load().aptp_macs_ratio_bwd(_ptr(arch), arch.stride(0), arch.shape[0], _ptr(gates_dev), n_gates, _ptr(subs_dev),
+                                     n_subs, _ptr(dcur), _ptr(darch), darch.stride(0), darch.shape[1], _stream()),
+          "aptp_macs_ratio_bwd")

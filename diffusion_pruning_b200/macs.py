@@ -100,7 +100,9 @@ def _ratio(g: torch.Tensor) -> torch.Tensor:
     return hg.sum(dim=1, keepdim=True) / hg.shape[1]
 
 
-def calc_macs(model) -> Dict[str, Any]:
+def _calc_macs_torch(model) -> Dict[str, Any]:
+    """The closed form in torch ops, sub-block by sub-block (host-side accounting on CPU gate tensors:
+    count_macs() at construction time, CPU tests of the closed form against the reference's hook formulas)."""
     ri = model._macs_table
     total, prunable = ri["fixed"], 0.0
     cur_p, cur_t = 0.0, ri["fixed"]
@@ -130,6 +132,93 @@ def calc_macs(model) -> Dict[str, Any]:
         cur_p = cur_p + cp
         cur_t = cur_t + ct
     return {"total_macs": total, "prunable_macs": prunable, "cur_prunable_macs": cur_p, "cur_total_macs": cur_t}
+
+
+
+def _device_tables(model, device):
+    """aptp_macs_gate / aptp_macs_sub records (include/aptp_sm100.h) of the current resource table, resident on
+    `device`; sub-blocks in get_structure order, width columns first then the depth columns."""
+    import numpy as np
+
+    from . import kernels as K
+    ri = model._macs_table
+    cache = getattr(model, "_macs_dev", None)
+    if cache is not None and cache["table"] is ri and cache["device"] == device:
+        return cache
+    by_id = {id(m): (kind, mm) for kind, m, mm in ri["layers"]}
+    n_width = sum(w for m in model._gated for w in m.gate_widths())
+    gates, subs = [], []
+    col = di = 0
+    total, prunable = ri["fixed"], 0.0
+    for m in model._gated:
+        kind, mm = by_id[id(m)]
+        if kind == "res":
+            macs, fixed = [mm[0]], mm[1] - mm[0]
+        else:
+            macs, fixed = [mm["attn1"], mm["attn2"], mm["ff"]], mm["fixed"]
+        first = len(gates)
+        for wd, mc in zip(m.gate_widths(), macs):
+            gates.append((col, wd, mc))
+            col += wd
+        dcol = -1
+        if m.depth_gate is not None:
+            dcol = n_width + di
+            di += 1
+        subs.append((first, len(macs), dcol, 0, fixed))
+        prunable += sum(macs)
+        total += sum(macs) + fixed
+    g_np = np.array(gates, dtype=K.MACS_GATE_DTYPE)
+    s_np = np.array(subs, dtype=K.MACS_SUB_DTYPE)
+    cache = {"table": ri, "device": device, "n_gates": len(gates), "n_subs": len(subs), "dim": n_width + di,
+             "gates": torch.from_numpy(g_np.view(np.uint8).copy()).to(device),
+             "subs": torch.from_numpy(s_np.view(np.uint8).copy()).to(device),
+             "fixed": ri["fixed"], "total": total, "prunable": prunable}
+    model._macs_dev = cache
+    return cache
+
+
+class _MacsRatio(torch.autograd.Function):
+    """(cur_prunable_macs, cur_total_macs) [B, 1] from the [B, 1620] gate matrix: aptp_macs_ratio_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, arch: torch.Tensor, tab):
+        from . import kernels as K
+        arch = arch.detach().contiguous()
+        B = arch.shape[0]
+        cur_p = torch.empty(B, device=arch.device, dtype=torch.float32)
+        cur_t = torch.empty(B, device=arch.device, dtype=torch.float32)
+        K.macs_ratio_fwd(arch, tab["gates"], tab["n_gates"], tab["subs"], tab["n_subs"], tab["fixed"], cur_p, cur_t)
+        ctx.save_for_backward(arch)
+        ctx.tab = tab
+        cur_p, cur_t = cur_p.unsqueeze(1), cur_t.unsqueeze(1)
+        ctx.mark_non_differentiable(cur_t)
+        return cur_p, cur_t
+
+    @staticmethod
+    def backward(ctx, dcur_p, _dcur_t):
+        from . import kernels as K
+        (arch,) = ctx.saved_tensors
+        tab = ctx.tab
+        darch = torch.empty_like(arch)
+        K.macs_ratio_bwd(arch, tab["gates"], tab["n_gates"], tab["subs"], tab["n_subs"],
+                         dcur_p.reshape(-1).to(torch.float32).contiguous(), darch)
+        return darch, None
+
+
+def calc_macs(model) -> Dict[str, Any]:
+    """unet_2d_conditional.py:2124-2163. Gates resident on the GPU (every call of the train / sampling path): one
+    kernel over the concatenated gate matrix; CPU gate tensors: the same closed form in torch ops."""
+    flat_w, flat_d = model._flat_gates
+    if not flat_w[0].is_cuda:
+        return _calc_macs_torch(model)
+    tab = _device_tables(model, flat_w[0].device)
+    rows = flat_w[0].shape[0]
+    arch = torch.cat([w.reshape(rows, -1).to(torch.float32) for w in flat_w] +
+                     [d.reshape(rows, 1).to(torch.float32) for d in flat_d], dim=1)
+    assert arch.shape[1] == tab["dim"], (arch.shape, tab["dim"])
+    cur_p, cur_t = _MacsRatio.apply(arch, tab)
+    return {"total_macs": tab["total"], "prunable_macs": tab["prunable"], "cur_prunable_macs": cur_p,
+            "cur_total_macs": cur_t}
 
 
 def prunable_macs_list(model) -> List[List[float]]:

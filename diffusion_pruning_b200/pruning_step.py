@@ -20,6 +20,8 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from .losses import block_mse, min_snr_weights, prediction_losses
+
 
 @dataclass
 class PruningLossConfig:
@@ -142,20 +144,16 @@ def pruning_step(unet, hyper_net, quantizer, batch: Dict[str, torch.Tensor], cfg
     model_pred = unet(noisy, timesteps, enc).sample
     student_acts = dict(taps.acts)
 
-    if cfg.snr_gamma is None:                                          # :1197-1216
-        loss = F.mse_loss(model_pred.float(), target.float(), reduction="mean")
-    else:
+    # :1197-1225 on the K6 kernels: one pass over (pred, target, teacher pred) for the DDPM + distillation losses,
+    # one pass per hooked block output for the block losses (bf16 NHWC in place, gradient in the same layout)
+    w = None
+    if cfg.snr_gamma is not None:                                      # :1197-1216
         acp = alphas_cumprod() if acp is None else acp
-        snr = compute_snr(acp, timesteps)
-        if cfg.prediction_type == "v_prediction":
-            snr = snr + 1
-        w = torch.stack([snr, cfg.snr_gamma * torch.ones_like(timesteps)], dim=1).min(dim=1)[0] / snr
-        loss = F.mse_loss(model_pred.float(), target.float(), reduction="none")
-        loss = (loss.mean(dim=list(range(1, loss.ndim))) * w).mean()
-    distill = F.mse_loss(model_pred.float(), full_pred.float(), reduction="mean")    # :1218
+        w = min_snr_weights(acp, timesteps, cfg.snr_gamma, cfg.prediction_type == "v_prediction")
+    loss, distill = prediction_losses(model_pred, target, full_pred, w)  # :1197-1218
     block = torch.zeros((), device=noisy.device)
     for k in student_acts:                                             # :1220-1225
-        block = block + F.mse_loss(student_acts[k].float(), teacher_acts[k].detach().float(), reduction="mean")
+        block = block + block_mse(student_acts[k], teacher_acts[k])
     block = block / len(student_acts)
 
     macs = unet.calc_macs()                                            # :1227-1249

@@ -627,7 +627,7 @@ class UNetTrainFunction(torch.autograd.Function):
         ctx.eng = eng
         ctx.gate_shapes = [g.shape for g in gates]
         ctx.n_width_gates = len(eng.width_starts) - 1
-        outs = [y] + [t.nchw().float() for t in taps]
+        outs = [y] + [t.nchw() for t in taps]  # bf16 channels-last views of the taped block outputs (zero-copy)
         return tuple(outs)
 
     @staticmethod

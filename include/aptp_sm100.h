@@ -272,6 +272,59 @@ int aptp_add_rows(const void* src, int32_t lds, void* dst, int32_t ldd, int64_t 
 int aptp_upsample2x_bwd(const void* dy, void* dx, int32_t batch, int32_t H, int32_t W, int32_t C, void* stream);
 int aptp_zero_insert2x(const void* src, void* dst, int32_t batch, int32_t H, int32_t W, int32_t C, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K6  loss front/back end of the pruning train step, one HBM pass each.
+ * ------------------------------------------------------------------------------------------------ */
+/* DDIMScheduler.add_noise + get_velocity (pdm/training/trainer.py:1121-1123, :1181): noisy = sqrt(acp[t]) x0 +
+ * sqrt(1-acp[t]) n; target = sqrt(acp[t]) n - sqrt(1-acp[t]) x0 (v_prediction) or n (epsilon). fp32 [batch,
+ * per_sample]; timesteps int64 [batch]; sqrt_acp / sqrt_1m_acp = fp32 tables over the train timesteps; target may
+ * be NULL. */
+int aptp_add_noise_velocity(const float* latents, const float* noise, const int64_t* timesteps, const float* sqrt_acp,
+                            const float* sqrt_1m_acp, float* noisy, float* target, int32_t batch, int32_t per_sample,
+                            int32_t v_prediction, void* stream);
+/* Block-distillation MSE (trainer.py:1220-1225) between two bf16 NHWC row tensors: partial[i] (fp64, i <
+ * n_partial, every slot written) sums to sum((a-b)^2); the caller divides by the element count. */
+int aptp_mse_rows_fwd(const void* a, int32_t lda, const void* b, int32_t ldb, int64_t rows, int32_t C, double* partial,
+                      int32_t n_partial, void* stream);
+/* da = coef[0] * scale * (a - b) as bf16 rows (coef: device scalar = upstream gradient, scale = 2 / numel). */
+int aptp_mse_rows_bwd(const void* a, int32_t lda, const void* b, int32_t ldb, void* da, int32_t ldda, int64_t rows,
+                      int32_t C, const float* coef, float scale, void* stream);
+/* DDPM (min-SNR weighted) + distillation MSE on the fp32 predictions (trainer.py:1197-1218): partial[(b * chunks +
+ * c) * 2 + {0, 1}] = sums of (pred-target)^2 and (pred-teacher)^2 over chunk c of sample b. */
+int aptp_pred_losses_fwd(const float* pred, const float* target, const float* teacher, int32_t batch, int32_t per_sample,
+                         int32_t chunks, double* partial, void* stream);
+/* dpred = 2 / (batch * per_sample) * (g[0] * weight[b] * (pred-target) + g[1] * (pred-teacher)); weight may be NULL
+ * (plain mean); g = device [2] upstream gradients of the two losses. */
+int aptp_pred_losses_bwd(const float* pred, const float* target, const float* teacher, const float* weight,
+                         const float* g, float* dpred, int32_t batch, int32_t per_sample, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7  closed-form MAC accounting on the [B, 1620] gate matrix.
+ * replaces: UNet2DConditionModelGated.calc_macs tree walk (unet_2d_conditional.py:2124-2163 and the per-block
+ * calc_macs methods, blocks.py:103-119 ... :1373-1413) with its hard_concrete calls (estimation_utils.py:67-75).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t col;    /* first column of this width gate in the gate matrix */
+  int32_t width;  /* number of columns */
+  double macs;    /* prunable MACs that scale with the gate's kept ratio (op_counter.py constants) */
+} aptp_macs_gate;
+typedef struct {
+  int32_t first_gate, n_gates; /* its width gates (contiguous in get_structure order) */
+  int32_t depth_col;           /* column of its depth gate, -1 if none */
+  int32_t reserved;
+  double fixed;                /* non-prunable MACs of the sub-block (total - prunable) */
+} aptp_macs_sub;
+/* cur_prunable[b], cur_total[b] (fp32 [batch]) = calc_macs()['cur_prunable_macs' / 'cur_total_macs'] for gate row b;
+ * fixed_total = MACs outside the gated sub-blocks. Gates are thresholded at 0.5 (hard_concrete). */
+int aptp_macs_ratio_fwd(const float* arch, int32_t ld, int32_t batch, const aptp_macs_gate* gates, int32_t n_gates,
+                        const aptp_macs_sub* subs, int32_t n_subs, double fixed_total, float* cur_prunable,
+                        float* cur_total, void* stream);
+/* Straight-through gradient of cur_prunable to every gate column: darch[b, :dim] = dcur_prunable[b] * d cur_prunable[b]
+ * / d arch[b, :] (cur_total carries none, as in the reference's .detach()). */
+int aptp_macs_ratio_bwd(const float* arch, int32_t ld, int32_t batch, const aptp_macs_gate* gates, int32_t n_gates,
+                        const aptp_macs_sub* subs, int32_t n_subs, const float* dcur_prunable, float* darch, int32_t ldd,
+                        int32_t dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

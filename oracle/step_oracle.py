@@ -18,6 +18,32 @@ def alphas_cumprod(n=1000, b0=0.00085, b1=0.012):
     return torch.cumprod(1.0 - betas, dim=0)
 
 
+def add_noise(latents: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor, acp: torch.Tensor) -> torch.Tensor:
+    """diffusers 0.23.1 DDIMScheduler.add_noise as called at trainer.py:1121-1123."""
+    sa = (acp ** 0.5)[timesteps].flatten()
+    sb = ((1 - acp) ** 0.5)[timesteps].flatten()
+    while sa.dim() < latents.dim():
+        sa, sb = sa.unsqueeze(-1), sb.unsqueeze(-1)
+    return sa * latents + sb * noise
+
+
+def get_velocity(latents: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor, acp: torch.Tensor) -> torch.Tensor:
+    """diffusers 0.23.1 DDIMScheduler.get_velocity as called at trainer.py:1181."""
+    sa = (acp ** 0.5)[timesteps].flatten()
+    sb = ((1 - acp) ** 0.5)[timesteps].flatten()
+    while sa.dim() < latents.dim():
+        sa, sb = sa.unsqueeze(-1), sb.unsqueeze(-1)
+    return sa * noise - sb * latents
+
+
+def min_snr_weights(acp: torch.Tensor, timesteps: torch.Tensor, snr_gamma: float, v_prediction: bool) -> torch.Tensor:
+    """trainer.py:1201-1212 with compute_snr of pdm/utils/metric_utils.py:3-26."""
+    snr = ((acp ** 0.5)[timesteps] / ((1 - acp) ** 0.5)[timesteps]) ** 2
+    if v_prediction:
+        snr = snr + 1
+    return torch.stack([snr, snr_gamma * torch.ones_like(timesteps)], dim=1).min(dim=1)[0] / snr
+
+
 def split(arch: torch.Tensor, layout: R.ArchLayout) -> Dict[str, list]:
     """hypernet.py:86-101."""
     ws = layout.width_starts

@@ -189,6 +189,11 @@ ALL = [
     ("bwd_attention_cross77", lambda: check_attention_bwd(Nkv=77)),
     ("bwd_attention_small", lambda: check_attention_bwd(B=3, heads=2, kept=(2, 0, 1), Nq=64, Nkv=64)),
     ("bwd_attention_long", lambda: check_attention_bwd(B=1, heads=1, kept=(1,), Nq=1024, Nkv=640)),
+    # ragged tiles: query count not a multiple of the 64-query tile (per-warp LSE / delta slots fold the bounds in),
+    # key count not a multiple of 128 / 256 (one- and two-tile CTAs with a partial tile)
+    ("bwd_attention_ragged", lambda: check_attention_bwd(B=2, heads=2, kept=(2, 1), Nq=200, Nkv=328)),
+    ("bwd_attention_576", lambda: check_attention_bwd(B=1, heads=2, kept=(2,), Nq=576, Nkv=576)),
+    ("bwd_attention_144", lambda: check_attention_bwd(B=2, heads=1, kept=(1, 1), Nq=144, Nkv=144)),
     ("bwd_scale_cols", check_scale_cols),
     ("bwd_scale_cols_wide", lambda: check_scale_cols(B=2, hw=64, C=3840, group=64)),
     ("bwd_geglu", check_geglu_train),
