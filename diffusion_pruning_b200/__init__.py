@@ -3,7 +3,7 @@ SD-2.1 U-Net denoising step and its router, as hand-written sm_100a CUDA behind 
 `pdm.models` interface. See DESIGN.md / INTEGRATION.md."""
 from .hypernet import HyperStructure
 from .quantizer import StructureVectorQuantizer, hard_concrete
-from .unet import UNet2DConditionModelGated, UNet2DConditionOutput
+from .unet import UNet2DConditionModelGated, UNet2DConditionModelPruned, UNet2DConditionOutput
 
-__all__ = ["UNet2DConditionModelGated", "UNet2DConditionOutput", "HyperStructure", "StructureVectorQuantizer",
+__all__ = ["UNet2DConditionModelGated", "UNet2DConditionModelPruned", "UNet2DConditionOutput", "HyperStructure", "StructureVectorQuantizer",
            "hard_concrete"]

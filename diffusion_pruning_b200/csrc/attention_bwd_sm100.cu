@@ -403,30 +403,31 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
       const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + w * TW;
       const float* Lp = p.lse2 + ((size_t)b * p.max_heads + head) * p.n_q;
       const float* Dp = p.delta + ((size_t)b * p.max_heads + head) * p.n_q;
-      float* ld_slot = reinterpret_cast<float*>(smem + AK_SMEM_LD) + (warp - 4) * 256;  // [2][L 64 | D 64]
-      uint8_t* op_p = smem + AK_SMEM_OP + w * 2 * AB_BIG + r * 128;  // this key's 128-byte row of P^T
-      uint8_t* op_ds = op_p + AB_BIG;
+      const uint32_t ld_slot = smem_u32(smem + AK_SMEM_LD) + (warp - 4) * 1024;  // [2][-L 64 | -D 64] fp32
+      const uint32_t op_p = smem_u32(smem + AK_SMEM_OP + w * 2 * AB_BIG) + r * 128;  // this key's 128-byte row of P^T
+      const uint32_t op_ds = op_p + AB_BIG;
       const int swz = r & 7;
-      // out-of-range queries: L = +inf makes P^T = 0 and dS^T = 0 * finite = 0
+      // the slots hold -L and -D (operands of the packed fma / add); out-of-range queries: -L = -inf makes
+      // P^T = 0 and dS^T = 0 * finite = 0
       auto fetch = [&](int j, float& l0, float& l1, float& d0, float& d1) {
         const int qa = j * 64 + lane, qc = qa + 32;
-        l0 = (qa < p.n_q) ? __ldg(Lp + qa) : INFINITY;
-        l1 = (qc < p.n_q) ? __ldg(Lp + qc) : INFINITY;
-        d0 = (qa < p.n_q) ? __ldg(Dp + qa) : 0.f;
-        d1 = (qc < p.n_q) ? __ldg(Dp + qc) : 0.f;
+        l0 = (qa < p.n_q) ? -__ldg(Lp + qa) : -INFINITY;
+        l1 = (qc < p.n_q) ? -__ldg(Lp + qc) : -INFINITY;
+        d0 = (qa < p.n_q) ? -__ldg(Dp + qa) : 0.f;
+        d1 = (qc < p.n_q) ? -__ldg(Dp + qc) : 0.f;
       };
       {
         float l0, l1, d0, d1;
         fetch(0, l0, l1, d0, d1);
-        ld_slot[lane] = l0;
-        ld_slot[32 + lane] = l1;
-        ld_slot[64 + lane] = d0;
-        ld_slot[96 + lane] = d1;
+        sts_f32(ld_slot + lane * 4, l0);
+        sts_f32(ld_slot + (32 + lane) * 4, l1);
+        sts_f32(ld_slot + (64 + lane) * 4, d0);
+        sts_f32(ld_slot + (96 + lane) * 4, d1);
         __syncwarp();
       }
       bool ok = true;
       for (int j = 0; j < n_tiles; ++j) {
-        float nl0 = INFINITY, nl1 = INFINITY, nd0 = 0.f, nd1 = 0.f;
+        float nl0 = -INFINITY, nl1 = -INFINITY, nd0 = 0.f, nd1 = 0.f;
         const bool more = j + 1 < n_tiles;
         if (more) fetch(j + 1, nl0, nl1, nd0, nd1);
         ok = mbar_wait(&B.s_full[w], j & 1, p.abort_flag);
@@ -434,46 +435,64 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dkv_kernel(const __gri
         tc_fence_after();
         uint32_t s[64], dp[64];
         tmem_ld_32x32(t, s);
-        tmem_ld_32x32(t + 32, s + 32);
         tmem_ld_32x32(t + 64, dp);
+        tmem_ld_wait();
+        tmem_ld_32x32(t + 32, s + 32);   // second half of the tile arrives under the first half's math
         tmem_ld_32x32(t + 96, dp + 32);
+        const uint32_t Ls = ld_slot + (j & 1) * 512;  // -L[64] | -D[64] of this query tile
+        const uint32_t Ds = Ls + 256;
+        const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        uint32_t pp[32], ds[32];
+        // P^T = 2^(S^T c - L), dS^T = P^T (dP^T - D) for queries [32 h, 32 h + 32): packed fp32x2 math
+        auto half = [&](int h) {
+#pragma unroll
+          for (int i = 32 * h; i < 32 * h + 32; i += 4) {
+            uint64_t nL0, nL1, nD0, nD1;
+            lds_f32x2x2(Ls + i * 4, nL0, nL1);
+            lds_f32x2x2(Ds + i * 4, nD0, nD1);
+            float x0, x1, x2, x3;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), scale2, nL0), x0, x1);
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])), scale2, nL1), x2, x3);
+            // ordered: the exponentials of half 0 stay ahead of the wait for half 1's TMEM loads
+            const float p0 = ex2_approx_ordered(x0), p1 = ex2_approx_ordered(x1), p2 = ex2_approx_ordered(x2),
+                        p3 = ex2_approx_ordered(x3);
+            pp[(i >> 1)] = pack_bf16(p0, p1);
+            pp[(i >> 1) + 1] = pack_bf16(p2, p3);
+            const uint64_t t01 = add_f32x2(pack_f32x2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), nD0);
+            const uint64_t t23 = add_f32x2(pack_f32x2(__uint_as_float(dp[i + 2]), __uint_as_float(dp[i + 3])), nD1);
+            float d0, d1, d2, d3;
+            unpack_f32x2(fma_f32x2(pack_f32x2(p0, p1), t01, 0ull), d0, d1);
+            unpack_f32x2(fma_f32x2(pack_f32x2(p2, p3), t23, 0ull), d2, d3);
+            ds[(i >> 1)] = pack_bf16(d0, d1);
+            ds[(i >> 1) + 1] = pack_bf16(d2, d3);
+          }
+        };
+        // always true, but opaque to the compiler: the branch makes half 0 its own basic block, which keeps ptxas from
+        // sinking its math below the wait for half 1's loads (register-only instructions may otherwise move freely
+        // across tcgen05.wait / mbarrier.arrive)
+        if (p.n_q > 0) half(0);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&B.s_free[w]);
-        const float* Ls = ld_slot + (j & 1) * 128;
-        const float* Ds = Ls + 64;
-        uint32_t pp[32], ds[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const float4 L4 = *reinterpret_cast<const float4*>(Ls + i);
-          const float4 D4 = *reinterpret_cast<const float4*>(Ds + i);
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[i + 0]), p.scale_log2, -L4.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -L4.y));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), p.scale_log2, -L4.z));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), p.scale_log2, -L4.w));
-          pp[(i >> 1)] = pack_bf16(p0, p1);
-          pp[(i >> 1) + 1] = pack_bf16(p2, p3);
-          ds[(i >> 1)] = pack_bf16(p0 * (__uint_as_float(dp[i + 0]) - D4.x), p1 * (__uint_as_float(dp[i + 1]) - D4.y));
-          ds[(i >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(dp[i + 2]) - D4.z), p3 * (__uint_as_float(dp[i + 3]) - D4.w));
-        }
+        if (lane == 0) mbar_arrive(&B.s_free[w]);  // S^T / dP^T are in registers: the next tile's MMAs may overwrite them
+        half(1);
         if (j > 0) {  // the accumulate MMAs of the previous tile must have finished reading P^T / dS^T
           ok = mbar_wait(&B.acc_done[w], (j - 1) & 1, p.abort_flag);
           if (!ok) break;
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {  // 16-byte chunk c of row r sits at chunk (c ^ (r & 7)): the TMA 128B swizzle
-          const int off = (c ^ swz) << 4;
-          *reinterpret_cast<uint4*>(op_p + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
-          *reinterpret_cast<uint4*>(op_ds + off) = make_uint4(ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]);
+          const uint32_t off = (uint32_t)((c ^ swz) << 4);
+          sts_u32x4(op_p + off, pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+          sts_u32x4(op_ds + off, ds[4 * c], ds[4 * c + 1], ds[4 * c + 2], ds[4 * c + 3]);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor pipe's async-proxy reads
         if (more) {
-          float* nx = ld_slot + ((j + 1) & 1) * 128;
-          nx[lane] = nl0;
-          nx[32 + lane] = nl1;
-          nx[64 + lane] = nd0;
-          nx[96 + lane] = nd1;
+          const uint32_t nx = ld_slot + ((j + 1) & 1) * 512;
+          sts_f32(nx + lane * 4, nl0);
+          sts_f32(nx + (32 + lane) * 4, nl1);
+          sts_f32(nx + (64 + lane) * 4, nd0);
+          sts_f32(nx + (96 + lane) * 4, nd1);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&B.p_full[w]);

@@ -96,11 +96,7 @@ __device__ __forceinline__ void reduce_groups(float* bins, const float (&acc)[NQ
   }
 }
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float phi = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  return phi + x * 0.3989422804014327f * __expf(-0.5f * x * x);
-}
+// exact-erf GELU and its derivative: gelu_erf_fast / gelu_erf_fast_grad (common.cuh), the forms the GEMM epilogue uses
 
 // ------------------------------------------------------------------------------------------------
 // y = gate[b, c / group] * u   (WidthGate / LinearWidthGate on q,k,v: gates.py:15-21, blocks.py:250-255)
@@ -171,7 +167,7 @@ __global__ void __launch_bounds__(BW_THREADS)
     unpack8b(ldv(hg + row * ld + g.c0), h);
     unpack8b(ldv(hg + row * ld + inner + g.c0), t);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = (gv[e] * h[e]) * gelu_exact(gv[e] * t[e]);
+    for (int e = 0; e < 8; ++e) o[e] = (gv[e] * h[e]) * gelu_erf_fast(gv[e] * t[e]);
     stv(out + row * ldo + g.c0, pack8b(o));
   }
 }
@@ -198,8 +194,10 @@ __global__ void __launch_bounds__(BW_THREADS)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float hh = gv[e] * h[e], tt = gv[e] * t[e];
-        const float dhh = d[e] * gelu_exact(tt);       // d/d(g h)
-        const float dtt = d[e] * hh * gelu_grad(tt);   // d/d(g gate)
+        float gl, gg;
+        gelu_erf_fast_grad(tt, gl, gg);
+        const float dhh = d[e] * gl;        // d/d(g h)
+        const float dtt = d[e] * hh * gg;   // d/d(g gate)
         oh[e] = gv[e] * dhh;
         ot[e] = gv[e] * dtt;
         acc[0][e] += dhh * h[e] + dtt * t[e];

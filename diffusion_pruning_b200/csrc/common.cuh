@@ -263,6 +263,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Same instruction, but pinned in program order relative to the other volatile asm statements (tcgen05.ld /
+// tcgen05.wait / mbarrier ops): software-pipelined loops use it so the compiler cannot sink the math of chunk k
+// below the wait for chunk k+1.
+__device__ __forceinline__ float ex2_approx_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Explicit shared-space 16-byte accesses (a pointer derived from the aligned dynamic-smem base by integer
+// arithmetic is generic to the compiler, which then emits LD.E / ST.E instead of LDS / STS).
+__device__ __forceinline__ void lds_f32x2x2(uint32_t addr, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand, 128B swizzle: rows of 64 bf16 (128 B), 8-row
 // atoms of 1024 B (SBO), LBO field = 1 (unused for swizzled K-major), version = 1 (Blackwell).
 __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
@@ -388,6 +408,34 @@ __device__ __forceinline__ float silu_tanh_f(float x) {
   return fmaf(h, t, h);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (blocks.py:50) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16
+// resolution): two MUFU ops (rcp, ex2) + 9 FMA-pipe ops, branch-free. The same exp(-x^2/2) is the density term
+// of the derivative, so value and gradient share both MUFU ops:
+//   Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  gelu = x Phi,  gelu' = Phi + x exp(-x^2 / 2) / sqrt(2 pi)
+__device__ __forceinline__ void gelu_erf_fast_parts(float x, float& Phi, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float half_erf = fmaf(-0.5f * poly, e, 0.5f);  // 0.5 * erf(|x|/sqrt2)
+  Phi = 0.5f + copysignf(half_erf, x);
+}
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  float Phi, e;
+  gelu_erf_fast_parts(x, Phi, e);
+  return x * Phi;
+}
+__device__ __forceinline__ void gelu_erf_fast_grad(float x, float& value, float& grad) {
+  float Phi, e;
+  gelu_erf_fast_parts(x, Phi, e);
+  value = x * Phi;
+  grad = fmaf(x * 0.3989422804014327f, e, Phi);
+}
 #endif  // __CUDACC__
 
 }  // namespace aptp

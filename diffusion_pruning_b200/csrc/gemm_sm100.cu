@@ -70,23 +70,6 @@ __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int stages)
   }
 }
 
-// Exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16
-// resolution): two MUFU ops (rcp, ex2) + 9 FMA-pipe ops, branch-free.
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-  const float half_erf = fmaf(-0.5f * poly, e, 0.5f);  // 0.5 * erf(|x|/sqrt2)
-  return x * (0.5f + copysignf(half_erf, x));
-}
-
 // tile-local row r (0..127) -> global output row; conv tiles are bw x bh x bb pixel boxes.
 struct TileGeom {
   int linear;

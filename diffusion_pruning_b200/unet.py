@@ -322,6 +322,9 @@ class UNet2DConditionModelGated(nn.Module):
         self.total_macs = None
         self._engine: Optional["_Engine"] = None
         self._gate_state: Optional[Dict[str, Any]] = None
+        # False: gated semantics (a zero-gated GroupNorm group still feeds silu(beta) into conv2);
+        # True: the semantics of the reference's prune() (blocks.py:451-463 deletes those channels)
+        self.pruned_semantics = False
         self.set_all_ones_structure()
 
     # ---------------------------------------------------------------------------------------------
@@ -458,6 +461,64 @@ class UNet2DConditionModelGated(nn.Module):
             return (out,)
         return UNet2DConditionOutput(sample=out)
 
+    # ---------------------------------------------------------------------------------------------
+    # on-disk format: the diffusers layout the reference reads and writes (`<dir>/unet/config.json` +
+    # `diffusion_pytorch_model.safetensors`; trainer.py:285-292, :1452-1462; gates add no tensors, gates.py:13)
+    # ---------------------------------------------------------------------------------------------
+    _STOCK_TO_GATED = {"CrossAttnDownBlock2D": "CrossAttnDownBlock2DHalfGated", "DownBlock2D": "DownBlock2DHalfGated",
+                       "UpBlock2D": "UpBlock2DHalfGated", "CrossAttnUpBlock2D": "CrossAttnUpBlock2DHalfGated",
+                       "UNetMidBlock2DCrossAttn": "UNetMidBlock2DCrossAttnWidthGated"}
+
+    def save_pretrained(self, save_directory: str, **unused) -> None:
+        import json
+        import os
+        from safetensors.torch import save_file
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in self.config.items()}
+        cfg.update(_class_name=type(self).__name__, gated_ff=True, mid_block_type="UNetMidBlock2DCrossAttnWidthGated",
+                   use_linear_projection=True)
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()},
+                  os.path.join(save_directory, "diffusion_pytorch_model.safetensors"))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None, **overrides):
+        """Local directories only (no hub access). A stock SD-2.1 `unet/config.json` is accepted: its block type
+        names are mapped to the gated ones unless the caller overrides them, as the reference's callers do
+        (trainer.py:730-740, :1452-1462)."""
+        import json
+        import os
+        directory = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        with open(os.path.join(directory, "config.json")) as f:
+            cfg = json.load(f)
+        for k in ("revision", "torch_dtype", "variant", "use_safetensors", "low_cpu_mem_usage"):
+            overrides.pop(k, None)
+        extra = {k: overrides.pop(k) for k in ("arch_vector", "random_pruning_ratio") if k in overrides}
+        cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}
+        cfg.update(overrides)
+        for key in ("down_block_types", "up_block_types"):
+            cfg[key] = tuple(cls._STOCK_TO_GATED.get(t, t) for t in cfg[key])
+        cfg["mid_block_type"] = cls._STOCK_TO_GATED.get(cfg.get("mid_block_type"), cfg.get("mid_block_type"))
+        cfg.setdefault("gated_ff", True)
+        if not cfg.get("use_linear_projection", True):
+            raise NotImplementedError("use_linear_projection=False (SD-1.x) is not part of the APTP SD-2.1 hot path")
+        model = cls(**cfg)
+        st_path = os.path.join(directory, "diffusion_pytorch_model.safetensors")
+        if os.path.exists(st_path):
+            from safetensors.torch import load_file
+            sd = load_file(st_path)
+        else:
+            sd = torch.load(os.path.join(directory, "diffusion_pytorch_model.bin"), map_location="cpu")
+        model.load_state_dict(sd)
+        model.eval()
+        model._post_load(directory, **extra)
+        return model
+
+    def _post_load(self, directory: str, **extra) -> None:
+        if extra:
+            raise TypeError(f"unexpected arguments for {type(self).__name__}.from_pretrained: {sorted(extra)}")
+
     def _get_train_engine(self, device):
         from .train import TrainEngine
         te = getattr(self, "_train_engine", None)
@@ -472,6 +533,46 @@ class UNet2DConditionModelGated(nn.Module):
 # --------------------------------------------------------------------------------------------------
 # engine
 # --------------------------------------------------------------------------------------------------
+class UNet2DConditionModelPruned(UNet2DConditionModelGated):
+    """One static expert (reference: unet_2d_conditional.py:2183-2436): the gated U-Net fixed to ONE architecture
+    vector with prune() semantics. The reference slices the weights at load time (`m.prune()` / `m.prune_module()`,
+    :2425-2436); here the dense diffusers weights stay as loaded and the compacted per-expert blocks the kernels
+    consume are derived from them (plan.py), so the same checkpoint serves any code and `state_dict()` keeps the
+    stock key names. `arch_vector` is [1, 1620] (soft values are thresholded at 0.5 like hard_concrete in prune());
+    forwards of any batch size run the expert's compacted GEMMs only."""
+
+    def __init__(self, *args, arch_vector: Optional[torch.Tensor] = None, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.pruned_semantics = True
+        self.arch_vector = None
+        if arch_vector is not None:
+            self.prune_to(arch_vector)
+
+    def prune_to(self, arch_vector: torch.Tensor) -> None:
+        from .hypernet import HyperStructure
+        from .quantizer import hard_concrete
+        assert arch_vector.dim() == 2 and arch_vector.shape[0] == 1, "Pruning is only supported for single batch size"
+        self.arch_vector = arch_vector.detach().clone()
+        hard = hard_concrete(arch_vector.detach().float()).detach()
+        self.set_structure(HyperStructure.transform_arch_vector(hard, self.get_structure()))
+        self.invalidate_weight_cache()
+
+    def _post_load(self, directory: str, arch_vector=None, random_pruning_ratio=None) -> None:
+        """arch_vector.pt next to the unet/ folder (written by FineTuner, trainer.py:1449-1450), unless given."""
+        import os
+        from .hypernet import HyperStructure
+        if arch_vector is None:
+            for cand in (os.path.join(os.path.dirname(os.path.normpath(directory)), "arch_vector.pt"),
+                         os.path.join(directory, "arch_vector.pt")):
+                if os.path.exists(cand):
+                    arch_vector = torch.load(cand, map_location="cpu")
+                    break
+        if random_pruning_ratio is not None:
+            arch_vector = HyperStructure.get_random_arch_vector(random_pruning_ratio, self.get_structure())
+        if arch_vector is not None:
+            self.prune_to(arch_vector)
+
+
 class _Engine:
     def __init__(self, model: UNet2DConditionModelGated, device):
         self.m = model
@@ -788,8 +889,11 @@ class _Engine:
             gam[v, :len(k)] = g2.index_select(0, idx)
             bet[v, :len(k)] = b2.index_select(0, idx)
         d["gamma2"], d["beta2"] = gam.contiguous(), bet.contiguous()
-        tab = P.border_table(r.conv2.weight.detach().to(self.device), b2, pruned_c)
-        d["tab"] = tab.contiguous() if bool((tab != 0).any().item()) else None
+        if self.m.pruned_semantics:
+            d["tab"] = None  # prune() removed the gated-off channels: nothing of them reaches conv2
+        else:
+            tab = P.border_table(r.conv2.weight.detach().to(self.device), b2, pruned_c)
+            d["tab"] = tab.contiguous() if bool((tab != 0).any().item()) else None
         d["b2"] = r.conv2.bias.detach().to(self.device, torch.float32).contiguous()
         d["g1"] = r.norm1.weight.detach().to(self.device, torch.float32).contiguous()
         d["b1"] = r.norm1.bias.detach().to(self.device, torch.float32).contiguous()

@@ -105,22 +105,51 @@ class Resnet(nn.Module):
         self.depth_gated, self.skip_dim = depth_gated, skip_dim
         self.gate = torch.ones(1, groups)
         self.depth = torch.ones(1)
+        self.pruned = self.dropped = False
 
     def widths(self):
         return [self.groups]
 
+    @torch.no_grad()
+    def prune(self):
+        """Physical compaction for ONE code (blocks.py:424-465; depth-gated variant :641-697): conv1 rows, the
+        time-embedding rows, norm2 (kept groups only) and conv2 input columns are sliced by the kept GroupNorm
+        groups; a depth-dropped block becomes the identity on its (non-skip) input."""
+        assert self.gate.shape[0] == 1 and self.depth.shape[0] == 1, "Pruning is only supported for single batch size"
+        if self.depth_gated and float(self.depth[0]) < 0.5:
+            self.dropped = True
+            return
+        keep_g = self.gate[0] >= 0.5
+        gs = self.cout // self.groups
+        keep = keep_g.repeat_interleave(gs)
+        n = int(keep.sum())
+        conv1 = nn.Conv2d(self.cin, n, 3, padding=1)
+        conv1.weight.data, conv1.bias.data = self.conv1.weight.data[keep].clone(), self.conv1.bias.data[keep].clone()
+        tproj = nn.Linear(self.time_emb_proj.in_features, n)
+        tproj.weight.data, tproj.bias.data = (self.time_emb_proj.weight.data[keep].clone(),
+                                              self.time_emb_proj.bias.data[keep].clone())
+        norm2 = nn.GroupNorm(int(keep_g.sum()), n, eps=self.norm2.eps)
+        norm2.weight.data, norm2.bias.data = self.norm2.weight.data[keep].clone(), self.norm2.bias.data[keep].clone()
+        conv2 = nn.Conv2d(n, self.cout, 3, padding=1)
+        conv2.weight.data, conv2.bias.data = self.conv2.weight.data[:, keep].clone(), self.conv2.bias.data.clone()
+        self.conv1, self.time_emb_proj, self.norm2, self.conv2 = conv1, tproj, norm2, conv2
+        self.pruned = True
+
     def forward(self, x, temb):
         # blocks.py:485-495: depth-gate input is the non-skip part of the concatenated up-block input
         x_in = x[:, : x.shape[1] - self.skip_dim] if (self.depth_gated and self.skip_dim) else x
+        if self.dropped:  # blocks.py:497-498
+            return x_in
         h = F.silu(self.norm1(x))
         h = self.conv1(h)
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = width_gate(h, self.gate)  # blocks.py:345-348 -- BEFORE norm2
+        if not self.pruned:
+            h = width_gate(h, self.gate)  # blocks.py:345-348 -- BEFORE norm2
         h = F.silu(self.norm2(h))
         h = self.conv2(h)
         sc = self.conv_shortcut(x) if self.conv_shortcut is not None else x
         out = sc + h  # output_scale_factor = 1
-        if self.depth_gated:
+        if self.depth_gated and not self.pruned:
             out = depth_gate(x_in, out, self.depth)  # blocks.py:577-582
         return out
 
@@ -422,6 +451,16 @@ class GatedUNetOracle(nn.Module):
                     tb.attn1.gate, tb.attn2.gate, tb.ff.gate = ws
                 if d is not None:
                     m.depth = d
+
+    @torch.no_grad()
+    def prune(self) -> None:
+        """UNet2DConditionModelPruned.from_pretrained (unet_2d_conditional.py:2425-2436) for the code currently set
+        with batch-1 hard gates: ResNets are compacted physically (Resnet.prune). Attention heads, FF groups and
+        depth-dropped transformers keep their (hard) gates: gating there yields exact zeros, so it equals the
+        reference's slicing (blocks.py:52-67, :121-129, :153-187, :1427-1438) bit for bit in fp32."""
+        for m in self.modules():
+            if isinstance(m, Resnet):
+                m.prune()
 
     def set_all_ones(self, batch: int = 1) -> None:
         st = self.get_structure()

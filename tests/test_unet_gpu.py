@@ -34,3 +34,10 @@ def test_tiny_cfg_batch_doubling():
 def test_full_sd21_hard_b2_h32():
     import unet_checks as U
     _assert(U.check_hard(tiny=False, B=2, H=32, code_ids=(0, 3)))
+
+
+def test_tiny_pruned_static_expert_matches_pruned_oracle():
+    import unet_checks as U
+    res, gap = U.check_pruned_expert()
+    _assert(res)
+    assert gap > U.MAX_ABS_TOL, gap  # the case really separates prune() from gate semantics

@@ -87,3 +87,36 @@ def check_cfg_doubling(tiny=True, H=32):
     arch = codes[[1, 5]]
     got, ref = run_pair(model, oracle, arch, 4, H, model.config["cross_attention_dim"])
     return metrics(got, ref)
+
+
+def check_pruned_expert(B=3, H=32, code_id=3, beta_std=0.1):
+    """UNet2DConditionModelPruned (one static expert, prune() semantics) vs the oracle after its physical prune()
+    (blocks.py:424-465, unet_2d_conditional.py:2425-2436), GroupNorm beta != 0 so that pruned != gated. Returns
+    (metrics vs pruned oracle, max-abs distance of the product from the GATED oracle on the same code)."""
+    import copy
+    from diffusion_pruning_b200 import UNet2DConditionModelPruned
+    ocfg = UNetConfig.tiny()
+    oracle = GatedUNetOracle(ocfg).eval()
+    seeded_init(oracle, 0, beta_std)
+    model = UNet2DConditionModelPruned(**TINY)
+    model.load_state_dict(oracle.state_dict())
+    model = model.cuda().eval()
+    st = model.get_structure()
+    code = synthetic_codes(st, 8)[code_id:code_id + 1].float()
+    soft = code * 0.9 + 0.05  # soft codebook row; prune() thresholds it
+    sample, t, ctx = inputs(B, H, model.config["cross_attention_dim"])
+    oracle.set_structure(split_arch(code.clone(), st))
+    with torch.no_grad():
+        ref_gated = oracle(sample, t, ctx)
+    pruned = copy.deepcopy(oracle)
+    pruned.prune()
+    with torch.no_grad():
+        ref = pruned(sample, t, ctx)
+    model.prune_to(soft)
+    with torch.no_grad():
+        got = model(sample.cuda(), t.cuda(), ctx.cuda()).sample
+    torch.cuda.synchronize()
+    from diffusion_pruning_b200 import kernels as K
+    K.check_abort()
+    gap = (ref - ref_gated).abs().max().item() / max(1.0, ref.abs().max().item())
+    return metrics(got, ref), gap
