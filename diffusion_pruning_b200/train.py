@@ -87,19 +87,36 @@ class TrainEngine(_Engine):
 
     def _gn_fwd(self, x: torch.Tensor, ld: int, C: int, B: int, hw: int, groups: int, eps: float, gamma, beta,
                 out: torch.Tensor, silu: bool, gate=None) -> torch.Tensor:
-        stats = torch.zeros(B, groups, 2, device=self.device, dtype=torch.float32)
+        stats = self._take_stats(B, groups)
         gs = C // groups
         K.groupnorm_stats(x, C, ld, None, 0, 0, B, hw, gs, None, stats, groups)
         K.groupnorm_apply(x, C, ld, None, 0, 0, out, C, B, hw, gs, eps, stats, groups, gamma, beta, C, None, None, gate,
-                          groups, silu)
+                          gate.stride(0) if gate is not None else groups, silu)
         self.launches += 2
         return stats
+
+    def _take_stats(self, B: int, groups: int) -> torch.Tensor:
+        """[B, groups, 2] zeroed fp32 slice of this step's statistics pool (ONE fill per step instead of one per
+        GroupNorm; the slices live on the tape until the backward has consumed them)."""
+        n = B * groups * 2
+        if self._stats_pool is None or self._stats_used + n > self._stats_pool.numel():
+            self._stats_pool = torch.zeros(max(96 * n, 1 << 16), device=self.device, dtype=torch.float32)
+            self._stats_used = 0
+        v = self._stats_pool[self._stats_used:self._stats_used + n].view(B, groups, 2)
+        self._stats_used += n
+        return v
+
+    def _dgate(self, gate_idx: int) -> torch.Tensor:
+        """Gradient slot of one width gate: a VIEW into the [B, 1620] accumulator (same row pitch as the gate
+        matrix; the backward kernels accumulate into it atomically)."""
+        s, e = self.width_starts[gate_idx], self.width_starts[gate_idx + 1]
+        return self.darch[:, s:e]
 
     def _gn_bwd(self, x, ld, C, B, hw, groups, eps, stats, gamma, beta, da, dx: torch.Tensor, lddx: int,
                 accumulate: bool, silu: bool, gate=None, dgate=None):
         bstats = self.buf("gn_bstats", B, groups * 2, torch.float32)
         K.groupnorm_bwd(x, ld, da, C, dx, lddx, accumulate, B, hw, C, C // groups, eps, stats, groups, gamma, beta, gate,
-                        groups, silu, bstats, dgate)
+                        gate.stride(0) if gate is not None else groups, silu, bstats, dgate)
         self.launches += 2
 
     # ------------------------------------------------------------------------------------------
@@ -132,7 +149,11 @@ class TrainEngine(_Engine):
             self.gate_cols[mod.uid] = {"w": list(range(gi, gi + n)), "d": (di if mod.depth_gate is not None else None)}
             gi += n
             di += int(mod.depth_gate is not None)
-        self.darch = torch.zeros_like(self.soft_arch)  # gradient accumulator, same column layout
+        self.darch = torch.zeros_like(self.soft_arch)  # gradient accumulator, same column layout and row pitch
+        assert self.darch.stride(0) == self.soft_arch.stride(0)
+        self.ddepth_T = torch.zeros(self.soft_arch.shape[1] - self.n_width, B, device=self.device,
+                                    dtype=torch.float32)  # [14, B] depth-gate gradients (contiguous per gate)
+        self._stats_pool, self._stats_used = None, 0
         self.tape: List[Tuple] = []
         self.first_uid = m._gated[0].uid  # nothing upstream of it needs a gradient
 
@@ -263,11 +284,8 @@ class TrainEngine(_Engine):
         if r.depth_gate is not None:
             dxin = self._new(M, r.cin, zero=(s["keep"] != r.cin))
             dy = self._new(M, r.cout)
-            dd = self.darch[:, self.n_width + cidx["d"]]
-            ddc = torch.zeros(B, device=self.device, dtype=torch.float32)
             K.depth_lerp_bwd(dout.t, dout.ld, xin.t, xin.ld, s["y"], r.cout, dy, r.cout, dxin, r.cin, False, B, hw,
-                             s["keep"], s["d"], ddc)
-            dd.add_(ddc)
+                             s["keep"], s["d"], self.ddepth_T[cidx["d"]])
             dyg = _G(dy, r.cout, r.cout)
             have = True
         else:
@@ -293,11 +311,8 @@ class TrainEngine(_Engine):
         self._mm(("c2.T", r.uid), dyg.t, dyg.ld, r.cout, M, self._wT("c2." + r.uid, r.conv2), r.cout, da2, r.cout,
                  conv=(B, H, W), k_tap_pitch=r.cout, rows_per_sample=hw)
         dh1 = self.buf("bw_b", M, r.cout)
-        gcol = self.width_starts[cidx["w"][0]]
-        dg = torch.zeros(B, r.groups, device=self.device, dtype=torch.float32)
         self._gn_bwd(s["h1"], r.cout, r.cout, B, hw, r.groups, r.eps, s["st2"], pk["gamma2"], pk["beta2"], da2, dh1,
-                     r.cout, False, True, gate=s["gate"], dgate=dg)
-        self.darch[:, gcol:gcol + r.groups].add_(dg)
+                     r.cout, False, True, gate=s["gate"], dgate=self._dgate(cidx["w"][0]))
         if not need_in:
             return None
         da1 = self.buf("bw_c", M, r.cin)
@@ -331,9 +346,9 @@ class TrainEngine(_Engine):
                      rows_per_sample=n_kv)
             gq = self._new(M, C)
             gkv = self._new(Mkv, 2 * C)
-            K.scale_cols(uq, C, gq, C, B, hw, C, gate, heads, 64)
-            K.scale_cols(ukv, 2 * C, gkv, 2 * C, B, n_kv, C, gate, heads, 64)
-            K.scale_cols(ukv[:, C:], 2 * C, gkv[:, C:], 2 * C, B, n_kv, C, gate, heads, 64)
+            K.scale_cols(uq, C, gq, C, B, hw, C, gate, gate.stride(0), 64)
+            K.scale_cols(ukv, 2 * C, gkv, 2 * C, B, n_kv, C, gate, gate.stride(0), 64)
+            K.scale_cols(ukv[:, C:], 2 * C, gkv[:, C:], 2 * C, B, n_kv, C, gate, gate.stride(0), 64)
             q, ldq, kk, vv, ldkv = gq, C, gkv, gkv[:, C:], 2 * C
             saved = dict(uq=uq, ukv=ukv, gq=gq, gkv=gkv)
         else:
@@ -341,7 +356,7 @@ class TrainEngine(_Engine):
             self._mm(("qkv", uid), xn, C, C, M, wcat, 3 * C, u, 3 * C, rows_per_sample=hw)
             g = self._new(M, 3 * C)
             for j in range(3):
-                K.scale_cols(u[:, j * C:], 3 * C, g[:, j * C:], 3 * C, B, hw, C, gate, heads, 64)
+                K.scale_cols(u[:, j * C:], 3 * C, g[:, j * C:], 3 * C, B, hw, C, gate, gate.stride(0), 64)
             q, ldq, kk, vv, ldkv = g, 3 * C, g[:, C:], g[:, 2 * C:], 3 * C
             saved = dict(u=u, g=g)
         o = self._new(M, C)
@@ -368,7 +383,9 @@ class TrainEngine(_Engine):
         do = self.buf("bw_do", M, C)
         self._mm(("o.T", uid), dtok, C, C, M, self._wT("o." + uid, attn.to_out[0]), C, do, C, rows_per_sample=hw)
         delta = self.buf("bw_delta", B * heads, hw, torch.float32)
-        dg = torch.zeros(B, heads, device=self.device, dtype=torch.float32)
+        gate = s["gate"]
+        gld = gate.stride(0)
+        dg = self._dgate(gate_idx)
         if cross:
             dq = self.buf("bw_dq", M, C)
             dkv = self.buf("bw_dkv", Mkv, 2 * C)
@@ -377,10 +394,9 @@ class TrainEngine(_Engine):
                             dkv[:, C:], 2 * C, B, hw, n_kv, s["sh"], heads, 0.125)
             duq = self.buf("bw_duq", M, C)
             dukv = self.buf("bw_dukv", Mkv, 2 * C)  # dk, dv only feed the gate gradient (ctx needs none)
-            K.scale_cols_bwd(s["uq"], C, dq, C, duq, C, B, hw, C, s["gate"], heads, 64, dg)
-            K.scale_cols_bwd(s["ukv"], 2 * C, dkv, 2 * C, dukv, 2 * C, B, n_kv, C, s["gate"], heads, 64, dg)
-            K.scale_cols_bwd(s["ukv"][:, C:], 2 * C, dkv[:, C:], 2 * C, dukv[:, C:], 2 * C, B, n_kv, C, s["gate"], heads,
-                             64, dg)
+            K.scale_cols_bwd(s["uq"], C, dq, C, duq, C, B, hw, C, gate, gld, 64, dg)
+            K.scale_cols_bwd(s["ukv"], 2 * C, dkv, 2 * C, dukv, 2 * C, B, n_kv, C, gate, gld, 64, dg)
+            K.scale_cols_bwd(s["ukv"][:, C:], 2 * C, dkv[:, C:], 2 * C, dukv[:, C:], 2 * C, B, n_kv, C, gate, gld, 64, dg)
             dln = self.buf("bw_dln", M, C)
             self._mm(("q.T", uid), duq, C, C, M, self._wT("q." + uid, attn.to_q), C, dln, C, rows_per_sample=hw)
         else:
@@ -391,14 +407,12 @@ class TrainEngine(_Engine):
             du = self.buf("bw_du", M, 3 * C)
             for j in range(3):
                 K.scale_cols_bwd(s["u"][:, j * C:], 3 * C, dqkv[:, j * C:], 3 * C, du[:, j * C:], 3 * C, B, hw, C,
-                                 s["gate"], heads, 64, dg)
+                                 gate, gld, 64, dg)
             key = "wqkv.T." + uid
             if key not in self.dense:
                 self.dense[key] = self.dense["wqkv." + uid].t().contiguous()  # [C, 3C]
             dln = self.buf("bw_dln", M, C)
             self._mm(("qkv.T", uid), du, 3 * C, 3 * C, M, self.dense[key], C, dln, C, rows_per_sample=hw)
-        gcol = self.width_starts[gate_idx]
-        self.darch[:, gcol:gcol + heads].add_(dg)
         self.launches += 8
         return dln
 
@@ -433,7 +447,7 @@ class TrainEngine(_Engine):
         self._mm(("ffp", t.uid), xn, C, C, M, wp["w"], 2 * inner, hg, 2 * inner, bias=wp["b"], rows_per_sample=hw)
         fgate = self._soft_gate(cidx["w"][2])
         f = self.buf("ff", M, inner)
-        K.geglu(hg, 2 * inner, f, inner, B, hw, inner, fgate, t.gate_width, inner // t.gate_width)
+        K.geglu(hg, 2 * inner, f, inner, B, hw, inner, fgate, fgate.stride(0), inner // t.gate_width)
         w2 = self._w("ff2." + t.uid, tb.ff.net[2])
         tok3 = self.buf("tok3", M, C)
         self._mm(("ff2", t.uid), f, inner, inner, M, w2["w"], C, tok3, C, bias=w2["b"], residual=tok2, res_ld=C,
@@ -462,9 +476,8 @@ class TrainEngine(_Engine):
         if t.depth_gate is not None:
             dy = self._new(M, C)
             dx = self._new(M, C)
-            ddc = torch.zeros(B, device=self.device, dtype=torch.float32)
-            K.depth_lerp_bwd(dout.t, dout.ld, x.t, x.ld, s["y"], C, dy, C, dx, C, False, B, hw, C, s["d"], ddc)
-            self.darch[:, self.n_width + cidx["d"]].add_(ddc)
+            K.depth_lerp_bwd(dout.t, dout.ld, x.t, x.ld, s["y"], C, dy, C, dx, C, False, B, hw, C, s["d"],
+                             self.ddepth_T[cidx["d"]])
             K.add_rows(dy, C, dx, C, M, C)  # residual x of proj_out
         else:
             if dout.ld == C:
@@ -481,11 +494,8 @@ class TrainEngine(_Engine):
         self._mm(("ff2.T", t.uid), dtok, C, C, M, self._wT("ff2." + t.uid, tb.ff.net[2]), inner, df, inner,
                  rows_per_sample=hw)
         dhg = self.buf("bw_dhg", M, 2 * inner)
-        dgf = torch.zeros(B, t.gate_width, device=self.device, dtype=torch.float32)
-        K.geglu_bwd(s["hg"], 2 * inner, df, inner, dhg, 2 * inner, B, hw, inner, s["fgate"], t.gate_width,
-                    inner // t.gate_width, dgf)
-        gcol = self.width_starts[cidx["w"][2]]
-        self.darch[:, gcol:gcol + t.gate_width].add_(dgf)
+        K.geglu_bwd(s["hg"], 2 * inner, df, inner, dhg, 2 * inner, B, hw, inner, s["fgate"], s["fgate"].stride(0),
+                    inner // t.gate_width, self._dgate(cidx["w"][2]))
         dln = self.buf("bw_dln", M, C)
         self._mm(("ffp.T", t.uid), dhg, 2 * inner, 2 * inner, M, self._wT("ffp." + t.uid, tb.ff.net[0].proj), C, dln, C,
                  rows_per_sample=hw)
@@ -609,6 +619,7 @@ class TrainEngine(_Engine):
                 self._acc(grads, s["x"], self.b_downsample(mod, s, g))
             elif kind == "up":
                 self._acc(grads, s["x"], self.b_upsample(mod, s, g))
+        self.darch[:, self.n_width:].add_(self.ddepth_T.t())
         d = self.darch
         if self.gate_rows != B:  # gates were tiled along the batch (gates.py:18-19): fold the copies back
             d = d.reshape(B // self.gate_rows, self.gate_rows, -1).sum(0)

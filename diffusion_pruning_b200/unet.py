@@ -668,11 +668,18 @@ class _Engine:
         return torch.as_tensor(arr, device=self.device).to(dtype)
 
     def _soft_gate(self, gate_idx: int) -> torch.Tensor:
+        """Columns of one width gate as a VIEW of the [B, 1620] gate matrix: the kernels take the row pitch
+        (`gate.stride(0)`), so no per-layer slice copies are launched."""
         s, e = self.width_starts[gate_idx], self.width_starts[gate_idx + 1]
-        return self.soft_arch[:, s:e].contiguous()
+        return self.soft_arch[:, s:e]
 
     def _soft_depth(self, depth_idx: int) -> torch.Tensor:
-        return self.soft_arch[:, self.n_width + depth_idx].contiguous()
+        """[B] contiguous depth gate: one transposed copy of the 14 depth columns per gate matrix."""
+        dt = getattr(self, "_depth_T", None)
+        if dt is None or self._depth_T_src is not self.soft_arch:
+            dt = self.soft_arch[:, self.n_width:].t().contiguous()
+            self._depth_T, self._depth_T_src = dt, self.soft_arch
+        return dt[depth_idx]
 
     def _expert_active(self, uid: str) -> np.ndarray:
         """[E] bool: False where the block is depth-dropped for that expert."""
@@ -789,7 +796,7 @@ class _Engine:
         stats.zero_()
         K.groupnorm_stats(x, C, ld, None, 0, 0, B, hw, gs, sample_channels, stats, groups_full)
         K.groupnorm_apply(x, C, ld, None, 0, 0, out, out_ld, B, hw, gs, eps, stats, groups_full, gamma, beta, affine_ld,
-                          sample_seg, sample_channels, gate, groups_full, silu)
+                          sample_seg, sample_channels, gate, gate.stride(0) if gate is not None else groups_full, silu)
         self.launches += 3
 
     # ---- time embedding --------------------------------------------------------------------------
@@ -1099,7 +1106,7 @@ class _Engine:
         if "wqkv" not in pk:
             pk["wqkv"] = torch.cat([pk["wq"], pk["wk"], pk["wv"]], 0).contiguous() if not is_cross else None
             pk["wkv"] = torch.cat([pk["wk"], pk["wv"]], 0).contiguous() if is_cross else None
-        gkw = dict(gate=gate, gate_ld=attn.heads, gate_group=64) if gate is not None else {}
+        gkw = dict(gate=gate, gate_ld=gate.stride(0), gate_group=64) if gate is not None else {}
         if is_cross:
             self._gemm(s["q"], xn, pk["wq"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=C, rows_per_sample=hw, **gkw)
             self._gemm(s["kv"], ctx, pk["wkv"], kvb, a_ld=kkv, a_k=kkv, a_rows=Mkv, out_ld=2 * C, rows_per_sample=n_kv,
@@ -1182,7 +1189,7 @@ class _Engine:
             return s
         s = self._sched(("ff", t.uid, hw), build_ff)
         gate = self._soft_gate(cidx["w"][2]) if not self.compact else None
-        gkw = dict(gate=gate, gate_ld=t.gate_width, gate_group=fk["gs"]) if gate is not None else {}
+        gkw = dict(gate=gate, gate_ld=gate.stride(0), gate_group=fk["gs"]) if gate is not None else {}
         self._gemm(s["p"], xn, fk["wp"], ffb, a_ld=C, a_k=C, a_rows=M, out_ld=inner, bias=fk["bp"], flags=EPI_GEGLU,
                    rows_per_sample=hw, **gkw)
         self._gemm(s["o"], ffb, fk["w2"], tok, a_ld=inner, a_k=inner, a_rows=M, out_ld=C, bias=fk["b2"], residual=tok,
