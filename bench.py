@@ -365,6 +365,115 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_sample(args):
+    """BASELINE configs[3]: expert-routed 25-step DDIM sampling at 96x96 latents with classifier-free guidance. Every
+    rank routes its own prompts (hypernet + eval cosine argmax), an all-to-all sends each prompt to the GPU that owns
+    its expert (expert e lives on rank e % world), the whole scheduler loop runs there (gated U-Net on the doubled CFG
+    batch + the fused CFG/DDIM kernel), a second all-to-all returns the final latents. A bench "step" is one such
+    sampling pass over the rank's prompts; value counts prompt x DDIM-step units (each is TWO U-Net samples: cond +
+    uncond)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from diffusion_pruning_b200 import HyperStructure, StructureVectorQuantizer
+    from diffusion_pruning_b200 import kernels as K
+    from diffusion_pruning_b200 import sampling as S
+    from diffusion_pruning_b200.synthetic import DEPTH_ORDER, synthetic_codes
+    from diffusion_pruning_b200.unet import UNet2DConditionModelGated
+    P, H, STEPS = args.prompts, args.sample_latent, args.ddim_steps
+    torch.manual_seed(1234)
+    with torch.device(device):
+        unet = UNet2DConditionModelGated()
+    unet.eval()
+    st = unet.get_structure()
+    torch.manual_seed(7)
+    hyper = HyperStructure(structure=st, input_dim=768, wn_flag=False, linear_bias=True).to(device).eval()
+    quant = StructureVectorQuantizer(n_e=N_CODES, structure=st, beta=0.25, temperature=0.4, base=3,
+                                     depth_order=list(DEPTH_ORDER), non_zero_width=True,
+                                     resource_aware_normalization=False, optimal_transport=True).to(device)
+    quant.eval()
+    codes = synthetic_codes(st, N_CODES).float()
+    quant.embedding_gs.data = (codes * 0.9 + 0.05).to(device)  # soft codebook rows; eval routing thresholds them
+    g = torch.Generator().manual_seed(300 + rank)
+    # Synthetic prompt embeddings that the (random-init, linear) hypernet maps near the codes in round-robin order, so
+    # that the router really spreads the prompts over the experts: least-squares pre-images of +-4 logits, plus noise.
+    with torch.no_grad():
+        Wh = torch.cat([l.weight for l in hyper.mh_fc], 0).float().cpu()
+        bh = torch.cat([l.bias for l in hyper.mh_fc], 0).float().cpu()
+        want = (2.0 * codes[(torch.arange(P) + rank * P) % N_CODES] - 1.0) * 4.0 - bh
+        prompt = torch.linalg.lstsq(Wh, want.t()).solution.t().contiguous()
+        prompt = prompt + 0.02 * prompt.std() * torch.randn(P, 768, generator=g)
+    host = {"prompt": prompt.pin_memory(),
+            "latents": torch.randn(P, 4, H, H, generator=g).pin_memory(),
+            "cond": torch.randn(P, N_CTX, CTX_DIM, generator=g).pin_memory(),
+            "uncond": torch.randn(1, N_CTX, CTX_DIM, generator=g).expand(P, -1, -1).contiguous().pin_memory()}
+    acp = S.alphas_cumprod()
+    result = torch.empty(P, 4, H, H).pin_memory()
+
+    def step():
+        d = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        out, idx = S.routed_sampling(unet, hyper, quant, d["prompt"], d["latents"], d["cond"], d["uncond"],
+                                     num_inference_steps=STEPS, guidance_scale=7.5, acp=acp)
+        result.copy_(out, non_blocking=True)
+        return idx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        idx = step()
+    K.check_abort()
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        idx = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    counts = torch.bincount(idx, minlength=N_CODES).float()
+    if world > 1:
+        tt = torch.tensor([ms], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        dist.all_reduce(counts)
+    clk = clocks.stop()
+    K.check_abort()
+    assert torch.isfinite(result).all(), "sampling produced non-finite latents"
+    value = P * world * STEPS * args.steps / (ms / 1e3)
+    if rank == 0:
+        out = {"metric": "routed_sampling_prompt_steps_per_s", "value": round(value, 2), "unit": "prompts*steps/s",
+               "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+               "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": f"configs[3]: expert-routed {STEPS}-step DDIM sampling with CFG 7.5, {H}x{H} "
+                                      f"latent, {N_CODES} experts (expert e on rank e % world), all-to-all prompt "
+                                      f"dispatch + return, random-init weights",
+                          "prompts_per_gpu": P, "latent": H, "ddim_steps": STEPS, "codes": N_CODES,
+                          "unet_samples_per_prompt_step": 2, "parallelism": f"ep{world} over experts",
+                          "prompts_per_expert": [int(c) for c in counts.tolist()],
+                          "l2": "activations exceed L2"},
+               "prompts_per_s": round(P * world * args.steps / (ms / 1e3), 3),
+               "unet_samples_steps_per_s": round(2 * value, 2),
+               "e2e": {"value": round(value, 2), "unit": "prompts*steps/s",
+                       "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
+                       "d2h_bytes_per_step": int(result.numel() * result.element_size())},
+               "gpu_launches": None, "clocks": clk}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def build_oracle_fast():
     """Full-size fp32 oracle with cheap deterministic init (fan-in scaled uniform)."""
     import math
@@ -437,13 +546,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="forward", choices=["forward", "train"])
+    ap.add_argument("--workload", default="forward", choices=["forward", "train", "sample"])
     ap.add_argument("--train-batch", type=int, default=32)
+    ap.add_argument("--prompts", type=int, default=16, help="--workload sample: prompts per GPU")
+    ap.add_argument("--sample-latent", type=int, default=96)
+    ap.add_argument("--ddim-steps", type=int, default=25)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":
         run_train(args)
+    elif args.workload == "sample":
+        run_sample(args)
     else:
         run_ours(args)
 

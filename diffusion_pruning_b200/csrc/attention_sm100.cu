@@ -17,6 +17,7 @@
 //               rescaling), so the steady state is: TMEM read S, 128 x (FFMA + EX2), TMEM write P.
 // With short KV (cross-attention, 77 keys) a CTA loops over several query pairs to amortise TMEM
 // allocation and barrier setup.
+#include <type_traits>
 #include "common.cuh"
 #include "../../include/aptp_sm100.h"
 
@@ -252,9 +253,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       const int q0 = qp * 2 * ATT_BM + w * ATT_BM;
       if (q0 >= p.n_q) continue;  // second tile of a short sequence: nothing to do (warpgroup-uniform)
       float m_used = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < n_tiles; ++j, ++g) {
-        ok = mbar_wait(&s_full[w], g & 1, p.abort_flag);
-        if (!ok) break;
+      // One key tile. `ragged` is a compile-time tag: only the last tile of a key count that is not a multiple of 128
+      // masks its tail; full tiles carry no per-element compare / select (they were 36 % of the instructions of this
+      // issue-bound loop when the mask was a run-time condition that ptxas if-converted).
+      auto key_tile = [&](int j, auto ragged) -> bool {
+        if (!mbar_wait(&s_full[w], g & 1, p.abort_flag)) return false;
         tc_fence_after();
         uint32_t s[ATT_BN];
         tmem_ld_32x32(s_addr, s);
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           }
         };
         auto max_chunk = [&](int c) {
-          if (kv_left < ATT_BN) {  // ragged last key tile: -inf -> p = 0
+          if constexpr (decltype(ragged)::value) {  // ragged last key tile: -inf -> p = 0
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= kv_left) s[c * 32 + i] = 0xff800000u;
@@ -316,9 +319,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         max_chunk(1);
         if (optimistic) exp_chunk(1, pk1);
         if (j > 0) {  // PV of the previous tile must be complete before P is overwritten / O rescaled
-          ok = mbar_wait(&pv_done[w], gd & 1, p.abort_flag);
+          const bool done = mbar_wait(&pv_done[w], gd & 1, p.abort_flag);
           ++gd;
-          if (!ok) break;
+          if (!done) return false;
           tc_fence_after();
         }
         if (optimistic) {
@@ -369,6 +372,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[w]);
+        return true;
+      };
+      for (int j = 0; j < n_tiles && ok; ++j, ++g) {
+        if (p.n_kv - j * ATT_BN >= ATT_BN) {
+          ok = key_tile(j, std::false_type{});
+        } else {
+          ok = key_tile(j, std::true_type{});
+        }
       }
       if (!ok) break;
       ok = mbar_wait(&pv_done[w], gd & 1, p.abort_flag);
