@@ -109,6 +109,8 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "aptp_macs_ratio_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                     c_int, c_void_p]),
+    "aptp_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "aptp_pred_losses_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_void_p]),
 }

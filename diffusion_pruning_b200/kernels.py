@@ -368,3 +368,24 @@ def macs_ratio_bwd(arch, gates_dev, n_gates, subs_dev, n_subs, dcur, darch):
     check(load().aptp_macs_ratio_bwd(_ptr(arch), arch.stride(0), arch.shape[0], _ptr(gates_dev), n_gates, _ptr(subs_dev),
                                      n_subs, _ptr(dcur), _ptr(darch), darch.stride(0), darch.shape[1], _stream()),
           "aptp_macs_ratio_bwd")
+
+
+# --------------------------------------------------------------------------------------------
+# K8: weight gradients
+# --------------------------------------------------------------------------------------------
+def wgrad(dy, ld_dy, a, ld_a, dw, dbias, rows, n_out, k_in, conv=None, splits=0):
+    """dw [n_out, taps * k_in] fp32 (+)= dy^T a over the rows; conv = (batch, H, W) selects the 3x3 taps (OHWI layout).
+    splits = 0 picks a split-K factor that fills the GPU."""
+    taps = 9 if conv is not None else 1
+    if conv is not None:
+        batch, H, W = conv
+        bw, bh, bb = conv_box(W, H)
+        n_stages = (W // bw) * (H // bh) * (batch // bb)
+    else:
+        batch = H = W = bw = bh = bb = 1
+        n_stages = (rows + 127) // 128
+    if splits <= 0:
+        tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128) * taps
+        splits = max(1, min(n_stages, (4 * 148 + tiles - 1) // tiles))
+    check(load().aptp_wgrad(_ptr(dy), ld_dy, _ptr(a), ld_a, _ptr(dw), dw.stride(0), _ptr(dbias), rows, n_out, k_in,
+                            int(conv is not None), batch, H, W, bw, bh, bb, splits, _stream()), "aptp_wgrad")

@@ -325,6 +325,19 @@ int aptp_macs_ratio_bwd(const float* arch, int32_t ld, int32_t batch, const aptp
                         const aptp_macs_sub* subs, int32_t n_subs, const float* dcur_prunable, float* darch, int32_t ldd,
                         int32_t dim, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K8  weight gradients on tcgen05 (the fine-tune step of a compacted expert,
+ * pdm/training/trainer.py:1683-1765, differentiates F.conv2d / F.linear w.r.t. the weights).
+ *   dw[n, tap, c] += sum_rows dy[row, n] * a[shift_tap(row), c]     (fp32, OHWI; taps = 9 if conv3x3 else 1)
+ *   dbias[n]      += sum_rows dy[row, n]                            (optional)
+ * dy: bf16 [rows, n_out] (pitch ld_dy), a: bf16 [rows, k_in] NHWC rows (pitch ld_a), rows = batch * H * W for the conv
+ * (stride 1, zero padding 1); (bw, bh, bb) = pixel box of one reduction stage (bw * bh * bb = 128, tiles the images);
+ * splits = split-K factor over the rows (partial sums meet in dw through fp32 atomics: the caller zeroes dw / dbias).
+ * ------------------------------------------------------------------------------------------------ */
+int aptp_wgrad(const void* dy, int32_t ld_dy, const void* a, int32_t ld_a, float* dw, int64_t ld_dw, float* dbias,
+               int64_t rows, int32_t n_out, int32_t k_in, int32_t conv3x3, int32_t batch, int32_t H, int32_t W,
+               int32_t bw, int32_t bh, int32_t bb, int32_t splits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,7 +184,48 @@ def check_attention_bwd(B=2, heads=3, kept=(3, 1), Nq=256, Nkv=256, seed=0):
             assert (g[:, kb:] == 9.0).all(), f"attention_bwd {name}: pruned heads must not be written"
 
 
+def check_wgrad_linear(rows=1000, n_out=200, k_in=136, ld_extra=8, splits=0, seed=0):
+    """aptp_wgrad (linear): dW = dY^T A and db = column sums vs fp32 torch on the same bf16 operands; ragged rows /
+    columns (not multiples of 128 / 64), pitched inputs, split-K through fp32 atomics."""
+    ldy, lda = n_out + ld_extra, k_in + ld_extra
+    dy = _rand(rows, ldy, seed=seed).bfloat16()
+    a = _rand(rows, lda, seed=seed + 1).bfloat16()
+    dw = torch.zeros(n_out, k_in, device=DEV)
+    db = torch.zeros(n_out, device=DEV)
+    K.wgrad(dy, ldy, a, lda, dw, db, rows, n_out, k_in, splits=splits)
+    K.check_abort()
+    ref = dy[:, :n_out].float().t() @ a[:, :k_in].float()
+    scale = ref.abs().max().item()
+    _close(dw, ref, 2e-3 * scale, 2e-3, f"wgrad linear rows{rows} n{n_out} k{k_in} splits{splits}")
+    _close(db, dy[:, :n_out].float().sum(0), 2e-3 * rows ** 0.5, 2e-3, "wgrad bias")
+
+
+def check_wgrad_conv(B=2, H=16, W=16, cin=72, cout=136, splits=0, seed=3):
+    """aptp_wgrad (3x3 conv, stride 1, zero padding): vs autograd of F.conv2d w.r.t. the weight, OHWI layout."""
+    rows = B * H * W
+    a = _rand(rows, cin, seed=seed).bfloat16()
+    dy = _rand(rows, cout, seed=seed + 1).bfloat16()
+    dw = torch.zeros(cout, 9 * cin, device=DEV)
+    db = torch.zeros(cout, device=DEV)
+    K.wgrad(dy, cout, a, cin, dw, db, rows, cout, cin, conv=(B, H, W), splits=splits)
+    K.check_abort()
+    x = a.float().reshape(B, H, W, cin).permute(0, 3, 1, 2)
+    w = torch.zeros(cout, cin, 3, 3, device=DEV, requires_grad=True)
+    y = torch.nn.functional.conv2d(x, w, padding=1)
+    y.backward(dy.float().reshape(B, H, W, cout).permute(0, 3, 1, 2))
+    ref = w.grad.permute(0, 2, 3, 1).reshape(cout, 9 * cin)  # OIHW -> OHWI
+    scale = ref.abs().max().item()
+    _close(dw, ref, 2e-3 * scale, 2e-3, f"wgrad conv B{B} {H}x{W} cin{cin} cout{cout} splits{splits}")
+    _close(db, dy.float().sum(0), 2e-3 * rows ** 0.5, 2e-3, "wgrad conv bias")
+
+
 ALL = [
+    ("wgrad_linear", check_wgrad_linear),
+    ("wgrad_linear_1split", lambda: check_wgrad_linear(rows=4096, n_out=320, k_in=320, ld_extra=0, splits=1)),
+    ("wgrad_linear_small", lambda: check_wgrad_linear(rows=77, n_out=64, k_in=1024, splits=0)),
+    ("wgrad_conv", check_wgrad_conv),
+    ("wgrad_conv_8x8", lambda: check_wgrad_conv(B=3, H=8, W=8, cin=256, cout=128, splits=2)),
+    ("wgrad_conv_64", lambda: check_wgrad_conv(B=1, H=64, W=64, cin=64, cout=64, splits=4)),
     ("bwd_attention", check_attention_bwd),
     ("bwd_attention_cross77", lambda: check_attention_bwd(Nkv=77)),
     ("bwd_attention_small", lambda: check_attention_bwd(B=3, heads=2, kept=(2, 0, 1), Nq=64, Nkv=64)),

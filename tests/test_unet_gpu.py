@@ -41,3 +41,10 @@ def test_tiny_pruned_static_expert_matches_pruned_oracle():
     res, gap = U.check_pruned_expert()
     _assert(res)
     assert gap > U.MAX_ABS_TOL, gap  # the case really separates prune() from gate semantics
+
+
+def test_full_sd21_hard_b8_h64_eight_codes():
+    """SURVEY 8(d) config 2 parity slice: full-size SD-2.1 weights, 64x64 latents, 8 samples on 8 distinct codes (width +
+    depth gating), GroupNorm beta != 0; bf16 CUDA path vs the fp32 CPU oracle."""
+    import unet_checks as U
+    _assert(U.check_hard(tiny=False, B=8, H=64, code_ids=(0, 1, 2, 3, 4, 5, 6, 7), beta_std=0.1))
