@@ -109,6 +109,10 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "aptp_macs_ratio_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                     c_int, c_void_p]),
+    "aptp_groupnorm_bwd_affine": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "aptp_layernorm_affine_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "aptp_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "aptp_pred_losses_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

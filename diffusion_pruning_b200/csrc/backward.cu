@@ -261,12 +261,16 @@ __device__ __forceinline__ float silu_grad(float y) {
   return s * (1.f + y * (1.f - s));
 }
 
-__global__ void __launch_bounds__(BW_THREADS) gn_bwd_stats_kernel(GnB a, float* __restrict__ bstats, int ppc) {
+// kAffine: also accumulate the affine gradients daffine[c] = (dgamma, dbeta) = (sum dy xh, sum dy) over all samples and
+// pixels (dy = dL/d(xh gamma + beta), i.e. after the SiLU derivative) -- the weight-training backward of nn.GroupNorm.
+template <bool kAffine>
+__global__ void __launch_bounds__(BW_THREADS) gn_bwd_stats_kernel(GnB a, float* __restrict__ bstats,
+                                                                  float* __restrict__ daffine, int ppc) {
   extern __shared__ float bins[];
   const Geo g = make_geo(a.C, a.hw, ppc);
-  float acc[2][8];
+  float acc[2][8], aff[2][8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
+  for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = aff[0][e] = aff[1][e] = 0.f;
   if (g.v_ok) {
     float mean[8], rstd[8], gm[8], bt[8], gt[8];
     gn_coeffs(a, g.b, g.c0, mean, rstd, gm, bt, gt);
@@ -297,11 +301,19 @@ __global__ void __launch_bounds__(BW_THREADS) gn_bwd_stats_kernel(GnB a, float* 
           const float dxh = dy * gm[e];
           acc[0][e] += dxh;
           acc[1][e] += dxh * xh;
+          if (kAffine) {
+            aff[0][e] += dy * xh;
+            aff[1][e] += dy;
+          }
         }
       }
     }
   }
   reduce_groups<2>(bins, acc, g.c0, a.C, a.gs, g.v_ok, bstats, a.stats_groups, g.b);
+  if (kAffine) {
+    __syncthreads();  // the bins are reused: per-channel "groups" of one, destination [C][2], no sample index
+    reduce_groups<2>(bins, aff, g.c0, a.C, 1, g.v_ok, daffine, 0, 0);
+  }
 }
 
 __global__ void __launch_bounds__(BW_THREADS)
@@ -435,6 +447,79 @@ __global__ void __launch_bounds__(256)
       for (int e = 0; e < 8; ++e) o[e] += rstd * (fd[q][e] - m1 - fx[q][e] * m2);
       stv(dx + row * lddx + v * 8, pack8b(o));
     }
+  }
+}
+
+// LayerNorm affine gradients: daffine[c] = (dgamma, dbeta) = (sum_rows dy xh, sum_rows dy). Persistent warps stride over
+// the rows with the statistics recomputed per row (exact two-pass, like the forward); per-lane sums meet in shared
+// memory and leave the CTA as one atomic per (channel, quantity).
+template <int SLOTS>
+__global__ void __launch_bounds__(256)
+    layernorm_affine_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ dy, int lddy,
+                                long long rows, int C, float eps, float* __restrict__ daffine) {
+  extern __shared__ float sh_aff[];  // [2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cv = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sh_aff[i] = 0.f;
+  __syncthreads();
+  float ag[SLOTS][8], ab[SLOTS][8];
+#pragma unroll
+  for (int q = 0; q < SLOTS; ++q)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ag[q][e] = ab[q][e] = 0.f;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+    float fx[SLOTS][8], fd[SLOTS][8];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      const int v = lane + q * 32;
+      if (v < cv) {
+        unpack8b(ldv(x + row * ldx + v * 8), fx[q]);
+        unpack8b(ldv(dy + row * lddy + v * 8), fd[q]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) fx[q][e] = fd[q][e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += fx[q][e];
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      if (lane + q * 32 < cv) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = fx[q][e] - mean;
+          ss += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        ag[q][e] += fd[q][e] * (fx[q][e] - mean) * rstd;
+        ab[q][e] += fd[q][e];
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < SLOTS; ++q) {
+    const int v = lane + q * 32;
+    if (v < cv) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&sh_aff[v * 8 + e], ag[q][e]);
+        atomicAdd(&sh_aff[C + v * 8 + e], ab[q][e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    atomicAdd(&daffine[2 * i], sh_aff[i]);
+    atomicAdd(&daffine[2 * i + 1], sh_aff[C + i]);
   }
 }
 
@@ -638,11 +723,11 @@ extern "C" int aptp_geglu_bwd(const void* hg, int32_t ld, const void* df, int32_
   return APTP_OK;
 }
 
-extern "C" int aptp_groupnorm_bwd(const void* x, int32_t ldx, const void* da, int32_t ldda, void* dx, int32_t lddx,
+static int groupnorm_bwd_impl(const void* x, int32_t ldx, const void* da, int32_t ldda, void* dx, int32_t lddx,
                                   int32_t accumulate, int32_t batch, int32_t hw, int32_t C, int32_t group_size, float eps,
                                   const float* stats, int32_t stats_groups, const float* gamma, const float* beta,
                                   const float* gate, int32_t gate_ld, int32_t silu, float* bstats, float* dgate,
-                                  void* stream_) {
+                                  float* daffine, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   APTP_REQUIRE(x && da && dx && stats && gamma && beta && bstats, "aptp_groupnorm_bwd: null pointer");
   APTP_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldda % 8 == 0 && lddx % 8 == 0 && group_size > 0,
@@ -668,10 +753,58 @@ extern "C" int aptp_groupnorm_bwd(const void* x, int32_t ldx, const void* da, in
   a.silu = silu;
   BW_GRID(C, hw, batch);
   APTP_CUDA_CHECK(cudaMemsetAsync(bstats, 0, (size_t)batch * stats_groups * 2 * sizeof(float), stream));
-  gn_bwd_stats_kernel<<<grid, BW_THREADS, bins_bytes(C, group_size, 2), stream>>>(a, bstats, ppc);
+  if (daffine) {
+    const size_t sm = bins_bytes(C, group_size, 2) > bins_bytes(C, 1, 2) ? bins_bytes(C, group_size, 2) : bins_bytes(C, 1, 2);
+    gn_bwd_stats_kernel<true><<<grid, BW_THREADS, sm, stream>>>(a, bstats, daffine, ppc);
+  } else {
+    gn_bwd_stats_kernel<false><<<grid, BW_THREADS, bins_bytes(C, group_size, 2), stream>>>(a, bstats, nullptr, ppc);
+  }
   APTP_CUDA_CHECK(cudaGetLastError());
   gn_bwd_apply_kernel<<<grid, BW_THREADS, bins_bytes(C, group_size, 1), stream>>>(
       a, bstats, reinterpret_cast<__nv_bfloat16*>(dx), lddx, accumulate, gate ? dgate : nullptr, ppc);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_groupnorm_bwd(const void* x, int32_t ldx, const void* da, int32_t ldda, void* dx, int32_t lddx,
+                                  int32_t accumulate, int32_t batch, int32_t hw, int32_t C, int32_t group_size, float eps,
+                                  const float* stats, int32_t stats_groups, const float* gamma, const float* beta,
+                                  const float* gate, int32_t gate_ld, int32_t silu, float* bstats, float* dgate,
+                                  void* stream_) {
+  return groupnorm_bwd_impl(x, ldx, da, ldda, dx, lddx, accumulate, batch, hw, C, group_size, eps, stats, stats_groups, gamma,
+                            beta, gate, gate_ld, silu, bstats, dgate, nullptr, stream_);
+}
+
+extern "C" int aptp_groupnorm_bwd_affine(const void* x, int32_t ldx, const void* da, int32_t ldda, void* dx, int32_t lddx,
+                                         int32_t accumulate, int32_t batch, int32_t hw, int32_t C, int32_t group_size,
+                                         float eps, const float* stats, int32_t stats_groups, const float* gamma,
+                                         const float* beta, const float* gate, int32_t gate_ld, int32_t silu, float* bstats,
+                                         float* dgate, float* daffine, void* stream_) {
+  APTP_REQUIRE(daffine != nullptr, "aptp_groupnorm_bwd_affine: null daffine");
+  return groupnorm_bwd_impl(x, ldx, da, ldda, dx, lddx, accumulate, batch, hw, C, group_size, eps, stats, stats_groups, gamma,
+                            beta, gate, gate_ld, silu, bstats, dgate, daffine, stream_);
+}
+
+extern "C" int aptp_layernorm_affine_bwd(const void* x, int32_t ldx, const void* dy, int32_t lddy, int64_t rows, int32_t C,
+                                         float eps, float* daffine, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(x && dy && daffine, "aptp_layernorm_affine_bwd: null pointer");
+  APTP_REQUIRE(C % 8 == 0 && C <= 32 * 8 * 5 && ldx % 8 == 0 && lddy % 8 == 0,
+               "aptp_layernorm_affine_bwd: unsupported C=%d (multiple of 8, at most 1280)", C);
+  if (rows == 0) return APTP_OK;
+  const int slots = (C / 8 + 31) / 32;
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  const size_t sm = (size_t)2 * C * sizeof(float);
+#define APTP_LNA_LAUNCH(S)                                                                                       \
+  layernorm_affine_bwd_kernel<S><<<(unsigned)blocks, 256, sm, stream>>>(                                         \
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<const __nv_bfloat16*>(dy), lddy, rows, C, eps, daffine)
+  if (slots <= 1) APTP_LNA_LAUNCH(1);
+  else if (slots == 2) APTP_LNA_LAUNCH(2);
+  else if (slots == 3) APTP_LNA_LAUNCH(3);
+  else APTP_LNA_LAUNCH(5);
+#undef APTP_LNA_LAUNCH
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

@@ -389,3 +389,17 @@ def wgrad(dy, ld_dy, a, ld_a, dw, dbias, rows, n_out, k_in, conv=None, splits=0)
         splits = max(1, min(n_stages, (4 * 148 + tiles - 1) // tiles))
     check(load().aptp_wgrad(_ptr(dy), ld_dy, _ptr(a), ld_a, _ptr(dw), dw.stride(0), _ptr(dbias), rows, n_out, k_in,
                             int(conv is not None), batch, H, W, bw, bh, bb, splits, _stream()), "aptp_wgrad")
+
+
+def groupnorm_bwd_affine(x, ldx, da, ldda, dx, lddx, accumulate, batch, hw, C_, group_size, eps, stats, stats_groups, gamma,
+                         beta, gate, gate_ld, silu, bstats, dgate, daffine):
+    """groupnorm_bwd that also accumulates daffine [C, 2] = (dgamma, dbeta)."""
+    check(load().aptp_groupnorm_bwd_affine(_ptr(x), ldx, _ptr(da), ldda, _ptr(dx), lddx, int(accumulate), batch, hw, C_,
+                                           group_size, eps, _ptr(stats), stats_groups, _ptr(gamma), _ptr(beta), _ptr(gate),
+                                           gate_ld, int(silu), _ptr(bstats), _ptr(dgate), _ptr(daffine), _stream()),
+          "aptp_groupnorm_bwd_affine")
+
+
+def layernorm_affine_bwd(x, ldx, dy, lddy, rows, C_, eps, daffine):
+    check(load().aptp_layernorm_affine_bwd(_ptr(x), ldx, _ptr(dy), lddy, rows, C_, eps, _ptr(daffine), _stream()),
+          "aptp_layernorm_affine_bwd")

@@ -338,6 +338,18 @@ int aptp_wgrad(const void* dy, int32_t ld_dy, const void* a, int32_t ld_a, float
                int64_t rows, int32_t n_out, int32_t k_in, int32_t conv3x3, int32_t batch, int32_t H, int32_t W,
                int32_t bw, int32_t bh, int32_t bb, int32_t splits, void* stream);
 
+/* Weight-training variants of the norm backward (affine parameters trainable, as in the fine-tune stage):
+ * aptp_groupnorm_bwd_affine = aptp_groupnorm_bwd that ALSO accumulates daffine[c] = (dgamma[c], dbeta[c]) (fp32 [C][2],
+ * caller zeroes) in the same pass over x and da; aptp_layernorm_affine_bwd accumulates the same pair for LayerNorm
+ * (dy = gradient of the LayerNorm output) in one extra pass with per-row statistics recomputed. */
+int aptp_groupnorm_bwd_affine(const void* x, int32_t ldx, const void* da, int32_t ldda, void* dx, int32_t lddx,
+                              int32_t accumulate, int32_t batch, int32_t hw, int32_t C, int32_t group_size, float eps,
+                              const float* stats, int32_t stats_groups, const float* gamma, const float* beta,
+                              const float* gate, int32_t gate_ld, int32_t silu, float* bstats, float* dgate,
+                              float* daffine, void* stream);
+int aptp_layernorm_affine_bwd(const void* x, int32_t ldx, const void* dy, int32_t lddy, int64_t rows, int32_t C, float eps,
+                              float* daffine, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,49 @@ def check_groupnorm_bwd(B=3, hw=256, C=320, groups=32, silu=True, use_gate=True,
         _close(dg, g.grad, 0.3, 2e-2, "groupnorm_bwd dgate")
 
 
+def check_groupnorm_affine(B=3, hw=200, C=320, groups=32, silu=True, use_gate=False, seed=5):
+    """aptp_groupnorm_bwd_affine: dx as before plus (dgamma, dbeta) vs autograd."""
+    gs = C // groups
+    x = (_rand(B * hw, C, seed=seed) * 2 + 0.5).bfloat16()
+    da = _rand(B * hw, C, seed=seed + 1).bfloat16()
+    gamma = _rand(C, seed=seed + 2) * 0.2 + 1
+    beta = _rand(C, seed=seed + 3) * 0.2
+    gate = (torch.rand(B, groups, device=DEV) * 0.9 + 0.05) if use_gate else None
+    stats = torch.zeros(B, groups, 2, device=DEV)
+    K.groupnorm_stats(x, C, C, None, 0, 0, B, hw, gs, None, stats, groups)
+    dx = torch.full_like(x, float("nan"))
+    bstats = torch.empty(B, groups, 2, device=DEV)
+    dg = torch.zeros(B, groups, device=DEV)
+    daff = torch.zeros(C, 2, device=DEV)
+    K.groupnorm_bwd_affine(x, C, da, C, dx, C, False, B, hw, C, gs, 1e-5, stats, groups, gamma, beta, gate, groups, silu,
+                           bstats, dg if use_gate else None, daff)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    xin = xr.reshape(B, hw, C).permute(0, 2, 1)
+    if use_gate:
+        xin = xin * gate.repeat_interleave(gs, 1)[:, :, None]
+    y = F.group_norm(xin, groups, gr, br, 1e-5)
+    if silu:
+        y = F.silu(y)
+    y.backward(da.float().reshape(B, hw, C).permute(0, 2, 1))
+    _close(dx, xr.grad, 3e-2, 2e-2, "groupnorm_bwd_affine dx")
+    _close(daff[:, 0], gr.grad, 2e-2 * gr.grad.abs().max().item(), 1e-2, "groupnorm dgamma")
+    _close(daff[:, 1], br.grad, 2e-2 * br.grad.abs().max().item(), 1e-2, "groupnorm dbeta")
+
+
+def check_layernorm_affine(rows=777, C=640, seed=6):
+    x = (_rand(rows, C, seed=seed) * 3 + 1).bfloat16()
+    dy = _rand(rows, C, seed=seed + 1).bfloat16()
+    daff = torch.zeros(C, 2, device=DEV)
+    K.layernorm_affine_bwd(x, C, dy, C, rows, C, 1e-5, daff)
+    xr = x.float()
+    g = torch.ones(C, device=DEV, requires_grad=True)
+    b = torch.zeros(C, device=DEV, requires_grad=True)
+    F.layer_norm(xr, (C,), g, b, 1e-5).backward(dy.float())
+    _close(daff[:, 0], g.grad, 2e-3 * g.grad.abs().max().item(), 2e-3, "layernorm dgamma")
+    _close(daff[:, 1], b.grad, 2e-3 * b.grad.abs().max().item(), 2e-3, "layernorm dbeta")
+
+
 def check_layernorm_bwd(rows=777, C=640, accumulate=True, seed=0):
     x = (_rand(rows, C, seed=seed) * 3 + 1).bfloat16()
     dy = _rand(rows, C, seed=seed + 1).bfloat16()
@@ -220,6 +263,11 @@ def check_wgrad_conv(B=2, H=16, W=16, cin=72, cout=136, splits=0, seed=3):
 
 
 ALL = [
+    ("affine_groupnorm", check_groupnorm_affine),
+    ("affine_groupnorm_gate_plain", lambda: check_groupnorm_affine(B=2, hw=64, C=1280, silu=False, use_gate=True)),
+    ("affine_layernorm", check_layernorm_affine),
+    ("affine_layernorm_320", lambda: check_layernorm_affine(rows=4100, C=320)),
+    ("affine_layernorm_1280", lambda: check_layernorm_affine(rows=64, C=1280)),
     ("wgrad_linear", check_wgrad_linear),
     ("wgrad_linear_1split", lambda: check_wgrad_linear(rows=4096, n_out=320, k_in=320, ld_extra=0, splits=1)),
     ("wgrad_linear_small", lambda: check_wgrad_linear(rows=77, n_out=64, k_in=1024, splits=0)),

@@ -48,3 +48,14 @@ def test_full_sd21_hard_b8_h64_eight_codes():
     depth gating), GroupNorm beta != 0; bf16 CUDA path vs the fp32 CPU oracle."""
     import unet_checks as U
     _assert(U.check_hard(tiny=False, B=8, H=64, code_ids=(0, 1, 2, 3, 4, 5, 6, 7), beta_std=0.1))
+
+
+@pytest.mark.parametrize("B,H,code_ids", [
+    (1, 32, (5,)),                 # a single sample / single expert
+    (5, 16, (2, 2, 2, 2, 2)),      # odd batch, every sample on the same expert (one bucket)
+    (2, 96, (1, 6)),               # sampling resolution: 9216 / 2304 / 576 / 144 tokens (ragged last key tiles)
+    (3, 24, (0, 7, 4)),            # 24x24: 8x8x2 conv boxes with a partial batch box, 576 / 144 / 36 / 9 tokens
+])
+def test_tiny_hard_edge_shapes(B, H, code_ids):
+    import unet_checks as U
+    _assert(U.check_hard(B=B, H=H, code_ids=code_ids, beta_std=0.1))
