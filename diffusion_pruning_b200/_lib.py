@@ -113,6 +113,7 @@ SIGNATURES = {
                                           c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_void_p, c_void_p, c_void_p, c_void_p]),
     "aptp_layernorm_affine_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p]),
+    "aptp_col_sum_groups": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "aptp_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "aptp_pred_losses_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -31,7 +31,8 @@ struct WgradParams {
   float* dw;
   long long ld_dw;
   int n_out, k_in, taps;
-  int conv;               // 0: linear (2-D maps), 1: 3x3 stride-1 conv (4-D maps)
+  int conv;               // 0: linear (2-D maps), 1: 3x3 stride-1 conv (4-D maps), 2: 3x3 stride-2 conv (5-D map of a)
+  int ld_a;               // pitch of a (stride-2 view: the two x-parities sit ld_a apart in the fastest dimension)
   int bw, bh, bb;         // pixel box of a stage (bw * bh * bb == 128)
   int Wt, Ht, Bt;         // boxes per image row / column / batch
   int n_stages;           // row stages in total
@@ -91,11 +92,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         mbar_expect_tx(&full_bar[stage], WG_STAGE_BYTES);
         if (p.conv) {
           const int bx = s % p.Wt, by = (s / p.Wt) % p.Ht, bz = s / (p.Wt * p.Ht);
-          const int x0 = bx * p.bw, y0 = by * p.bh, b0 = bz * p.bb;
+          const int x0 = bx * p.bw, y0 = by * p.bh, b0 = bz * p.bb;  // box origin in OUTPUT pixels
           tma_load_4d(st, &p.tmap_dy, &full_bar[stage], n0, x0, y0, b0);
           tma_load_4d(st + WG_ATOM_BYTES, &p.tmap_dy, &full_bar[stage], n0 + 64, x0, y0, b0);
-          tma_load_4d(st + 2 * WG_ATOM_BYTES, &p.tmap_a, &full_bar[stage], c0, x0 + dx, y0 + dy, b0);
-          tma_load_4d(st + 3 * WG_ATOM_BYTES, &p.tmap_a, &full_bar[stage], c0 + 64, x0 + dx, y0 + dy, b0);
+          if (p.conv == 1) {
+            tma_load_4d(st + 2 * WG_ATOM_BYTES, &p.tmap_a, &full_bar[stage], c0, x0 + dx, y0 + dy, b0);
+            tma_load_4d(st + 3 * WG_ATOM_BYTES, &p.tmap_a, &full_bar[stage], c0 + 64, x0 + dx, y0 + dy, b0);
+          } else {
+            // input y = 2 oy + dy: dy = -1 -> (parity 1, shift -1); 0 -> (0, 0); +1 -> (1, 0)   (same for x)
+            const int py = (dy == 0) ? 0 : 1, sy = (dy < 0) ? -1 : 0;
+            const int px = (dx == 0) ? 0 : 1, sx = (dx < 0) ? -1 : 0;
+            tma_load_5d(st + 2 * WG_ATOM_BYTES, &p.tmap_a, &full_bar[stage], px * p.ld_a + c0, x0 + sx, py, y0 + sy, b0);
+            tma_load_5d(st + 3 * WG_ATOM_BYTES, &p.tmap_a, &full_bar[stage], px * p.ld_a + c0 + 64, x0 + sx, py, y0 + sy,
+                        b0);
+          }
         } else {
           const int r0 = s * WG_ROWS;
           tma_load_2d(st, &p.tmap_dy, &full_bar[stage], n0, r0);
@@ -197,6 +207,39 @@ __global__ void __launch_bounds__(256) col_sum_kernel(const __nv_bfloat16* __res
   }
 }
 
+// out[g, n] += sum over the rows of group g (rows_per_group consecutive rows) of dy[row, n]
+__global__ void __launch_bounds__(256) col_sum_groups_kernel(const __nv_bfloat16* __restrict__ dy, int ld, int rows_per_group,
+                                                             int n_out, float* __restrict__ out, int out_ld, int chunks,
+                                                             int rows_per_cta) {
+  __shared__ float red[32][65];
+  const int v = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int col = blockIdx.x * 64 + v * 8;
+  const int grp = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
+  const long long base = (long long)grp * rows_per_group;
+  const int r_begin = chunk * rows_per_cta;
+  const int r_end = min(rows_per_group, r_begin + rows_per_cta);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < n_out) {
+    for (int r = r_begin + rl; r < r_end; r += 32) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(dy + (base + r) * ld + col));
+      acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x);
+      acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+      acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z);
+      acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][v * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < n_out) atomicAdd(out + (size_t)grp * out_ld + c, s);
+  }
+}
+
 static int g_wg_smem_set = 0;
 
 }  // namespace aptp
@@ -218,22 +261,36 @@ extern "C" int aptp_wgrad(const void* dy, int32_t ld_dy, const void* a, int32_t 
   WgradParams p;
   memset(&p, 0, sizeof(p));
   if (conv3x3) {
-    APTP_REQUIRE((int64_t)batch * H * W == rows, "aptp_wgrad: rows != batch * H * W");
-    APTP_REQUIRE(bw * bh * bb == WG_ROWS && W % bw == 0 && H % bh == 0,
+    // H, W = INPUT size; the reduction runs over the output pixels (Ho x Wo = H x W, or H/2 x W/2 for stride 2)
+    APTP_REQUIRE(conv3x3 == 1 || conv3x3 == 2, "aptp_wgrad: conv3x3 must be 0 (linear), 1 (stride 1) or 2 (stride 2)");
+    const int Ho = conv3x3 == 2 ? H / 2 : H, Wo = conv3x3 == 2 ? W / 2 : W;
+    APTP_REQUIRE(conv3x3 == 1 || (H % 2 == 0 && W % 2 == 0 && k_in == ld_a),
+                 "aptp_wgrad: the stride-2 conv needs even H, W and k_in == ld_a");
+    APTP_REQUIRE((int64_t)batch * Ho * Wo == rows, "aptp_wgrad: rows != batch * Ho * Wo");
+    APTP_REQUIRE(bw * bh * bb == WG_ROWS && Wo % bw == 0 && Ho % bh == 0,
                  "aptp_wgrad: the pixel box must hold 128 pixels and tile the image");  // a partial batch box is zero-filled
-    uint64_t dims_y[4] = {(uint64_t)n_out, (uint64_t)W, (uint64_t)H, (uint64_t)batch};
-    uint64_t str_y[3] = {(uint64_t)ld_dy * 2, (uint64_t)W * ld_dy * 2, (uint64_t)H * W * ld_dy * 2};
-    uint64_t dims_a[4] = {(uint64_t)k_in, (uint64_t)W, (uint64_t)H, (uint64_t)batch};
-    uint64_t str_a[3] = {(uint64_t)ld_a * 2, (uint64_t)W * ld_a * 2, (uint64_t)H * W * ld_a * 2};
+    uint64_t dims_y[4] = {(uint64_t)n_out, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)batch};
+    uint64_t str_y[3] = {(uint64_t)ld_dy * 2, (uint64_t)Wo * ld_dy * 2, (uint64_t)Ho * Wo * ld_dy * 2};
     uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
     int rc = make_tmap_bf16(&p.tmap_dy, dy, 4, dims_y, str_y, box);
-    rc = rc ? rc : make_tmap_bf16(&p.tmap_a, a, 4, dims_a, str_a, box);
+    if (conv3x3 == 1) {
+      uint64_t dims_a[4] = {(uint64_t)k_in, (uint64_t)W, (uint64_t)H, (uint64_t)batch};
+      uint64_t str_a[3] = {(uint64_t)ld_a * 2, (uint64_t)W * ld_a * 2, (uint64_t)H * W * ld_a * 2};
+      rc = rc ? rc : make_tmap_bf16(&p.tmap_a, a, 4, dims_a, str_a, box);
+    } else {
+      // view [b][H/2][2][W/2][2][C] as dims (fastest first): (px*C + c), W/2, py, H/2, b -- as the forward implicit GEMM
+      uint64_t dims_a[5] = {(uint64_t)2 * ld_a, (uint64_t)Wo, 2, (uint64_t)Ho, (uint64_t)batch};
+      uint64_t str_a[4] = {(uint64_t)2 * ld_a * 2, (uint64_t)W * ld_a * 2, (uint64_t)2 * W * ld_a * 2,
+                           (uint64_t)H * W * ld_a * 2};
+      uint32_t box5[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bb};
+      rc = rc ? rc : make_tmap_bf16(&p.tmap_a, a, 5, dims_a, str_a, box5);
+    }
     if (rc) return rc;
     p.bw = bw;
     p.bh = bh;
     p.bb = bb;
-    p.Wt = W / bw;
-    p.Ht = H / bh;
+    p.Wt = Wo / bw;
+    p.Ht = Ho / bh;
     p.Bt = (batch + bb - 1) / bb;
     p.n_stages = p.Wt * p.Ht * p.Bt;
   } else {
@@ -247,7 +304,8 @@ extern "C" int aptp_wgrad(const void* dy, int32_t ld_dy, const void* a, int32_t 
     if (rc) return rc;
     p.n_stages = (int)((rows + WG_ROWS - 1) / WG_ROWS);
   }
-  p.conv = conv3x3 ? 1 : 0;
+  p.conv = conv3x3;
+  p.ld_a = ld_a;
   p.dw = dw;
   p.ld_dw = ld_dw;
   p.n_out = n_out;
@@ -273,5 +331,22 @@ extern "C" int aptp_wgrad(const void* dy, int32_t ld_dy, const void* a, int32_t 
                                             rows_per_cta);
     APTP_CUDA_CHECK(cudaGetLastError());
   }
+  return APTP_OK;
+}
+
+extern "C" int aptp_col_sum_groups(const void* dy, int32_t ld, int32_t groups, int32_t rows_per_group, int32_t n_out,
+                                   float* out, int32_t out_ld, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(dy && out, "aptp_col_sum_groups: null pointer");
+  APTP_REQUIRE(ld % 8 == 0 && n_out > 0 && n_out % 8 == 0 && rows_per_group > 0 && out_ld >= n_out,
+               "aptp_col_sum_groups: bad sizes");
+  if (groups == 0) return APTP_OK;
+  const int rows_per_cta = 2048;
+  const int chunks = (rows_per_group + rows_per_cta - 1) / rows_per_cta;
+  APTP_REQUIRE((long long)groups * chunks <= 65535, "aptp_col_sum_groups: grid too large");
+  dim3 grid((n_out + 63) / 64, (unsigned)(groups * chunks));
+  col_sum_groups_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld, rows_per_group, n_out, out,
+                                                 out_ld, chunks, rows_per_cta);
+  APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

@@ -373,14 +373,15 @@ def macs_ratio_bwd(arch, gates_dev, n_gates, subs_dev, n_subs, dcur, darch):
 # --------------------------------------------------------------------------------------------
 # K8: weight gradients
 # --------------------------------------------------------------------------------------------
-def wgrad(dy, ld_dy, a, ld_a, dw, dbias, rows, n_out, k_in, conv=None, splits=0):
-    """dw [n_out, taps * k_in] fp32 (+)= dy^T a over the rows; conv = (batch, H, W) selects the 3x3 taps (OHWI layout).
-    splits = 0 picks a split-K factor that fills the GPU."""
+def wgrad(dy, ld_dy, a, ld_a, dw, dbias, rows, n_out, k_in, conv=None, splits=0, stride=1):
+    """dw [n_out, taps * k_in] fp32 (+)= dy^T a over the rows; conv = (batch, H, W) of the INPUT selects the 3x3 taps
+    (OHWI layout), stride 1 or 2. splits = 0 picks a split-K factor that fills the GPU."""
     taps = 9 if conv is not None else 1
     if conv is not None:
         batch, H, W = conv
-        bw, bh, bb = conv_box(W, H)
-        n_stages = (W // bw) * (H // bh) * (batch // bb)
+        Ho, Wo = H // stride, W // stride
+        bw, bh, bb = conv_box(Wo, Ho)
+        n_stages = (Wo // bw) * (Ho // bh) * ((batch + bb - 1) // bb)
     else:
         batch = H = W = bw = bh = bb = 1
         n_stages = (rows + 127) // 128
@@ -388,7 +389,12 @@ def wgrad(dy, ld_dy, a, ld_a, dw, dbias, rows, n_out, k_in, conv=None, splits=0)
         tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128) * taps
         splits = max(1, min(n_stages, (4 * 148 + tiles - 1) // tiles))
     check(load().aptp_wgrad(_ptr(dy), ld_dy, _ptr(a), ld_a, _ptr(dw), dw.stride(0), _ptr(dbias), rows, n_out, k_in,
-                            int(conv is not None), batch, H, W, bw, bh, bb, splits, _stream()), "aptp_wgrad")
+                            (stride if conv is not None else 0), batch, H, W, bw, bh, bb, splits, _stream()), "aptp_wgrad")
+
+
+def col_sum_groups(dy, ld, groups, rows_per_group, n_out, out):
+    check(load().aptp_col_sum_groups(_ptr(dy), ld, groups, rows_per_group, n_out, _ptr(out), out.stride(0), _stream()),
+          "aptp_col_sum_groups")
 
 
 def groupnorm_bwd_affine(x, ldx, da, ldda, dx, lddx, accumulate, batch, hw, C_, group_size, eps, stats, stats_groups, gamma,

@@ -42,6 +42,34 @@ class TrainEngine(_Engine):
         f = torch.zeros if zero else torch.empty
         return f(rows, cols, device=self.device, dtype=dtype)
 
+    # ---- weight gradients (fine-tune stage: every U-Net parameter trains, trainer.py:1683-1765) ----------
+    train_weights = False  # set by UNetFineTuneFunction; the pruning stage keeps the U-Net frozen
+
+    def _wg_buf(self, param: torch.Tensor, shape) -> torch.Tensor:
+        """fp32 accumulator of one parameter's gradient in KERNEL layout (OHWI for convs, [C, 2] = (gamma, beta) pairs
+        are handled by _affine): zero-filled once per step, the kernels accumulate into it."""
+        g = self.wg.get(id(param))
+        if g is None:
+            g = torch.zeros(*shape, device=self.device, dtype=torch.float32)
+            self.wg[id(param)] = g
+        return g
+
+    def _wgrad(self, weight, bias, dy: torch.Tensor, ld_dy: int, a: torch.Tensor, ld_a: int, rows: int, n_out: int,
+               k_in: int, conv=None, stride: int = 1):
+        if not self.train_weights:
+            return
+        taps = 9 if conv is not None else 1
+        dw = self._wg_buf(weight, (n_out, taps * k_in))
+        db = self._wg_buf(bias, (n_out,)) if bias is not None else None
+        K.wgrad(dy, ld_dy, a, ld_a, dw, db, rows, n_out, k_in, conv=conv, stride=stride)
+        self.launches += 1
+
+    def _affine(self, norm: nn.Module) -> Optional[torch.Tensor]:
+        """[C, 2] accumulator of (dgamma, dbeta) of a GroupNorm / LayerNorm, or None when the weights are frozen."""
+        if not self.train_weights:
+            return None
+        return self._wg_buf(norm.weight, (norm.weight.shape[0], 2))
+
     def _mm(self, key, a: torch.Tensor, a_ld: int, a_k: int, M: int, w: torch.Tensor, N: int, out: torch.Tensor,
             out_ld: int, *, bias=None, residual=None, res_ld=0, rows_per_sample=1, flags=0, out_col_off=0,
             conv: Optional[Tuple[int, int, int]] = None, k_tap_pitch=0, rowvec=None, rowvec_ld=0, out_mode=OUT_BF16):
@@ -85,6 +113,14 @@ class TrainEngine(_Engine):
     def _w(self, name: str, mod: nn.Module) -> Dict[str, torch.Tensor]:
         return self._dense_linear(name, mod)
 
+    def _gn_again(self, x: torch.Tensor, ld: int, C: int, B: int, hw: int, groups: int, eps: float, gamma, beta,
+                  out: torch.Tensor, silu: bool, stats: torch.Tensor, gate=None):
+        """Recompute a GroupNorm(+gate, +SiLU) output from the statistics saved on the tape (one HBM pass): the
+        activations feeding a conv / linear are not kept for the backward, only the block inputs are."""
+        K.groupnorm_apply(x, C, ld, None, 0, 0, out, C, B, hw, C // groups, eps, stats, groups, gamma, beta, C, None, None,
+                          gate, gate.stride(0) if gate is not None else groups, silu)
+        self.launches += 1
+
     def _gn_fwd(self, x: torch.Tensor, ld: int, C: int, B: int, hw: int, groups: int, eps: float, gamma, beta,
                 out: torch.Tensor, silu: bool, gate=None) -> torch.Tensor:
         stats = self._take_stats(B, groups)
@@ -113,10 +149,15 @@ class TrainEngine(_Engine):
         return self.darch[:, s:e]
 
     def _gn_bwd(self, x, ld, C, B, hw, groups, eps, stats, gamma, beta, da, dx: torch.Tensor, lddx: int,
-                accumulate: bool, silu: bool, gate=None, dgate=None):
+                accumulate: bool, silu: bool, gate=None, dgate=None, daffine=None):
         bstats = self.buf("gn_bstats", B, groups * 2, torch.float32)
-        K.groupnorm_bwd(x, ld, da, C, dx, lddx, accumulate, B, hw, C, C // groups, eps, stats, groups, gamma, beta, gate,
-                        gate.stride(0) if gate is not None else groups, silu, bstats, dgate)
+        gld = gate.stride(0) if gate is not None else groups
+        if daffine is not None:
+            K.groupnorm_bwd_affine(x, ld, da, C, dx, lddx, accumulate, B, hw, C, C // groups, eps, stats, groups, gamma,
+                                   beta, gate, gld, silu, bstats, dgate, daffine)
+        else:
+            K.groupnorm_bwd(x, ld, da, C, dx, lddx, accumulate, B, hw, C, C // groups, eps, stats, groups, gamma, beta,
+                            gate, gld, silu, bstats, dgate)
         self.launches += 2
 
     # ------------------------------------------------------------------------------------------
@@ -161,6 +202,8 @@ class TrainEngine(_Engine):
             timestep = torch.tensor([float(timestep)], device=self.device)
         sample = sample.detach().to(self.device, torch.float32).contiguous()
         ctx = ctx.detach().to(self.device).contiguous()
+        self.wg: Dict[int, torch.Tensor] = {}
+        self.param_grads: Dict[int, torch.Tensor] = {}
         self.n_ctx = ctx.shape[1]
         cdim = ctx.shape[2]
         ctx16 = self.buf("ctx", B * self.n_ctx, cdim)
@@ -171,6 +214,19 @@ class TrainEngine(_Engine):
         self.ctx = ctx16
         self.time_embed(timestep)
         c0 = m.config["block_out_channels"][0]
+        if self.train_weights:
+            # the time-embedding MLP stores only its activated outputs (SiLU fused into the epilogues); the weight
+            # backward needs the pre-activations: two more [B, 1280] GEMMs without the SiLU, fp32 out
+            tdim = c0 * 4
+            te_m = m.time_embedding
+            d1, d2 = self._dense_linear("te1", te_m.linear_1), self._dense_linear("te2", te_m.linear_2)
+            self.te_z1 = torch.empty(B, tdim, device=self.device, dtype=torch.float32)
+            self.te_z2 = torch.empty(B, tdim, device=self.device, dtype=torch.float32)
+            self._mm(("te1z",), self.buf("t_sin", B, c0), c0, c0, B, d1["w"], tdim, self.te_z1, tdim, bias=d1["b"],
+                     out_mode=OUT_F32)
+            self._mm(("te2z",), self.buf("t_h", B, tdim), tdim, tdim, B, d2["w"], tdim, self.te_z2, tdim, bias=d2["b"],
+                     out_mode=OUT_F32)
+            self.dproj_all = torch.zeros(B, m._temb_total, device=self.device, dtype=torch.float32)
         col = self.buf("im2col", B * H * W, 64)
         K.im2col_input(sample, col, B, cin, H, W)
         d = self.dense.get("conv_in")
@@ -183,6 +239,7 @@ class TrainEngine(_Engine):
         x0 = self._new(B * H * W, c0)
         self._mm("conv_in", col, 64, 64, B * H * W, d["w"], c0, x0, c0, bias=d["b"], rows_per_sample=H * W)
         x = Act(x0, B, H, W, c0)
+        self.x0_act, self.im2col = x, col
         taps: List[Act] = []
         skips = [x]
         for blk in m.down_blocks:
@@ -279,7 +336,7 @@ class TrainEngine(_Engine):
         B, H, W, hw, M = xin.B, xin.H, xin.W, xin.hw, xin.rows
         pk = self._resnet_pack(r)
         cidx = self.gate_cols[r.uid]
-        need_in = r.uid != self.first_uid
+        need_in = r.uid != self.first_uid or self.train_weights  # norm1 / conv1 gradients need the input-side pass
         dxin = None
         if r.depth_gate is not None:
             dxin = self._new(M, r.cin, zero=(s["keep"] != r.cin))
@@ -298,6 +355,7 @@ class TrainEngine(_Engine):
                     dxin = self._new(M, r.cin)
                 self._mm(("sc.T", r.uid), dyg.t, dyg.ld, r.cout, M, wt, r.cin, dxin, r.cin,
                          residual=dxin if have else None, res_ld=r.cin, rows_per_sample=hw)
+                self._wgrad(r.conv_shortcut.weight, r.conv_shortcut.bias, dyg.t, dyg.ld, xin.t, xin.ld, M, r.cout, r.cin)
             else:
                 if have:
                     K.add_rows(dyg.t, dyg.ld, dxin, r.cin, M, r.cout)
@@ -310,16 +368,33 @@ class TrainEngine(_Engine):
         da2 = self.buf("bw_a", M, r.cout)
         self._mm(("c2.T", r.uid), dyg.t, dyg.ld, r.cout, M, self._wT("c2." + r.uid, r.conv2), r.cout, da2, r.cout,
                  conv=(B, H, W), k_tap_pitch=r.cout, rows_per_sample=hw)
+        if self.train_weights:  # conv2: its input silu(GN2(gate * h1)) is recomputed from the saved statistics
+            a2 = self.buf("gn_b", M, r.cout)
+            self._gn_again(s["h1"], r.cout, r.cout, B, hw, r.groups, r.eps, pk["gamma2"], pk["beta2"], a2, True, s["st2"],
+                           gate=s["gate"])
+            self._wgrad(r.conv2.weight, r.conv2.bias, dyg.t, dyg.ld, a2, r.cout, M, r.cout, r.cout, conv=(B, H, W))
         dh1 = self.buf("bw_b", M, r.cout)
         self._gn_bwd(s["h1"], r.cout, r.cout, B, hw, r.groups, r.eps, s["st2"], pk["gamma2"], pk["beta2"], da2, dh1,
-                     r.cout, False, True, gate=s["gate"], dgate=self._dgate(cidx["w"][0]))
+                     r.cout, False, True, gate=s["gate"], dgate=self._dgate(cidx["w"][0]), daffine=self._affine(r.norm2))
         if not need_in:
             return None
+        if self.train_weights:
+            a1 = self.buf("gn_a", M, r.cin)
+            self._gn_again(xin.t, xin.ld, r.cin, B, hw, r.groups, r.eps, pk["g1"], pk["b1"], a1, True, s["st1"])
+            self._wgrad(r.conv1.weight, None, dh1, r.cout, a1, r.cin, M, r.cout, r.cin, conv=(B, H, W))
+            # h1 = conv1(a1) + (time_emb_proj(silu(temb)) + both biases)[b] broadcast over the sample's pixels
+            off = self.m._temb_off[r.uid]
+            K.col_sum_groups(dh1, r.cout, B, hw, r.cout, self.dproj_all[:, off:off + r.cout])
         da1 = self.buf("bw_c", M, r.cin)
         self._mm(("c1.T", r.uid), dh1, r.cout, r.cout, M, self._wT("c1." + r.uid, r.conv1), r.cin, da1, r.cin,
                  conv=(B, H, W), k_tap_pitch=r.cout, rows_per_sample=hw)
-        self._gn_bwd(xin.t, xin.ld, r.cin, B, hw, r.groups, r.eps, s["st1"], pk["g1"], pk["b1"], da1, dxin, r.cin, True,
-                     True)
+        if dxin is None:  # first resnet of the net when only the weights need this pass
+            dxin = self._new(M, r.cin)
+            self._gn_bwd(xin.t, xin.ld, r.cin, B, hw, r.groups, r.eps, s["st1"], pk["g1"], pk["b1"], da1, dxin, r.cin,
+                         False, True, daffine=self._affine(r.norm1))
+        else:
+            self._gn_bwd(xin.t, xin.ld, r.cin, B, hw, r.groups, r.eps, s["st1"], pk["g1"], pk["b1"], da1, dxin, r.cin,
+                         True, True, daffine=self._affine(r.norm1))
         return _G(dxin, r.cin, r.cin)
 
     # ---- transformer -----------------------------------------------------------------------------
@@ -374,14 +449,21 @@ class TrainEngine(_Engine):
         saved.update(o=o, lse=lse, gate=gate, sh=sh, n_kv=n_kv, cross=cross)
         return saved
 
-    def _b_attn(self, uid: str, attn, gate_idx: int, s: Dict[str, Any], dtok: torch.Tensor, B: int, hw: int, C: int):
-        """dtok is d(tok_out); returns d(ln) [M, C] (gradient of the LayerNorm output feeding q / qkv)."""
+    def _b_attn(self, uid: str, attn, gate_idx: int, s: Dict[str, Any], dtok: torch.Tensor, B: int, hw: int, C: int,
+                ln_in: Optional[torch.Tensor] = None, ln_g=None, ln_b=None):
+        """dtok is d(tok_out); returns d(ln) [M, C] (gradient of the LayerNorm output feeding q / qkv). ln_in / ln_g /
+        ln_b: input and affine of that LayerNorm, to recompute its output for the q / k / v weight gradients."""
         M = B * hw
         heads = attn.heads
         n_kv, cross = s["n_kv"], s["cross"]
         Mkv = B * n_kv
         do = self.buf("bw_do", M, C)
         self._mm(("o.T", uid), dtok, C, C, M, self._wT("o." + uid, attn.to_out[0]), C, do, C, rows_per_sample=hw)
+        self._wgrad(attn.to_out[0].weight, attn.to_out[0].bias, dtok, C, s["o"], C, M, C, C)
+        xn = None
+        if self.train_weights:
+            xn = self.buf("ln", M, C)
+            K.layernorm(ln_in, C, xn, C, M, C, 1e-5, ln_g, ln_b)
         delta = self.buf("bw_delta", B * heads, hw, torch.float32)
         gate = s["gate"]
         gld = gate.stride(0)
@@ -397,6 +479,11 @@ class TrainEngine(_Engine):
             K.scale_cols_bwd(s["uq"], C, dq, C, duq, C, B, hw, C, gate, gld, 64, dg)
             K.scale_cols_bwd(s["ukv"], 2 * C, dkv, 2 * C, dukv, 2 * C, B, n_kv, C, gate, gld, 64, dg)
             K.scale_cols_bwd(s["ukv"][:, C:], 2 * C, dkv[:, C:], 2 * C, dukv[:, C:], 2 * C, B, n_kv, C, gate, gld, 64, dg)
+            if self.train_weights:
+                self._wgrad(attn.to_q.weight, None, duq, C, xn, C, M, C, C)
+                dwkv = torch.zeros(2 * C, attn.ctx_dim, device=self.device, dtype=torch.float32)
+                K.wgrad(dukv, 2 * C, self.ctx, attn.ctx_dim, dwkv, None, Mkv, 2 * C, attn.ctx_dim)
+                self.wg[id(attn.to_k.weight)], self.wg[id(attn.to_v.weight)] = dwkv[:C], dwkv[C:]
             dln = self.buf("bw_dln", M, C)
             self._mm(("q.T", uid), duq, C, C, M, self._wT("q." + uid, attn.to_q), C, dln, C, rows_per_sample=hw)
         else:
@@ -408,6 +495,11 @@ class TrainEngine(_Engine):
             for j in range(3):
                 K.scale_cols_bwd(s["u"][:, j * C:], 3 * C, dqkv[:, j * C:], 3 * C, du[:, j * C:], 3 * C, B, hw, C,
                                  gate, gld, 64, dg)
+            if self.train_weights:
+                dwqkv = torch.zeros(3 * C, C, device=self.device, dtype=torch.float32)
+                K.wgrad(du, 3 * C, xn, C, dwqkv, None, M, 3 * C, C)
+                for j, lin in enumerate((attn.to_q, attn.to_k, attn.to_v)):
+                    self.wg[id(lin.weight)] = dwqkv[j * C:(j + 1) * C]
             key = "wqkv.T." + uid
             if key not in self.dense:
                 self.dense[key] = self.dense["wqkv." + uid].t().contiguous()  # [C, 3C]
@@ -449,7 +541,7 @@ class TrainEngine(_Engine):
         f = self.buf("ff", M, inner)
         K.geglu(hg, 2 * inner, f, inner, B, hw, inner, fgate, fgate.stride(0), inner // t.gate_width)
         w2 = self._w("ff2." + t.uid, tb.ff.net[2])
-        tok3 = self.buf("tok3", M, C)
+        tok3 = self._new(M, C) if self.train_weights else self.buf("tok3", M, C)  # proj_out's input (its wgrad needs it)
         self._mm(("ff2", t.uid), f, inner, inner, M, w2["w"], C, tok3, C, bias=w2["b"], residual=tok2, res_ld=C,
                  rows_per_sample=hw)
         po = self._w("po." + t.uid, t.proj_out)
@@ -464,7 +556,8 @@ class TrainEngine(_Engine):
         self.launches += 6
         o = Act(out, B, H, W, C)
         self.tape.append(("tr", t, dict(x=x, st=st, tok0=tok0, tok1=tok1, tok2=tok2, s1=s1, s2=s2, hg=hg, fgate=fgate,
-                                        inner=inner, y=y, d=d, out=o, dn=dn)))
+                                        inner=inner, y=y, d=d, out=o, dn=dn,
+                                        tok3=tok3 if self.train_weights else None)))
         return o
 
     def b_transformer(self, t: Transformer2DModelWidthGated, s: Dict[str, Any], dout: _G) -> _G:
@@ -488,27 +581,50 @@ class TrainEngine(_Engine):
             dx = dy  # out = proj_out(.) + x: the incoming buffer becomes dx after its last read as dy
         dtok = self._new(M, C)
         self._mm(("po.T", t.uid), dy, C, C, M, self._wT("po." + t.uid, t.proj_out), C, dtok, C, rows_per_sample=hw)
+        if self.train_weights:
+            self._wgrad(t.proj_out.weight, t.proj_out.bias, dy, C, s["tok3"], C, M, C, C)
         # feed-forward
         inner = s["inner"]
         df = self.buf("bw_df", M, inner)
         self._mm(("ff2.T", t.uid), dtok, C, C, M, self._wT("ff2." + t.uid, tb.ff.net[2]), inner, df, inner,
                  rows_per_sample=hw)
+        if self.train_weights:  # net.2's input f = GEGLU(hg) is recomputed
+            fg = s["fgate"]
+            f = self.buf("ff", M, inner)
+            K.geglu(s["hg"], 2 * inner, f, inner, B, hw, inner, fg, fg.stride(0), inner // t.gate_width)
+            self._wgrad(tb.ff.net[2].weight, tb.ff.net[2].bias, dtok, C, f, inner, M, C, inner)
         dhg = self.buf("bw_dhg", M, 2 * inner)
         K.geglu_bwd(s["hg"], 2 * inner, df, inner, dhg, 2 * inner, B, hw, inner, s["fgate"], s["fgate"].stride(0),
                     inner // t.gate_width, self._dgate(cidx["w"][2]))
+        if self.train_weights:
+            xn = self.buf("ln", M, C)
+            K.layernorm(s["tok2"], C, xn, C, M, C, 1e-5, dn["lg2"], dn["lb2"])
+            proj = tb.ff.net[0].proj
+            self._wgrad(proj.weight, proj.bias, dhg, 2 * inner, xn, C, M, 2 * inner, C)
         dln = self.buf("bw_dln", M, C)
         self._mm(("ffp.T", t.uid), dhg, 2 * inner, 2 * inner, M, self._wT("ffp." + t.uid, tb.ff.net[0].proj), C, dln, C,
                  rows_per_sample=hw)
+        if self.train_weights:
+            K.layernorm_affine_bwd(s["tok2"], C, dln, C, M, C, 1e-5, self._affine(tb.norm3))
         K.layernorm_bwd(s["tok2"], C, dln, C, dtok, C, True, M, C, 1e-5, dn["lg2"])
         # cross-attention, self-attention
-        dln = self._b_attn(t.uid + ".a2", tb.attn2, cidx["w"][1], s["s2"], dtok, B, hw, C)
+        dln = self._b_attn(t.uid + ".a2", tb.attn2, cidx["w"][1], s["s2"], dtok, B, hw, C, s["tok1"], dn["lg1"], dn["lb1"])
+        if self.train_weights:
+            K.layernorm_affine_bwd(s["tok1"], C, dln, C, M, C, 1e-5, self._affine(tb.norm2))
         K.layernorm_bwd(s["tok1"], C, dln, C, dtok, C, True, M, C, 1e-5, dn["lg1"])
-        dln = self._b_attn(t.uid + ".a1", tb.attn1, cidx["w"][0], s["s1"], dtok, B, hw, C)
+        dln = self._b_attn(t.uid + ".a1", tb.attn1, cidx["w"][0], s["s1"], dtok, B, hw, C, s["tok0"], dn["lg0"], dn["lb0"])
+        if self.train_weights:
+            K.layernorm_affine_bwd(s["tok0"], C, dln, C, M, C, 1e-5, self._affine(tb.norm1))
         K.layernorm_bwd(s["tok0"], C, dln, C, dtok, C, True, M, C, 1e-5, dn["lg0"])
         # proj_in, GroupNorm
+        if self.train_weights:
+            xn = self.buf("ln", M, C)
+            self._gn_again(x.t, x.ld, C, B, hw, t.groups, 1e-6, dn["g"], dn["b"], xn, False, s["st"])
+            self._wgrad(t.proj_in.weight, t.proj_in.bias, dtok, C, xn, C, M, C, C)
         dxn = self.buf("bw_dxn", M, C)
         self._mm(("pi.T", t.uid), dtok, C, C, M, self._wT("pi." + t.uid, t.proj_in), C, dxn, C, rows_per_sample=hw)
-        self._gn_bwd(x.t, x.ld, C, B, hw, t.groups, 1e-6, s["st"], dn["g"], dn["b"], dxn, dx, C, True, False)
+        self._gn_bwd(x.t, x.ld, C, B, hw, t.groups, 1e-6, s["st"], dn["g"], dn["b"], dxn, dx, C, True, False,
+                     daffine=self._affine(t.norm))
         self.launches += 8
         return _G(dx, C, C)
 
@@ -527,6 +643,10 @@ class TrainEngine(_Engine):
         if dout.ld != x.C:
             dyc = self._new(o.rows, x.C)
             K.copy_rows(dout.t, dout.ld, dyc, x.C, o.rows, x.C)
+        if self.train_weights:
+            assert x.ld == x.C, "stride-2 wgrad reads the input through a dense parity view"
+            self._wgrad(smp.conv.weight, smp.conv.bias, dyc, x.C, x.t, x.ld, o.rows, x.C, x.C, conv=(x.B, x.H, x.W),
+                        stride=2)
         up = self.buf("bw_zi", x.rows, x.C)
         K.zero_insert2x(dyc, up, x.B, o.H, o.W, x.C)
         dx = self._new(x.rows, x.C)
@@ -547,6 +667,10 @@ class TrainEngine(_Engine):
     def b_upsample(self, smp, s, dout: _G) -> _G:
         x: Act = s["x"]
         o: Act = s["out"]
+        if self.train_weights:  # the conv's input (nearest-neighbour 2x of x) is recomputed
+            xu = self.buf("up", o.rows, x.C)
+            K.upsample2x(x.t, xu, x.B, x.H, x.W, x.C)
+            self._wgrad(smp.conv.weight, smp.conv.bias, dout.t, dout.ld, xu, x.C, o.rows, x.C, x.C, conv=(o.B, o.H, o.W))
         dup = self.buf("bw_zi", o.rows, x.C)
         self._mm(("us.T", id(smp)), dout.t, dout.ld, x.C, o.rows, self._wT("us.%d" % id(smp), smp.conv), x.C, dup, x.C,
                  conv=(o.B, o.H, o.W), k_tap_pitch=x.C, rows_per_sample=o.hw)
@@ -591,9 +715,16 @@ class TrainEngine(_Engine):
             da = self.buf("bw_a", x.rows, x.C)
             self._mm(("conv_out.T",), dp, 64, 64, x.rows, self._wT("conv_out", m.conv_out, pad_out_to=64), x.C, da, x.C,
                      conv=(x.B, x.H, x.W), k_tap_pitch=64, rows_per_sample=x.hw)
+            if self.train_weights:  # conv_out: input silu(GN(x)) recomputed; dy is the 64-column padded prediction gradient
+                a = self.buf("gn_a", x.rows, x.C)
+                self._gn_again(x.t, x.ld, x.C, B, x.hw, groups, m.config["norm_eps"], dn["g"], dn["b"], a, True, stats)
+                dw64 = torch.zeros(64, 9 * x.C, device=self.device, dtype=torch.float32)
+                db64 = torch.zeros(64, device=self.device, dtype=torch.float32)
+                K.wgrad(dp, 64, a, x.C, dw64, db64, x.rows, 64, x.C, conv=(x.B, x.H, x.W))
+                self.wg[id(m.conv_out.weight)], self.wg[id(m.conv_out.bias)] = dw64[:cout], db64[:cout]
             dxl = self._new(x.rows, x.C)
             self._gn_bwd(x.t, x.ld, x.C, B, x.hw, groups, m.config["norm_eps"], stats, dn["g"], dn["b"], da, dxl, x.C,
-                         False, True)
+                         False, True, daffine=self._affine(m.conv_norm_out))
             self._acc(grads, x, _G(dxl, x.C, x.C))
         for act, dt in zip(self.tap_acts, dtaps):
             if dt is not None:
@@ -619,6 +750,8 @@ class TrainEngine(_Engine):
                 self._acc(grads, s["x"], self.b_downsample(mod, s, g))
             elif kind == "up":
                 self._acc(grads, s["x"], self.b_upsample(mod, s, g))
+        if self.train_weights:
+            self._finish_weight_grads(grads)
         self.darch[:, self.n_width:].add_(self.ddepth_T.t())
         d = self.darch
         if self.gate_rows != B:  # gates were tiled along the batch (gates.py:18-19): fold the copies back
@@ -626,6 +759,104 @@ class TrainEngine(_Engine):
         self.tape = []
         self.final = None
         return d
+
+
+def _silu_grad(z: torch.Tensor) -> torch.Tensor:
+    sg = torch.sigmoid(z)
+    return sg * (1.0 + z * (1.0 - sg))
+
+
+def _finish_weight_grads(self: TrainEngine, grads: Dict[int, _G]) -> None:
+    """conv_in, the time-embedding chain, and the conversion of the kernel-layout accumulators to parameter shapes."""
+    m = self.m
+    B = self.B
+    c0 = m.config["block_out_channels"][0]
+    cin = m.config["in_channels"]
+    tdim = c0 * 4
+    # conv_in: linear wgrad over the im2col rows ([rows, 64], OHWI tap order, K = 9 * cin zero-padded to 64)
+    g0 = grads.pop(id(self.x0_act), None)
+    if g0 is not None:
+        dw_in = torch.zeros(c0, 64, device=self.device, dtype=torch.float32)
+        db_in = torch.zeros(c0, device=self.device, dtype=torch.float32)
+        K.wgrad(g0.t, g0.ld, self.im2col, 64, dw_in, db_in, self.x0_act.rows, c0, 64)
+        self.wg[id(m.conv_in.weight)], self.wg[id(m.conv_in.bias)] = dw_in[:, :9 * cin], db_in
+    # time embedding: h1 += (time_emb_proj(silu(temb)) + time_emb_proj.bias + conv1.bias)[b] in all 22 ResNets
+    dproj = self.dproj_all                                   # [B, temb_total] fp32 (per-sample column sums of dh1)
+    ntot = m._temb_total
+    dproj16 = dproj.to(BF16)
+    te = self.buf("t_e", B, tdim)                            # silu(temb), bf16
+    dw_all = torch.zeros(ntot, tdim, device=self.device, dtype=torch.float32)
+    K.wgrad(dproj16, ntot, te, tdim, dw_all, None, B, ntot, tdim)
+    db_all = dproj.sum(0)
+    for r in m._resnets:
+        off = m._temb_off[r.uid]
+        self.wg[id(r.time_emb_proj.weight)] = dw_all[off:off + r.cout]
+        self.wg[id(r.time_emb_proj.bias)] = db_all[off:off + r.cout]
+        self.wg[id(r.conv1.bias)] = db_all[off:off + r.cout]
+    key = "temb_all.T"
+    if key not in self.dense:
+        self.dense[key] = self._temb_pack()["w"][:ntot].t().contiguous()   # [tdim, temb_total]
+    dte = self._new(B, tdim)
+    self._mm(("temb.T",), dproj16, ntot, ntot, B, self.dense[key], tdim, dte, tdim)
+    te_m = m.time_embedding
+    dz2 = (dte.float() * _silu_grad(self.te_z2)).to(BF16)
+    self._wgrad(te_m.linear_2.weight, te_m.linear_2.bias, dz2, tdim, self.buf("t_h", B, tdim), tdim, B, tdim, tdim)
+    dh = self._new(B, tdim)
+    self._mm(("te2.T",), dz2, tdim, tdim, B, self._wT("te2", te_m.linear_2), tdim, dh, tdim)
+    dz1 = (dh.float() * _silu_grad(self.te_z1)).to(BF16)
+    self._wgrad(te_m.linear_1.weight, te_m.linear_1.bias, dz1, tdim, self.buf("t_sin", B, c0), c0, B, tdim, c0)
+    # kernel layout -> parameter layout
+    out: Dict[int, torch.Tensor] = {}
+    for mod in m.modules():
+        if isinstance(mod, (nn.GroupNorm, nn.LayerNorm)):
+            g = self.wg.get(id(mod.weight))
+            if g is not None:
+                out[id(mod.weight)], out[id(mod.bias)] = g[:, 0], g[:, 1]
+        elif isinstance(mod, nn.Conv2d):
+            g = self.wg.get(id(mod.weight))
+            if g is not None:
+                co, ci, kh, kw = mod.weight.shape
+                out[id(mod.weight)] = g.reshape(co, kh, kw, ci).permute(0, 3, 1, 2)   # OHWI -> OIHW
+            if mod.bias is not None and id(mod.bias) in self.wg:
+                out[id(mod.bias)] = self.wg[id(mod.bias)]
+        elif isinstance(mod, nn.Linear):
+            if id(mod.weight) in self.wg:
+                out[id(mod.weight)] = self.wg[id(mod.weight)]
+            if mod.bias is not None and id(mod.bias) in self.wg:
+                out[id(mod.bias)] = self.wg[id(mod.bias)]
+    self.param_grads = out
+
+
+TrainEngine._finish_weight_grads = _finish_weight_grads
+
+
+class UNetFineTuneFunction(torch.autograd.Function):
+    """(prediction, 9 block activations) = U-Net(sample, t, ctx; weights) with gradients to EVERY U-Net parameter: the
+    student forward / backward of the fine-tune stage (trainer.py:1727-1729). The gates are constants here (one static
+    expert or the all-ones teacher layout); weights are re-packed from the parameters on every call."""
+
+    @staticmethod
+    def forward(ctx, model, sample, timestep, enc, n_taps_out, *params):
+        eng = model._get_train_engine(sample.device)
+        eng.train_weights = True
+        eng.dense, eng.expert = {}, {}  # the parameters changed since the last step: re-derive the packed bf16 copies
+        flat_w, flat_d = model._flat_gates
+        y, taps = eng.run_train(sample, timestep, enc, [g.detach() for g in list(flat_w) + list(flat_d)])
+        ctx.eng = eng
+        ctx.params = params
+        return tuple([y] + [t.nchw() for t in taps])
+
+    @staticmethod
+    def backward(ctx, dy, *dtaps):
+        eng = ctx.eng
+        eng.backward(dy, list(dtaps))
+        eng.train_weights = False
+        pg = eng.param_grads
+        grads = []
+        for p in ctx.params:
+            g = pg.get(id(p))
+            grads.append(None if g is None else g.to(p.dtype).reshape(p.shape).contiguous())
+        return (None, None, None, None, None, *grads)
 
 
 class UNetTrainFunction(torch.autograd.Function):

@@ -372,6 +372,14 @@ class UNet2DConditionModelGated(nn.Module):
         self.set_structure({"width": [torch.ones(batch, w, device=device) for ws in st["width"] for w in ws],
                             "depth": [torch.ones(batch, device=device) for d in st["depth"] if d == [1]]})
 
+    def enable_weight_training(self, on: bool = True) -> None:
+        """Opt in to the fine-tune path: forwards under autograd then differentiate w.r.t. every parameter that
+        requires grad (FineTuner: `unet.train()` + an optimizer over `unet.parameters()`, trainer.py:1560-1600).
+        Off (default): the U-Net is treated as frozen, as the pruning stage and sampling do."""
+        self._train_weights = bool(on)
+        self._engine = None
+        self._train_engine = None
+
     def freeze(self) -> None:
         """unet_2d_conditional.py:2118-2122."""
         for name, p in self.named_parameters():
@@ -440,7 +448,13 @@ class UNet2DConditionModelGated(nn.Module):
         want_taps = any(len(b._forward_hooks) > 0 for b in blocks)
         flat_w, flat_d = self._flat_gates
         gates = list(flat_w) + list(flat_d)
-        if torch.is_grad_enabled() and any(g.requires_grad for g in gates):
+        if torch.is_grad_enabled() and getattr(self, "_train_weights", False):
+            # fine-tune stage (trainer.py:1683-1765): gradients to every U-Net parameter, gates are constants
+            from .train import UNetFineTuneFunction
+            params = [p for p in self.parameters() if p.requires_grad]
+            outs = UNetFineTuneFunction.apply(self, sample, timestep, encoder_hidden_states, len(blocks), *params)
+            out, taps = outs[0], list(outs[1:])
+        elif torch.is_grad_enabled() and any(g.requires_grad for g in gates):
             # differentiable student forward of the pruning step (trainer.py:1192-1195): one autograd node
             from .train import UNetTrainFunction
             outs = UNetTrainFunction.apply(self, sample, timestep, encoder_hidden_states, len(blocks), *gates)

@@ -331,12 +331,18 @@ int aptp_macs_ratio_bwd(const float* arch, int32_t ld, int32_t batch, const aptp
  *   dw[n, tap, c] += sum_rows dy[row, n] * a[shift_tap(row), c]     (fp32, OHWI; taps = 9 if conv3x3 else 1)
  *   dbias[n]      += sum_rows dy[row, n]                            (optional)
  * dy: bf16 [rows, n_out] (pitch ld_dy), a: bf16 [rows, k_in] NHWC rows (pitch ld_a), rows = batch * H * W for the conv
- * (stride 1, zero padding 1); (bw, bh, bb) = pixel box of one reduction stage (bw * bh * bb = 128, tiles the images);
+ * (conv3x3 = 1: stride 1, zero padding 1; conv3x3 = 2: stride 2 -- H, W are the INPUT size, rows = batch * H/2 * W/2 and
+ * k_in == ld_a); (bw, bh, bb) = box of OUTPUT pixels of one reduction stage (bw * bh * bb = 128, tiles the images);
  * splits = split-K factor over the rows (partial sums meet in dw through fp32 atomics: the caller zeroes dw / dbias).
  * ------------------------------------------------------------------------------------------------ */
 int aptp_wgrad(const void* dy, int32_t ld_dy, const void* a, int32_t ld_a, float* dw, int64_t ld_dw, float* dbias,
                int64_t rows, int32_t n_out, int32_t k_in, int32_t conv3x3, int32_t batch, int32_t H, int32_t W,
                int32_t bw, int32_t bh, int32_t bb, int32_t splits, void* stream);
+/* out[g, n] += sum of dy[row, n] over the rows_per_group consecutive rows of group g (fp32 [groups, n_out], row pitch out_ld, caller zeroes):
+ * per-sample column sums = gradient of the time-embedding projection that is broadcast over a sample's pixels
+ * (blocks.py:331-343). */
+int aptp_col_sum_groups(const void* dy, int32_t ld, int32_t groups, int32_t rows_per_group, int32_t n_out, float* out,
+                        int32_t out_ld, void* stream);
 
 /* Weight-training variants of the norm backward (affine parameters trainable, as in the fine-tune stage):
  * aptp_groupnorm_bwd_affine = aptp_groupnorm_bwd that ALSO accumulates daffine[c] = (dgamma[c], dbeta[c]) (fp32 [C][2],

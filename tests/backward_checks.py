@@ -262,7 +262,34 @@ def check_wgrad_conv(B=2, H=16, W=16, cin=72, cout=136, splits=0, seed=3):
     _close(db, dy.float().sum(0), 2e-3 * rows ** 0.5, 2e-3, "wgrad conv bias")
 
 
+def check_wgrad_conv_s2(B=2, H=16, W=16, C=128, cout=72, seed=7):
+    """aptp_wgrad, 3x3 stride-2 conv (the down-samplers) vs autograd of F.conv2d(stride=2, padding=1)."""
+    Ho, Wo = H // 2, W // 2
+    a = _rand(B * H * W, C, seed=seed).bfloat16()
+    dy = _rand(B * Ho * Wo, cout + 8, seed=seed + 1).bfloat16()
+    dw = torch.zeros(cout, 9 * C, device=DEV)
+    K.wgrad(dy, cout + 8, a, C, dw, None, B * Ho * Wo, cout, C, conv=(B, H, W), stride=2)
+    K.check_abort()
+    x = a.float().reshape(B, H, W, C).permute(0, 3, 1, 2)
+    w = torch.zeros(cout, C, 3, 3, device=DEV, requires_grad=True)
+    y = torch.nn.functional.conv2d(x, w, stride=2, padding=1)
+    y.backward(dy[:, :cout].float().reshape(B, Ho, Wo, cout).permute(0, 3, 1, 2))
+    ref = w.grad.permute(0, 2, 3, 1).reshape(cout, 9 * C)
+    _close(dw, ref, 2e-3 * ref.abs().max().item(), 2e-3, "wgrad conv stride 2")
+
+
+def check_col_sum_groups(B=3, hw=5000, C=136, seed=8):
+    dy = _rand(B * hw, C + 8, seed=seed).bfloat16()
+    out = torch.zeros(B, C, device=DEV)
+    K.col_sum_groups(dy, C + 8, B, hw, C, out)
+    ref = dy[:, :C].float().reshape(B, hw, C).sum(1)
+    _close(out, ref, 2e-3 * hw ** 0.5, 2e-3, "col_sum_groups")
+
+
 ALL = [
+    ("wgrad_conv_stride2", check_wgrad_conv_s2),
+    ("wgrad_conv_stride2_64", lambda: check_wgrad_conv_s2(B=1, H=64, W=64, C=64, cout=64)),
+    ("col_sum_groups", check_col_sum_groups),
     ("affine_groupnorm", check_groupnorm_affine),
     ("affine_groupnorm_gate_plain", lambda: check_groupnorm_affine(B=2, hw=64, C=1280, silu=False, use_gate=True)),
     ("affine_layernorm", check_layernorm_affine),

@@ -19,3 +19,9 @@ def test_pruning_step_losses_and_grads_vs_oracle():
     vs oracle autograd."""
     import train_checks as T
     T.assert_step(*T.check_pruning_step())
+
+
+def test_finetune_backward_all_parameter_gradients_match_oracle_autograd():
+    import train_checks as T
+    out = T.check_finetune_grads()
+    T.assert_finetune(out)

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import torch
 
-from diffusion_pruning_b200.synthetic import split_arch
+from diffusion_pruning_b200.synthetic import split_arch, synthetic_codes
 from unet_checks import build_pair, inputs, metrics
 
 # gate-gradient tolerance (bf16 activations / gradients vs fp32 autograd): per gate family, the relative L2
@@ -153,3 +153,64 @@ def assert_step(lg, lr, gm, rel_tol=2e-2):
             f"{k}: got {lg[k]:.6g} ref {lr[k]:.6g}"
     for k, (rel, cos, nrm) in gm.items():
         assert rel <= 5e-2 and cos >= 0.998, f"grad {k}: relative L2 error {rel:.4g} cosine {cos:.6f} (|ref| {nrm:.3g})"
+
+
+def check_finetune_grads(B=2, H=16, code_id=3, seed=11, beta_std=0.1):
+    """Fine-tune backward (trainer.py:1683-1765): gradients of a scalar loss on (prediction, 9 block outputs) w.r.t. EVERY
+    U-Net parameter of one static expert (hard gates as constants) vs fp32 autograd of the CPU oracle.
+    Returns {param name: (relative L2 error, cosine, |ref|)}."""
+    model, oracle = build_pair(True, beta_std=beta_std)
+    st = model.get_structure()
+    codes = synthetic_codes(st, 8)
+    arch = codes[[code_id] * B].float()
+    sample, t, ctx = inputs(B, H, model.config["cross_attention_dim"])
+    for p in oracle.parameters():
+        p.requires_grad_(True)
+    oracle.set_structure(split_arch(arch.clone(), st))
+    pred_ref, taps_ref = oracle(sample, t, ctx, return_blocks=True)
+    _loss(pred_ref, taps_ref).backward()
+    acts = {}
+    handles = []
+    blocks = list(model.down_blocks) + [model.mid_block] + list(model.up_blocks)
+    for i, blk in enumerate(blocks):
+        def hook(mod, inp, out, i=i):
+            acts[i] = out[0] if mod.kind == "down" else out
+        handles.append(blk.register_forward_hook(hook))
+    model.enable_weight_training(True)
+    model.set_structure(split_arch(arch.clone().cuda(), st))
+    pred = model(sample.cuda(), t.cuda(), ctx.cuda()).sample
+    _loss(pred, [acts[i] for i in range(len(blocks))]).backward()
+    torch.cuda.synchronize()
+    from diffusion_pruning_b200 import kernels as K
+    K.check_abort()
+    for h in handles:
+        h.remove()
+    model.enable_weight_training(False)
+    ref = dict(oracle.named_parameters())
+    out = {}
+    for name, p in model.named_parameters():
+        r = ref[name].grad
+        if p.grad is None:
+            out[name] = (float("inf"), 0.0, 0.0 if r is None else r.norm().item())
+            continue
+        g = p.grad.detach().float().cpu()
+        rn = r.norm().item()
+        rel = ((g - r).norm() / max(rn, 1e-20)).item()
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
+        out[name] = (rel, cos, rn)
+    return out
+
+
+def assert_finetune(out, rel_tol=8e-2, cos_tol=0.995):
+    """Every parameter with a non-negligible reference gradient must match; parameters whose reference gradient is
+    (numerically) zero -- rows / columns of gated-off channels -- must be (numerically) zero here too."""
+    big = max(v[2] for v in out.values())
+    bad = []
+    for name, (rel, cos, rn) in out.items():
+        if rn > 1e-6 * big:
+            if not (rel <= rel_tol and cos >= cos_tol):
+                bad.append((name, rel, cos, rn))
+        elif rel != rel and rn == 0.0:
+            bad.append((name, rel, cos, rn))
+    assert not bad, f"{len(bad)} of {len(out)} parameter gradients off: " + "; ".join(
+        f"{n}: rel {r:.3g} cos {c:.5f} |ref| {m:.3g}" for n, r, c, m in bad[:12])
