@@ -474,6 +474,122 @@ def run_sample(args):
         dist.destroy_process_group()
 
 
+def run_finetune(args):
+    """the fine-tune step of one static expert (FineTuner.step, trainer.py:1683-1765, from the encoded
+    batch on): dense teacher forward (no grad), student forward + backward to EVERY U-Net parameter (dgrad + tcgen05
+    wgrad + norm-affine + attention backward), DDPM / distillation / block losses, AdamW over the 866 M parameters."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from diffusion_pruning_b200 import finetune as FT
+    from diffusion_pruning_b200 import kernels as K
+    from diffusion_pruning_b200 import pruning_step as PS
+    from diffusion_pruning_b200.synthetic import split_arch, synthetic_codes
+    from diffusion_pruning_b200.unet import UNet2DConditionModelGated
+    Bt = args.train_batch
+    torch.manual_seed(1234)
+    with torch.device(device):
+        unet = UNet2DConditionModelGated()
+        teacher = UNet2DConditionModelGated()
+    teacher.load_state_dict(unet.state_dict())
+    teacher.eval()
+    teacher.freeze()
+    teacher.set_all_ones_structure(1, device=device)
+    unet.train()
+    unet.enable_weight_training(True)
+    st = unet.get_structure()
+    code = synthetic_codes(st, N_CODES)[3:4].float().to(device)
+    unet.set_structure(split_arch(code.clone(), st))
+    cfg = FT.FinetuneLossConfig()
+    taps, ttaps = PS.BlockTaps(unet), PS.BlockTaps(teacher)
+    params = [p for p in unet.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=0.0, fused=True)
+    g = torch.Generator().manual_seed(100 + rank)
+    host = {"noisy_latents": torch.randn(Bt, 4, LATENT, LATENT, generator=g).pin_memory(),
+            "timesteps": torch.randint(0, 1000, (Bt,), generator=g).pin_memory(),
+            "target": torch.randn(Bt, 4, LATENT, LATENT, generator=g).pin_memory(),
+            "encoder_hidden_states": torch.randn(Bt, N_CTX, CTX_DIM, generator=g).pin_memory()}
+    acp = PS.alphas_cumprod().to(device)
+
+    def step():
+        batch = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        unet.set_structure(split_arch(code.clone(), st))
+        out = FT.finetune_step(unet, teacher, batch, cfg, taps, ttaps, acp=acp)
+        opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
+        if world > 1:  # DDP semantics: mean of the gradients
+            for p in params:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+                    p.grad.div_(world)
+        opt.step()
+        return out["loss"].detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step()
+    K.check_abort()
+    if os.environ.get("APTP_CUDA_PROFILE"):
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+        loss_h = float(loss)  # the trainer reads the loss every step (D2H)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    clk = clocks.stop()
+    K.check_abort()
+    peaks = load_peaks()
+    value = Bt * world * args.steps / (ms / 1e3)
+    # dense-equivalent FLOPs per sample: teacher forward + student forward + dgrad + wgrad of the conv / linear layers
+    # (+ 2.5x forward attention FLOPs for its backward): 2 * (2 * 388.35 + 2 * 325.3 + 2.5 * 63.0) GMAC
+    flop_per_sample = 2.0 * (2 * 388.35 + 2 * 325.3 + 2.5 * 63.0) * 1e9
+    if rank == 0:
+        out = {"metric": "finetune_samples_steps_per_s", "value": round(value, 2), "unit": UNIT, "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": "fine-tune step of one static expert (SURVEY 8f rank 4; FineTuner.step): dense teacher "
+                                      "forward, student forward + backward to all 866 M U-Net parameters, 3 losses, AdamW, "
+                                      "64x64 latent", "batch_per_gpu": Bt, "latent": LATENT,
+                          "parallelism": f"dp{world} + grad all-reduce", "l2": "activations exceed L2"},
+               "e2e": {"value": round(value, 2), "unit": UNIT,
+                       "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
+                       "d2h_bytes_per_step": 4},
+               "gpu_launches": None, "clocks": clk, "final_loss": loss_h,
+               "roofline": {"bound": "tensor", "achieved": round(flop_per_sample * Bt * args.steps / (ms / 1e3) / 1e12, 1),
+                            "peak": peaks["tflops"], "unit": "TFLOP/s",
+                            "frac": round(flop_per_sample * Bt * args.steps / (ms / 1e3) / 1e12 / peaks["tflops"], 4),
+                            "traffic": None,
+                            "note": "whole-step dense-equivalent FLOPs (3.17 TFLOP/sample) / step time; the student computes "
+                                    "gated-off channels too (dense weights)"}}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def build_oracle_fast():
     """Full-size fp32 oracle with cheap deterministic init (fan-in scaled uniform)."""
     import math
@@ -546,7 +662,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="forward", choices=["forward", "train", "sample"])
+    ap.add_argument("--workload", default="forward", choices=["forward", "train", "sample", "finetune"])
     ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--prompts", type=int, default=16, help="--workload sample: prompts per GPU")
     ap.add_argument("--sample-latent", type=int, default=96)
@@ -558,6 +674,8 @@ def main():
         run_train(args)
     elif args.workload == "sample":
         run_sample(args)
+    elif args.workload == "finetune":
+        run_finetune(args)
     else:
         run_ours(args)
 

@@ -92,3 +92,22 @@ def pruning_step(unet, hyper_w: torch.Tensor, hyper_b: torch.Tensor, codebook: t
     return {"loss": total, "diff_loss": loss.detach(), "distillation_loss": distill, "block_loss": block,
             "contrastive_loss": c_loss, "resource_loss": r_loss, "resource_ratio": ratios.mean().detach(),
             "idx": idx, "arch_q": arch_q}
+
+
+def finetune_step(student, teacher, batch: Dict[str, torch.Tensor], cfg):
+    """FineTuner.step (pdm/training/trainer.py:1683-1765) from the encoded batch on: `student` = GatedUNetOracle fixed
+    to one code, `teacher` = the dense oracle (all-ones gates)."""
+    noisy, timesteps, target = batch["noisy_latents"], batch["timesteps"], batch["target"]
+    enc = batch["encoder_hidden_states"]
+    with torch.no_grad():
+        full_pred, t_taps = teacher(noisy, timesteps, enc, return_blocks=True)
+    pred, s_taps = student(noisy, timesteps, enc, return_blocks=True)
+    acp = alphas_cumprod()
+    w = min_snr_weights(acp, timesteps, cfg.snr_gamma, cfg.prediction_type == "v_prediction")
+    diff = (F.mse_loss(pred, target, reduction="none").mean(dim=[1, 2, 3]) * w).mean()
+    loss = cfg.diffusion_weight * diff
+    block = sum(F.mse_loss(a, b.detach()) for a, b in zip(s_taps, t_taps)) / len(s_taps)
+    loss = loss + cfg.block_weight * block
+    distill = F.mse_loss(pred, full_pred)
+    loss = loss + cfg.distillation_weight * distill
+    return {"loss": loss, "diff_loss": diff.detach(), "distillation_loss": distill, "block_loss": block}

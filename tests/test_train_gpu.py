@@ -25,3 +25,13 @@ def test_finetune_backward_all_parameter_gradients_match_oracle_autograd():
     import train_checks as T
     out = T.check_finetune_grads()
     T.assert_finetune(out)
+
+
+def test_finetune_step_losses_and_gradients_match_oracle():
+    import train_checks as T
+    lg, lr, gm, moved = T.check_finetune_step()
+    floor = {"distillation_loss": 3e-4, "block_loss": 3e-3}
+    for k in lr:
+        assert abs(lg[k] - lr[k]) <= 2e-2 * max(abs(lr[k]), 1e-3) + floor.get(k, 0.0), f"{k}: got {lg[k]:.6g} ref {lr[k]:.6g}"
+    T.assert_finetune(gm)
+    assert not moved, f"parameters of depth-dropped blocks moved: {moved[:5]}"

@@ -214,3 +214,67 @@ def assert_finetune(out, rel_tol=8e-2, cos_tol=0.995):
             bad.append((name, rel, cos, rn))
     assert not bad, f"{len(bad)} of {len(out)} parameter gradients off: " + "; ".join(
         f"{n}: rel {r:.3g} cos {c:.5f} |ref| {m:.3g}" for n, r, c, m in bad[:12])
+
+
+def check_finetune_step(B=2, H=16, code_id=5, seed=31):
+    """Whole fine-tune step (trainer.py:1683-1765 from the encoded batch on): losses + every parameter gradient of the
+    combined loss vs the CPU oracle's autograd; then one AdamW step must move only parameters with a gradient."""
+    import copy
+    from diffusion_pruning_b200 import finetune as FT
+    from diffusion_pruning_b200 import pruning_step as PS
+    from diffusion_pruning_b200.unet import UNet2DConditionModelGated
+    from oracle import step_oracle as SO
+    from unet_checks import TINY
+    model, oracle = build_pair(True, beta_std=0.1)
+    teacher_oracle = copy.deepcopy(oracle)
+    teacher = UNet2DConditionModelGated(**TINY)
+    teacher.load_state_dict(oracle.state_dict())
+    teacher = teacher.cuda().eval()
+    teacher.freeze()
+    st = model.get_structure()
+    arch = synthetic_codes(st, 8)[[code_id] * B].float()
+    g = torch.Generator().manual_seed(seed)
+    cd = model.config["cross_attention_dim"]
+    batch = {"noisy_latents": torch.randn(B, 4, H, H, generator=g), "timesteps": torch.tensor([981, 341, 661, 21][:B]),
+             "target": torch.randn(B, 4, H, H, generator=g), "encoder_hidden_states": torch.randn(B, 77, cd, generator=g)}
+    cfg = FT.FinetuneLossConfig(diffusion_weight=1.0)  # weight 1 so that all three losses shape the gradient
+    # oracle
+    for p in oracle.parameters():
+        p.requires_grad_(True)
+    oracle.set_structure(split_arch(arch.clone(), st))
+    teacher_oracle.set_all_ones(1)
+    ref = SO.finetune_step(oracle, teacher_oracle, batch, cfg)
+    ref["loss"].backward()
+    # product
+    model.enable_weight_training(True)
+    model.set_structure(split_arch(arch.clone().cuda(), st))
+    teacher.set_all_ones_structure(1, device="cuda")
+    taps, ttaps = PS.BlockTaps(model), PS.BlockTaps(teacher)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.0)  # configs/finetuning/...:100
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    got = FT.finetune_step(model, teacher, cb, cfg, taps, ttaps)
+    opt.zero_grad(set_to_none=True)
+    got["loss"].backward()
+    opt.step()
+    torch.cuda.synchronize()
+    from diffusion_pruning_b200 import kernels as K
+    K.check_abort()
+    taps.remove()
+    ttaps.remove()
+    model.enable_weight_training(False)
+    names = ["loss", "diff_loss", "distillation_loss", "block_loss"]
+    lg = {k: float(got[k].detach()) for k in names}
+    lr = {k: float(ref[k].detach()) for k in names}
+    refp = dict(oracle.named_parameters())
+    gm = {}
+    moved_without_grad = []
+    for name, p in model.named_parameters():
+        r = refp[name].grad
+        gg = p.grad.detach().float().cpu() if p.grad is not None else torch.zeros_like(r)
+        rn = r.norm().item()
+        gm[name] = (((gg - r).norm() / max(rn, 1e-20)).item(),
+                    torch.nn.functional.cosine_similarity(gg.flatten(), r.flatten(), dim=0).item(), rn)
+        if rn == 0.0 and not torch.equal(p.detach(), before[name]):
+            moved_without_grad.append(name)
+    return lg, lr, gm, moved_without_grad
