@@ -12,6 +12,8 @@ outputs are the prediction plus the nine hooked block activations (trainer.py:49
 """
 from __future__ import annotations
 
+import os
+
 from typing import Any, Dict, List, Optional, Tuple
 
 import torch
@@ -96,19 +98,15 @@ class TrainEngine(_Engine):
 
     def _wT(self, name: str, mod: nn.Module, pad_out_to: int = 0) -> torch.Tensor:
         """Transposed weight for the dgrad: Linear / 1x1 conv -> [K, N]; 3x3 conv -> [Cin, 9*Cout] tap-flipped."""
-        key = name + ".T"
-        d = self.dense.get(key)
-        if d is None:
+        def build():
             w = mod.weight.detach().to(self.device)
             if w.ndim == 4 and w.shape[-1] == 3:
                 if pad_out_to and w.shape[0] < pad_out_to:
                     w = torch.cat([w, torch.zeros(pad_out_to - w.shape[0], *w.shape[1:], device=self.device,
                                                   dtype=w.dtype)], 0)
-                d = P.pack_conv_weight_dgrad(w).to(BF16).contiguous()
-            else:
-                d = w.reshape(w.shape[0], -1).t().to(BF16).contiguous()
-            self.dense[key] = d
-        return d
+                return P.pack_conv_weight_dgrad(w).to(BF16).contiguous()
+            return w.reshape(w.shape[0], -1).t().to(BF16).contiguous()
+        return self._pack(self.dense, name + ".T", build)
 
     def _w(self, name: str, mod: nn.Module) -> Dict[str, torch.Tensor]:
         return self._dense_linear(name, mod)
@@ -229,13 +227,12 @@ class TrainEngine(_Engine):
             self.dproj_all = torch.zeros(B, m._temb_total, device=self.device, dtype=torch.float32)
         col = self.buf("im2col", B * H * W, 64)
         K.im2col_input(sample, col, B, cin, H, W)
-        d = self.dense.get("conv_in")
-        if d is None:
+        def build_conv_in():
             w = m.conv_in.weight.detach().to(self.device)
             wp = torch.zeros(c0, 64, device=self.device, dtype=BF16)
             wp[:, :9 * cin] = w.permute(0, 2, 3, 1).reshape(c0, 9 * cin).to(BF16)
-            d = {"w": wp, "b": m.conv_in.bias.detach().to(self.device, torch.float32).contiguous()}
-            self.dense["conv_in"] = d
+            return {"w": wp, "b": m.conv_in.bias.detach().to(self.device, torch.float32).contiguous()}
+        d = self._pack(self.dense, "conv_in", build_conv_in)
         x0 = self._new(B * H * W, c0)
         self._mm("conv_in", col, 64, 64, B * H * W, d["w"], c0, x0, c0, bias=d["b"], rows_per_sample=H * W)
         x = Act(x0, B, H, W, c0)
@@ -406,13 +403,10 @@ class TrainEngine(_Engine):
         n_kv = self.n_ctx if cross else hw
         Mkv = B * n_kv
         wq, wk, wv = self._w("q." + uid, attn.to_q), self._w("k." + uid, attn.to_k), self._w("v." + uid, attn.to_v)
-        key = "wqkv." + uid
-        if key not in self.dense:
-            if cross:
-                self.dense[key] = torch.cat([wk["w"], wv["w"]], 0).contiguous()
-            else:
-                self.dense[key] = torch.cat([wq["w"], wk["w"], wv["w"]], 0).contiguous()
-        wcat = self.dense[key]
+        if cross:
+            wcat = self._pack(self.dense, "wqkv." + uid, lambda: torch.cat([wk["w"], wv["w"]], 0).contiguous())
+        else:
+            wcat = self._pack(self.dense, "wqkv." + uid, lambda: torch.cat([wq["w"], wk["w"], wv["w"]], 0).contiguous())
         if cross:
             uq = self._new(M, C)
             ukv = self._new(Mkv, 2 * C)
@@ -500,11 +494,10 @@ class TrainEngine(_Engine):
                 K.wgrad(du, 3 * C, xn, C, dwqkv, None, M, 3 * C, C)
                 for j, lin in enumerate((attn.to_q, attn.to_k, attn.to_v)):
                     self.wg[id(lin.weight)] = dwqkv[j * C:(j + 1) * C]
-            key = "wqkv.T." + uid
-            if key not in self.dense:
-                self.dense[key] = self.dense["wqkv." + uid].t().contiguous()  # [C, 3C]
+            wcat = self.dense["wqkv." + uid]
+            wcat_t = self._pack(self.dense, "wqkv.T." + uid, lambda: wcat.t().contiguous())  # [C, 3C]
             dln = self.buf("bw_dln", M, C)
-            self._mm(("qkv.T", uid), du, 3 * C, 3 * C, M, self.dense[key], C, dln, C, rows_per_sample=hw)
+            self._mm(("qkv.T", uid), du, 3 * C, 3 * C, M, wcat_t, C, dln, C, rows_per_sample=hw)
         self.launches += 8
         return dln
 
@@ -793,11 +786,9 @@ def _finish_weight_grads(self: TrainEngine, grads: Dict[int, _G]) -> None:
         self.wg[id(r.time_emb_proj.weight)] = dw_all[off:off + r.cout]
         self.wg[id(r.time_emb_proj.bias)] = db_all[off:off + r.cout]
         self.wg[id(r.conv1.bias)] = db_all[off:off + r.cout]
-    key = "temb_all.T"
-    if key not in self.dense:
-        self.dense[key] = self._temb_pack()["w"][:ntot].t().contiguous()   # [tdim, temb_total]
+    wt_all = self._pack(self.dense, "temb_all.T", lambda: self._temb_pack()["w"][:ntot].t().contiguous())  # [tdim, temb_total]
     dte = self._new(B, tdim)
-    self._mm(("temb.T",), dproj16, ntot, ntot, B, self.dense[key], tdim, dte, tdim)
+    self._mm(("temb.T",), dproj16, ntot, ntot, B, wt_all, tdim, dte, tdim)
     te_m = m.time_embedding
     dz2 = (dte.float() * _silu_grad(self.te_z2)).to(BF16)
     self._wgrad(te_m.linear_2.weight, te_m.linear_2.bias, dz2, tdim, self.buf("t_h", B, tdim), tdim, B, tdim, tdim)
@@ -839,7 +830,14 @@ class UNetFineTuneFunction(torch.autograd.Function):
     def forward(ctx, model, sample, timestep, enc, n_taps_out, *params):
         eng = model._get_train_engine(sample.device)
         eng.train_weights = True
-        eng.dense, eng.expert = {}, {}  # the parameters changed since the last step: re-derive the packed bf16 copies
+        model._engine = None  # the inference engine's packed weights go stale as soon as the optimizer steps
+        # the parameters changed since the last step (optimizer): re-derive the packed bf16 copies -- in place, as one
+        # CUDA-graph replay of the registered builders (first call: nothing is packed yet, the forward builds them)
+        if getattr(eng, "_ft_packs_ready", False):
+            eng.refresh_packs()
+        else:
+            eng.dense, eng.expert, eng._packs, eng._pack_graph = {}, {}, [], None
+            eng._ft_packs_ready = True
         flat_w, flat_d = model._flat_gates
         y, taps = eng.run_train(sample, timestep, enc, [g.detach() for g in list(flat_w) + list(flat_d)])
         ctx.eng = eng

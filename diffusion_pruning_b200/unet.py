@@ -426,6 +426,7 @@ class UNet2DConditionModelGated(nn.Module):
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._engine = None
+        self._train_engine = None
         return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor,
@@ -595,6 +596,9 @@ class _Engine:
         self.expert: Dict[Tuple[bytes, str], Dict[str, Any]] = {}
         self.sched: Dict[Any, Any] = {}
         self.arena: Dict[Any, torch.Tensor] = {}
+        self._packs: List[tuple] = []     # (device tensors derived from parameters, their builder): see _pack()
+        self._pack_graph = None
+        self._pack_graph_n = -1
         self.flops = 0.0          # kept GEMM-class FLOPs of the last forward (roofline accounting)
         self.gemm_bytes = 0.0     # algorithmic HBM bytes of the grouped-GEMM launches of the last forward
         self.launches = 0
@@ -620,6 +624,45 @@ class _Engine:
         return t
 
     # ---- gates -> mode / experts -------------------------------------------------------------------
+    # ---- parameter-derived device tensors ("packs") ---------------------------------------------------
+    def _pack(self, store: dict, key, builder):
+        """store[key], built once by `builder()` (a tensor, or a dict holding tensors and host-side data). The pair is
+        registered so that refresh_packs() can re-derive the device tensors IN PLACE after an optimizer step changed the
+        parameters (fine-tune stage); inference and the pruning stage (frozen U-Net) never refresh."""
+        d = store.get(key)
+        if d is None:
+            d = builder()
+            store[key] = d
+            self._packs.append((d, builder))
+        return d
+
+    def _refresh_packs_eager(self) -> None:
+        for old, builder in self._packs:
+            new = builder()
+            if torch.is_tensor(old):
+                if new.data_ptr() != old.data_ptr():
+                    old.copy_(new)
+            else:
+                for k, v in new.items():
+                    o = old.get(k)
+                    if torch.is_tensor(v) and torch.is_tensor(o) and v.data_ptr() != o.data_ptr():
+                        o.copy_(v)
+
+    def refresh_packs(self) -> None:
+        """Re-derive every registered pack from the current parameter values. The builders are pure torch ops on the
+        parameters' (static) storage, so the whole pass is captured once into a CUDA graph and replayed afterwards:
+        one launch instead of a few thousand small ones per training step."""
+        if self._pack_graph is not None and self._pack_graph_n == len(self._packs):
+            self._pack_graph.replay()
+            return
+        self._refresh_packs_eager()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._refresh_packs_eager()
+        self._pack_graph, self._pack_graph_n = g, len(self._packs)
+        g.replay()
+
     def _prepare_gates(self, B: int):
         m = self.m
         st = m._gate_state
@@ -757,8 +800,7 @@ class _Engine:
 
     # ---- dense (unpruned) weights ---------------------------------------------------------------
     def _dense_linear(self, name: str, lin: nn.Module, n_pad_to: int = 0) -> Dict[str, torch.Tensor]:
-        d = self.dense.get(name)
-        if d is None:
+        def build():
             w = lin.weight.detach()
             if w.ndim == 4:
                 w = P.pack_conv_weight(w) if w.shape[-1] == 3 else w.reshape(w.shape[0], w.shape[1])
@@ -766,9 +808,8 @@ class _Engine:
             if n_pad_to and w.shape[0] < n_pad_to:
                 w = torch.cat([w, torch.zeros(n_pad_to - w.shape[0], w.shape[1], device=self.device, dtype=BF16)], 0)
             b = lin.bias.detach().to(self.device, torch.float32).contiguous() if lin.bias is not None else None
-            d = {"w": w, "b": b}
-            self.dense[name] = d
-        return d
+            return {"w": w, "b": b}
+        return self._pack(self.dense, name, build)
 
     def linear(self, name: str, lin: nn.Module, x: torch.Tensor, rows: int, k: int, ld: int, out: torch.Tensor,
                out_ld: int, hw: int, *, residual=None, res_ld=0, flags=0, active=None, out_mode=OUT_BF16,
@@ -821,6 +862,9 @@ class _Engine:
         d = self.expert.get(key)
         if d is not None:
             return d
+        return self._pack(self.expert, key, self._build_temb_pack)
+
+    def _build_temb_pack(self) -> Dict[str, Any]:
         m = self.m
         E = self.eset.n_experts if self.compact else 1
         ntot = m._temb_total
@@ -840,9 +884,7 @@ class _Engine:
                     rows = torch.arange(r.cout, device=self.device)
                 w[e * ntot + off: e * ntot + off + len(rows)] = wt.index_select(0, rows).to(BF16)
                 b[e * ntot + off: e * ntot + off + len(rows)] = bt.index_select(0, rows)
-        d = {"w": w, "b": b}
-        self.expert[key] = d
-        return d
+        return {"w": w, "b": b}
 
     def time_embed(self, timestep: torch.Tensor):
         m = self.m
@@ -887,6 +929,18 @@ class _Engine:
         d = self.expert.get(key)
         if d is not None:
             return d
+        return self._pack(self.expert, key, lambda: self._build_resnet_pack(r))
+
+    def _build_resnet_pack(self, r: ResnetBlock2DWidthGated) -> Dict[str, Any]:
+        if not self.compact:
+            # soft gates: every channel is kept, one variant = the dense weights (pure device ops: this builder is what
+            # refresh_packs() replays, under CUDA-graph capture, after each optimizer step of the fine-tune stage)
+            f32 = lambda p: p.detach().to(self.device, torch.float32).contiguous()
+            return {"vid": np.zeros(1, dtype=np.int64), "n1": np.asarray([r.cout]), "V": 1,
+                    "w1": P.pack_conv_weight(r.conv1.weight.detach().to(self.device)).to(BF16).contiguous(),
+                    "w2": P.pack_conv_weight(r.conv2.weight.detach().to(self.device)).to(BF16).contiguous(),
+                    "gamma2": f32(r.norm2.weight).reshape(1, r.cout), "beta2": f32(r.norm2.bias).reshape(1, r.cout),
+                    "tab": None, "b2": f32(r.conv2.bias), "g1": f32(r.norm1.weight), "b1": f32(r.norm1.bias)}
         gs = r.cout // r.groups
         w1 = P.pack_conv_weight(r.conv1.weight.detach().to(self.device))
         w2 = P.pack_conv_weight(r.conv2.weight.detach().to(self.device))
@@ -910,15 +964,15 @@ class _Engine:
             gam[v, :len(k)] = g2.index_select(0, idx)
             bet[v, :len(k)] = b2.index_select(0, idx)
         d["gamma2"], d["beta2"] = gam.contiguous(), bet.contiguous()
-        if self.m.pruned_semantics:
-            d["tab"] = None  # prune() removed the gated-off channels: nothing of them reaches conv2
+        if self.m.pruned_semantics or not self.compact:
+            # prune() removed the gated-off channels: nothing of them reaches conv2; soft gates keep every channel
+            d["tab"] = None
         else:
             tab = P.border_table(r.conv2.weight.detach().to(self.device), b2, pruned_c)
             d["tab"] = tab.contiguous() if bool((tab != 0).any().item()) else None
         d["b2"] = r.conv2.bias.detach().to(self.device, torch.float32).contiguous()
         d["g1"] = r.norm1.weight.detach().to(self.device, torch.float32).contiguous()
         d["b1"] = r.norm1.bias.detach().to(self.device, torch.float32).contiguous()
-        self.expert[key] = d
         return d
 
     def resnet(self, r: ResnetBlock2DWidthGated, x: Act, skip: Optional[Act] = None) -> Act:

@@ -262,7 +262,16 @@ def check_finetune_step(B=2, H=16, code_id=5, seed=31):
     K.check_abort()
     taps.remove()
     ttaps.remove()
+    # after the optimizer step the packed bf16 weight copies are re-derived in place (refresh_packs: eager the first
+    # time, then one CUDA-graph replay); both must equal a full rebuild from the updated parameters bit for bit
+    xs = (cb["noisy_latents"], cb["timesteps"], cb["encoder_hidden_states"])
+    pred_refresh = model(*xs).sample.detach().clone()
+    pred_replay = model(*xs).sample.detach().clone()
+    model.enable_weight_training(True)   # drops the engines -> full rebuild
+    pred_rebuild = model(*xs).sample.detach().clone()
+    stale = {"refresh": not torch.equal(pred_refresh, pred_rebuild), "replay": not torch.equal(pred_replay, pred_rebuild)}
     model.enable_weight_training(False)
+    assert not any(stale.values()), f"stale packed weights after the optimizer step: {stale}"
     names = ["loss", "diff_loss", "distillation_loss", "block_loss"]
     lg = {k: float(got[k].detach()) for k in names}
     lr = {k: float(ref[k].detach()) for k in names}
