@@ -253,6 +253,8 @@ def check_finetune_step(B=2, H=16, code_id=5, seed=31):
     cb = {k: v.cuda() for k, v in batch.items()}
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.0)  # configs/finetuning/...:100
     before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    # (the engine holds ONE tape: nothing may run the student between a forward and its backward)
+    pred_before_step = model(cb["noisy_latents"], cb["timesteps"], cb["encoder_hidden_states"]).sample.detach().float().clone()
     got = FT.finetune_step(model, teacher, cb, cfg, taps, ttaps)
     opt.zero_grad(set_to_none=True)
     got["loss"].backward()
@@ -263,15 +265,23 @@ def check_finetune_step(B=2, H=16, code_id=5, seed=31):
     taps.remove()
     ttaps.remove()
     # after the optimizer step the packed bf16 weight copies are re-derived in place (refresh_packs: eager the first
-    # time, then one CUDA-graph replay); both must equal a full rebuild from the updated parameters bit for bit
+    # time, then one CUDA-graph replay); both must reproduce a full rebuild from the updated parameters. Forwards are
+    # not bit-reproducible (GroupNorm statistics are accumulated with fp32 atomics), so the comparison is relative to
+    # the prediction change the optimizer step caused and to the run-to-run noise of two identical forwards.
     xs = (cb["noisy_latents"], cb["timesteps"], cb["encoder_hidden_states"])
-    pred_refresh = model(*xs).sample.detach().clone()
-    pred_replay = model(*xs).sample.detach().clone()
+    pred_refresh = model(*xs).sample.detach().float().clone()
+    pred_replay = model(*xs).sample.detach().float().clone()
     model.enable_weight_training(True)   # drops the engines -> full rebuild
-    pred_rebuild = model(*xs).sample.detach().clone()
-    stale = {"refresh": not torch.equal(pred_refresh, pred_rebuild), "replay": not torch.equal(pred_replay, pred_rebuild)}
+    pred_rebuild = model(*xs).sample.detach().float().clone()
+    pred_rebuild2 = model(*xs).sample.detach().float().clone()
     model.enable_weight_training(False)
-    assert not any(stale.values()), f"stale packed weights after the optimizer step: {stale}"
+    step_effect = (pred_rebuild - pred_before_step).abs().max().item()
+    noise = (pred_rebuild2 - pred_rebuild).abs().max().item()
+    e_refresh = (pred_refresh - pred_rebuild).abs().max().item()
+    e_replay = (pred_replay - pred_rebuild).abs().max().item()
+    assert step_effect > 20 * max(noise, 1e-6), f"the optimizer step barely moved the prediction ({step_effect} vs noise {noise})"
+    assert e_refresh <= 0.03 * step_effect + 4 * noise and e_replay <= 0.03 * step_effect + 4 * noise, \
+        f"stale packed weights after the optimizer step: refresh {e_refresh}, replay {e_replay}, step effect {step_effect}, noise {noise}"
     names = ["loss", "diff_loss", "distillation_loss", "block_loss"]
     lg = {k: float(got[k].detach()) for k in names}
     lr = {k: float(ref[k].detach()) for k in names}
