@@ -536,6 +536,9 @@ class UNet2DConditionModelGated(nn.Module):
 
     def _get_train_engine(self, device):
         from .train import TrainEngine
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:  # "cuda" and "cuda:0" must not look like two devices
+            device = torch.device("cuda", torch.cuda.current_device())
         te = getattr(self, "_train_engine", None)
         if te is None or te.device != device:
             te = TrainEngine(self, device)
