@@ -6,10 +6,12 @@ code with `enable_weight_training()`: its forward / backward run on the tape eng
 produce gradients for every U-Net parameter through the sm_100a kernels (dgrad, K8 wgrad, norm-affine, attention
 backward); the teacher is the dense U-Net (all-ones gates) under `torch.no_grad()`; the losses are the K6 kernels.
 
-Semantics note: the student keeps GATED semantics with its dense weights (a gated-off GroupNorm group still feeds
-silu(beta) into conv2) and computes the gated-off channels too; gradients of gated-off rows /
-columns are exactly zero, so an optimizer step never moves them. The reference fine-tunes the physically sliced model
-(prune() semantics, smaller GEMMs): compacting this backward like the hard-gate forward is the next step.
+Semantics: a `UNet2DConditionModelGated` student trains with gated semantics (a gated-off GroupNorm group still feeds
+silu(beta) into conv2); a `UNet2DConditionModelPruned` student -- what the reference's FineTuner
+trains (trainer.py:1452-1462) -- trains with prune() semantics: on the dense weights that is norm2.bias masked by the
+expert's hard gate (and a masked bias gradient), checked against the autograd of the physically sliced oracle. Either
+way the gated-off channels are still computed (dense GEMMs) and their gradients are exactly zero, so an optimizer step
+never moves them; compacting the training GEMMs like the hard-gate forward is the next step.
 """
 from __future__ import annotations
 

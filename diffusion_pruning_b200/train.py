@@ -798,11 +798,16 @@ def _finish_weight_grads(self: TrainEngine, grads: Dict[int, _G]) -> None:
     self._wgrad(te_m.linear_1.weight, te_m.linear_1.bias, dz1, tdim, self.buf("t_sin", B, c0), c0, B, tdim, c0)
     # kernel layout -> parameter layout
     out: Dict[int, torch.Tensor] = {}
+    pruned_beta = {}
+    if m.pruned_semantics:  # norm2.bias of a removed channel does not exist in the sliced model: no gradient
+        pruned_beta = {id(r.norm2): self._resnet_keep_mask(r).reshape(-1) for r in m._resnets}
     for mod in m.modules():
         if isinstance(mod, (nn.GroupNorm, nn.LayerNorm)):
             g = self.wg.get(id(mod.weight))
             if g is not None:
                 out[id(mod.weight)], out[id(mod.bias)] = g[:, 0], g[:, 1]
+                if id(mod) in pruned_beta:
+                    out[id(mod.bias)] = g[:, 1] * pruned_beta[id(mod)]
         elif isinstance(mod, nn.Conv2d):
             g = self.wg.get(id(mod.weight))
             if g is not None:

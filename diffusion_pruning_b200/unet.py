@@ -574,6 +574,7 @@ class UNet2DConditionModelPruned(UNet2DConditionModelGated):
         hard = hard_concrete(arch_vector.detach().float()).detach()
         self.set_structure(HyperStructure.transform_arch_vector(hard, self.get_structure()))
         self.invalidate_weight_cache()
+        self._train_engine = None
 
     def _post_load(self, directory: str, arch_vector=None, random_pruning_ratio=None) -> None:
         """arch_vector.pt next to the unet/ folder (written by FineTuner, trainer.py:1449-1450), unless given."""
@@ -934,15 +935,36 @@ class _Engine:
             return d
         return self._pack(self.expert, key, lambda: self._build_resnet_pack(r))
 
+    def _resnet_keep_mask(self, r: ResnetBlock2DWidthGated) -> torch.Tensor:
+        """[1, cout] 0/1 mask of the channels whose GroupNorm group is kept by the (single, static) expert's code: row 0 of
+        the gate matrix of the current forward, thresholded like hard_concrete. Device ops only (graph-capturable)."""
+        cache = self.__dict__.setdefault("_keep_masks", {})
+        mask = cache.get(r.uid)
+        if mask is None:
+            # computed ONCE per engine into a persistent tensor: refresh_packs() replays a captured graph, which must not
+            # read the per-step gate matrix (re-allocated every forward). prune_to() drops the engine when the code changes.
+            gi = self.gate_cols[r.uid]["w"][0]
+            s0, e0 = self.width_starts[gi], self.width_starts[gi + 1]
+            keep_g = (self.soft_arch[:1, s0:e0] >= 0.5).to(torch.float32)
+            mask = keep_g.repeat_interleave(r.cout // r.groups, dim=1).contiguous()
+            cache[r.uid] = mask
+        return mask
+
     def _build_resnet_pack(self, r: ResnetBlock2DWidthGated) -> Dict[str, Any]:
         if not self.compact:
             # soft gates: every channel is kept, one variant = the dense weights (pure device ops: this builder is what
             # refresh_packs() replays, under CUDA-graph capture, after each optimizer step of the fine-tune stage)
             f32 = lambda p: p.detach().to(self.device, torch.float32).contiguous()
+            beta2 = f32(r.norm2.bias).reshape(1, r.cout)
+            if self.m.pruned_semantics:
+                # prune() semantics on dense weights (blocks.py:451-463 deletes the channels of gated-off groups, so no
+                # silu(beta) of theirs reaches conv2): with the gate at 0 the group normalises to 0 and emerges as beta,
+                # hence masking beta with the (hard, per-expert) gate reproduces the sliced model exactly
+                beta2 = beta2 * self._resnet_keep_mask(r)
             return {"vid": np.zeros(1, dtype=np.int64), "n1": np.asarray([r.cout]), "V": 1,
                     "w1": P.pack_conv_weight(r.conv1.weight.detach().to(self.device)).to(BF16).contiguous(),
                     "w2": P.pack_conv_weight(r.conv2.weight.detach().to(self.device)).to(BF16).contiguous(),
-                    "gamma2": f32(r.norm2.weight).reshape(1, r.cout), "beta2": f32(r.norm2.bias).reshape(1, r.cout),
+                    "gamma2": f32(r.norm2.weight).reshape(1, r.cout), "beta2": beta2,
                     "tab": None, "b2": f32(r.conv2.bias), "g1": f32(r.norm1.weight), "b1": f32(r.norm1.bias)}
         gs = r.cout // r.groups
         w1 = P.pack_conv_weight(r.conv1.weight.detach().to(self.device))

@@ -35,3 +35,12 @@ def test_finetune_step_losses_and_gradients_match_oracle():
         assert abs(lg[k] - lr[k]) <= 2e-2 * max(abs(lr[k]), 1e-3) + floor.get(k, 0.0), f"{k}: got {lg[k]:.6g} ref {lr[k]:.6g}"
     T.assert_finetune(gm)
     assert not moved, f"parameters of depth-dropped blocks moved: {moved[:5]}"
+
+
+def test_finetune_of_pruned_expert_matches_physically_pruned_oracle():
+    import train_checks as T
+    import unet_checks as U
+    out, outside, fwd = T.check_finetune_pruned_semantics()
+    assert fwd[0] <= 2 * U.MAX_ABS_TOL and fwd[1] >= U.COS_TOL - 5e-4, fwd
+    T.assert_finetune(out)
+    assert outside and max(outside.values()) == 0.0, {k: v for k, v in outside.items() if v != 0.0}

@@ -297,3 +297,66 @@ def check_finetune_step(B=2, H=16, code_id=5, seed=31):
         if rn == 0.0 and not torch.equal(p.detach(), before[name]):
             moved_without_grad.append(name)
     return lg, lr, gm, moved_without_grad
+
+
+def check_finetune_pruned_semantics(B=2, H=16, code_id=3, seed=13, beta_std=0.1):
+    """Fine-tuning a UNet2DConditionModelPruned (what FineTuner trains, trainer.py:1452-1462): prune() semantics on the
+    dense weights. Reference: autograd of the oracle after its PHYSICAL prune() (sliced conv1 / time_emb_proj / norm2 /
+    conv2). Our gradients restricted to the kept rows / columns must match the sliced model's, the rest must be zero."""
+    import copy
+    from diffusion_pruning_b200 import UNet2DConditionModelPruned
+    from oracle.unet_oracle import GatedUNetOracle, Resnet, UNetConfig, seeded_init
+    from unet_checks import TINY
+    oracle = GatedUNetOracle(UNetConfig.tiny()).eval()
+    seeded_init(oracle, 0, beta_std)
+    model = UNet2DConditionModelPruned(**TINY)
+    model.load_state_dict(oracle.state_dict())
+    model = model.cuda().eval()
+    st = model.get_structure()
+    code = synthetic_codes(st, 8)[code_id:code_id + 1].float()
+    sample, t, ctx = inputs(B, H, model.config["cross_attention_dim"])
+    oracle.set_structure(split_arch(code.clone(), st))
+    keep = {}
+    for name, mod in oracle.named_modules():
+        if isinstance(mod, Resnet):
+            keep[name] = (mod.gate[0] >= 0.5).repeat_interleave(mod.cout // mod.groups)
+    pruned = copy.deepcopy(oracle)
+    pruned.prune()
+    for p in pruned.parameters():
+        p.requires_grad_(True)
+    pred_ref, taps_ref = pruned(sample, t, ctx, return_blocks=True)
+    _loss(pred_ref, taps_ref).backward()
+    acts = {}
+    handles = []
+    blocks = list(model.down_blocks) + [model.mid_block] + list(model.up_blocks)
+    for i, blk in enumerate(blocks):
+        def hook(mod, inp, out, i=i):
+            acts[i] = out[0] if mod.kind == "down" else out
+        handles.append(blk.register_forward_hook(hook))
+    model.prune_to(code * 0.9 + 0.05)
+    model.enable_weight_training(True)
+    pred = model(sample.cuda(), t.cuda(), ctx.cuda()).sample
+    _loss(pred, [acts[i] for i in range(len(blocks))]).backward()
+    torch.cuda.synchronize()
+    from diffusion_pruning_b200 import kernels as K
+    K.check_abort()
+    for h in handles:
+        h.remove()
+    model.enable_weight_training(False)
+    ref = dict(pruned.named_parameters())
+    out, outside = {}, {}
+    for name, p in model.named_parameters():
+        g = p.grad.detach().float().cpu() if p.grad is not None else torch.zeros(p.shape)
+        r = ref[name].grad
+        if r is None:  # depth-dropped block: its parameters are unused after prune()
+            r = torch.zeros_like(ref[name])
+        if r.shape != g.shape:
+            rn_name, leaf = name.rsplit(".", 2)[0], name.split(".")[-2]
+            k = keep[rn_name]
+            outside[name] = (g[:, ~k] if leaf == "conv2" else g[~k]).abs().max().item() if (~k).any() else 0.0
+            g = g[:, k] if leaf == "conv2" else g[k]
+        rn = r.norm().item()
+        out[name] = (((g - r).norm() / max(rn, 1e-20)).item(),
+                     torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item(), rn)
+    gap = metrics(pred.detach(), pred_ref.detach())
+    return out, outside, gap
