@@ -491,21 +491,21 @@ def run_finetune(args):
     from diffusion_pruning_b200 import kernels as K
     from diffusion_pruning_b200 import pruning_step as PS
     from diffusion_pruning_b200.synthetic import split_arch, synthetic_codes
-    from diffusion_pruning_b200.unet import UNet2DConditionModelGated
+    from diffusion_pruning_b200.unet import UNet2DConditionModelGated, UNet2DConditionModelPruned
     Bt = args.train_batch
     torch.manual_seed(1234)
     with torch.device(device):
-        unet = UNet2DConditionModelGated()
+        unet = UNet2DConditionModelPruned()   # what FineTuner trains (trainer.py:1452-1462): prune() semantics
         teacher = UNet2DConditionModelGated()
     teacher.load_state_dict(unet.state_dict())
     teacher.eval()
     teacher.freeze()
     teacher.set_all_ones_structure(1, device=device)
     unet.train()
-    unet.enable_weight_training(True)
     st = unet.get_structure()
     code = synthetic_codes(st, N_CODES)[3:4].float().to(device)
-    unet.set_structure(split_arch(code.clone(), st))
+    unet.prune_to(code * 0.9 + 0.05)      # soft codebook row (quantizer_embeddings.pt), thresholded like prune()
+    unet.enable_weight_training(True)
     cfg = FT.FinetuneLossConfig()
     taps, ttaps = PS.BlockTaps(unet), PS.BlockTaps(teacher)
     params = [p for p in unet.parameters() if p.requires_grad]
@@ -519,7 +519,6 @@ def run_finetune(args):
 
     def step():
         batch = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-        unet.set_structure(split_arch(code.clone(), st))
         out = FT.finetune_step(unet, teacher, batch, cfg, taps, ttaps, acp=acp)
         opt.zero_grad(set_to_none=True)
         out["loss"].backward()

@@ -96,3 +96,50 @@ def test_sharded_sinkhorn_and_contrastive_gather_match_single_process(tmp_path):
     for r in range(world):
         assert torch.allclose(res[r]["loss"], ref_loss.detach(), rtol=1e-5, atol=1e-7)
         assert torch.allclose(res[r]["darch"], arch.grad[r * B_local:(r + 1) * B_local], rtol=1e-4, atol=1e-7)
+
+
+def _sampling_worker(rank, world, port, out_path, P):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diffusion_pruning_b200 import sampling as S
+    g = torch.Generator().manual_seed(50 + rank)
+    prompt = torch.randn(P, 8, generator=g)
+    latents = torch.randn(P, 4, 6, 6, generator=g)
+    cond = torch.randn(P, 5, 16, generator=g)
+    uncond = torch.randn(P, 5, 16, generator=g)
+    idx = torch.randint(0, 8, (P,), generator=g)          # code index of every local prompt
+    arch = torch.nn.functional.one_hot(idx, 8).float()    # stands in for the [P, 1620] hard architecture vectors
+
+    def fake_route(hyper_net, quantizer, prompt_embeddings):
+        return arch, idx
+
+    def fake_denoise(unet, hyper_net, arch_vectors, lat, c, u, num_inference_steps=25, guidance_scale=7.5, acp=None,
+                     prediction_type="v_prediction"):
+        # every prompt that arrives here must belong to an expert this rank owns, with ITS OWN conditioning rows
+        codes = arch_vectors.argmax(dim=1)
+        assert bool((codes % world == rank).all()), (rank, codes)
+        tag = c.mean(dim=(1, 2)) + 2.0 * u.mean(dim=(1, 2))
+        return lat * 2.0 + tag[:, None, None, None] + 1000.0 * rank + 10.0 * codes[:, None, None, None].float()
+
+    S.route_prompts, S.denoise = fake_route, fake_denoise
+    out, got_idx = S.routed_sampling(None, None, None, prompt, latents, cond, uncond)
+    tag = cond.mean(dim=(1, 2)) + 2.0 * uncond.mean(dim=(1, 2))
+    want = latents * 2.0 + tag[:, None, None, None] + 1000.0 * (idx % world)[:, None, None, None].float() + \
+        10.0 * idx[:, None, None, None].float()
+    torch.save({"ok": bool(torch.allclose(out, want, rtol=0, atol=1e-5)), "idx_ok": bool(torch.equal(got_idx, idx)),
+                "owners": torch.bincount(idx % world, minlength=world)}, f"{out_path}.{rank}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_routed_sampling_dispatch_and_return_over_all_to_all(tmp_path, world):
+    """BASELINE configs[3] host logic (sampling.routed_sampling): prompts go to the rank that owns their expert (code %
+    world), are processed there with their own latents / text rows, and come back to the asking rank in the caller's
+    order -- uneven expert load, variable split sizes. `denoise` is replaced by a tagging function."""
+    out = str(tmp_path / "res")
+    mp.spawn(_sampling_worker, args=(world, _free_port(), out, 11), nprocs=world, join=True)
+    res = [torch.load(f"{out}.{r}") for r in range(world)]
+    assert all(r["ok"] for r in res) and all(r["idx_ok"] for r in res), res

@@ -102,3 +102,32 @@ def test_oracle_prune_equals_gated_iff_groupnorm_beta_is_zero():
             y_pruned = p(x, t, c)
         diff = (y_gated - y_pruned).abs().max().item()
         assert (diff < 1e-4) if same else (diff > 1e-3), (beta_std, diff)
+
+
+def test_macs_device_tables_cover_the_gate_matrix_and_reproduce_the_closed_form():
+    """Host logic of the K7 kernel (macs._device_tables): the aptp_macs_gate / aptp_macs_sub records must tile the
+    [B, 1620-like] gate matrix exactly once (width columns, then depth columns, get_structure order) and carry the same
+    constants as the torch closed form (evaluated here on CPU gates)."""
+    import numpy as np
+    from diffusion_pruning_b200 import macs as M
+    m = UNet2DConditionModelGated(**TINY)
+    m.count_macs(16, 16)
+    tab = M._device_tables(m, torch.device("cpu"))
+    from diffusion_pruning_b200 import kernels as K
+    gates = tab["gates"].numpy().view(K.MACS_GATE_DTYPE)
+    subs = tab["subs"].numpy().view(K.MACS_SUB_DTYPE)
+    st = m.get_structure()
+    widths = [w for ws in st["width"] for w in ws]
+    n_depth = sum(1 for d in st["depth"] if d == [1])
+    assert len(gates) == len(widths) == tab["n_gates"] and len(subs) == len(st["width"]) == tab["n_subs"]
+    assert gates["width"].tolist() == widths
+    assert gates["col"].tolist() == np.concatenate([[0], np.cumsum(widths)[:-1]]).tolist()
+    dcols = [int(c) for c in subs["depth_col"] if c >= 0]
+    assert dcols == list(range(sum(widths), sum(widths) + n_depth)) and tab["dim"] == sum(widths) + n_depth
+    assert subs["first_gate"].tolist() == np.concatenate([[0], np.cumsum(subs["n_gates"])[:-1]]).tolist()
+    # all-ones gates: cur_prunable = sum of gate MACs + fixed parts of the depth-gated sub-blocks; totals match the closed form
+    d = M._calc_macs_torch(m)
+    depth_fixed = float(sum(s["fixed"] for s in subs if s["depth_col"] >= 0))
+    assert abs(float(gates["macs"].sum()) + depth_fixed - float(d["cur_prunable_macs"])) <= 1e-6 * float(d["cur_prunable_macs"])
+    assert abs(tab["total"] - d["total_macs"]) <= 1e-9 * d["total_macs"]
+    assert abs(tab["prunable"] - d["prunable_macs"]) <= 1e-9 * d["prunable_macs"]
