@@ -187,12 +187,19 @@ __global__ void __launch_bounds__(256) col_sum_kernel(const __nv_bfloat16* __res
   const long long r_end = min(rows, r_begin + rows_per_cta);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < n_out) {
-    for (long long r = r_begin + rl; r < r_end; r += 32) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(dy + r * ld + col));
-      acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x);
-      acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
-      acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z);
-      acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+    for (long long r = r_begin + rl; r < r_end; r += 128) {  // 4 independent 16-byte loads in flight per thread
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        q[u] = (r + 32 * u < r_end) ? __ldg(reinterpret_cast<const uint4*>(dy + (r + 32 * u) * ld + col))
+                                    : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16_lo(q[u].x); acc[1] += bf16_hi(q[u].x);
+        acc[2] += bf16_lo(q[u].y); acc[3] += bf16_hi(q[u].y);
+        acc[4] += bf16_lo(q[u].z); acc[5] += bf16_hi(q[u].z);
+        acc[6] += bf16_lo(q[u].w); acc[7] += bf16_hi(q[u].w);
+      }
     }
   }
 #pragma unroll
@@ -220,12 +227,19 @@ __global__ void __launch_bounds__(256) col_sum_groups_kernel(const __nv_bfloat16
   const int r_end = min(rows_per_group, r_begin + rows_per_cta);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < n_out) {
-    for (int r = r_begin + rl; r < r_end; r += 32) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(dy + (base + r) * ld + col));
-      acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x);
-      acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
-      acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z);
-      acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+    for (int r = r_begin + rl; r < r_end; r += 128) {  // 4 independent 16-byte loads in flight per thread
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        q[u] = (r + 32 * u < r_end) ? __ldg(reinterpret_cast<const uint4*>(dy + (base + r + 32 * u) * ld + col))
+                                    : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16_lo(q[u].x); acc[1] += bf16_hi(q[u].x);
+        acc[2] += bf16_lo(q[u].y); acc[3] += bf16_hi(q[u].y);
+        acc[4] += bf16_lo(q[u].z); acc[5] += bf16_hi(q[u].z);
+        acc[6] += bf16_lo(q[u].w); acc[7] += bf16_hi(q[u].w);
+      }
     }
   }
 #pragma unroll
@@ -325,7 +339,7 @@ extern "C" int aptp_wgrad(const void* dy, int32_t ld_dy, const void* a, int32_t 
   wgrad_kernel<<<dim3(tiles, splits), WG_THREADS, WG_SMEM_BYTES, stream>>>(p);
   APTP_CUDA_CHECK(cudaGetLastError());
   if (dbias) {
-    const int rows_per_cta = 4096;
+    const int rows_per_cta = 1024;  // ~4 CTAs per SM at the 64x64 level: enough loads in flight to cover HBM latency
     dim3 grid((n_out + 63) / 64, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
     col_sum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), ld_dy, rows, n_out, dbias,
                                             rows_per_cta);
@@ -341,7 +355,7 @@ extern "C" int aptp_col_sum_groups(const void* dy, int32_t ld, int32_t groups, i
   APTP_REQUIRE(ld % 8 == 0 && n_out > 0 && n_out % 8 == 0 && rows_per_group > 0 && out_ld >= n_out,
                "aptp_col_sum_groups: bad sizes");
   if (groups == 0) return APTP_OK;
-  const int rows_per_cta = 2048;
+  const int rows_per_cta = 1024;
   const int chunks = (rows_per_group + rows_per_cta - 1) / rows_per_cta;
   APTP_REQUIRE((long long)groups * chunks <= 65535, "aptp_col_sum_groups: grid too large");
   dim3 grid((n_out + 63) / 64, (unsigned)(groups * chunks));
