@@ -14,7 +14,7 @@ Only the scalar loss algebra on top of the kernel outputs uses PyTorch ops.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, Optional
 
 import torch
 import torch.distributed as dist

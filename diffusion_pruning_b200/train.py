@@ -12,8 +12,6 @@ outputs are the prediction plus the nine hooked block activations (trainer.py:49
 """
 from __future__ import annotations
 
-import os
-
 from typing import Any, Dict, List, Optional, Tuple
 
 import torch
