@@ -222,23 +222,34 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_dq_kernel(const __grid
         tc_fence_after();
         uint32_t s[64], dp[64];
         tmem_ld_32x32(t, s);
-        tmem_ld_32x32(t + 32, s + 32);
         tmem_ld_32x32(t + 64, dp);
+        tmem_ld_wait();
+        tmem_ld_32x32(t + 32, s + 32);   // keys 32..63 of the tile arrive under the first half's math
         tmem_ld_32x32(t + 96, dp + 32);
+        const int kv_left = p.n_kv - j * 64;
+        const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        const uint64_t nL2 = pack_f32x2(-L, -L), ndl2 = pack_f32x2(-dl, -dl);
+        uint32_t pk[32];
+        // dS = 2^(S c - L) (dP - delta) for keys [32 h, 32 h + 32), packed fp32x2 math; masked past the last key
+        auto half = [&](int h) {
+#pragma unroll
+          for (int i = 32 * h; i < 32 * h + 32; i += 2) {
+            float x0, x1, d0, d1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), scale2, nL2), x0, x1);
+            float p0 = ex2_approx_ordered(x0), p1 = ex2_approx_ordered(x1);
+            if (i >= kv_left) p0 = 0.f;
+            if (i + 1 >= kv_left) p1 = 0.f;
+            const uint64_t t2 = add_f32x2(pack_f32x2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), ndl2);
+            unpack_f32x2(fma_f32x2(pack_f32x2(p0, p1), t2, 0ull), d0, d1);
+            pk[i >> 1] = pack_bf16(d0, d1);
+          }
+        };
+        if (p.n_q > 0) half(0);  // always true; the branch keeps ptxas from sinking this half below the next wait
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&B.s_free[w]);
-        const int kv_left = p.n_kv - j * 64;
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), p.scale_log2, -L));
-          float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -L));
-          if (i >= kv_left) p0 = 0.f;
-          if (i + 1 >= kv_left) p1 = 0.f;
-          pk[i >> 1] = pack_bf16(p0 * (__uint_as_float(dp[i]) - dl), p1 * (__uint_as_float(dp[i + 1]) - dl));
-        }
+        if (p.n_kv > 0) half(1);  // (opaque as above: keeps the early s_free ahead of this half's math)
         if (j > 0) {  // the dQ MMA of the previous step must have consumed dS
           ok = mbar_wait(&B.acc_done[w], (j - 1) & 1, p.abort_flag);
           if (!ok) break;
