@@ -43,7 +43,7 @@ class GemmArgs(C.Structure):
 
 A_LINEAR, A_CONV3X3, A_CONV3X3_S2 = 0, 1, 2
 OUT_BF16, OUT_F32, OUT_F32_NCHW = 0, 1, 2
-EPI_GEGLU, EPI_SILU, EPI_GN_STATS = 1, 2, 4
+EPI_GEGLU, EPI_SILU, EPI_GN_STATS, EPI_RES_F32 = 1, 2, 4, 8
 
 # name -> (restype, argtypes); must list every symbol declared in include/aptp_sm100.h
 SIGNATURES = {
@@ -51,11 +51,17 @@ SIGNATURES = {
     "aptp_last_error": (C.c_char_p, []),
     "aptp_check_abort": (c_int, [c_void_p]),
     "aptp_grouped_gemm_fwd": (c_int, [C.POINTER(GemmArgs), c_void_p]),
-    "aptp_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                     c_void_p, c_int, c_void_p]),
-    "aptp_groupnorm_apply": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,
-                                     c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                     c_void_p, c_int, c_int, c_void_p]),
+    "aptp_groupnorm_stats_workspace": (c_int64, [c_int, c_int, c_int]),
+    "aptp_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "aptp_groupnorm_apply": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                     c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "aptp_copy_rows_cvt": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
+                                   c_void_p]),
+    "aptp_depth_lerp_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int,
+                                    c_void_p]),
+    "aptp_upsample2x_cvt": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "aptp_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p,
                                c_void_p, c_int, c_void_p]),
     "aptp_depth_lerp": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int,

@@ -83,6 +83,106 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
   }
 }
 
+// ---- fp32 residual-stream variants (round 2: the stream between blocks is fp32) ----
+// 8 channels per work item, read as bf16 (16 B) or fp32 (32 B), written as bf16 or fp32.
+template <bool kF32>
+__device__ __forceinline__ void load8(const void* base, long long elem_off, float* f) {
+  if constexpr (kF32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8e(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off)), f);
+  }
+}
+template <bool kF32>
+__device__ __forceinline__ void store8(void* base, long long elem_off, const float* f) {
+  if constexpr (kF32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
+    p[0] = make_float4(f[0], f[1], f[2], f[3]);
+    p[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]);
+    o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]);
+    o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = o;
+  }
+}
+
+template <bool kSrcF32, bool kDstF32>
+__global__ void __launch_bounds__(256) copy_rows_cvt_kernel(const void* __restrict__ src, int lds, void* __restrict__ dst,
+                                                            int ldd, long long rows, int cv,
+                                                            const uint8_t* __restrict__ mask, int rows_per_sample) {
+  const long long total = rows * cv;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * T) {
+    float val[2][8];
+    long long off[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * T;
+      off[u] = -1;
+      if (i < total) {
+        const long long row = i / cv;
+        const int v = (int)(i - row * cv);
+        if (!mask || mask[row / rows_per_sample]) {
+          load8<kSrcF32>(src, row * lds + v * 8, val[u]);
+          off[u] = row * ldd + v * 8;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (off[u] >= 0) store8<kDstF32>(dst, off[u], val[u]);
+  }
+}
+
+// out = (1-d[b]) * x + d[b] * y, all fp32 rows (DepthGate on the fp32 stream)
+__global__ void __launch_bounds__(256) depth_lerp_f32_kernel(const float* x, int ldx, const float* y, int ldy,
+                                                             float* out, int ldo, long long rows, int cv,
+                                                             const float* __restrict__ d, int rows_per_sample) {
+  const long long total = rows * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / cv;
+    const int v = (int)(i - row * cv);
+    const float dd = d[row / rows_per_sample];
+    // plain (coherent) loads: `out` may alias `y`
+    const float4* xp = reinterpret_cast<const float4*>(x + row * ldx + v * 8);
+    const float4* yp = reinterpret_cast<const float4*>(y + row * ldy + v * 8);
+    const float4 a0 = xp[0], a1 = xp[1], b0 = yp[0], b1 = yp[1];
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = (1.f - dd) * a[e] + dd * b[e];
+    store8<true>(out, row * ldo + v * 8, r);
+  }
+}
+
+template <bool kSrcF32>
+__global__ void __launch_bounds__(256) upsample2x_cvt_kernel(const void* __restrict__ src,
+                                                             __nv_bfloat16* __restrict__ dst, int batch, int H, int W,
+                                                             int cv) {
+  const long long total = (long long)batch * (2 * H) * (2 * W) * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long pix = i / cv;
+    const int ox = (int)(pix % (2 * W));
+    pix /= (2 * W);
+    const int oy = (int)(pix % (2 * H));
+    const int b = (int)(pix / (2 * H));
+    const long long sp = ((long long)b * H + (oy >> 1)) * W + (ox >> 1);
+    float f[8];
+    load8<kSrcF32>(src, (sp * cv + v) * 8, f);
+    store8<false>(dst, i * 8, f);
+  }
+}
+
 // conv_in as a GEMM: rows = pixels, K = (tap, cin) zero-padded to 64.
 __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ dst,
                                                            int batch, int Cin, int H, int W) {
@@ -122,6 +222,16 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
                                                             long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16(src[i]);
+}
+
+// n % 8 == 0 and 16-byte aligned pointers: 32-byte loads, 16-byte stores
+__global__ void __launch_bounds__(256) cast_f32_bf16_vec_kernel(const float* __restrict__ src,
+                                                                __nv_bfloat16* __restrict__ dst, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    load8<true>(src, i * 8, f);
+    store8<false>(dst, i * 8, f);
+  }
 }
 
 __global__ void __launch_bounds__(256) silu_bf16_kernel(const __nv_bfloat16* __restrict__ src,
@@ -194,6 +304,55 @@ extern "C" int aptp_copy_rows(const void* src, int32_t lds, void* dst, int32_t l
   return APTP_OK;
 }
 
+extern "C" int aptp_copy_rows_cvt(const void* src, int32_t src_f32, int32_t lds, void* dst, int32_t dst_f32,
+                                  int32_t ldd, int64_t rows, int32_t C, const uint8_t* sample_mask,
+                                  int32_t rows_per_sample, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(src && dst, "aptp_copy_rows_cvt: null pointer");
+  APTP_REQUIRE(C % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0 && rows_per_sample > 0,
+               "aptp_copy_rows_cvt: C and pitches must be multiples of 8");
+  if (rows == 0) return APTP_OK;
+  const unsigned grid = grid_for(rows * (C / 8));
+#define APTP_CVT(SF, DF) \
+  copy_rows_cvt_kernel<SF, DF><<<grid, 256, 0, stream>>>(src, lds, dst, ldd, rows, C / 8, sample_mask, rows_per_sample)
+  if (src_f32 && dst_f32) APTP_CVT(true, true);
+  else if (src_f32) APTP_CVT(true, false);
+  else if (dst_f32) APTP_CVT(false, true);
+  else APTP_CVT(false, false);
+#undef APTP_CVT
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_depth_lerp_f32(const float* x, int32_t ldx, const float* y, int32_t ldy, float* out, int32_t ldo,
+                                   int64_t rows, int32_t C, const float* d, int32_t rows_per_sample, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(x && y && out && d, "aptp_depth_lerp_f32: null pointer");
+  APTP_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldo % 8 == 0 && rows_per_sample > 0,
+               "aptp_depth_lerp_f32: C and pitches must be multiples of 8");
+  if (rows == 0) return APTP_OK;
+  depth_lerp_f32_kernel<<<grid_for(rows * (C / 8)), 256, 0, stream>>>(x, ldx, y, ldy, out, ldo, rows, C / 8, d,
+                                                                     rows_per_sample);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_upsample2x_cvt(const void* src, int32_t src_f32, void* dst, int32_t batch, int32_t H, int32_t W,
+                                   int32_t C, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(src && dst && C % 8 == 0, "aptp_upsample2x_cvt: bad arguments");
+  const long long total = (long long)batch * 4 * H * W * (C / 8);
+  if (total == 0) return APTP_OK;
+  if (src_f32)
+    upsample2x_cvt_kernel<true><<<grid_for(total), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), batch,
+                                                                    H, W, C / 8);
+  else
+    upsample2x_cvt_kernel<false><<<grid_for(total), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), batch,
+                                                                     H, W, C / 8);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
 extern "C" int aptp_upsample2x(const void* src, void* dst, int32_t batch, int32_t H, int32_t W, int32_t C,
                                void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -232,7 +391,10 @@ extern "C" int aptp_cast_f32_bf16(const float* src, void* dst, int64_t n, void* 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   APTP_REQUIRE(src && dst, "aptp_cast_f32_bf16: null pointer");
   if (n == 0) return APTP_OK;
-  cast_f32_bf16_kernel<<<grid_for(n), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  if (n % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+    cast_f32_bf16_vec_kernel<<<grid_for(n / 8), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n / 8);
+  else
+    cast_f32_bf16_kernel<<<grid_for(n), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

@@ -53,7 +53,7 @@ struct GemmParams {
   const float* bias;
   const float* rowvec;
   int rowvec_ld, rows_per_sample;
-  const __nv_bfloat16* residual;
+  const void* residual;  // bf16 rows, or fp32 rows with APTP_EPI_RES_F32 (fp32 residual stream)
   int res_ld;
   const float* gate;
   int gate_ld, gate_group;
@@ -368,8 +368,22 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         for (int it = 0; it < 4; ++it) {
           rres[it] = make_uint4(0u, 0u, 0u, 0u);
           if (co_ok[it] && col0 + co_q * 8 < seg.n_valid)
-            rres[it] = *reinterpret_cast<const uint4*>(p.residual + (size_t)co_row[it] * p.res_ld +
-                                                       seg.out_col_off + col0 + co_q * 8);  // may alias `out`
+            rres[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                       (size_t)co_row[it] * p.res_ld + seg.out_col_off + col0 +
+                                                       co_q * 8);  // may alias `out`
+        }
+      };
+      // fp32 residual stream (block outputs): every lane reads the 32 floats of ITS OWN row
+      // (128 contiguous bytes) and adds them before the fp32 store; the chunk's loads are issued one chunk ahead
+      const bool use_res32 = !kGeglu && (p.residual != nullptr) && (p.out_mode == APTP_OUT_F32) &&
+                             (p.flags & APTP_EPI_RES_F32) != 0;
+      float4 rres32[8];
+      auto load_res32 = [&](int col0) {
+        const float* rp = reinterpret_cast<const float*>(p.residual) + (size_t)row * p.res_ld + seg.out_col_off + col0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          rres32[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && col0 + q * 4 < seg.n_valid) rres32[q] = *reinterpret_cast<const float4*>(rp + q * 4);  // may alias `out`
         }
       };
       // this tile's chunks are dealt round-robin to the EPI_PER_QUAD warps of the quadrant, continuing where the
@@ -393,6 +407,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       };
       if (c_first < n_chunks) {
         if (use_res && ocol_base + c_first * 32 < seg.n_store) load_res(ocol_base + c_first * 32);
+        if (use_res32 && ocol_base + c_first * 32 < seg.n_store) load_res32(ocol_base + c_first * 32);
         load_bias(c_first);
       }
 
@@ -524,13 +539,25 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           for (int it = 0; it < 4; ++it)
             if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o4[it];
           __syncwarp();
-        } else if (valid) {
+        } else if (use_res32 || valid) {
+          if (use_res32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              v[q * 4 + 0] += rres32[q].x;
+              v[q * 4 + 1] += rres32[q].y;
+              v[q * 4 + 2] += rres32[q].z;
+              v[q * 4 + 3] += rres32[q].w;
+            }
+            if (more) load_res32(col0 + 32 * EPI_PER_QUAD);  // warp-uniform condition
+          }
           if (n_ok < 32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j >= n_ok) v[j] = 0.f;
           }
-          if (p.out_mode == APTP_OUT_F32) {
+          if (!valid) {
+            // nothing to store for this row
+          } else if (p.out_mode == APTP_OUT_F32) {
             float* op = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_ld + seg.out_col_off + col0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -584,8 +611,13 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
                    (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
                "aptp_grouped_gemm_fwd: operands must be 16-byte aligned");
   APTP_REQUIRE(a->rows_per_sample > 0, "aptp_grouped_gemm_fwd: rows_per_sample must be > 0");
-  APTP_REQUIRE(a->residual == nullptr || (a->out_mode == APTP_OUT_BF16 && a->res_ld % 8 == 0),
-               "aptp_grouped_gemm_fwd: residual needs a bf16 output and res_ld %% 8 == 0");
+  if (a->flags & APTP_EPI_RES_F32)
+    APTP_REQUIRE(a->residual != nullptr && a->out_mode == APTP_OUT_F32 && a->res_ld % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0,
+                 "aptp_grouped_gemm_fwd: APTP_EPI_RES_F32 needs an fp32 residual (16-byte aligned rows) and APTP_OUT_F32");
+  else
+    APTP_REQUIRE(a->residual == nullptr || (a->out_mode == APTP_OUT_BF16 && a->res_ld % 8 == 0),
+                 "aptp_grouped_gemm_fwd: a bf16 residual needs a bf16 output and res_ld %% 8 == 0");
   APTP_REQUIRE(a->a_rows < (1ll << 31), "aptp_grouped_gemm_fwd: too many rows");
   APTP_REQUIRE(!(a->flags & APTP_EPI_GN_STATS), "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS not implemented yet");
   if (a->flags & APTP_EPI_GEGLU) {
@@ -662,7 +694,7 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   p.rowvec = a->rowvec;
   p.rowvec_ld = a->rowvec_ld;
   p.rows_per_sample = a->rows_per_sample;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.residual = a->residual;
   p.res_ld = a->res_ld;
   p.gate = a->gate;
   p.gate_ld = a->gate_ld;

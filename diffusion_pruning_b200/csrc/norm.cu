@@ -17,16 +17,10 @@ constexpr int NORM_THREADS = 256;
 constexpr int MAX_SLOTS = 2;  // 8-channel vectors per thread: supports up to 256*2*8 = 4096 channels
 
 struct Src2 {
-  const __nv_bfloat16* x0;
-  const __nv_bfloat16* x1;
+  const void* x0;  // bf16 or fp32 (kF32) rows
+  const void* x1;
   int c0, ld0, c1, ld1;
 };
-
-__device__ __forceinline__ uint4 load_vec(const Src2& s, long long pix, int c) {
-  // c is a multiple of 8; c0 is a multiple of 8 so a vector never straddles the two sources
-  if (c < s.c0) return __ldg(reinterpret_cast<const uint4*>(s.x0 + pix * s.ld0 + c));
-  return __ldg(reinterpret_cast<const uint4*>(s.x1 + pix * s.ld1 + (c - s.c0)));
-}
 
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
@@ -35,45 +29,61 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
 }
 
-// Merge a thread's 8 per-channel partial sums into per-group runs before touching shared memory.
-__device__ __forceinline__ void flush_runs(float* bins, const float* sum, const float* sq, int c_first, int ctot,
-                                           int gs) {
-  int g_run = -1;
-  float s_run = 0.f, q_run = 0.f;
+// 8 consecutive channels of one pixel as raw 16-byte vectors: one for bf16 rows, two for fp32 rows (the residual
+// stream between blocks is kept in fp32).
+template <bool kF32>
+struct Vec8 {
+  uint4 q[kF32 ? 2 : 1];
+  __device__ __forceinline__ void zero() {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = c_first + e;
-    if (c >= ctot) break;
-    const int g = c / gs;
-    if (g != g_run) {
-      if (g_run >= 0) {
-        atomicAdd(&bins[2 * g_run], s_run);
-        atomicAdd(&bins[2 * g_run + 1], q_run);
-      }
-      g_run = g;
-      s_run = 0.f;
-      q_run = 0.f;
+    for (int i = 0; i < (kF32 ? 2 : 1); ++i) q[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __device__ __forceinline__ void to_float(float* f) const {
+    if constexpr (kF32) {
+      f[0] = __uint_as_float(q[0].x); f[1] = __uint_as_float(q[0].y);
+      f[2] = __uint_as_float(q[0].z); f[3] = __uint_as_float(q[0].w);
+      f[4] = __uint_as_float(q[1].x); f[5] = __uint_as_float(q[1].y);
+      f[6] = __uint_as_float(q[1].z); f[7] = __uint_as_float(q[1].w);
+    } else {
+      unpack8(q[0], f);
     }
-    s_run += sum[e];
-    q_run += sq[e];
   }
-  if (g_run >= 0) {
-    atomicAdd(&bins[2 * g_run], s_run);
-    atomicAdd(&bins[2 * g_run + 1], q_run);
+};
+
+template <bool kF32>
+__device__ __forceinline__ Vec8<kF32> load_vec(const Src2& s, long long pix, int c) {
+  // c is a multiple of 8; c0 is a multiple of 8 so a vector never straddles the two sources
+  Vec8<kF32> r;
+  if constexpr (kF32) {
+    const float* p = (c < s.c0) ? reinterpret_cast<const float*>(s.x0) + pix * s.ld0 + c
+                                : reinterpret_cast<const float*>(s.x1) + pix * s.ld1 + (c - s.c0);
+    r.q[0] = __ldg(reinterpret_cast<const uint4*>(p));
+    r.q[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  } else {
+    const __nv_bfloat16* p = (c < s.c0) ? reinterpret_cast<const __nv_bfloat16*>(s.x0) + pix * s.ld0 + c
+                                        : reinterpret_cast<const __nv_bfloat16*>(s.x1) + pix * s.ld1 + (c - s.c0);
+    r.q[0] = __ldg(reinterpret_cast<const uint4*>(p));
   }
+  return r;
 }
 
-__global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(Src2 s, int hw, int gs, const int* __restrict__ sample_channels,
-                                                                float* __restrict__ stats, int stats_groups,
-                                                                int pix_per_cta) {
-  extern __shared__ float bins[];  // [2 * stats_groups]
+// Statistics pass. DETERMINISTIC (round 2; round 1 used fp32 atomics, so a forward was not bit-reproducible):
+//   1. every thread keeps per-channel partial sums of its pixels in registers and stores them to shared memory,
+//   2. one warp per group sums the group's (pixel-row, channel) cells in a fixed order + a fixed shuffle tree,
+//   3. the CTA writes its per-group partials to the workspace; the LAST CTA of a sample to arrive (ticket counter)
+//      adds the chunks' partials in chunk order, whichever CTA that happens to be, and resets the counter.
+template <bool kF32>
+__global__ void __launch_bounds__(NORM_THREADS)
+    gn_stats_kernel(Src2 s, int hw, int gs, const int* __restrict__ sample_channels, float* __restrict__ stats,
+                    int stats_groups, int pix_per_cta, unsigned int* __restrict__ tickets, float* __restrict__ partial) {
+  extern __shared__ float cells[];  // [2][rows_per_iter][cv * 8]  (sum plane, then sum-of-squares plane)
+  __shared__ int s_last;
   const int b = blockIdx.y;
   const int ctot = sample_channels ? sample_channels[b] : (s.c0 + s.c1);
-  if (ctot <= 0) return;
+  if (ctot <= 0) return;  // uniform over the sample's CTAs
   const int cv = (ctot + 7) / 8;
   const int groups = (ctot + gs - 1) / gs;
-  for (int i = threadIdx.x; i < 2 * stats_groups; i += NORM_THREADS) bins[i] = 0.f;
-  __syncthreads();
+  const int cpad = cv * 8;
 
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(hw, p_begin + pix_per_cta);
@@ -83,19 +93,22 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(Src2 s, int hw, 
 #pragma unroll
     for (int e = 0; e < 8; ++e) sum[q][e] = sq[q][e] = 0.f;
 
+  int n_rows;  // pixel rows held in shared memory
   if (cv <= NORM_THREADS) {
     const int rows_per_iter = NORM_THREADS / cv;
+    n_rows = rows_per_iter;
     const int v = threadIdx.x % cv;
     const int prow = threadIdx.x / cv;
     if (prow < rows_per_iter) {
       // software pipeline: the 4 loads of the NEXT step are in flight while this step's values are reduced
       const int step = 4 * rows_per_iter;
-      uint4 cur[4], nxt[4];
-      auto load4 = [&](uint4* dst, int p) {
+      Vec8<kF32> cur[4], nxt[4];
+      auto load4 = [&](Vec8<kF32>* dst, int p) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int pp = p + u * rows_per_iter;
-          dst[u] = (pp < p_end) ? load_vec(s, (long long)b * hw + pp, v * 8) : make_uint4(0u, 0u, 0u, 0u);
+          if (pp < p_end) dst[u] = load_vec<kF32>(s, (long long)b * hw + pp, v * 8);
+          else dst[u].zero();
         }
       };
       load4(cur, p_begin + prow);
@@ -104,7 +117,7 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(Src2 s, int hw, 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float f[8];
-          unpack8(cur[u], f);
+          cur[u].to_float(f);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             sum[0][e] += f[e];
@@ -114,16 +127,21 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(Src2 s, int hw, 
 #pragma unroll
         for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
       }
-      flush_runs(bins, sum[0], sq[0], v * 8, ctot, gs);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        cells[prow * cpad + v * 8 + e] = sum[0][e];
+        cells[(n_rows + prow) * cpad + v * 8 + e] = sq[0][e];
+      }
     }
   } else {
+    n_rows = 1;
     for (int p = p_begin; p < p_end; ++p) {
 #pragma unroll
       for (int q = 0; q < MAX_SLOTS; ++q) {
         const int v = threadIdx.x + q * NORM_THREADS;
         if (v < cv) {
           float f[8];
-          unpack8(load_vec(s, (long long)b * hw + p, v * 8), f);
+          load_vec<kF32>(s, (long long)b * hw + p, v * 8).to_float(f);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             sum[q][e] += f[e];
@@ -136,15 +154,57 @@ __global__ void __launch_bounds__(NORM_THREADS) gn_stats_kernel(Src2 s, int hw, 
     for (int q = 0; q < MAX_SLOTS; ++q) {
       const int v = threadIdx.x + q * NORM_THREADS;
       if (v < cv) {
-        flush_runs(bins, sum[q], sq[q], v * 8, ctot, gs);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          cells[v * 8 + e] = sum[q][e];
+          cells[cpad + v * 8 + e] = sq[q][e];
+        }
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * groups; i += NORM_THREADS)
-    atomicAdd(&stats[(size_t)b * stats_groups * 2 + i], bins[i]);
+  // fixed-order reduction: warp w owns groups w, w + 8, ...; lane l adds cells l, l + 32, ... then a shuffle tree
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* my_partial = partial + ((size_t)b * gridDim.x + blockIdx.x) * (2 * stats_groups);
+  for (int g = warp; g < groups; g += NORM_THREADS / 32) {
+    const int c_lo = g * gs, c_hi = min(ctot, c_lo + gs);
+    const int width = c_hi - c_lo;
+    const int n_cells = n_rows * width;
+    float a = 0.f, q2 = 0.f;
+    for (int i = lane; i < n_cells; i += 32) {
+      const int r = i / width, c = c_lo + (i - r * width);
+      a += cells[r * cpad + c];
+      q2 += cells[(n_rows + r) * cpad + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+    }
+    if (lane == 0) {
+      my_partial[2 * g] = a;
+      my_partial[2 * g + 1] = q2;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[b], 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pb = partial + (size_t)b * gridDim.x * (2 * stats_groups);
+  for (int i = threadIdx.x; i < 2 * groups; i += NORM_THREADS) {
+    float acc = 0.f;
+    for (unsigned int ch = 0; ch < gridDim.x; ++ch) acc += __ldcg(pb + (size_t)ch * (2 * stats_groups) + i);
+    stats[(size_t)b * stats_groups * 2 + i] = acc;
+  }
+  if (threadIdx.x == 0) tickets[b] = 0u;  // ready for the next launch on this stream
 }
 
+template <bool kF32>
 __global__ void __launch_bounds__(NORM_THREADS)
     gn_apply_kernel(Src2 s, __nv_bfloat16* __restrict__ y, int ldy, int hw, int gs, float eps,
                     const float* __restrict__ stats, int stats_groups, const float* __restrict__ gamma,
@@ -195,12 +255,13 @@ __global__ void __launch_bounds__(NORM_THREADS)
     }
     const bool has_data = v * 8 < ctot;
     const int step = 4 * rows_per_iter;
-    uint4 cur[4], nxt[4];
-    auto load4 = [&](uint4* dst, int p) {
+    Vec8<kF32> cur[4], nxt[4];
+    auto load4 = [&](Vec8<kF32>* dst, int p) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int pp = p + u * rows_per_iter;
-        dst[u] = (has_data && pp < p_end) ? load_vec(s, (long long)b * hw + pp, v * 8) : make_uint4(0u, 0u, 0u, 0u);
+        if (has_data && pp < p_end) dst[u] = load_vec<kF32>(s, (long long)b * hw + pp, v * 8);
+        else dst[u].zero();
       }
     };
     load4(cur, p_begin + prow);
@@ -211,7 +272,7 @@ __global__ void __launch_bounds__(NORM_THREADS)
         const int pp = p + u * rows_per_iter;
         if (pp >= p_end) break;
         float f[8];
-        unpack8(cur[u], f);
+        cur[u].to_float(f);
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -431,38 +492,70 @@ static int check_src(const void* x0, int c0, int ld0, const void* x1, int c1, in
   return APTP_OK;
 }
 
+// workspace of aptp_groupnorm_stats: [batch] ticket counters (zero on entry, left zero) + per-CTA partials
+static long long gn_ws_bytes(int batch, int hw, int stats_groups) {
+  const int ppc = pick_pix_per_cta(hw, batch);
+  const long long chunks = (hw + ppc - 1) / ppc;
+  const long long tickets = ((long long)batch * 4 + 255) & ~255LL;
+  return tickets + (long long)batch * chunks * 2 * stats_groups * 4;
+}
+
+extern "C" int64_t aptp_groupnorm_stats_workspace(int32_t batch, int32_t hw, int32_t stats_groups) {
+  if (batch <= 0 || hw <= 0 || stats_groups <= 0) return 0;
+  return gn_ws_bytes(batch, hw, stats_groups);
+}
+
 extern "C" int aptp_groupnorm_stats(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
-                                    int32_t batch, int32_t hw, int32_t group_size, const int32_t* sample_channels,
-                                    float* stats, int32_t stats_groups, void* stream_) {
+                                    int32_t x_f32, int32_t batch, int32_t hw, int32_t group_size,
+                                    const int32_t* sample_channels, float* stats, int32_t stats_groups,
+                                    void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int rc = check_src(x0, c0, ld0, x1, c1, ld1, "aptp_groupnorm_stats");
   if (rc) return rc;
   APTP_REQUIRE(stats && group_size > 0 && batch > 0 && hw > 0, "aptp_groupnorm_stats: bad arguments");
   APTP_REQUIRE((c0 + c1 + group_size - 1) / group_size <= stats_groups, "aptp_groupnorm_stats: stats_groups too small");
-  Src2 s{reinterpret_cast<const __nv_bfloat16*>(x0), reinterpret_cast<const __nv_bfloat16*>(x1), c0, ld0, c1, ld1};
+  APTP_REQUIRE(workspace && workspace_bytes >= gn_ws_bytes(batch, hw, stats_groups) &&
+                   (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+               "aptp_groupnorm_stats: workspace too small (%lld bytes needed, see aptp_groupnorm_stats_workspace)",
+               gn_ws_bytes(batch, hw, stats_groups));
+  Src2 s{x0, x1, c0, ld0, c1, ld1};
   const int ppc = pick_pix_per_cta(hw, batch);
   dim3 grid((hw + ppc - 1) / ppc, batch);
-  gn_stats_kernel<<<grid, NORM_THREADS, 2 * stats_groups * sizeof(float), stream>>>(s, hw, group_size, sample_channels,
-                                                                                 stats, stats_groups, ppc);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + (((long long)batch * 4 + 255) & ~255LL));
+  const int C = c0 + c1;
+  const size_t smem = (size_t)2 * (C > NORM_THREADS * 8 ? C : NORM_THREADS * 8) * sizeof(float);
+  if (x_f32)
+    gn_stats_kernel<true><<<grid, NORM_THREADS, smem, stream>>>(s, hw, group_size, sample_channels, stats,
+                                                               stats_groups, ppc, tickets, partial);
+  else
+    gn_stats_kernel<false><<<grid, NORM_THREADS, smem, stream>>>(s, hw, group_size, sample_channels, stats,
+                                                                stats_groups, ppc, tickets, partial);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }
 
 extern "C" int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
-                                    void* y, int32_t ldy, int32_t batch, int32_t hw, int32_t group_size, float eps,
-                                    const float* stats, int32_t stats_groups, const float* gamma, const float* beta,
-                                    int32_t affine_ld, const int32_t* sample_seg, const int32_t* sample_channels,
-                                    const float* gate, int32_t gate_ld, int32_t silu, void* stream_) {
+                                    int32_t x_f32, void* y, int32_t ldy, int32_t batch, int32_t hw,
+                                    int32_t group_size, float eps, const float* stats, int32_t stats_groups,
+                                    const float* gamma, const float* beta, int32_t affine_ld,
+                                    const int32_t* sample_seg, const int32_t* sample_channels, const float* gate,
+                                    int32_t gate_ld, int32_t silu, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int rc = check_src(x0, c0, ld0, x1, c1, ld1, "aptp_groupnorm_apply");
   if (rc) return rc;
   APTP_REQUIRE(y && stats && gamma && beta && ldy % 8 == 0, "aptp_groupnorm_apply: bad arguments");
-  Src2 s{reinterpret_cast<const __nv_bfloat16*>(x0), reinterpret_cast<const __nv_bfloat16*>(x1), c0, ld0, c1, ld1};
+  Src2 s{x0, x1, c0, ld0, c1, ld1};
   const int ppc = pick_pix_per_cta(hw, batch);
   dim3 grid((hw + ppc - 1) / ppc, batch);
-  gn_apply_kernel<<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size, eps,
-                                                     stats, stats_groups, gamma, beta, affine_ld, sample_seg,
-                                                     sample_channels, gate, gate_ld, silu, ppc);
+  if (x_f32)
+    gn_apply_kernel<true><<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size,
+                                                            eps, stats, stats_groups, gamma, beta, affine_ld, sample_seg,
+                                                            sample_channels, gate, gate_ld, silu, ppc);
+  else
+    gn_apply_kernel<false><<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size,
+                                                             eps, stats, stats_groups, gamma, beta, affine_ld, sample_seg,
+                                                             sample_channels, gate, gate_ld, silu, ppc);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

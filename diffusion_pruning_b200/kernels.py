@@ -157,18 +157,40 @@ def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Sch
 # --------------------------------------------------------------------------------------------
 # norms / elementwise
 # --------------------------------------------------------------------------------------------
-def groupnorm_stats(x0, c0, ld0, x1, c1, ld1, batch, hw, group_size, sample_channels, stats, stats_groups):
-    check(load().aptp_groupnorm_stats(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, batch, hw, group_size,
-                                      _ptr(sample_channels), _ptr(stats), stats_groups, _stream()),
-          "aptp_groupnorm_stats")
+_GN_WS = {}  # device index -> zero-initialised workspace of aptp_groupnorm_stats (ticket counters + partials)
+
+
+def _gn_workspace(device, need: int) -> torch.Tensor:
+    """Workspace of the deterministic GroupNorm statistics reduction: one per device (the engine issues its kernels
+    on one stream at a time; CUDA-graph replays run on that stream too), allocated once with room to spare (its first
+    bytes are ticket counters that every launch leaves at zero) and grown only outside CUDA-graph capture."""
+    key = torch.device(device).index
+    ws = _GN_WS.get(key)
+    if ws is None or ws.numel() < need:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("aptp_groupnorm_stats workspace must be sized before CUDA-graph capture "
+                               "(run one eager forward of the same shapes first)")
+        ws = torch.zeros(max(need, 8 << 20), dtype=torch.uint8, device=device)
+        _GN_WS[key] = ws
+    return ws
+
+
+def groupnorm_stats(x0, c0, ld0, x1, c1, ld1, batch, hw, group_size, sample_channels, stats, stats_groups,
+                    x_f32: bool = False):
+    lib = load()
+    need = int(lib.aptp_groupnorm_stats_workspace(batch, hw, stats_groups))
+    ws = _gn_workspace(stats.device, need)
+    check(lib.aptp_groupnorm_stats(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, int(x_f32), batch, hw, group_size,
+                                   _ptr(sample_channels), _ptr(stats), stats_groups, ws.data_ptr(), ws.numel(),
+                                   _stream()), "aptp_groupnorm_stats")
 
 
 def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps, stats, stats_groups, gamma, beta,
-                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu):
-    check(load().aptp_groupnorm_apply(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, _ptr(y), ldy, batch, hw, group_size,
-                                      float(eps), _ptr(stats), stats_groups, _ptr(gamma), _ptr(beta), affine_ld,
-                                      _ptr(sample_seg), _ptr(sample_channels), _ptr(gate), gate_ld, int(silu),
-                                      _stream()), "aptp_groupnorm_apply")
+                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, x_f32: bool = False):
+    check(load().aptp_groupnorm_apply(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, int(x_f32), _ptr(y), ldy, batch, hw,
+                                      group_size, float(eps), _ptr(stats), stats_groups, _ptr(gamma), _ptr(beta),
+                                      affine_ld, _ptr(sample_seg), _ptr(sample_channels), _ptr(gate), gate_ld,
+                                      int(silu), _stream()), "aptp_groupnorm_apply")
 
 
 def layernorm(x, ldx, y, ldy, rows, C_, eps, gamma, beta, sample_active=None, rows_per_sample=1):
@@ -184,6 +206,23 @@ def depth_lerp(x, ldx, y, ldy, out, ldo, rows, C_, d, rows_per_sample):
 def copy_rows(src, lds, dst, ldd, rows, C_, sample_mask=None, rows_per_sample=1):
     check(load().aptp_copy_rows(_ptr(src), lds, _ptr(dst), ldd, rows, C_, _ptr(sample_mask), rows_per_sample,
                                 _stream()), "aptp_copy_rows")
+
+
+def copy_rows_cvt(src, lds, dst, ldd, rows, C_, sample_mask=None, rows_per_sample=1):
+    """Row copy with conversion: src / dst are bf16 or fp32 tensors (dtype decides)."""
+    check(load().aptp_copy_rows_cvt(_ptr(src), int(src.dtype == torch.float32), lds, _ptr(dst),
+                                    int(dst.dtype == torch.float32), ldd, rows, C_, _ptr(sample_mask), rows_per_sample,
+                                    _stream()), "aptp_copy_rows_cvt")
+
+
+def depth_lerp_f32(x, ldx, y, ldy, out, ldo, rows, C_, d, rows_per_sample):
+    check(load().aptp_depth_lerp_f32(_ptr(x), ldx, _ptr(y), ldy, _ptr(out), ldo, rows, C_, _ptr(d), rows_per_sample,
+                                     _stream()), "aptp_depth_lerp_f32")
+
+
+def upsample2x_cvt(src, dst, batch, H, W, C_):
+    check(load().aptp_upsample2x_cvt(_ptr(src), int(src.dtype == torch.float32), _ptr(dst), batch, H, W, C_, _stream()),
+          "aptp_upsample2x_cvt")
 
 
 def upsample2x(src, dst, batch, H, W, C_):

@@ -30,7 +30,8 @@ import torch.nn as nn
 
 from . import kernels as K
 from . import plan as P
-from ._lib import A_CONV3X3, A_CONV3X3_S2, A_LINEAR, EPI_GEGLU, EPI_SILU, OUT_BF16, OUT_F32, OUT_F32_NCHW
+from ._lib import (A_CONV3X3, A_CONV3X3_S2, A_LINEAR, EPI_GEGLU, EPI_RES_F32, EPI_SILU, OUT_BF16, OUT_F32,
+                   OUT_F32_NCHW)
 
 BF16 = torch.bfloat16
 
@@ -226,11 +227,15 @@ class _TimestepEmbedding(nn.Module):
 # activations in engine layout
 # --------------------------------------------------------------------------------------------------
 class Act:
-    """[B*H*W, ld] bf16 rows of C valid channels (NHWC / token-major), samples in engine order."""
-    __slots__ = ("t", "B", "H", "W", "C", "ld")
+    """[B*H*W, ld] rows of C valid channels (NHWC / token-major), samples in engine order. `t` holds bf16 rows (what
+    every GEMM A operand is), `f` fp32 rows: the tensors BETWEEN blocks (ResNet / transformer / sampler outputs, i.e.
+    the residual stream of unet_2d_conditional.py:1629-1715) are kept in fp32 by the inference engine so the running
+    residual sum is not re-rounded to bf16 at every block; a bf16 copy is made only where a GEMM
+    reads the tensor directly. The training engine keeps bf16 rows throughout."""
+    __slots__ = ("t", "f", "B", "H", "W", "C", "ld")
 
-    def __init__(self, t, B, H, W, C, ld=None):
-        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+    def __init__(self, t, B, H, W, C, ld=None, f=None):
+        self.t, self.f, self.B, self.H, self.W, self.C = t, f, B, H, W, C
         self.ld = ld if ld is not None else C
 
     @property
@@ -243,7 +248,8 @@ class Act:
 
     def nchw(self) -> torch.Tensor:
         """Zero-copy [B, C, H, W] view (channels-last strides), as the reference's hooks see it."""
-        return self.t.view(self.B, self.H, self.W, self.ld)[..., : self.C].permute(0, 3, 1, 2)
+        src = self.t if self.t is not None else self.f
+        return src.view(self.B, self.H, self.W, self.ld)[..., : self.C].permute(0, 3, 1, 2)
 
 
 class UNet2DConditionModelGated(nn.Module):
@@ -799,8 +805,9 @@ class _Engine:
             K.grouped_gemm(a, w, out, sched, **kw)
         self.launches += 1
         self.flops += sched.flops
+        res_bytes = 0 if kw.get('residual') is None else (4 if kw.get('flags', 0) & EPI_RES_F32 else 2)
         self.gemm_bytes += sched.bytes_in + sched.out_elems * ((2 if kw.get('out_mode', OUT_BF16) == OUT_BF16 else 4)
-                                                               + (2 if kw.get('residual') is not None else 0))
+                                                               + res_bytes)
 
     # ---- dense (unpruned) weights ---------------------------------------------------------------
     def _dense_linear(self, name: str, lin: nn.Module, n_pad_to: int = 0) -> Dict[str, torch.Tensor]:
@@ -850,13 +857,28 @@ class _Engine:
     # ---- group norm ------------------------------------------------------------------------------
     def groupnorm(self, x: torch.Tensor, C: int, ld: int, B: int, hw: int, groups_full: int, gs: int, eps: float,
                   gamma: torch.Tensor, beta: torch.Tensor, affine_ld: int, out: torch.Tensor, out_ld: int, silu: bool,
-                  sample_seg=None, sample_channels=None, gate=None):
+                  sample_seg=None, sample_channels=None, gate=None, x1: Optional[torch.Tensor] = None, c1: int = 0,
+                  ld1: int = 0):
+        """GroupNorm [+ soft width gate] [+ SiLU] -> bf16 rows. `x` (and the optional second source `x1` = the skip half
+        of an up-block torch.cat) are bf16 or fp32 rows (dtype decides). Statistics: deterministic two-stage reduction
+        (no atomics), see csrc/norm.cu."""
+        f32 = x.dtype == torch.float32
+        assert x1 is None or (x1.dtype == torch.float32) == f32
         stats = self.buf("gnstats", B, groups_full * 2, torch.float32)
-        stats.zero_()
-        K.groupnorm_stats(x, C, ld, None, 0, 0, B, hw, gs, sample_channels, stats, groups_full)
-        K.groupnorm_apply(x, C, ld, None, 0, 0, out, out_ld, B, hw, gs, eps, stats, groups_full, gamma, beta, affine_ld,
-                          sample_seg, sample_channels, gate, gate.stride(0) if gate is not None else groups_full, silu)
-        self.launches += 3
+        K.groupnorm_stats(x, C, ld, x1, c1, ld1, B, hw, gs, sample_channels, stats, groups_full, x_f32=f32)
+        K.groupnorm_apply(x, C, ld, x1, c1, ld1, out, out_ld, B, hw, gs, eps, stats, groups_full, gamma, beta, affine_ld,
+                          sample_seg, sample_channels, gate, gate.stride(0) if gate is not None else groups_full, silu,
+                          x_f32=f32)
+        self.launches += 2
+
+    def _bf16(self, x: Act) -> torch.Tensor:
+        """bf16 rows of an fp32 stream tensor, for a GEMM that reads it directly (shortcut 1x1 conv, down-sampler)."""
+        if x.t is None:
+            t = torch.empty(x.rows, x.C, device=self.device, dtype=BF16)
+            K.cast_f32_bf16(x.f, t, x.rows * x.C)
+            self.launches += 1
+            x.t, x.ld = t, x.C
+        return x.t
 
     # ---- time embedding --------------------------------------------------------------------------
     def _temb_pack(self) -> Dict[str, Any]:
@@ -1001,18 +1023,12 @@ class _Engine:
         return d
 
     def resnet(self, r: ResnetBlock2DWidthGated, x: Act, skip: Optional[Act] = None) -> Act:
-        """ResnetBlock2DWidthGated / WidthDepthGated forward (blocks.py:293-371, :482-584)."""
+        """ResnetBlock2DWidthGated / WidthDepthGated forward (blocks.py:293-371, :482-584). Input and output live on the
+        fp32 residual stream (Act.f); everything a GEMM reads is bf16."""
         B, H, W, hw = x.B, x.H, x.W, x.hw
         M = x.rows
-        if skip is not None:  # up block: hidden_states = torch.cat([hidden_states, res_hidden_states], dim=1)
-            cat = self.buf("cat", M, x.C + skip.C)
-            K.copy_rows(x.t, x.ld, cat, x.C + skip.C, M, x.C)
-            K.copy_rows(skip.t, skip.ld, cat[:, x.C:], x.C + skip.C, M, skip.C)
-            self.launches += 2
-            xin = Act(cat, B, H, W, x.C + skip.C)
-        else:
-            xin = x
-        assert xin.C == r.cin, f"{r.uid}: expected {r.cin} input channels, got {xin.C}"
+        cin = x.C + (skip.C if skip is not None else 0)
+        assert cin == r.cin, f"{r.uid}: expected {r.cin} input channels, got {cin}"
         pk = self._resnet_pack(r)
         E = self.eset.n_experts if self.compact else 1
         vid = pk["vid"]
@@ -1031,10 +1047,15 @@ class _Engine:
             return aux
         aux = self._sched(("res_aux", r.uid), build_aux)
 
-        # norm1 + SiLU
+        # norm1 + SiLU straight from the fp32 stream; an up block's torch.cat([hidden_states, res_hidden_states], 1)
+        # (blocks.py: inherited UpBlock2D.forward) is read as two sources, never materialised in fp32
         a1 = self.buf("gn_a", M, r.cin)
-        self.groupnorm(xin.t, r.cin, xin.ld, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
-                       sample_channels=aux.get("ch_in"))
+        if skip is not None:
+            self.groupnorm(x.f, x.C, x.C, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
+                           sample_channels=aux.get("ch_in"), x1=skip.f, c1=skip.C, ld1=skip.C)
+        else:
+            self.groupnorm(x.f, x.C, x.C, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
+                           sample_channels=aux.get("ch_in"))
         # conv1 (N-compacted) + time embedding (+ conv1/time biases, folded into the row vector)
         h1 = self.buf("res_h1", M, r.cout)
 
@@ -1053,14 +1074,24 @@ class _Engine:
         self.groupnorm(h1, r.cout, r.cout, B, hw, r.groups, gs, r.eps, pk["gamma2"], pk["beta2"], r.cout, a2, r.cout,
                        True, sample_seg=aux.get("seg_mid"),
                        sample_channels=aux.get("ch_mid"), gate=gate)
-        # shortcut
-        out = torch.empty(M, r.cout, device=self.device, dtype=BF16)
+        # shortcut: 1x1 conv over the bf16 copy of the (concatenated) input, written fp32 and added in place by conv2
+        out = torch.empty(M, r.cout, device=self.device, dtype=torch.float32)
         if r.conv_shortcut is not None:
-            self.linear("sc." + r.uid, r.conv_shortcut, xin.t, M, r.cin, xin.ld, out, r.cout, hw, active=active)
+            if skip is not None:
+                xin16 = self.buf("cat", M, r.cin)
+                K.copy_rows_cvt(x.f, x.C, xin16, r.cin, M, x.C)
+                K.copy_rows_cvt(skip.f, skip.C, xin16[:, x.C:], r.cin, M, skip.C)
+                self.launches += 2
+                xin_ld = r.cin
+            else:
+                xin16, xin_ld = self._bf16(x), x.ld
+            self.linear("sc." + r.uid, r.conv_shortcut, xin16, M, r.cin, xin_ld, out, r.cout, hw, active=active,
+                        out_mode=OUT_F32)
             res, res_ld = out, r.cout
         else:
-            res, res_ld = xin.t, xin.ld
-        # conv2 (K-compacted) + bias + border table + residual
+            assert skip is None
+            res, res_ld = x.f, x.C
+        # conv2 (K-compacted) + bias + border table + fp32 residual -> fp32 stream
 
         def build_c2():
             bn = P.choose_bn([r.cout])
@@ -1070,19 +1101,19 @@ class _Engine:
             return K.build_schedule(segs, bn, self.device, mode=A_CONV3X3, Ho=H, Wo=W)
         sched = self._sched(("res_c2", r.uid, H, W), build_c2)
         self._gemm(sched, a2, pk["w2"], out, a_ld=r.cout, a_k=r.cout, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W,
-                   k_tap_pitch=r.cout, out_ld=r.cout, bias=pk["b2"], residual=res, res_ld=res_ld, rows_per_sample=hw,
-                   border_tab=pk["tab"], tab_ld=r.cout)
-        # depth gate
+                   k_tap_pitch=r.cout, out_ld=r.cout, out_mode=OUT_F32, bias=pk["b2"], residual=res, res_ld=res_ld,
+                   flags=EPI_RES_F32, rows_per_sample=hw, border_tab=pk["tab"], tab_ld=r.cout)
+        # depth gate: the non-skip part of the input is the identity branch (blocks.py:485-495)
         if r.depth_gate is not None:
-            keep_c = xin.C - (r.skip_connection_dim or 0)  # blocks.py:485-495
+            keep_c = x.C if skip is not None else x.C - (r.skip_connection_dim or 0)
             if self.compact:
                 if aux["drop_mask"] is not None:  # dropped experts: identity on the (non-skip) input
-                    K.copy_rows(xin.t, xin.ld, out, r.cout, M, keep_c, aux["drop_mask"], hw)
+                    K.copy_rows_cvt(x.f, x.C, out, r.cout, M, keep_c, aux["drop_mask"], hw)
                     self.launches += 1
             else:
-                K.depth_lerp(xin.t, xin.ld, out, r.cout, out, r.cout, M, keep_c, self._soft_depth(cidx["d"]), hw)
+                K.depth_lerp_f32(x.f, x.C, out, r.cout, out, r.cout, M, keep_c, self._soft_depth(cidx["d"]), hw)
                 self.launches += 1
-        return Act(out, B, H, W, r.cout)
+        return Act(None, B, H, W, r.cout, f=out)
 
     # ---- transformer -------------------------------------------------------------------------------
     def _attn_pack(self, uid: str, attn: _Attention, gate_idx: int) -> Dict[str, Any]:
@@ -1252,7 +1283,7 @@ class _Engine:
         aux = self._sched(("tr_aux", t.uid), build_aux)
         gs = C // t.groups
         xn = self.buf("ln", M, C)
-        self.groupnorm(x.t, C, x.ld, B, hw, t.groups, gs, 1e-6, dn["g"], dn["b"], C, xn, C, False,
+        self.groupnorm(x.f, C, C, B, hw, t.groups, gs, 1e-6, dn["g"], dn["b"], C, xn, C, False,
                        sample_channels=aux["ch"])
         tok = self.buf("tok", M, C)
         self.linear("pi." + t.uid, t.proj_in, xn, M, C, C, tok, C, hw, active=active)
@@ -1287,33 +1318,35 @@ class _Engine:
                    rows_per_sample=hw, **gkw)
         self._gemm(s["o"], ffb, fk["w2"], tok, a_ld=inner, a_k=inner, a_rows=M, out_ld=C, bias=fk["b2"], residual=tok,
                    res_ld=C, rows_per_sample=hw)
-        # proj_out + residual
-        out = torch.empty(M, C, device=self.device, dtype=BF16)
-        self.linear("po." + t.uid, t.proj_out, tok, M, C, C, out, C, hw, residual=x.t, res_ld=x.ld, active=active)
+        # proj_out + residual: back onto the fp32 stream
+        out = torch.empty(M, C, device=self.device, dtype=torch.float32)
+        self.linear("po." + t.uid, t.proj_out, tok, M, C, C, out, C, hw, residual=x.f, res_ld=C, active=active,
+                    out_mode=OUT_F32, flags=EPI_RES_F32)
         if t.depth_gate is not None:
             if self.compact:
                 if aux["drop"] is not None:
-                    K.copy_rows(x.t, x.ld, out, C, M, C, aux["drop"], hw)
+                    K.copy_rows_cvt(x.f, C, out, C, M, C, aux["drop"], hw)
                     self.launches += 1
             else:
-                K.depth_lerp(x.t, x.ld, out, C, out, C, M, C, self._soft_depth(cidx["d"]), hw)
+                K.depth_lerp_f32(x.f, C, out, C, out, C, M, C, self._soft_depth(cidx["d"]), hw)
                 self.launches += 1
-        return Act(out, B, H, W, C)
+        return Act(None, B, H, W, C, f=out)
 
     # ---- samplers ----------------------------------------------------------------------------------
     def downsample(self, s: _Sampler, x: Act) -> Act:
-        out = torch.empty(x.rows // 4, x.C, device=self.device, dtype=BF16)
-        self.conv3x3("ds.%d" % id(s), s.conv, x, out, x.C, stride=2)
-        return Act(out, x.B, x.H // 2, x.W // 2, x.C)
+        out = torch.empty(x.rows // 4, x.C, device=self.device, dtype=torch.float32)
+        x16 = Act(self._bf16(x), x.B, x.H, x.W, x.C)
+        self.conv3x3("ds.%d" % id(s), s.conv, x16, out, x.C, stride=2, out_mode=OUT_F32)
+        return Act(None, x.B, x.H // 2, x.W // 2, x.C, f=out)
 
     def upsample(self, s: _Sampler, x: Act) -> Act:
         up = self.buf("up", x.rows * 4, x.C)
-        K.upsample2x(x.t, up, x.B, x.H, x.W, x.C)
+        K.upsample2x_cvt(x.f, up, x.B, x.H, x.W, x.C)
         self.launches += 1
         xu = Act(up, x.B, x.H * 2, x.W * 2, x.C)
-        out = torch.empty(xu.rows, x.C, device=self.device, dtype=BF16)
-        self.conv3x3("us.%d" % id(s), s.conv, xu, out, x.C)
-        return Act(out, xu.B, xu.H, xu.W, x.C)
+        out = torch.empty(xu.rows, x.C, device=self.device, dtype=torch.float32)
+        self.conv3x3("us.%d" % id(s), s.conv, xu, out, x.C, out_mode=OUT_F32)
+        return Act(None, xu.B, xu.H, xu.W, x.C, f=out)
 
     # ---- CUDA-graph replay of the hard-gate forward -------------------------------------------------
     def run_graphed(self, sample: torch.Tensor, timestep, ctx: torch.Tensor, want_taps: bool = False):
@@ -1395,12 +1428,12 @@ class _Engine:
             wp[:, :9 * cin] = w.permute(0, 2, 3, 1).reshape(c0, 9 * cin).to(BF16)
             d = {"w": wp, "b": m.conv_in.bias.detach().to(self.device, torch.float32).contiguous()}
             self.dense["conv_in"] = d
-        x0 = torch.empty(B * H * W, c0, device=self.device, dtype=BF16)
+        x0 = torch.empty(B * H * W, c0, device=self.device, dtype=torch.float32)
         sched = self._sched(("conv_in", H, W), lambda: K.build_schedule(
             [K.Segment(0, B * H * W, c0, 1)], P.choose_bn([c0]), self.device))
-        self._gemm(sched, col, d["w"], x0, a_ld=64, a_k=64, a_rows=B * H * W, out_ld=c0, bias=d["b"],
+        self._gemm(sched, col, d["w"], x0, a_ld=64, a_k=64, a_rows=B * H * W, out_ld=c0, out_mode=OUT_F32, bias=d["b"],
                    rows_per_sample=H * W)
-        x = Act(x0, B, H, W, c0)
+        x = Act(None, B, H, W, c0, f=x0)
         skips = [x]
         tap_acts = []
         for blk in m.down_blocks:
@@ -1421,7 +1454,7 @@ class _Engine:
             self.dense[key] = dn
         groups = m.config["norm_num_groups"]
         a = self.buf("gn_a", x.rows, x.C)
-        self.groupnorm(x.t, x.C, x.ld, B, x.hw, groups, x.C // groups, m.config["norm_eps"], dn["g"], dn["b"], x.C, a,
+        self.groupnorm(x.f, x.C, x.C, B, x.hw, groups, x.C // groups, m.config["norm_eps"], dn["g"], dn["b"], x.C, a,
                        x.C, True)
         cout = m.config["out_channels"]
         y = torch.empty(B, cout, x.H, x.W, device=self.device, dtype=torch.float32)
@@ -1431,19 +1464,21 @@ class _Engine:
         self._gemm(sched, a, dco["w"], y, a_ld=x.C, a_k=x.C, a_rows=x.rows, mode=A_CONV3X3, batch=B, H=x.H, W=x.W,
                    k_tap_pitch=x.C, out_ld=cout, out_mode=OUT_F32_NCHW, bias=dco["b"], rows_per_sample=x.hw)
         taps = []
+        identity = True
         if self.compact:
             identity = bool((self.layout.inv_perm == np.arange(B)).all())
             inv = self._dev_index("inv_perm")
             if not identity:
                 y = y.index_select(0, inv)
-            if want_taps:
-                # block outputs as the reference's hooks see them ([B, C, H, W]), kept channels-last: the gather back
-                # to the caller's sample order runs over whole NHWC samples (contiguous chunks), and losses computed
-                # on these tensors stay on PyTorch's dense vectorised kernels
-                for t in tap_acts:
-                    v = t.t.view(t.B, t.H, t.W, t.ld)[..., : t.C]
-                    v = v.clone() if identity else v.index_select(0, inv)
-                    taps.append(v.permute(0, 3, 1, 2))
-        elif want_taps:
-            taps = [t.nchw().clone() for t in tap_acts]  # block outputs live in reused buffers
+        if want_taps:
+            # block outputs as the reference's hooks see them ([B, C, H, W]) in bf16 channels-last (what the fused loss
+            # kernels read in place): one conversion pass off the fp32 stream into a tensor the caller owns; with expert
+            # bucketing the gather back to the caller's sample order runs over whole NHWC samples (contiguous chunks)
+            for t in tap_acts:
+                v = torch.empty(t.rows, t.C, device=self.device, dtype=BF16)
+                K.copy_rows_cvt(t.f, t.C, v, t.C, t.rows, t.C)
+                v = v.view(t.B, t.H, t.W, t.C)
+                if not identity:
+                    v = v.index_select(0, inv)
+                taps.append(v.permute(0, 3, 1, 2))
         return y, taps

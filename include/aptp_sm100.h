@@ -70,7 +70,8 @@ enum { APTP_OUT_BF16 = 0, APTP_OUT_F32 = 1, APTP_OUT_F32_NCHW = 2 };
 enum {
   APTP_EPI_GEGLU = 1,      /* tile columns are [bn/2 h | bn/2 g]; out = h * gelu_erf(g)            */
   APTP_EPI_SILU = 2,       /* out = silu(out) (time-embedding MLP)                                 */
-  APTP_EPI_GN_STATS = 4    /* accumulate per-(sample,group) sum / sumsq of the stored values       */
+  APTP_EPI_GN_STATS = 4,   /* accumulate per-(sample,group) sum / sumsq of the stored values       */
+  APTP_EPI_RES_F32 = 8     /* `residual` holds fp32 rows (fp32 residual stream); needs APTP_OUT_F32 */
 };
 
 typedef struct aptp_gemm_args {
@@ -98,7 +99,7 @@ typedef struct aptp_gemm_args {
   const float* rowvec;    /* per-sample vector: rowvec[sample*rowvec_ld + col] (time embedding)    */
   int32_t rowvec_ld;
   int32_t rows_per_sample;
-  const void* residual;   /* bf16 [rows, res_ld], added after everything else                      */
+  const void* residual;   /* bf16 [rows, res_ld] (fp32 with APTP_EPI_RES_F32), added after everything else; may alias out */
   int32_t res_ld;
   const float* gate;      /* soft gates: out *= gate[sample*gate_ld + col/gate_group]              */
   int32_t gate_ld, gate_group;
@@ -122,23 +123,30 @@ int aptp_grouped_gemm_fwd(const aptp_gemm_args* args, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * K2  HBM-bound fused normalisation / gate / residual kernels.
  * ---------------------------------------------------------------------------------------------- */
-/* GroupNorm statistics over NHWC bf16 (two sources = fused torch.cat of an up-block input).
+/* GroupNorm statistics over NHWC rows (two sources = fused torch.cat of an up-block input); x_f32 != 0: the
+ * sources are fp32 rows (the fp32 residual stream between blocks), else bf16.
  * replaces: the reduction half of nn.GroupNorm at blocks.py:299,:353,:505,:559, Transformer2DModel.norm
  * (blocks.py:1227) and conv_norm_out (unet_2d_conditional.py:1719).
- * stats[sample][group] = (sum, sumsq) accumulated in fp32 (buffer must be zeroed by the caller). */
+ * stats[sample][group] = (sum, sumsq) in fp32, OVERWRITTEN (no zeroing needed). The reduction is deterministic:
+ * fixed-order partial sums per CTA, merged in chunk order by the last CTA of each sample. `workspace` (device,
+ * 16-byte aligned, >= aptp_groupnorm_stats_workspace(batch, hw, stats_groups) bytes) must have its first
+ * 4*batch bytes zero before the FIRST call; every call leaves them zero. One workspace per stream. */
+int64_t aptp_groupnorm_stats_workspace(int32_t batch, int32_t hw, int32_t stats_groups);
 int aptp_groupnorm_stats(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
-                         int32_t batch, int32_t hw, int32_t group_size, const int32_t* sample_channels,
-                         float* stats, int32_t stats_groups, void* stream);
+                         int32_t x_f32, int32_t batch, int32_t hw, int32_t group_size,
+                         const int32_t* sample_channels, float* stats, int32_t stats_groups, void* workspace,
+                         int64_t workspace_bytes, void* stream);
 /* y = [silu]( (x*g - mean)*rstd*gamma + beta ) written bf16 with row pitch ldy; channels in
  * [c_valid, c_store) are written as zeros. `sample_seg[b]` selects the per-expert compacted
  * gamma/beta block (offset sample_seg[b]*affine_ld) and c_valid (sample_channels[b]).
  * `gate` (optional, fp32 [batch, gate_ld]) is the soft width gate applied *before* the norm
- * (blocks.py:345-353): with hard gates the engine compacts instead. */
+ * (blocks.py:345-353): with hard gates the engine compacts instead. x_f32 as above. */
 int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
-                         void* y, int32_t ldy, int32_t batch, int32_t hw, int32_t group_size, float eps,
-                         const float* stats, int32_t stats_groups, const float* gamma, const float* beta,
-                         int32_t affine_ld, const int32_t* sample_seg, const int32_t* sample_channels,
-                         const float* gate, int32_t gate_ld, int32_t silu, void* stream);
+                         int32_t x_f32, void* y, int32_t ldy, int32_t batch, int32_t hw, int32_t group_size,
+                         float eps, const float* stats, int32_t stats_groups, const float* gamma,
+                         const float* beta, int32_t affine_ld, const int32_t* sample_seg,
+                         const int32_t* sample_channels, const float* gate, int32_t gate_ld, int32_t silu,
+                         void* stream);
 /* LayerNorm over the channel dim of [rows, C] bf16 (eps 1e-5, affine); replaces
  * BasicTransformerBlock.norm1/2/3 (blocks.py:782,:808-810,:821). row_active (optional, per sample)
  * skips depth-dropped samples. */
@@ -154,6 +162,16 @@ int aptp_copy_rows(const void* src, int32_t lds, void* dst, int32_t ldd, int64_t
                    const uint8_t* sample_mask, int32_t rows_per_sample, void* stream);
 /* nearest x2 upsample NHWC (diffusers Upsample2D: F.interpolate(scale_factor=2, mode="nearest")). */
 int aptp_upsample2x(const void* src, void* dst, int32_t batch, int32_t H, int32_t W, int32_t C, void* stream);
+/* fp32-residual-stream variants (the tensors between ResNet / transformer blocks are kept in fp32 so that the
+ * residual sums of unet_2d_conditional.py:1629-1715 are not re-rounded to bf16 at every block; GEMM A operands
+ * stay bf16): row copy with conversion (src / dst each bf16 or fp32), DepthGate lerp on fp32 rows (out may alias
+ * y), nearest x2 upsample from fp32 or bf16 rows to bf16 rows. */
+int aptp_copy_rows_cvt(const void* src, int32_t src_f32, int32_t lds, void* dst, int32_t dst_f32, int32_t ldd,
+                       int64_t rows, int32_t C, const uint8_t* sample_mask, int32_t rows_per_sample, void* stream);
+int aptp_depth_lerp_f32(const float* x, int32_t ldx, const float* y, int32_t ldy, float* out, int32_t ldo,
+                        int64_t rows, int32_t C, const float* d, int32_t rows_per_sample, void* stream);
+int aptp_upsample2x_cvt(const void* src, int32_t src_f32, void* dst, int32_t batch, int32_t H, int32_t W, int32_t C,
+                        void* stream);
 /* NCHW fp32 sample -> im2col rows [B*H*W, 64] bf16 (K = 9*Cin zero-padded to 64) for conv_in. */
 int aptp_im2col_input(const float* sample_nchw, void* dst, int32_t batch, int32_t Cin, int32_t H, int32_t W,
                       void* stream);

@@ -138,7 +138,8 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
             O[rb // rows_per_sample:nb, :nv] = acc[:, :nv].reshape(-1, rows_per_sample, nv).permute(0, 2, 1)
 
 
-def groupnorm_stats(x0, c0, ld0, x1, c1, ld1, batch, hw, group_size, sample_channels, stats, stats_groups):
+def groupnorm_stats(x0, c0, ld0, x1, c1, ld1, batch, hw, group_size, sample_channels, stats, stats_groups,
+                    x_f32=False):
     X = _view(x0, batch * hw, c0, ld0).float()
     if c1:
         X = torch.cat([X, _view(x1, batch * hw, c1, ld1).float()], 1)
@@ -150,12 +151,12 @@ def groupnorm_stats(x0, c0, ld0, x1, c1, ld1, batch, hw, group_size, sample_chan
         xb = X[b * hw:(b + 1) * hw, :ct]
         g = (ct + group_size - 1) // group_size
         xg = xb.reshape(hw, g, group_size)
-        st[b, :g, 0] += xg.sum((0, 2))
-        st[b, :g, 1] += (xg * xg).sum((0, 2))
+        st[b, :g, 0] = xg.sum((0, 2))  # overwritten, not accumulated (deterministic two-stage reduction)
+        st[b, :g, 1] = (xg * xg).sum((0, 2))
 
 
 def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps, stats, stats_groups, gamma, beta,
-                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu):
+                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, x_f32=False):
     X = _view(x0, batch * hw, c0, ld0).float()
     if c1:
         X = torch.cat([X, _view(x1, batch * hw, c1, ld1).float()], 1)
@@ -212,6 +213,27 @@ def copy_rows(src, lds, dst, ldd, rows, C_, sample_mask=None, rows_per_sample=1)
         D.copy_(S)
 
 
+def copy_rows_cvt(src, lds, dst, ldd, rows, C_, sample_mask=None, rows_per_sample=1):
+    S = _view(src, rows, C_, lds).to(dst.dtype)
+    D = _view(dst, rows, C_, ldd)
+    if sample_mask is not None:
+        m = sample_mask.bool().repeat_interleave(rows_per_sample)
+        D[m] = S[m]
+    else:
+        D.copy_(S)
+
+
+def depth_lerp_f32(x, ldx, y, ldy, out, ldo, rows, C_, d, rows_per_sample):
+    X = _view(x, rows, C_, ldx)
+    Yv = _view(y, rows, C_, ldy).clone()
+    dd = d.repeat_interleave(rows_per_sample)[:, None]
+    _view(out, rows, C_, ldo).copy_((1 - dd) * X + dd * Yv)
+
+
+def upsample2x_cvt(src, dst, batch, H, W, C_):
+    upsample2x(src.to(torch.bfloat16), dst, batch, H, W, C_)
+
+
 def upsample2x(src, dst, batch, H, W, C_):
     s = src.view(batch, H, W, C_)
     dst.view(batch, 2 * H, 2 * W, C_).copy_(s.repeat_interleave(2, 1).repeat_interleave(2, 2))
@@ -257,6 +279,7 @@ def check_abort():
 
 def install(monkeypatch):
     for name in ("grouped_gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "depth_lerp", "copy_rows",
+                 "copy_rows_cvt", "depth_lerp_f32", "upsample2x_cvt",
                  "upsample2x", "im2col_input", "timestep_embedding", "cast_f32_bf16", "silu_bf16", "attention",
                  "check_abort"):
         monkeypatch.setattr(K, name, globals()[name])

@@ -9,8 +9,8 @@ import torch
 import torch.nn.functional as F
 
 from diffusion_pruning_b200 import kernels as K
-from diffusion_pruning_b200._lib import (A_CONV3X3, A_CONV3X3_S2, A_LINEAR, EPI_GEGLU, EPI_SILU, OUT_BF16, OUT_F32,
-                                         OUT_F32_NCHW)
+from diffusion_pruning_b200._lib import (A_CONV3X3, A_CONV3X3_S2, A_LINEAR, EPI_GEGLU, EPI_RES_F32, EPI_SILU, OUT_BF16,
+                                         OUT_F32, OUT_F32_NCHW)
 
 DEV = "cuda"
 
@@ -240,11 +240,14 @@ def check_out_modes(seed=0):
     _close(out2, a.float() @ w.float().t(), 1e-3, 1e-3, "out f32")
 
 
-def check_groupnorm(B=3, HW=256, C0=320, C1=0, groups=32, silu=True, gate=False, compact=False, seed=0):
+def check_groupnorm(B=3, HW=256, C0=320, C1=0, groups=32, silu=True, gate=False, compact=False, seed=0, f32=False):
     C = C0 + C1
     gs = C // groups
     x0 = _rand(B * HW, C0, seed=seed).bfloat16() * 2 + 0.5
     x1 = _rand(B * HW, C1, seed=seed + 1).bfloat16() if C1 else None
+    if f32:  # fp32 residual-stream rows (values that bf16 cannot represent exactly)
+        x0 = x0.float() + _rand(B * HW, C0, seed=seed + 7) * 1e-3
+        x1 = (x1.float() + _rand(B * HW, C1, seed=seed + 8) * 1e-3) if C1 else None
     gamma = _rand(2, C, seed=seed + 2) * 0.2 + 1
     beta = _rand(2, C, seed=seed + 3) * 0.2
     sample_seg = torch.tensor([i % 2 for i in range(B)], device=DEV, dtype=torch.int32)
@@ -255,10 +258,23 @@ def check_groupnorm(B=3, HW=256, C0=320, C1=0, groups=32, silu=True, gate=False,
     g = (torch.rand(B, groups, device=DEV) * 0.8 + 0.2) if gate else None
     stats = torch.zeros(B, groups, 2, device=DEV)
     y = torch.full((B * HW, C), float("nan"), device=DEV, dtype=torch.bfloat16)
-    K.groupnorm_stats(x0, C0, C0, x1, C1, C1, B, HW, gs, ch, stats, groups)
+    stats.fill_(float("nan"))  # the statistics pass overwrites (no zeroing contract any more)
+    K.groupnorm_stats(x0, C0, C0, x1, C1, C1, B, HW, gs, ch, stats, groups, x_f32=f32)
     K.groupnorm_apply(x0, C0, C0, x1, C1, C1, y, C, B, HW, gs, 1e-5, stats, groups, gamma, beta, C, sample_seg, ch, g,
-                      groups, silu)
+                      groups, silu, x_f32=f32)
     torch.cuda.synchronize()
+    # deterministic reduction: a second pass gives bit-identical statistics
+    stats2 = torch.full_like(stats, float("nan"))
+    K.groupnorm_stats(x0, C0, C0, x1, C1, C1, B, HW, gs, ch, stats2, groups, x_f32=f32)
+    torch.cuda.synchronize()
+    for b in range(B):
+        ng = (int(ch[b]) if compact else C) // gs
+        assert torch.equal(stats[b, :ng], stats2[b, :ng]), "groupnorm statistics are not bit-reproducible"
+        xs = (torch.cat([x0.float(), x1.float()], 1) if C1 else x0.float())[b * HW:(b + 1) * HW, :ng * gs]
+        ref_sum = xs.double().reshape(HW, ng, gs).sum(dim=(0, 2))
+        ref_sq = (xs.double() ** 2).reshape(HW, ng, gs).sum(dim=(0, 2))
+        _close(stats[b, :ng, 0], ref_sum, 1e-2, 1e-5, "groupnorm sum")
+        _close(stats[b, :ng, 1], ref_sq, 1e-2, 1e-5, "groupnorm sumsq")
     xf = torch.cat([x0.float(), x1.float()], 1) if C1 else x0.float()
     for b in range(B):
         cb = int(ch[b]) if compact else C
@@ -318,6 +334,71 @@ def check_elementwise(seed=0):
     f = torch.exp(-math.log(10000.0) * k / 160)
     ref = torch.cat([torch.cos(t[:, None] * f), torch.sin(t[:, None] * f)], 1)
     _close(emb, ref, 1e-2, 1e-2, "timestep_embedding")
+
+
+def check_stream_f32(seed=0):
+    """fp32 residual-stream helpers: converting row copies, fp32 depth lerp (in place), upsample from fp32, vector cast."""
+    B, H, W, C = 2, 8, 8, 64
+    M = B * H * W
+    x = _rand(M, C, seed=seed)
+    y = _rand(M, C, seed=seed + 1)
+    d = torch.tensor([0.25, 1.0], device=DEV)
+    dd = d.repeat_interleave(H * W)[:, None]
+    out = y.clone()
+    K.depth_lerp_f32(x, C, out, C, out, C, M, C, d, H * W)
+    _close(out, (1 - dd) * x + dd * y, 1e-6, 1e-6, "depth_lerp_f32")
+    mask = torch.tensor([0, 1], device=DEV, dtype=torch.uint8)
+    for sdt in (torch.float32, torch.bfloat16):
+        for ddt in (torch.float32, torch.bfloat16):
+            src = x.to(sdt)
+            dst = torch.full((M, 2 * C), 5.0, device=DEV, dtype=ddt)
+            K.copy_rows_cvt(src, C, dst[:, C:], 2 * C, M, C, mask, H * W)
+            torch.cuda.synchronize()
+            assert (dst[:H * W].float() == 5.0).all() and (dst[H * W:, :C].float() == 5.0).all()
+            assert torch.equal(dst[H * W:, C:], src[H * W:].to(ddt)), f"copy_rows_cvt {sdt} -> {ddt}"
+    up = torch.empty(B * 4 * H * W, C, device=DEV, dtype=torch.bfloat16)
+    K.upsample2x_cvt(x, up, B, H, W, C)
+    ref = F.interpolate(x.reshape(B, H, W, C).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    assert torch.equal(up, ref.permute(0, 2, 3, 1).reshape(-1, C).bfloat16()), "upsample2x_cvt"
+    c16 = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    K.cast_f32_bf16(x, c16, M * C)
+    assert torch.equal(c16, x.bfloat16()), "cast_f32_bf16 (vector path)"
+    c16b = torch.empty(M * C - 3, device=DEV, dtype=torch.bfloat16)
+    K.cast_f32_bf16(x.reshape(-1)[3:], c16b, M * C - 3)
+    assert torch.equal(c16b, x.reshape(-1)[3:].bfloat16()), "cast_f32_bf16 (scalar path)"
+
+
+def check_gemm_res_f32(conv=False, seed=0):
+    """fp32 output + fp32 residual (APTP_EPI_RES_F32), in place: the block outputs of the fp32 residual stream."""
+    if conv:
+        B, H, W, Cin, Cout, bn = 2, 16, 16, 128, 192, 192
+        x = _rand(B, Cin, H, W, seed=seed).bfloat16()
+        w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=seed + 1).bfloat16()
+        b = _rand(Cout, seed=seed + 2)
+        M = B * H * W
+        a = x.permute(0, 2, 3, 1).reshape(M, Cin).contiguous()
+        wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+        res = _rand(M, Cout, seed=seed + 3)
+        out = res.clone()
+        sched = K.build_schedule([K.Segment(0, M, Cout, (Cin + 63) // 64)], bn, DEV, mode=A_CONV3X3, Ho=H, Wo=W)
+        K.grouped_gemm(a, wp, out, sched, a_ld=Cin, a_k=Cin, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W,
+                       k_tap_pitch=Cin, out_ld=Cout, out_mode=OUT_F32, bias=b, residual=out, res_ld=Cout,
+                       flags=EPI_RES_F32, rows_per_sample=H * W)
+        K.check_abort()
+        ref = _conv_ref(x.float(), w.float(), b, 1).permute(0, 2, 3, 1).reshape(M, Cout) + res
+    else:
+        M, Kd, N, bn = 1000, 320, 320, 160
+        a = _rand(M, Kd, seed=seed).bfloat16()
+        w = _rand(N, Kd, scale=Kd ** -0.5, seed=seed + 1).bfloat16()
+        b = _rand(N, seed=seed + 2)
+        res = _rand(M, N, seed=seed + 3) * 3
+        out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+        sched = K.build_schedule([K.Segment(0, M, N, (Kd + 63) // 64)], bn, DEV)
+        K.grouped_gemm(a, w, out, sched, a_ld=Kd, a_k=Kd, a_rows=M, out_ld=N, out_mode=OUT_F32, bias=b, residual=res,
+                       res_ld=N, flags=EPI_RES_F32)
+        K.check_abort()
+        ref = a.float() @ w.float().t() + b + res
+    _close(out, ref, 2e-3, 1e-4, "gemm fp32 out + fp32 residual")
 
 
 def check_attention(B=2, heads=3, kept=(3, 1), Nq=256, Nkv=256, seed=0):
@@ -385,6 +466,14 @@ ALL = [
     ("groupnorm_wide", lambda: check_groupnorm(B=2, HW=64, C0=1280, C1=1280)),
     ("groupnorm_gate_compact", lambda: check_groupnorm(gate=True, compact=True)),
     ("groupnorm_tiny_groups", lambda: check_groupnorm(C0=64, HW=64)),
+    ("groupnorm_f32", lambda: check_groupnorm(f32=True)),
+    ("groupnorm_f32_two_src", lambda: check_groupnorm(C0=640, C1=320, silu=False, f32=True)),
+    ("groupnorm_f32_wide", lambda: check_groupnorm(B=2, HW=64, C0=1280, C1=1280, f32=True)),
+    ("groupnorm_f32_compact", lambda: check_groupnorm(compact=True, f32=True, HW=4096)),
+    ("groupnorm_big", lambda: check_groupnorm(B=8, HW=4096, C0=320)),
+    ("stream_f32", check_stream_f32),
+    ("gemm_res_f32", check_gemm_res_f32),
+    ("conv_res_f32", lambda: check_gemm_res_f32(conv=True)),
     ("layernorm", lambda: check_layernorm()),
     ("layernorm_1280", lambda: check_layernorm(rows=77, C=1280)),
     ("elementwise", check_elementwise),

@@ -10,11 +10,11 @@ HEADER = os.path.join(ROOT, "include", "aptp_sm100.h")
 
 
 def _declared():
-    """{name: number of parameters} of every `int aptp_*(...)` / `const char* aptp_*(...)` prototype in the header."""
+    """{name: number of parameters} of every `int aptp_*(...)` / `int64_t aptp_*(...)` / `const char* aptp_*(...)` prototype in the header."""
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)   # comments may mention entry points
     out = {}
-    for m in re.finditer(r"\b(?:int|const\s+char\s*\*)\s+(aptp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(?:int|int64_t|const\s+char\s*\*)\s+(aptp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
         params = m.group(2).strip()
         out[m.group(1)] = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
     return out

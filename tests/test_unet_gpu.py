@@ -10,6 +10,11 @@ def _assert(res):
     assert max_abs <= U.MAX_ABS_TOL and cos >= U.COS_TOL, (max_abs, cos)
 
 
+def test_forward_is_bit_reproducible():
+    import unet_checks as U
+    assert U.check_deterministic()
+
+
 def test_tiny_all_ones_equals_ungated():
     import unet_checks as U
     _assert(U.check_all_ones())

@@ -2,6 +2,9 @@
 (oracle/unet_oracle.py) on identical seeded weights, synthetic latents / text embeddings and codes."""
 from __future__ import annotations
 
+import json
+import os
+
 import torch
 
 from diffusion_pruning_b200.synthetic import split_arch, synthetic_codes
@@ -9,10 +12,32 @@ from diffusion_pruning_b200.unet import UNet2DConditionModelGated
 from oracle.unet_oracle import GatedUNetOracle, UNetConfig, seeded_init
 
 TINY = dict(block_out_channels=(64, 128, 256, 256), attention_head_dim=(1, 2, 4, 4), cross_attention_dim=128)
-# bf16 tolerance (stated in DESIGN.md): max-abs <= 2e-2 of the output scale and cosine >= 0.9998 vs the
-# fp32 oracle; torch's own bf16 autocast of the oracle scores ~0.99987 on the same weights.
+# bf16 tolerance of BASELINE.json's north_star (restated in DESIGN.md section 4): max-abs <= 2e-2 of the output scale
+# (scale = max(1, |ref|max); the absolute max-abs is logged next to it) and cosine >= 0.9999 vs the fp32 oracle.
 MAX_ABS_TOL = 2e-2
-COS_TOL = 0.9998
+COS_TOL = 0.9999
+PARITY_LOG = os.environ.get("APTP_PARITY_LOG") or os.path.join(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_metrics.jsonl")
+
+
+def record(name: str, got: torch.Tensor, ref: torch.Tensor, **extra):
+    """Append (name, max_abs / scale, absolute max_abs, cosine, margins) of one parity case to PARITY_LOG (JSON lines);
+    the GPU runs copy the file into profiles/."""
+    max_abs, cos = metrics(got, ref)
+    g, r = got.float().cpu().flatten(), ref.float().flatten()
+    row = {"case": name, "max_abs_over_scale": round(max_abs, 6), "max_abs": round((g - r).abs().max().item(), 6),
+           "cosine": round(cos, 7), "one_minus_cos": float(f"{1.0 - cos:.3e}"), "ref_absmax": round(r.abs().max().item(), 4),
+           "ref_std": round(r.std().item(), 4), "rel_l2": round(((g - r).norm() / r.norm()).item(), 6),
+           "max_abs_margin": round(1.0 - max_abs / MAX_ABS_TOL, 4),
+           "cos_margin": round(1.0 - (1.0 - cos) / (1.0 - COS_TOL), 4)}
+    row.update(extra)
+    try:
+        os.makedirs(os.path.dirname(PARITY_LOG), exist_ok=True)
+        with open(PARITY_LOG, "a") as f:
+            f.write(json.dumps(row) + "\n")
+    except OSError:
+        pass
+    return max_abs, cos
 
 
 def build_pair(tiny: bool = True, seed: int = 0, beta_std: float = 0.0):
@@ -61,14 +86,31 @@ def check_hard(tiny=True, B=4, H=32, code_ids=(0, 3, 3, 7), beta_std=0.0):
     codes = synthetic_codes(model.get_structure(), 8)
     arch = codes[list(code_ids)]
     got, ref = run_pair(model, oracle, arch, B, H, model.config["cross_attention_dim"])
-    return metrics(got, ref)
+    return record(f"hard tiny={tiny} B={B} H={H} codes={tuple(code_ids)} beta_std={beta_std}", got, ref)
+
+
+def check_deterministic(tiny=True, B=4, H=32, code_ids=(0, 3, 3, 7), beta_std=0.1, repeats=3):
+    """The forward is bit-reproducible: GroupNorm statistics use a fixed-order two-stage reduction (no atomics), so
+    eager forwards and CUDA-graph replays of the same inputs agree bit for bit."""
+    model, oracle = build_pair(tiny, beta_std=beta_std)
+    codes = synthetic_codes(model.get_structure(), 8)
+    arch = codes[list(code_ids)]
+    sample, t, ctx = inputs(B, H, model.config["cross_attention_dim"])
+    st = model.get_structure()
+    outs = []
+    for _ in range(repeats + 2):  # the third forward onwards replays a CUDA graph
+        model.set_structure(split_arch(arch.clone().cuda(), st))
+        with torch.no_grad():
+            outs.append(model(sample.cuda(), t.cuda(), ctx.cuda()).sample.clone())
+    torch.cuda.synchronize()
+    return all(torch.equal(outs[0], o) for o in outs[1:])
 
 
 def check_all_ones(tiny=True, B=2, H=32):
     model, oracle = build_pair(tiny)
     dim = sum(w for ws in model.get_structure()["width"] for w in ws) + 14
     got, ref = run_pair(model, oracle, torch.ones(B, dim), B, H, model.config["cross_attention_dim"])
-    return metrics(got, ref)
+    return record(f"all_ones tiny={tiny} B={B} H={H}", got, ref)
 
 
 def check_soft(tiny=True, B=3, H=32, seed=9):
@@ -77,7 +119,7 @@ def check_soft(tiny=True, B=3, H=32, seed=9):
     g = torch.Generator().manual_seed(seed)
     arch = torch.rand(B, dim, generator=g) * 0.9 + 0.05
     got, ref = run_pair(model, oracle, arch, B, H, model.config["cross_attention_dim"])
-    return metrics(got, ref)
+    return record(f"soft tiny={tiny} B={B} H={H}", got, ref)
 
 
 def check_cfg_doubling(tiny=True, H=32):
@@ -86,7 +128,7 @@ def check_cfg_doubling(tiny=True, H=32):
     codes = synthetic_codes(model.get_structure(), 8)
     arch = codes[[1, 5]]
     got, ref = run_pair(model, oracle, arch, 4, H, model.config["cross_attention_dim"])
-    return metrics(got, ref)
+    return record(f"cfg_doubling tiny={tiny} H={H}", got, ref)
 
 
 def check_pruned_expert(B=3, H=32, code_id=3, beta_std=0.1):
@@ -119,4 +161,4 @@ def check_pruned_expert(B=3, H=32, code_id=3, beta_std=0.1):
     from diffusion_pruning_b200 import kernels as K
     K.check_abort()
     gap = (ref - ref_gated).abs().max().item() / max(1.0, ref.abs().max().item())
-    return metrics(got, ref), gap
+    return record(f"pruned_expert B={B} H={H} code={code_id}", got, ref), gap
