@@ -373,18 +373,23 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
                                                        co_q * 8);  // may alias `out`
         }
       };
-      // fp32 residual stream (block outputs): every lane reads the 32 floats of ITS OWN row
-      // (128 contiguous bytes) and adds them before the fp32 store; the chunk's loads are issued one chunk ahead
-      const bool use_res32 = !kGeglu && (p.residual != nullptr) && (p.out_mode == APTP_OUT_F32) &&
-                             (p.flags & APTP_EPI_RES_F32) != 0;
-      float4 rres32[8];
+      // fp32 residual stream (block outputs): same coalesced shape as the bf16 path -- one
+      // instruction moves 8 rows x 64 contiguous bytes -- but 64 B are 16 fp32 columns, so a 32-column chunk goes
+      // through the per-warp staging tile as two halves. The chunk's residual is loaded one chunk ahead.
+      const bool f32_rows = !kGeglu && (p.out_mode == APTP_OUT_F32);
+      const bool use_res32 = f32_rows && (p.residual != nullptr) && (p.flags & APTP_EPI_RES_F32) != 0;
+      uint4 rres32[2][4];
       auto load_res32 = [&](int col0) {
-        const float* rp = reinterpret_cast<const float*>(p.residual) + (size_t)row * p.res_ld + seg.out_col_off + col0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          rres32[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid && col0 + q * 4 < seg.n_valid) rres32[q] = *reinterpret_cast<const float4*>(rp + q * 4);  // may alias `out`
-        }
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            rres32[h][it] = make_uint4(0u, 0u, 0u, 0u);
+            if (co_ok[it] && col0 + h * 16 + co_q * 4 < seg.n_valid)
+              rres32[h][it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) +
+                                                              (size_t)co_row[it] * p.res_ld + seg.out_col_off + col0 +
+                                                              h * 16 + co_q * 4);  // may alias `out`
+          }
       };
       // this tile's chunks are dealt round-robin to the EPI_PER_QUAD warps of the quadrant, continuing where the
       // previous tile stopped, so tiles whose chunk count is not a multiple of EPI_PER_QUAD still balance
@@ -539,34 +544,63 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           for (int it = 0; it < 4; ++it)
             if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o4[it];
           __syncwarp();
-        } else if (use_res32 || valid) {
-          if (use_res32) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              v[q * 4 + 0] += rres32[q].x;
-              v[q * 4 + 1] += rres32[q].y;
-              v[q * 4 + 2] += rres32[q].z;
-              v[q * 4 + 3] += rres32[q].w;
-            }
-            if (more) load_res32(col0 + 32 * EPI_PER_QUAD);  // warp-uniform condition
-          }
+        } else if (f32_rows) {
+          uint4* stg4 = reinterpret_cast<uint4*>(stg);
           if (n_ok < 32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j >= n_ok) v[j] = 0.f;
           }
-          if (!valid) {
-            // nothing to store for this row
-          } else if (p.out_mode == APTP_OUT_F32) {
-            float* op = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_ld + seg.out_col_off + col0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (col0 + q * 4 < seg.n_store) {  // n_store multiple of 4
-                *reinterpret_cast<float4*>(op + q * 4) =
-                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          for (int h = 0; h < 2; ++h) {
+            if (use_res32) {
+              // residual half: coalesced registers -> swizzled smem -> own row (columns beyond n_valid read as 0)
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int rl = it * 8 + (lane >> 2);
+                stg4[rl * 4 + (co_q ^ ((rl >> 1) & 3))] = rres32[h][it];
               }
+              __syncwarp();
+              uint4 w4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) w4[q] = stg4[lane * 4 + (q ^ own_sw)];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[h * 16 + q * 4 + 0] += __uint_as_float(w4[q].x);
+                v[h * 16 + q * 4 + 1] += __uint_as_float(w4[q].y);
+                v[h * 16 + q * 4 + 2] += __uint_as_float(w4[q].z);
+                v[h * 16 + q * 4 + 3] += __uint_as_float(w4[q].w);
+              }
+              __syncwarp();
             }
-          } else {  // fp32 NCHW: out[(sample*out_ld + col) * rows_per_sample + pixel]
+            // own row -> swizzled smem -> 8 rows x 64 B per store instruction
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              stg4[lane * 4 + (q ^ own_sw)] =
+                  make_uint4(__float_as_uint(v[h * 16 + q * 4 + 0]), __float_as_uint(v[h * 16 + q * 4 + 1]),
+                             __float_as_uint(v[h * 16 + q * 4 + 2]), __float_as_uint(v[h * 16 + q * 4 + 3]));
+            __syncwarp();
+            float* obase = reinterpret_cast<float*>(p.out) + seg.out_col_off + col0 + h * 16 + co_q * 4;
+            const bool col_ok = col0 + h * 16 + co_q * 4 < seg.n_store;  // n_store is a multiple of 4
+            uint4 o4[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int rl = it * 8 + (lane >> 2);
+              o4[it] = stg4[rl * 4 + (co_q ^ ((rl >> 1) & 3))];
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+              if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o4[it];
+            __syncwarp();
+          }
+          if (use_res32 && more) load_res32(col0 + 32 * EPI_PER_QUAD);  // after the stores: `residual` may alias `out`
+        } else if (valid) {
+          if (n_ok < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j >= n_ok) v[j] = 0.f;
+          }
+          {  // fp32 NCHW: out[(sample*out_ld + col) * rows_per_sample + pixel]
             float* op = reinterpret_cast<float*>(p.out);
             const int pix = row - sample * p.rows_per_sample;
 #pragma unroll

@@ -132,9 +132,6 @@ if __name__ == "__main__":
     if "router" in which:
         router_goldens()
     if "unet" in which:
-        try:
-            from tests.golden.make_unet_goldens import unet_goldens
-        except ImportError:
-            sys.path.insert(0, OUT)
-            from make_unet_goldens import unet_goldens
+        sys.path.insert(0, OUT)
+        from make_unet_goldens import unet_goldens
         unet_goldens()

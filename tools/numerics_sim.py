@@ -167,8 +167,11 @@ def main():
     O.seeded_init(oracle, 0, a.beta)
     st = oracle.get_structure()
     codes = synthetic_codes(st, 8)
-    ids = [int(c) for c in a.codes.split(",")][: a.B]
-    arch = codes[ids]
+    if a.codes == "ones":
+        arch = torch.ones(a.B, codes.shape[1])
+    else:
+        ids = [int(c) for c in a.codes.split(",")][: a.B]
+        arch = codes[ids]
     g = torch.Generator().manual_seed(1)
     sample = torch.randn(a.B, 4, a.H, a.H, generator=g)
     ctx = torch.randn(a.B, 77, cfg.cross_attention_dim, generator=g)
