@@ -85,6 +85,35 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+_DIST = {}
+
+
+def init_dist():
+    """(rank, world, local, device); the NCCL process group is created once per process and shared by every workload
+    measured in this run (forward, then the `secondary` train / sampling numbers)."""
+    import torch
+    import torch.distributed as dist
+    if _DIST:
+        return _DIST["v"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=device)
+    _DIST["v"] = (rank, world, local, device)
+    return _DIST["v"]
+
+
+def finish_dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def make_workload(device, seed):
     import torch
     from diffusion_pruning_b200.synthetic import split_arch, synthetic_codes
@@ -110,15 +139,7 @@ def make_workload(device, seed):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    rank, world, local, device = init_dist()
     from diffusion_pruning_b200 import kernels as K
     model, codes, assign, sample, ctx, t = make_workload(device, seed=1234 + rank)
     sample_h, ctx_h, t_h = sample.pin_memory(), ctx.pin_memory(), t.pin_memory()
@@ -194,8 +215,10 @@ def run_ours(args):
                 f.write(f"{kind}\t{ms:.4f}\t{fl / 1e9:.2f}\t{fl / max(ms, 1e-6) / 1e9:.1f}\t{label}\n")
     gemm = [(a.elapsed_time(b), fl) for kind, a, b, fl, _ in prof if kind == "gemm" and fl > 0]
     attn = [(a.elapsed_time(b), fl) for kind, a, b, fl, _ in prof if kind == "attn"]
+    hbm = [(a.elapsed_time(b), nb) for kind, a, b, nb, _ in prof if kind == "hbm"]
     g_ms, g_fl = sum(x for x, _ in gemm), sum(f for _, f in gemm)
     a_ms, a_fl = sum(x for x, _ in attn), sum(f for _, f in attn)
+    h_ms, h_bytes = sum(x for x, _ in hbm), sum(b for _, b in hbm)
     K.check_abort()
     peaks = load_peaks()
     traffic, traffic_src = {}, None
@@ -234,27 +257,43 @@ def run_ours(args):
                      "step_frac_of_peak_kept_work": round(kept_flops / (ms_step / 1e3) / 1e12 / peaks["tflops"], 4),
                      "dense_equivalent_tflops": round(BATCH * DENSE_TFLOP_PER_SAMPLE / (ms_step / 1e3), 1)},
     }
+    # flat copies of the per-kernel-class numbers (the nested dict above is kept for continuity with round 1)
+    out.update({
+        "attention_tflops": round(a_fl / (a_ms / 1e3) / 1e12, 1) if a_ms else None, "attention_ms": round(a_ms, 3),
+        "attention_frac": round(a_fl / (a_ms / 1e3) / 1e12 / peaks["tflops"], 4) if a_ms else None,
+        "gemm_tflops": round(g_fl / (g_ms / 1e3) / 1e12, 1) if g_ms else None, "gemm_ms": round(g_ms, 3),
+        "hbm_kernels_gbs": round(h_bytes / (h_ms / 1e3) / 1e9, 1) if h_ms else None, "hbm_kernels_ms": round(h_ms, 3),
+        "hbm_frac": round(h_bytes / (h_ms / 1e3) / 1e9 / peaks["hbm"], 4) if h_ms else None, "hbm_peak_gbs": peaks["hbm"],
+        "hbm_kernels": "GroupNorm statistics + apply(+SiLU/gate), LayerNorm: algorithmic bytes (read once, write once) "
+                       "/ CUDA-event time of each launch",
+        "step_frac_of_peak_kept_work": out["roofline"]["step_frac_of_peak_kept_work"],
+    })
+    # free the forward model before the other workloads
+    del model, eng
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_library_baseline:
+        lb = library_baseline(device, codes, assign) if rank == 0 else None
+        if rank == 0:
+            out["library_baseline"] = lb
+            if lb.get("mixed_expert"):
+                out["vs_library_mixed"] = round(value / lb["mixed_expert"]["value"], 3)
+                out["vs_library_dense"] = round(value / lb["dense"]["value"], 3)
+    if not args.no_secondary:
+        sec = secondary_workloads(args)
+        out["secondary"] = sec
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_steps=1)
     if rank == 0:
         print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_train(args):
+def measure_train(args):
     """BASELINE configs[2]: pruning train step (DDPM + distillation + block + resource + contrastive losses, gate
     backward, Sinkhorn router, AdamW on hypernet + codebook), 32 samples per GPU at 64x64, data parallel with a
     gradient all-reduce. Secondary workload (`--workload train`); the default bench line stays configs[1]."""
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    rank, world, local, device = init_dist()
     from diffusion_pruning_b200 import HyperStructure, StructureVectorQuantizer
     from diffusion_pruning_b200 import kernels as K
     from diffusion_pruning_b200 import pruning_step as PS
@@ -287,26 +326,28 @@ def run_train(args):
             "encoder_hidden_states": torch.randn(Bt, N_CTX, CTX_DIM, generator=g).pin_memory(),
             "mpnet_embeddings": torch.randn(Bt, 768, generator=g).pin_memory()}
     acp = PS.alphas_cumprod().to(device)
+    # DDP semantics (trainer.py:782, :922) without per-parameter copies: every trainable gradient is a VIEW of one flat
+    # fp32 buffer (autograd accumulates into the views in place), so the mean over ranks is ONE NCCL all-reduce of
+    # 1.26 M floats and "zero_grad" is one memset. The all-reduce is timed with CUDA events on its own.
     flat = torch.zeros(sum(p.numel() for p in params), device=device)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    ar_events = []
 
     def step():
         batch = {k: v.to(device, non_blocking=True) for k, v in host.items()}
         out = PS.pruning_step(unet, hyper, quant, batch, cfg, taps, p_actual, acp=acp)
-        opt.zero_grad(set_to_none=True)
+        flat.zero_()
         out["loss"].backward()
-        if world > 1:  # DDP semantics: mean of the 1.26 M trainable gradients, one NCCL all-reduce
-            off = 0
-            for p in params:
-                n = p.numel()
-                flat[off:off + n].copy_(p.grad.reshape(-1) if p.grad is not None else torch.zeros(n, device=device))
-                off += n
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             dist.all_reduce(flat)
             flat.div_(world)
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.grad = flat[off:off + n].view_as(p).clone()
-                off += n
+            e1.record()
+            ar_events.append((e0, e1))
         opt.step()
         return out["loss"].detach()
 
@@ -355,17 +396,17 @@ def run_train(args):
                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
                    "d2h_bytes_per_step": 4},
            "gpu_launches": None, "clocks": clk, "final_loss": loss_h,
+           "grad_allreduce_ms": (round(sum(a.elapsed_time(b) for a, b in ar_events[-args.steps:]) / args.steps, 3)
+                                 if ar_events else None),
            "roofline": {"bound": "tensor", "achieved": round(Bt * tflop_per_sample / (ms / args.steps / 1e3), 1),
                         "peak": peaks["tflops"], "unit": "TFLOP/s",
                         "frac": round(Bt * tflop_per_sample / (ms / args.steps / 1e3) / peaks["tflops"], 4),
                         "note": "whole-step dense-equivalent FLOPs (2.52 TFLOP/sample) / step time", "traffic": None}}
-    if rank == 0:
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    taps.remove() if hasattr(taps, "remove") else None
+    return out
 
 
-def run_sample(args):
+def measure_sample(args):
     """BASELINE configs[3]: expert-routed 25-step DDIM sampling at 96x96 latents with classifier-free guidance. Every
     rank routes its own prompts (hypernet + eval cosine argmax), an all-to-all sends each prompt to the GPU that owns
     its expert (expert e lives on rank e % world), the whole scheduler loop runs there (gated U-Net on the doubled CFG
@@ -374,13 +415,7 @@ def run_sample(args):
     uncond)."""
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    rank, world, local, device = init_dist()
     from diffusion_pruning_b200 import HyperStructure, StructureVectorQuantizer
     from diffusion_pruning_b200 import kernels as K
     from diffusion_pruning_b200 import sampling as S
@@ -451,7 +486,7 @@ def run_sample(args):
     K.check_abort()
     assert torch.isfinite(result).all(), "sampling produced non-finite latents"
     value = P * world * STEPS * args.steps / (ms / 1e3)
-    if rank == 0:
+    if True:
         out = {"metric": "routed_sampling_prompt_steps_per_s", "value": round(value, 2), "unit": "prompts*steps/s",
                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
                "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
@@ -469,24 +504,16 @@ def run_sample(args):
                        "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
                        "d2h_bytes_per_step": int(result.numel() * result.element_size())},
                "gpu_launches": None, "clocks": clk}
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
-def run_finetune(args):
+def measure_finetune(args):
     """the fine-tune step of one static expert (FineTuner.step, trainer.py:1683-1765, from the encoded
     batch on): dense teacher forward (no grad), student forward + backward to EVERY U-Net parameter (dgrad + tcgen05
     wgrad + norm-affine + attention backward), DDPM / distillation / block losses, AdamW over the 866 M parameters."""
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    rank, world, local, device = init_dist()
     from diffusion_pruning_b200 import finetune as FT
     from diffusion_pruning_b200 import kernels as K
     from diffusion_pruning_b200 import pruning_step as PS
@@ -566,7 +593,7 @@ def run_finetune(args):
     # dense-equivalent FLOPs per sample: teacher forward + student forward + dgrad + wgrad of the conv / linear layers
     # (+ 2.5x forward attention FLOPs for its backward): 2 * (2 * 388.35 + 2 * 325.3 + 2.5 * 63.0) GMAC
     flop_per_sample = 2.0 * (2 * 388.35 + 2 * 325.3 + 2.5 * 63.0) * 1e9
-    if rank == 0:
+    if True:
         out = {"metric": "finetune_samples_steps_per_s", "value": round(value, 2), "unit": UNIT, "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -584,9 +611,7 @@ def run_finetune(args):
                             "traffic": None,
                             "note": "whole-step dense-equivalent FLOPs (3.17 TFLOP/sample) / step time; the student computes "
                                     "gated-off channels too (dense weights)"}}
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 def build_oracle_fast():
@@ -608,6 +633,80 @@ def build_oracle_fast():
             else:
                 p.zero_()
     return o
+
+
+def library_baseline(device, codes, assign, steps: int = 20, warmup: int = 5):
+    """The "library bar" (BASELINE.md section 3): what the reference's real execution path -- eager PyTorch on
+    cuDNN / cuBLAS / flash-SDPA -- does on the SAME B200 for the SAME workload (configs[1]: batch 64, 64x64 latent, the same
+    8 codes and assignment). The reference U-Net (restated: oracle/unet_oracle.py; diffusers is not installable) is moved
+    to the GPU in bf16 / channels_last, hard gates are MULTIPLIED as the reference does (nothing is skipped), and the
+    dense case (all-ones gates) is timed beside it. A reported baseline, measured with CUDA events after warm-up."""
+    import torch
+    from diffusion_pruning_b200.synthetic import split_arch
+    out = {"unit": UNIT, "kind": "eager PyTorch " + torch.__version__ + " (cuDNN / cuBLAS / SDPA), bf16 weights and "
+                                 "activations, channels_last, torch.no_grad, gates multiplied as in the reference",
+           "steps": steps, "warmup": warmup, "batch": BATCH, "latent": LATENT}
+    try:
+        torch.backends.cudnn.benchmark = True
+        o = build_oracle_fast().to(device=device, dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+        st = o.get_structure()
+        g = torch.Generator().manual_seed(11)
+        sample = torch.randn(BATCH, 4, LATENT, LATENT, generator=g).to(device, torch.bfloat16)
+        sample = sample.contiguous(memory_format=torch.channels_last)
+        ctx = torch.randn(BATCH, N_CTX, CTX_DIM, generator=g).to(device, torch.bfloat16)
+        t = torch.randint(0, 1000, (BATCH,), generator=g).to(device)
+        for name, arch in (("mixed_expert", codes[assign]), ("dense", torch.ones(BATCH, codes.shape[1]))):
+            o.set_structure(split_arch(arch.to(device, torch.bfloat16), st))
+            with torch.no_grad():
+                for _ in range(warmup):
+                    o(sample, t, ctx)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    y = o(sample, t, ctx)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            assert torch.isfinite(y.float()).all()
+            out[name] = {"value": round(BATCH / (ms / 1e3), 2), "ms_per_step": round(ms, 3),
+                         "dense_equivalent_tflops": round(BATCH * DENSE_TFLOP_PER_SAMPLE / (ms / 1e3), 1)}
+        del o, sample, ctx, y
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001 -- a baseline leg must not take the bench line down with it
+        out["error"] = repr(e)[:300]
+    return out
+
+
+def secondary_workloads(args):
+    """BASELINE configs[2] (pruning train step, gradient all-reduce) and configs[3] (expert-routed sampling, all-to-all)
+    measured in the SAME process group as the headline forward, so the driver's per-N lines carry the two multi-GPU
+    splits north_star names. Flat keys."""
+    import copy
+    import torch
+    sec = {}
+    a = copy.copy(args)
+    a.steps, a.warmup = args.secondary_train_steps, 3
+    try:
+        tr = measure_train(a)
+        sec.update(train_samples_steps_per_s=tr["value"], train_ms=tr["ms_per_step"], train_batch_per_gpu=a.train_batch,
+                   train_frac_of_peak=tr["roofline"]["frac"], train_grad_allreduce_ms=tr.get("grad_allreduce_ms"),
+                   train_final_loss=tr.get("final_loss"))
+    except Exception as e:  # noqa: BLE001
+        sec["train_error"] = repr(e)[:300]
+    torch.cuda.empty_cache()
+    a = copy.copy(args)
+    a.steps, a.warmup = 1, 1
+    try:
+        sm = measure_sample(a)
+        sec.update(sample_prompt_steps_per_s=sm["value"], sample_ms_per_pass=sm["ms_per_step"],
+                   sample_prompts_per_gpu=a.prompts, sample_latent=a.sample_latent, sample_ddim_steps=a.ddim_steps,
+                   sample_unet_samples_steps_per_s=sm["unet_samples_steps_per_s"],
+                   sample_prompts_per_expert=sm["config"]["prompts_per_expert"])
+    except Exception as e:  # noqa: BLE001
+        sec["sample_error"] = repr(e)[:300]
+    torch.cuda.empty_cache()
+    return sec
 
 
 def cpu_baseline(sample_steps: int = 1):
@@ -661,6 +760,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU library bar (N=1)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2] / configs[3] numbers")
+    ap.add_argument("--secondary-train-steps", type=int, default=4)
     ap.add_argument("--workload", default="forward", choices=["forward", "train", "sample", "finetune"])
     ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--prompts", type=int, default=16, help="--workload sample: prompts per GPU")
@@ -669,14 +771,14 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "train":
-        run_train(args)
-    elif args.workload == "sample":
-        run_sample(args)
-    elif args.workload == "finetune":
-        run_finetune(args)
-    else:
+        return
+    if args.workload == "forward":
         run_ours(args)
+    else:
+        out = {"train": measure_train, "sample": measure_sample, "finetune": measure_finetune}[args.workload](args)
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps(out), flush=True)
+    finish_dist()
 
 
 if __name__ == "__main__":

@@ -129,14 +129,18 @@ def pruning_step(unet, hyper_net, quantizer, batch: Dict[str, torch.Tensor], cfg
                                                             hard=True).detach()
         q_emb = q_emb / q_emb.norm(dim=-1, keepdim=True)
         q_sim = q_emb @ q_emb.t()
-        text_list = [torch.zeros_like(text) for _ in range(world)]
-        arch_list = [torch.zeros_like(arch_norm) for _ in range(world)]
         if world > 1:
-            dist.all_gather(text_list, text.contiguous())
-            dist.all_gather(arch_list, arch_norm.detach().contiguous())
-    text_list[rank] = text
-    arch_list[rank] = arch_norm  # the local slice keeps its gradient (:1159-1160)
-    text_all, arch_all = torch.cat(text_list, 0), torch.cat(arch_list, 0)
+            # ONE collective for both gathers of trainer.py:1153-1154: [B, 768 + 1620] fp32 rows, gathered in rank order
+            packed = torch.cat([text.to(torch.float32), arch_norm.detach().to(torch.float32)], dim=1).contiguous()
+            gathered = torch.empty(world * packed.shape[0], packed.shape[1], device=packed.device, dtype=packed.dtype)
+            dist.all_gather_into_tensor(gathered, packed)
+    if world > 1:
+        Bl, nt = text.shape[0], text.shape[1]
+        text_all = gathered[:, :nt].to(text.dtype)
+        # the local slice keeps its gradient (:1159-1160); the other ranks' rows are constants
+        arch_all = torch.cat([gathered[:rank * Bl, nt:], arch_norm, gathered[(rank + 1) * Bl:, nt:]], 0)
+    else:
+        text_all, arch_all = text, arch_norm
     separated = hyper_net.transform_structure_vector(arch_vector if pretrain else arch_vector_quantized)
     c_loss, _ = contrastive_loss(text_all, arch_all, cfg.arch_vector_temperature, cfg.prompt_embedding_temperature)
 

@@ -794,6 +794,18 @@ class _Engine:
             self.sched[full] = s
         return s
 
+    def _hbm(self, nbytes: float, label: str, fn) -> None:
+        """Run an HBM-bound launch group; under `profile` bracket it with CUDA events and record its ALGORITHMIC bytes
+        (each operand read once, the result written once) for the roofline of the norm / gate kernels."""
+        if self.profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            self.profile.append(("hbm", e0, e1, float(nbytes), label))
+        else:
+            fn()
+
     def _gemm(self, sched: K.Schedule, a, w, out, **kw):
         if self.profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -858,17 +870,21 @@ class _Engine:
     def groupnorm(self, x: torch.Tensor, C: int, ld: int, B: int, hw: int, groups_full: int, gs: int, eps: float,
                   gamma: torch.Tensor, beta: torch.Tensor, affine_ld: int, out: torch.Tensor, out_ld: int, silu: bool,
                   sample_seg=None, sample_channels=None, gate=None, x1: Optional[torch.Tensor] = None, c1: int = 0,
-                  ld1: int = 0):
+                  ld1: int = 0, alg_elems: Optional[float] = None):
         """GroupNorm [+ soft width gate] [+ SiLU] -> bf16 rows. `x` (and the optional second source `x1` = the skip half
         of an up-block torch.cat) are bf16 or fp32 rows (dtype decides). Statistics: deterministic two-stage reduction
         (no atomics), see csrc/norm.cu."""
         f32 = x.dtype == torch.float32
         assert x1 is None or (x1.dtype == torch.float32) == f32
         stats = self.buf("gnstats", B, groups_full * 2, torch.float32)
-        K.groupnorm_stats(x, C, ld, x1, c1, ld1, B, hw, gs, sample_channels, stats, groups_full, x_f32=f32)
-        K.groupnorm_apply(x, C, ld, x1, c1, ld1, out, out_ld, B, hw, gs, eps, stats, groups_full, gamma, beta, affine_ld,
-                          sample_seg, sample_channels, gate, gate.stride(0) if gate is not None else groups_full, silu,
-                          x_f32=f32)
+        elems = float(alg_elems) if alg_elems is not None else float(B) * hw * (C + c1)
+        self._hbm(elems * (4 if f32 else 2), f"gn_stats C{C + c1} hw{hw} {'f32' if f32 else 'bf16'}",
+                  lambda: K.groupnorm_stats(x, C, ld, x1, c1, ld1, B, hw, gs, sample_channels, stats, groups_full,
+                                            x_f32=f32))
+        self._hbm(elems * ((4 if f32 else 2) + 2), f"gn_apply C{C + c1} hw{hw} {'f32' if f32 else 'bf16'} silu{int(silu)}",
+                  lambda: K.groupnorm_apply(x, C, ld, x1, c1, ld1, out, out_ld, B, hw, gs, eps, stats, groups_full, gamma,
+                                            beta, affine_ld, sample_seg, sample_channels, gate,
+                                            gate.stride(0) if gate is not None else groups_full, silu, x_f32=f32))
         self.launches += 2
 
     def _bf16(self, x: Act) -> torch.Tensor:
@@ -1046,16 +1062,22 @@ class _Engine:
                 aux["drop_mask"] = self._per_pos((~active).astype(np.uint8), torch.uint8) if (~active).any() else None
             return aux
         aux = self._sched(("res_aux", r.uid), build_aux)
+        if self.compact:  # algorithmic element counts of the two norms (dropped samples / pruned channels excluded)
+            pos = self.layout.expert_of_pos
+            el_in = float(np.where(active, r.cin, 0)[pos].sum()) * hw
+            el_mid = float(np.where(active, n1_e, 0)[pos].sum()) * hw
+        else:
+            el_in, el_mid = float(M) * r.cin, float(M) * r.cout
 
         # norm1 + SiLU straight from the fp32 stream; an up block's torch.cat([hidden_states, res_hidden_states], 1)
         # (blocks.py: inherited UpBlock2D.forward) is read as two sources, never materialised in fp32
         a1 = self.buf("gn_a", M, r.cin)
         if skip is not None:
             self.groupnorm(x.f, x.C, x.C, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
-                           sample_channels=aux.get("ch_in"), x1=skip.f, c1=skip.C, ld1=skip.C)
+                           sample_channels=aux.get("ch_in"), x1=skip.f, c1=skip.C, ld1=skip.C, alg_elems=el_in)
         else:
             self.groupnorm(x.f, x.C, x.C, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
-                           sample_channels=aux.get("ch_in"))
+                           sample_channels=aux.get("ch_in"), alg_elems=el_in)
         # conv1 (N-compacted) + time embedding (+ conv1/time biases, folded into the row vector)
         h1 = self.buf("res_h1", M, r.cout)
 
@@ -1073,7 +1095,7 @@ class _Engine:
         gate = self._soft_gate(cidx["w"][0]) if not self.compact else None
         self.groupnorm(h1, r.cout, r.cout, B, hw, r.groups, gs, r.eps, pk["gamma2"], pk["beta2"], r.cout, a2, r.cout,
                        True, sample_seg=aux.get("seg_mid"),
-                       sample_channels=aux.get("ch_mid"), gate=gate)
+                       sample_channels=aux.get("ch_mid"), gate=gate, alg_elems=el_mid)
         # shortcut: 1x1 conv over the bf16 copy of the (concatenated) input, written fp32 and added in place by conv2
         out = torch.empty(M, r.cout, device=self.device, dtype=torch.float32)
         if r.conv_shortcut is not None:
@@ -1283,18 +1305,22 @@ class _Engine:
         aux = self._sched(("tr_aux", t.uid), build_aux)
         gs = C // t.groups
         xn = self.buf("ln", M, C)
+        n_act = float(active[self.layout.expert_of_pos].sum()) if self.compact else float(B)
         self.groupnorm(x.f, C, C, B, hw, t.groups, gs, 1e-6, dn["g"], dn["b"], C, xn, C, False,
-                       sample_channels=aux["ch"])
+                       sample_channels=aux["ch"], alg_elems=n_act * hw * C)
         tok = self.buf("tok", M, C)
         self.linear("pi." + t.uid, t.proj_in, xn, M, C, C, tok, C, hw, active=active)
         # self-attention
-        K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg0"], dn["lb0"], aux["act"], hw)
+        self._hbm(n_act * hw * C * 4, f"layernorm C{C} hw{hw}",
+                  lambda: K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg0"], dn["lb0"], aux["act"], hw))
         self._attention(t.uid + ".a1", tb.attn1, cidx["w"][0], xn, tok, B, hw, C, active, None, 0)
         # cross-attention
-        K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg1"], dn["lb1"], aux["act"], hw)
+        self._hbm(n_act * hw * C * 4, f"layernorm C{C} hw{hw}",
+                  lambda: K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg1"], dn["lb1"], aux["act"], hw))
         self._attention(t.uid + ".a2", tb.attn2, cidx["w"][1], xn, tok, B, hw, C, active, self.ctx, self.n_ctx)
         # feed-forward: GEGLU (N-compacted, gated) then Linear (K-compacted) + residual
-        K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg2"], dn["lb2"], aux["act"], hw)
+        self._hbm(n_act * hw * C * 4, f"layernorm C{C} hw{hw}",
+                  lambda: K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg2"], dn["lb2"], aux["act"], hw))
         self.launches += 3
         fk = self._ff_pack(t.uid + ".ff", tb.ff, cidx["w"][2])
         vid, nf_e = fk["vid"], fk["nf"][fk["vid"]]

@@ -64,3 +64,12 @@ def test_full_sd21_hard_b8_h64_eight_codes():
 def test_tiny_hard_edge_shapes(B, H, code_ids):
     import unet_checks as U
     _assert(U.check_hard(B=B, H=H, code_ids=code_ids, beta_std=0.1))
+
+
+@pytest.mark.parametrize("case", ["hard", "soft", "cfg", "ones"])
+def test_tiny_vs_reference_executed_goldens(case):
+    """CUDA path vs outputs recorded from the reference's own forward (tests/golden/unet_ref.npz)."""
+    import unet_checks as U
+    res, tap_cos = U.check_vs_reference_golden(case)
+    _assert(res)
+    assert all(c >= 0.9995 for c in tap_cos), tap_cos  # the nine hooked block outputs (bf16 taps)

@@ -162,3 +162,41 @@ def check_pruned_expert(B=3, H=32, code_id=3, beta_std=0.1):
     K.check_abort()
     gap = (ref - ref_gated).abs().max().item() / max(1.0, ref.abs().max().item())
     return record(f"pruned_expert B={B} H={H} code={code_id}", got, ref), gap
+
+
+def check_vs_reference_golden(case: str):
+    """The CUDA path against OUTPUTS OF THE REFERENCE'S OWN CODE (tests/golden/unet_ref.npz: unet_2d_conditional.py /
+    blocks.py executed in place by tests/golden/make_unet_goldens.py), not only against the restated oracle: tiny
+    configuration, 16x16 latents, GroupNorm beta != 0; hard mixed experts, soft gates, CFG doubling, all-ones."""
+    import numpy as np
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    import make_unet_goldens as G
+    gold = np.load(os.path.join(gdir, "unet_ref.npz"))
+    model, oracle = build_pair(True, beta_std=0.1)
+    st = model.get_structure()
+    arch, B = G.unet_cases(st)[case]
+    sample, t, ctx = G.unet_inputs(B, G.TINY_H, model.config["cross_attention_dim"])
+    model.set_structure(split_arch(arch.clone().cuda(), st))
+    blocks = list(model.down_blocks) + [model.mid_block] + list(model.up_blocks)
+    taps = {}
+    handles = []
+    if case == "hard":
+        for i, b in enumerate(blocks):
+            handles.append(b.register_forward_hook(
+                lambda m, inp, o, i=i: taps.__setitem__(i, (o[0] if isinstance(o, tuple) else o).float().cpu())))
+    with torch.no_grad():
+        got = model(sample.cuda(), t.cuda(), ctx.cuda()).sample
+    torch.cuda.synchronize()
+    for h in handles:
+        h.remove()
+    from diffusion_pruning_b200 import kernels as K
+    K.check_abort()
+    res = record(f"vs reference-executed golden: {case} (tiny, H={G.TINY_H})", got, torch.from_numpy(gold[f"unet_{case}"]))
+    tap_cos = []
+    for i, tp in taps.items():
+        ref = torch.from_numpy(gold[f"hard_tap{i}"])
+        tap_cos.append(torch.nn.functional.cosine_similarity(tp.flatten(), ref.flatten(), dim=0).item())
+    return res, tap_cos
