@@ -40,35 +40,66 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region. The sampler is started before the warm-up
+    (nvidia-smi can take longer than a short timed region to print its first line); every line is time-stamped on
+    arrival and only lines inside [begin(), end()] count. If fewer than 3 lines fell inside (very short runs), the
+    caller keeps the same workload running untimed until enough samples under load exist (`extend`)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t0, self.t1, self.extended = None, None, False
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:  # noqa: BLE001
             self.proc = None
+        self.t0 = time.time()
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def in_window(self):
+        t1 = self.t1 if self.t1 is not None else time.time()
+        return [ln for ts, ln in self.lines if self.t0 <= ts <= t1 + 0.02]
+
+    def extend(self, fn, min_samples: int = 3, max_seconds: float = 3.0):
+        """Keep `fn` (one more untimed step of the same workload) running until min_samples lines exist under load."""
+        import torch
+        if self.proc is None or len(self.in_window()) >= min_samples:
+            return
+        self.extended = True
+        t_stop = time.time() + max_seconds
+        while time.time() < t_stop:
+            fn()
+            torch.cuda.synchronize()
+            self.t1 = time.time()
+            if len(self.in_window()) >= min_samples:
+                break
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.t1 = time.time()
+        time.sleep(0.08)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in self.in_window():
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -81,8 +112,11 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if self.extended:
+            out["note"] = "timed region shorter than the sampling latency: samples taken while the same step kept running"
+        return out
 
 
 _DIST = {}
@@ -180,17 +214,20 @@ def run_ours(args):
         barrier()
         return ms
 
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     K.check_abort()
-    clocks = ClockSampler(local)
-    clocks.start()
     if os.environ.get("APTP_CUDA_PROFILE"):  # ncu --profile-from-start off: capture exactly one step
         torch.cuda.profiler.start()
         step_resident()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+    clocks.begin()
     ms_total = timed(step_resident, args.steps)
+    clocks.end()
+    clocks.extend(step_resident)
     clk = clocks.stop()
     eng = model._engine
     launches_per_step = eng.launches

@@ -50,6 +50,7 @@ SIGNATURES = {
     "aptp_version": (c_int, []),
     "aptp_last_error": (C.c_char_p, []),
     "aptp_check_abort": (c_int, [c_void_p]),
+    "aptp_poll_abort": (c_int, [c_void_p]),
     "aptp_grouped_gemm_fwd": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "aptp_groupnorm_stats_workspace": (c_int64, [c_int, c_int, c_int]),
     "aptp_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

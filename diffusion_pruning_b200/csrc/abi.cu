@@ -101,6 +101,48 @@ extern "C" int aptp_version(void) { return APTP_ABI_VERSION; }
 
 extern "C" const char* aptp_last_error(void) { return aptp::g_err; }
 
+// Non-blocking variant for the hot path: every call (1) looks at the copy of the flag that the PREVIOUS call enqueued,
+// if that copy has landed, and (2) enqueues a fresh 4-byte D2H copy into pinned host memory behind the work already
+// on `stream`. No host synchronisation; a timeout is reported one call late at the latest by the next sync point.
+struct AbortPoll {
+  int* h_flag = nullptr;      // pinned
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+};
+static AbortPoll g_poll[64];
+
+extern "C" int aptp_poll_abort(void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return APTP_OK;
+  int* flag = aptp::device_abort_flag();
+  if (!flag) return APTP_OK;
+  AbortPoll& p = g_poll[dev];
+  if (!p.h_flag) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p.h_flag), sizeof(int), cudaHostAllocDefault) != cudaSuccess) return APTP_OK;
+    *p.h_flag = 0;
+    if (cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming) != cudaSuccess) return APTP_OK;
+  }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return APTP_OK;
+  if (p.pending && cudaEventQuery(p.ev) == cudaSuccess) {
+    p.pending = false;
+    if (*p.h_flag != 0) {
+      *p.h_flag = 0;
+      cudaMemsetAsync(flag, 0, sizeof(int), stream);
+      aptp::set_error("a pipelined kernel timed out on an mbarrier during an earlier launch (pipeline bug, bad tensor "
+                      "map, or a GPU time-sliced by a profiler / debugger); results since then are invalid");
+      return 1;
+    }
+  }
+  if (!p.pending) {
+    if (cudaMemcpyAsync(p.h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+        cudaEventRecord(p.ev, stream) == cudaSuccess)
+      p.pending = true;
+  }
+  return APTP_OK;
+}
+
 extern "C" int aptp_check_abort(void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int* flag = aptp::device_abort_flag();

@@ -92,7 +92,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must never hang the GPU box. On timeout (~2 s) the abort flag is
-// raised and the caller unwinds; the host entry point reports the failure.
+// raised and the caller unwinds; the host code polls the flag once per forward / step without synchronising
+// (aptp_poll_abort, called from UNet2DConditionModelGated.forward) and at its own sync points (aptp_check_abort).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* abort_flag) {
   if (mbar_try_wait(bar, parity)) return true;
   long long t0 = clock64();

@@ -35,6 +35,14 @@ def check_abort() -> None:
         check(rc, "aptp_check_abort")
 
 
+def poll_abort() -> None:
+    """Non-blocking mbarrier-timeout check, called once per U-Net forward / train step: raises if a pipelined kernel of
+    an EARLIER launch timed out (the flag makes later pipelined kernels unwind early, so their results are invalid)."""
+    rc = load().aptp_poll_abort(_stream())
+    if rc != 0:
+        check(rc, "aptp_poll_abort")
+
+
 # --------------------------------------------------------------------------------------------
 # GEMM schedule (segments = expert buckets, tiles = 128-row x bn-column work items)
 # --------------------------------------------------------------------------------------------

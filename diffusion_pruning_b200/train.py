@@ -165,6 +165,9 @@ class TrainEngine(_Engine):
         self.B = B
         self.flops, self.launches = 0.0, 0
         self.compact, self.eset, self.layout = False, None, None
+        # the tape holds ONE forward: stamp it so a backward that belongs to an older forward is refused, not silently
+        # run on the newer tape (two grad-enabled forwards before one backward)
+        self.tape_id = getattr(self, "tape_id", 0) + 1
         # gates: [B, 1620] fp32 in get_structure order (widths then depths), as the caller supplied them
         widths = [w for ws in m.get_structure()["width"] for w in ws]
         n_w = len(widths)
@@ -692,8 +695,14 @@ class TrainEngine(_Engine):
                 grads[k] = cur
             K.add_rows(g.t, g.ld, cur.t, cur.ld, act.rows, cur.C)
 
-    def backward(self, dpred: Optional[torch.Tensor], dtaps: List[Optional[torch.Tensor]]) -> torch.Tensor:
+    def backward(self, dpred: Optional[torch.Tensor], dtaps: List[Optional[torch.Tensor]],
+                 tape_id: Optional[int] = None) -> torch.Tensor:
         """Returns d(loss)/d(arch) [gate_rows, 1620] in fp32."""
+        if tape_id is not None and tape_id != self.tape_id:
+            raise RuntimeError(
+                f"backward of U-Net forward #{tape_id} requested, but the activation tape now holds forward #{self.tape_id}: "
+                "the training engine keeps ONE taped forward per model (run backward before the next grad-enabled "
+                "forward, as the reference's train loops do: trainer.py:918-933)")
         m = self.m
         grads: Dict[int, _G] = {}
         x, stats, dn = self.final
@@ -844,13 +853,14 @@ class UNetFineTuneFunction(torch.autograd.Function):
         flat_w, flat_d = model._flat_gates
         y, taps = eng.run_train(sample, timestep, enc, [g.detach() for g in list(flat_w) + list(flat_d)])
         ctx.eng = eng
+        ctx.tape_id = eng.tape_id
         ctx.params = params
         return tuple([y] + [t.nchw() for t in taps])
 
     @staticmethod
     def backward(ctx, dy, *dtaps):
         eng = ctx.eng
-        eng.backward(dy, list(dtaps))
+        eng.backward(dy, list(dtaps), tape_id=ctx.tape_id)
         eng.train_weights = False
         pg = eng.param_grads
         grads = []
@@ -868,6 +878,7 @@ class UNetTrainFunction(torch.autograd.Function):
         eng = model._get_train_engine(sample.device)
         y, taps = eng.run_train(sample, timestep, enc, list(gates))
         ctx.eng = eng
+        ctx.tape_id = eng.tape_id
         ctx.gate_shapes = [g.shape for g in gates]
         ctx.n_width_gates = len(eng.width_starts) - 1
         outs = [y] + [t.nchw() for t in taps]  # bf16 channels-last views of the taped block outputs (zero-copy)
@@ -876,7 +887,7 @@ class UNetTrainFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, *dtaps):
         eng = ctx.eng
-        darch = eng.backward(dy, list(dtaps))
+        darch = eng.backward(dy, list(dtaps), tape_id=ctx.tape_id)
         grads = []
         ws = eng.width_starts
         for i, shp in enumerate(ctx.gate_shapes):

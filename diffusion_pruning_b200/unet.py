@@ -21,6 +21,7 @@ from __future__ import annotations
 import os
 
 import math
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -39,6 +40,44 @@ BF16 = torch.bfloat16
 @dataclass
 class UNet2DConditionOutput:
     sample: torch.Tensor
+
+
+def _require_cuda(sample: torch.Tensor) -> None:
+    if not sample.is_cuda:
+        raise RuntimeError("UNet2DConditionModelGated runs on the sm_100a CUDA path only: move the model and "
+                           "inputs to a CUDA device (there is no CPU fallback)")
+
+
+class FrozenConfig(dict):
+    """`unet.config` as the reference's callers use it: attribute access (`unet.config.sample_size`,
+    pruning_pipelines.py:708, :772; trainer.py:1440) and item access, like diffusers' FrozenDict."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        raise AttributeError("the model config is read-only; use register_to_config(**kwargs)")
+
+
+# diffusers UNet2DConditionModel config keys whose only supported value(s) on this path are listed; anything else raises
+# instead of being silently ignored. Keys not listed here and not consumed by the constructor are kept verbatim in
+# `config` (and written back by save_pretrained): they do not change the arithmetic of the SD-2.1 layout.
+_ONLY_SUPPORTED = {
+    "act_fn": ("silu", "swish"), "center_input_sample": (False,), "dual_cross_attention": (False,),
+    "flip_sin_to_cos": (True,), "freq_shift": (0,), "downsample_padding": (1,), "mid_block_scale_factor": (1, 1.0),
+    "only_cross_attention": (False,), "num_class_embeds": (None,), "class_embed_type": (None,),
+    "addition_embed_type": (None,), "addition_time_embed_dim": (None,), "time_embedding_type": ("positional",),
+    "time_embedding_dim": (None,), "time_embedding_act_fn": (None,), "timestep_post_act": (None,),
+    "time_cond_proj_dim": (None,), "resnet_time_scale_shift": ("default",), "resnet_skip_time_act": (False,),
+    "resnet_out_scale_factor": (1, 1.0), "encoder_hid_dim": (None,), "encoder_hid_dim_type": (None,),
+    "transformer_layers_per_block": (1,), "conv_in_kernel": (3,), "conv_out_kernel": (3,),
+    "projection_class_embeddings_input_dim": (None,), "attention_type": ("default",),
+    "class_embeddings_concat": (False,), "mid_block_only_cross_attention": (None,), "cross_attention_norm": (None,),
+    "dropout": (0, 0.0), "num_attention_heads": (None,), "use_linear_projection": (True,),
+}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -264,8 +303,12 @@ class UNet2DConditionModelGated(nn.Module):
                                    "CrossAttnDownBlock2DHalfGated", "DownBlock2DHalfGated"),
                  mid_block_type="UNetMidBlock2DCrossAttnWidthGated",
                  up_block_types=("UpBlock2DHalfGated", "CrossAttnUpBlock2DHalfGated", "CrossAttnUpBlock2DHalfGated",
-                                 "CrossAttnUpBlock2DHalfGated"), sample_size=96, **unused):
+                                 "CrossAttnUpBlock2DHalfGated"), sample_size=96, **other):
         super().__init__()
+        for k, v in other.items():
+            if k in _ONLY_SUPPORTED and v not in _ONLY_SUPPORTED[k]:
+                raise NotImplementedError(f"UNet config {k}={v!r} is not part of the APTP SD-2.1 hot path "
+                                          f"(supported: {_ONLY_SUPPORTED[k]})")
         if not gated_ff:
             raise NotImplementedError("only gated_ff=True (the shipped configs) is supported")
         if mid_block_type != "UNetMidBlock2DCrossAttnWidthGated":
@@ -282,11 +325,14 @@ class UNet2DConditionModelGated(nn.Module):
         for t in tuple(down_block_types) + tuple(up_block_types):
             if not t.endswith("HalfGated"):
                 raise NotImplementedError(f"block type {t}: only the *HalfGated blocks of the shipped configs exist")
-        self.config = dict(in_channels=in_channels, out_channels=out_channels, block_out_channels=ch,
-                           attention_head_dim=heads, layers_per_block=layers_per_block,
-                           cross_attention_dim=cross_attention_dim, norm_num_groups=norm_num_groups,
-                           norm_eps=norm_eps, ff_gate_width=ff_gate_width, sample_size=sample_size,
-                           down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types))
+        cfg_d = {k: v for k, v in other.items() if not k.startswith("_")}  # unknown / inert keys are preserved
+        cfg_d.update(in_channels=in_channels, out_channels=out_channels, block_out_channels=ch,
+                     attention_head_dim=heads, layers_per_block=layers_per_block,
+                     cross_attention_dim=cross_attention_dim, norm_num_groups=norm_num_groups,
+                     norm_eps=norm_eps, gated_ff=gated_ff, ff_gate_width=ff_gate_width, sample_size=sample_size,
+                     down_block_types=tuple(down_block_types), mid_block_type=mid_block_type,
+                     up_block_types=tuple(up_block_types), use_linear_projection=True)
+        object.__setattr__(self, "_config", FrozenConfig(cfg_d))
         cfg = dict(layers_per_block=layers_per_block, temb=ch[0] * 4, groups=norm_num_groups, eps=norm_eps,
                    ctx_dim=cross_attention_dim, ff_gate_width=ff_gate_width)
         self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
@@ -328,10 +374,57 @@ class UNet2DConditionModelGated(nn.Module):
         self.total_macs = None
         self._engine: Optional["_Engine"] = None
         self._gate_state: Optional[Dict[str, Any]] = None
+        self._last_shape: Optional[Tuple[int, int, int]] = None  # (H, W, text tokens) of the last forward
+        self.gradient_checkpointing = False
         # False: gated semantics (a zero-gated GroupNorm group still feeds silu(beta) into conv2);
         # True: the semantics of the reference's prune() (blocks.py:451-463 deletes those channels)
         self.pruned_semantics = False
         self.set_all_ones_structure()
+
+    # ---------------------------------------------------------------------------------------------
+    # reference API: the ModelMixin / ConfigMixin surface its callers touch
+    # ---------------------------------------------------------------------------------------------
+    @property
+    def config(self) -> FrozenConfig:
+        return self.__dict__["_config"]
+
+    def register_to_config(self, **kwargs) -> None:
+        """ConfigMixin.register_to_config (unet_2d_conditional.py:872 uses it for encoder_hid_dim_type)."""
+        for k, v in kwargs.items():
+            if k in _ONLY_SUPPORTED and v not in _ONLY_SUPPORTED[k]:
+                raise NotImplementedError(f"UNet config {k}={v!r} is not part of the APTP SD-2.1 hot path")
+        d = dict(self.config)
+        d.update(kwargs)
+        object.__setattr__(self, "_config", FrozenConfig(d))
+
+    @property
+    def dtype(self) -> torch.dtype:
+        """Parameter dtype (ModelMixin.dtype); the kernels compute in bf16 with fp32 accumulation whatever it is."""
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    def enable_gradient_checkpointing(self) -> None:
+        """trainer.py:160. Accepted and recorded; the tape engine already keeps only what the backward kernels read."""
+        self.gradient_checkpointing = True
+
+    def disable_gradient_checkpointing(self) -> None:
+        self.gradient_checkpointing = False
+
+    def enable_xformers_memory_efficient_attention(self, *args, **kwargs) -> None:
+        """trainer.py:144-156. REFUSED: in the reference this call replaces HeadGatedAttnProcessor2 and silently turns head
+        gating off; the shipped configs keep it off (configs/pruning/sd-2-1_cc3m.yaml:84).
+        Attention here always runs the fused head-gated sm_100a kernel."""
+        raise NotImplementedError("enable_xformers_memory_efficient_attention would disable head gating in the reference "
+                                  "(blocks.py:140); attention already runs the fused head-gated tcgen05 kernel")
+
+    def disable_xformers_memory_efficient_attention(self) -> None:
+        pass
+
+    def set_attn_processor(self, processor) -> None:
+        raise NotImplementedError("attention processors are not pluggable on the sm_100a path (head gating is fused)")
 
     # ---------------------------------------------------------------------------------------------
     # reference API: structure
@@ -410,9 +503,18 @@ class UNet2DConditionModelGated(nn.Module):
         self.prunable_macs_list = [[e / d["prunable_macs"] for e in elem] for elem in self.get_prunable_macs()]
 
     def calc_macs(self) -> Dict[str, Any]:
-        from .macs import calc_macs
+        from .macs import build_resource_info, calc_macs
         if self._macs_table is None:
-            raise RuntimeError("call count_macs(H, W) first (the reference runs count_ops_and_params once)")
+            # The reference stamps `__macs__` on every leaf during ONE hooked forward (count_ops_and_params at
+            # trainer.py:1272) and calc_macs() reads those stamps ever after. Here the stamps are a closed form in the
+            # layer shapes, so the same call sequence -- set_structure(all ones); unet(sample, t, ctx); calc_macs() --
+            # works with the hooked forward replaced by a plain one: the table is derived from the shapes of the
+            # last forward, once, and kept (like the reference's stamps, it does not follow later resolutions).
+            if self._last_shape is None:
+                raise RuntimeError("calc_macs() needs one forward (the reference's count_ops_and_params pass, "
+                                   "trainer.py:1257-1296) or count_macs(H, W) first")
+            H, W, n_ctx = self._last_shape
+            self._macs_table = build_resource_info(self, H, W, n_ctx)
         return calc_macs(self)
 
     def get_prunable_macs(self):
@@ -448,9 +550,8 @@ class UNet2DConditionModelGated(nn.Module):
                         ("encoder_attention_mask", encoder_attention_mask)):
             if v is not None:
                 raise NotImplementedError(f"{name} is not part of the APTP hot path")
-        if not sample.is_cuda:
-            raise RuntimeError("UNet2DConditionModelGated runs on the sm_100a CUDA path only: move the model and "
-                               "inputs to a CUDA device (there is no CPU fallback)")
+        _require_cuda(sample)
+        self._last_shape = (int(sample.shape[2]), int(sample.shape[3]), int(encoder_hidden_states.shape[1]))
         blocks = list(self.down_blocks) + [self.mid_block] + list(self.up_blocks)
         want_taps = any(len(b._forward_hooks) > 0 for b in blocks)
         flat_w, flat_d = self._flat_gates
@@ -470,6 +571,8 @@ class UNet2DConditionModelGated(nn.Module):
             if self._engine is None or self._engine.device != sample.device:
                 self._engine = _Engine(self, sample.device)
             out, taps = self._engine.run_graphed(sample, timestep, encoder_hidden_states, want_taps=want_taps)
+        if sample.is_cuda:
+            K.poll_abort()  # no sync: reports an mbarrier timeout of an earlier launch instead of returning garbage
         if want_taps:
             # fire the hooks the trainer registers on down_blocks[i] / mid_block / up_blocks[i]
             # (trainer.py:496-511) with tensors shaped like the reference's outputs: down blocks return
@@ -490,7 +593,10 @@ class UNet2DConditionModelGated(nn.Module):
                        "UpBlock2D": "UpBlock2DHalfGated", "CrossAttnUpBlock2D": "CrossAttnUpBlock2DHalfGated",
                        "UNetMidBlock2DCrossAttn": "UNetMidBlock2DCrossAttnWidthGated"}
 
-    def save_pretrained(self, save_directory: str, **unused) -> None:
+    def save_pretrained(self, save_directory: str, sliced: bool = False, **unused) -> None:
+        """`sliced=True` (UNet2DConditionModelPruned only) writes the physically sliced tensors the reference's pruned
+        models hold (what its FineTuner checkpoints contain and scripts/metrics/generate_fid_images.py:100-102 loads);
+        the default writes the dense SD-2.1 tensors. Either file loads back through from_pretrained."""
         import json
         import os
         from safetensors.torch import save_file
@@ -500,7 +606,8 @@ class UNet2DConditionModelGated(nn.Module):
                    use_linear_projection=True)
         with open(os.path.join(save_directory, "config.json"), "w") as f:
             json.dump(cfg, f, indent=2)
-        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()},
+        sd = self.sliced_state_dict() if sliced else self.state_dict()
+        save_file({k: v.detach().cpu().contiguous() for k, v in sd.items()},
                   os.path.join(save_directory, "diffusion_pytorch_model.safetensors"))
 
     @classmethod
@@ -531,14 +638,17 @@ class UNet2DConditionModelGated(nn.Module):
             sd = load_file(st_path)
         else:
             sd = torch.load(os.path.join(directory, "diffusion_pytorch_model.bin"), map_location="cpu")
+        model._pre_load(directory, **extra)   # the pruned class fixes its code first (prune-then-load, :2425-2436)
         model.load_state_dict(sd)
         model.eval()
-        model._post_load(directory, **extra)
         return model
 
-    def _post_load(self, directory: str, **extra) -> None:
+    def _pre_load(self, directory: str, **extra) -> None:
         if extra:
             raise TypeError(f"unexpected arguments for {type(self).__name__}.from_pretrained: {sorted(extra)}")
+
+    def sliced_state_dict(self):
+        raise NotImplementedError("only UNet2DConditionModelPruned (one static code) has a physically sliced layout")
 
     def _get_train_engine(self, device):
         from .train import TrainEngine
@@ -582,8 +692,10 @@ class UNet2DConditionModelPruned(UNet2DConditionModelGated):
         self.invalidate_weight_cache()
         self._train_engine = None
 
-    def _post_load(self, directory: str, arch_vector=None, random_pruning_ratio=None) -> None:
-        """arch_vector.pt next to the unet/ folder (written by FineTuner, trainer.py:1449-1450), unless given."""
+    def _pre_load(self, directory: str, arch_vector=None, random_pruning_ratio=None) -> None:
+        """arch_vector.pt next to the unet/ folder (written by FineTuner, trainer.py:1449-1450), unless given. The code is
+        fixed BEFORE the weights are loaded, like the reference (unet_2d_conditional.py:2425-2436 prunes, then loads), so
+        that checkpoints holding physically sliced tensors can be scattered into place."""
         import os
         from .hypernet import HyperStructure
         if arch_vector is None:
@@ -592,10 +704,90 @@ class UNet2DConditionModelPruned(UNet2DConditionModelGated):
                 if os.path.exists(cand):
                     arch_vector = torch.load(cand, map_location="cpu")
                     break
+        if isinstance(arch_vector, str):
+            arch_vector = torch.load(arch_vector, map_location="cpu")
         if random_pruning_ratio is not None:
             arch_vector = HyperStructure.get_random_arch_vector(random_pruning_ratio, self.get_structure())
         if arch_vector is not None:
             self.prune_to(arch_vector)
+
+    # ---- the reference's physically sliced layout (blocks.py:52-67, :121-129, :153-187, :424-465, :641-697, :1427-1438) ----
+    def _slice_plan(self):
+        """[(parameter name, dim, kept index tensor | None)]: how every prunable tensor of the dense model is sliced for
+        the current code; None marks a parameter of a depth-dropped block (absent from the sliced layout: the reference
+        replaces those modules by nn.Identity). Parameters not listed are stored as they are."""
+        assert self.arch_vector is not None, "prune_to(arch_vector) first"
+        plan = []
+        hard = lambda g: (g.detach().float().reshape(-1) >= 0.5)  # noqa: E731
+        for name, m in self.named_modules():
+            if isinstance(m, ResnetBlock2DWidthGated):
+                if m.depth_gate is not None and not bool(hard(m.depth_gate.gate_f)[0]):
+                    plan += [(f"{name}.{k}", 0, None) for k, _ in m.named_parameters()]
+                    continue
+                keep = hard(m.gate.gate_f).repeat_interleave(m.cout // m.groups).nonzero().reshape(-1)
+                plan += [(f"{name}.conv1.weight", 0, keep), (f"{name}.conv1.bias", 0, keep),
+                         (f"{name}.time_emb_proj.weight", 0, keep), (f"{name}.time_emb_proj.bias", 0, keep),
+                         (f"{name}.norm2.weight", 0, keep), (f"{name}.norm2.bias", 0, keep),
+                         (f"{name}.conv2.weight", 1, keep)]
+            elif isinstance(m, Transformer2DModelWidthGated):
+                if m.depth_gate is not None and not bool(hard(m.depth_gate.gate_f)[0]):
+                    plan += [(f"{name}.{k}", 0, None) for k, _ in m.named_parameters()]
+                    continue
+                tb = m.transformer_blocks[0]
+                for an, attn in (("attn1", tb.attn1), ("attn2", tb.attn2)):
+                    keep = hard(attn.gate.gate_f).repeat_interleave(64).nonzero().reshape(-1)
+                    pre = f"{name}.transformer_blocks.0.{an}"
+                    plan += [(f"{pre}.to_q.weight", 0, keep), (f"{pre}.to_k.weight", 0, keep),
+                             (f"{pre}.to_v.weight", 0, keep), (f"{pre}.to_out.0.weight", 1, keep)]
+                proj = tb.ff.net[0].proj
+                inner = proj.weight.shape[0] // 2
+                kf = hard(tb.ff.net[0].gate.gate_f).repeat_interleave(inner // tb.ff.net[0].gate.width).nonzero().reshape(-1)
+                pre = f"{name}.transformer_blocks.0.ff.net"
+                both = torch.cat([kf, kf + inner])  # GEGLUGated.prune_gate: the same groups of both halves (blocks.py:55-57)
+                plan += [(f"{pre}.0.proj.weight", 0, both), (f"{pre}.0.proj.bias", 0, both), (f"{pre}.2.weight", 1, kf)]
+        return plan
+
+    def sliced_state_dict(self) -> Dict[str, torch.Tensor]:
+        """state_dict() as the reference's pruned model holds it: kept rows / columns only, no entries for
+        depth-dropped blocks (same keys and shapes as the prune sweep of unet_2d_conditional.py:2425-2436 produces)."""
+        sd = dict(self.state_dict())
+        for key, dim, keep in self._slice_plan():
+            if keep is None:
+                sd.pop(key, None)
+            else:
+                sd[key] = sd[key].index_select(dim, keep.to(sd[key].device))
+        return sd
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Accepts the dense SD-2.1 layout and, once a code is set, the reference's physically sliced layout: sliced
+        tensors are scattered into the dense parameters by the kept index lists of the code (pruned rows / columns and
+        depth-dropped blocks are zero-filled; prune() semantics never reads them)."""
+        dense = self.state_dict()
+        sliced = any(k in state_dict and tuple(state_dict[k].shape) != tuple(v.shape) for k, v in dense.items()) or \
+            (self.arch_vector is not None and any(k not in state_dict for k in dense))
+        if sliced:
+            if self.arch_vector is None:
+                raise RuntimeError("this checkpoint holds physically sliced tensors: pass arch_vector=... to from_pretrained "
+                                   "or call prune_to(arch_vector) before load_state_dict (the reference prunes, then loads)")
+            full = dict(state_dict)
+            for key, dim, keep in self._slice_plan():
+                tgt = torch.zeros_like(dense[key])
+                if keep is not None and key in state_dict:
+                    src = state_dict[key].to(tgt.dtype)
+                    want = list(tgt.shape)
+                    want[dim] = keep.numel()
+                    if list(src.shape) == list(tgt.shape):
+                        tgt = src.clone()  # a dense tensor inside an otherwise sliced file
+                    else:
+                        if list(src.shape) != want:
+                            raise RuntimeError(f"{key}: sliced shape {tuple(src.shape)} does not match the code "
+                                               f"(expected {tuple(want)})")
+                        tgt.index_copy_(dim, keep.to(tgt.device), src.to(tgt.device))
+                elif keep is not None and strict:
+                    raise RuntimeError(f"missing key {key} in a sliced checkpoint")
+                full[key] = tgt
+            state_dict = full
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
 
 
 class _Engine:
@@ -617,6 +809,14 @@ class _Engine:
         self.profile: Optional[list] = None  # set to [] to bracket every GEMM / attention launch with CUDA events
         self.graphs: Dict[Any, Any] = {}     # CUDA graphs of the hard-gate forward, keyed by shapes + structure content
         self.graph_seen: Dict[Any, int] = {}
+        # Bounded caches (the reference calls set_structure for EVERY prompt batch, pruning_pipelines.py:757-759, so a long
+        # sampling run walks through many prompt -> expert assignments): schedules / layouts are kept for the
+        # MAX_STATES most recently used (batch, code set, assignment) states, compacted weight packs for the MAX_ESETS
+        # most recently used code sets; older entries are dropped together with their device buffers.
+        self._states: "OrderedDict[Any, int]" = OrderedDict()
+        self._esets: "OrderedDict[Any, int]" = OrderedDict()
+        self._next_id = 0
+        self._sid = self._eid = -1
         # per-forward state
         self.B = 0
         self.compact = False
@@ -673,6 +873,27 @@ class _Engine:
         self._pack_graph, self._pack_graph_n = g, len(self._packs)
         g.replay()
 
+    MAX_STATES = 8
+    MAX_ESETS = 4
+
+    def _lru_id(self, table: "OrderedDict[Any, int]", key, limit: int, tag: str, store: dict) -> int:
+        """Small integer id of `key` in an LRU table; evicting a key drops every `store` entry tagged with its id."""
+        i = table.get(key)
+        if i is None:
+            i = self._next_id
+            self._next_id += 1
+            table[key] = i
+            while len(table) > limit:
+                _, old = table.popitem(last=False)
+                dead = [k for k in store if isinstance(k, tuple) and len(k) == 2 and k[0] == (tag, old)]
+                gone = {id(store.pop(k)) for k in dead}
+                if tag == "es" and gone:
+                    self._packs = [(d, b) for d, b in self._packs if id(d) not in gone]
+                    self._pack_graph, self._pack_graph_n = None, -1
+        else:
+            table.move_to_end(key)
+        return i
+
     def _prepare_gates(self, B: int):
         m = self.m
         st = m._gate_state
@@ -696,12 +917,17 @@ class _Engine:
         self.compact = st["hard"]
         if self.compact:
             self.eset = st["eset"]
-            lk = ("layout", self.eset.key(), st["eset"].sample_expert.tobytes(), B)
+            self._sid = self._lru_id(self._states, (B, self.eset.key(), self.eset.sample_expert.tobytes()),
+                                     self.MAX_STATES, "st", self.sched)
+            self._eid = self._lru_id(self._esets, self.eset.key(), self.MAX_ESETS, "es", self.expert)
+            lk = (("st", self._sid), "layout")
             if lk not in self.sched:
                 self.sched[lk] = P.BatchLayout.build(self.eset.sample_expert, self.eset.n_experts, B)
             self.layout = self.sched[lk]
         else:
             self.eset, self.layout = None, None
+            self._sid = self._lru_id(self._states, (B, b"soft"), self.MAX_STATES, "st", self.sched)
+            self._eid = self._lru_id(self._esets, b"soft", self.MAX_ESETS, "es", self.expert)
             arch = st["arch"]
             if B != st["bg"]:
                 arch = arch.repeat(B // st["bg"], 1)  # gates.py:18-19 (CFG batch doubling)
@@ -786,8 +1012,7 @@ class _Engine:
 
     def _sched(self, key, builder):
         self._label = str(key[:2])
-        full = (key, self.B, self.eset.key() if self.compact else b"soft",
-                self.layout.expert_of_pos.tobytes() if self.compact else b"")
+        full = (("st", self._sid), key)
         s = self.sched.get(full)
         if s is None:
             s = builder()
@@ -900,7 +1125,7 @@ class _Engine:
     def _temb_pack(self) -> Dict[str, Any]:
         """All 22 time_emb_proj Linears in one packed matrix (+ their bias + conv1 bias folded in), per
         distinct kept-set compacted in place inside each layer's block (blocks.py:442-449)."""
-        key = (self.eset.key() if self.compact else b"soft", "temb")
+        key = (("es", self._eid), "temb")
         d = self.expert.get(key)
         if d is not None:
             return d
@@ -967,7 +1192,7 @@ class _Engine:
 
     # ---- ResNet ------------------------------------------------------------------------------------
     def _resnet_pack(self, r: ResnetBlock2DWidthGated) -> Dict[str, Any]:
-        key = (self.eset.key() if self.compact else b"soft", r.uid)
+        key = (("es", self._eid), r.uid)
         d = self.expert.get(key)
         if d is not None:
             return d
@@ -1139,7 +1364,7 @@ class _Engine:
 
     # ---- transformer -------------------------------------------------------------------------------
     def _attn_pack(self, uid: str, attn: _Attention, gate_idx: int) -> Dict[str, Any]:
-        key = (self.eset.key() if self.compact else b"soft", uid)
+        key = (("es", self._eid), uid)
         d = self.expert.get(key)
         if d is not None:
             return d
@@ -1158,7 +1383,7 @@ class _Engine:
         return d
 
     def _ff_pack(self, uid: str, ff: _FeedForward, gate_idx: int) -> Dict[str, Any]:
-        key = (self.eset.key() if self.compact else b"soft", uid)
+        key = (("es", self._eid), uid)
         d = self.expert.get(key)
         if d is not None:
             return d
@@ -1394,6 +1619,8 @@ class _Engine:
         entry = self.graphs.get(key)
         if entry is None:
             seen = self.graph_seen.get(key, 0)
+            if len(self.graph_seen) >= 64 and key not in self.graph_seen:
+                self.graph_seen.pop(next(iter(self.graph_seen)))
             self.graph_seen[key] = seen + 1
             if seen < 2:  # two eager forwards build every schedule / packed weight and warm the allocator
                 return self.run(sample, timestep, ctx, want_taps)
@@ -1404,9 +1631,13 @@ class _Engine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 y, taps = self.run(st_s, st_t, st_c, want_taps)
-            entry = (g, st_s, st_t, st_c, y, taps, self.flops, self.launches, self.gemm_bytes)
+            # the captured kernels read this state's schedules and packed weights: the graph keeps them alive even if
+            # the LRU caches above drop the state in the meantime
+            keep = ([v for k, v in self.sched.items() if isinstance(k, tuple) and k[0] == ("st", self._sid)],
+                    [v for k, v in self.expert.items() if isinstance(k, tuple) and k[0] == ("es", self._eid)])
+            entry = (g, st_s, st_t, st_c, y, taps, self.flops, self.launches, self.gemm_bytes, keep)
             self.graphs[key] = entry
-        g, st_s, st_t, st_c, y, taps, self.flops, self.launches, self.gemm_bytes = entry
+        g, st_s, st_t, st_c, y, taps, self.flops, self.launches, self.gemm_bytes, _keep = entry
         st_s.copy_(sample, non_blocking=True)
         st_t.copy_(timestep, non_blocking=True)
         st_c.copy_(ctx, non_blocking=True)

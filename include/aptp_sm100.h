@@ -29,6 +29,9 @@ int aptp_version(void);
 const char* aptp_last_error(void);
 /* returns 1 if a pipelined kernel hit an mbarrier timeout since the last call (and clears it); syncs `stream`. */
 int aptp_check_abort(void* stream);
+/* non-blocking: returns 1 if the flag copy enqueued by the previous call shows a timeout (and clears it), then enqueues
+ * a new 4-byte copy behind the work on `stream`. Called by every forward / step of the host code (no host sync). */
+int aptp_poll_abort(void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  grouped, expert-bucketed GEMM / implicit-GEMM conv on tcgen05 + TMEM fed by TMA.

@@ -44,3 +44,22 @@ def test_finetune_of_pruned_expert_matches_physically_pruned_oracle():
     assert fwd[0] <= 2 * U.MAX_ABS_TOL and fwd[1] >= U.COS_TOL - 5e-4, fwd
     T.assert_finetune(out)
     assert outside and max(outside.values()) == 0.0, {k: v for k, v in outside.items() if v != 0.0}
+
+
+def test_stale_tape_backward_is_refused():
+    """two grad-enabled forwards before one backward must raise, not run on the newer tape."""
+    import torch
+    import unet_checks as U
+    from diffusion_pruning_b200.synthetic import split_arch
+    model, _ = U.build_pair(True)
+    st = model.get_structure()
+    dim = sum(w for ws in st["width"] for w in ws) + 14
+    sample, t, ctx = U.inputs(2, 16, model.config["cross_attention_dim"])
+    arch = (torch.rand(2, dim) * 0.9 + 0.05).cuda().requires_grad_(True)
+    model.set_structure(split_arch(arch * 1.0, st))
+    y1 = model(sample.cuda(), t.cuda(), ctx.cuda()).sample
+    model.set_structure(split_arch(arch * 1.0, st))
+    y2 = model(sample.cuda(), t.cuda(), ctx.cuda()).sample
+    y2.float().sum().backward()          # newest tape: fine
+    with pytest.raises(RuntimeError, match="tape"):
+        y1.float().sum().backward()

@@ -1,5 +1,6 @@
 """GPU parity: the CUDA U-Net path vs the fp32 CPU oracle on identical seeded weights and inputs."""
 import pytest
+import torch
 
 pytestmark = pytest.mark.gpu
 
@@ -73,3 +74,31 @@ def test_tiny_vs_reference_executed_goldens(case):
     res, tap_cos = U.check_vs_reference_golden(case)
     _assert(res)
     assert all(c >= 0.9995 for c in tap_cos), tap_cos  # the nine hooked block outputs (bf16 taps)
+
+
+def test_engine_caches_stay_bounded_over_many_assignments():
+    """schedules / packs must not grow without bound when every batch brings a new prompt -> expert assignment
+    (pruning_pipelines.py:757-759 calls set_structure per batch), and CUDA graphs must survive the eviction."""
+    import unet_checks as U
+    from diffusion_pruning_b200.synthetic import split_arch, synthetic_codes
+    model, oracle = U.build_pair(True, beta_std=0.1)
+    st = model.get_structure()
+    codes = synthetic_codes(st, 8)
+    sample, t, ctx = U.inputs(4, 16, model.config["cross_attention_dim"])
+    g = torch.Generator().manual_seed(0)
+    first = None
+    assign0 = [0, 3, 3, 7]
+    sizes = []
+    for it in range(40):
+        assign = assign0 if it % 13 < 3 else torch.randint(0, 8, (4,), generator=g).tolist()
+        model.set_structure(split_arch(codes[assign].clone().cuda(), st))
+        with torch.no_grad():
+            y = model(sample.cuda(), t.cuda(), ctx.cuda()).sample
+        if assign == assign0:
+            first = y.clone() if first is None else first
+            assert torch.equal(y, first), "a replayed / re-built state must reproduce the same bits"
+        eng = model._engine
+        sizes.append((len(eng.sched), len(eng.expert), len(eng.graphs), len(eng.graph_seen)))
+    assert len(eng._states) <= eng.MAX_STATES and len(eng._esets) <= eng.MAX_ESETS
+    assert max(s[0] for s in sizes[20:]) <= max(s[0] for s in sizes[:20]) * 1.5 + 50, sizes[-1]
+    assert sizes[-1][2] <= 4
