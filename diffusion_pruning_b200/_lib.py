@@ -38,12 +38,14 @@ class GemmArgs(C.Structure):
         ("gn_stats", c_void_p), ("gn_group", c_int), ("gn_groups", c_int),
         ("flags", c_int),
         ("segs", c_void_p), ("n_segs", c_int), ("tiles", c_void_p), ("n_tiles", c_int),
+        ("ln_colsum", c_void_p), ("ln_partial", c_void_p), ("ln_chunks", c_int), ("ln_width", c_int), ("ln_eps", c_float),
+        ("rowstat_out", c_void_p), ("rowstat_chunks", c_int),
     ]
 
 
 A_LINEAR, A_CONV3X3, A_CONV3X3_S2 = 0, 1, 2
 OUT_BF16, OUT_F32, OUT_F32_NCHW = 0, 1, 2
-EPI_GEGLU, EPI_SILU, EPI_GN_STATS, EPI_RES_F32 = 1, 2, 4, 8
+EPI_GEGLU, EPI_SILU, EPI_GN_STATS, EPI_RES_F32, EPI_LN_FOLD = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); must list every symbol declared in include/aptp_sm100.h
 SIGNATURES = {

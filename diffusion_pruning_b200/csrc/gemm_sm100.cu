@@ -33,7 +33,7 @@ constexpr int STG_WARP_BYTES = 32 * 64;            // per-warp staging: 32 rows 
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 constexpr int MAX_SMEM_SEGS = 96;                   // expert-bucket records cached in shared memory (else read from global)
 constexpr int SSEG_BYTES = MAX_SMEM_SEGS * 48;
-constexpr int SBIAS_BYTES = EPI_WARPS * 64 * 4;     // per epilogue warp: the bias slice of its current chunk (32, or 2 x 32 for GEGLU)
+constexpr int SBIAS_BYTES = EPI_WARPS * 128 * 4;    // per epilogue warp: bias slice of its current chunk (32, or 2 x 32 for GEGLU) + the LN-fold column sums
 
 struct GemmParams {
   CUtensorMap tmap_a;
@@ -60,6 +60,16 @@ struct GemmParams {
   const float* border_tab;
   int tab_ld;
   int flags;
+  // LayerNorm folded into this GEMM (APTP_EPI_LN_FOLD): A holds the RAW rows x, the weights are W*gamma, and
+  //   out = rstd[row] * (acc - mu[row] * colsum[n]) + bias'[n]
+  // with (mu, rstd) derived per row from the (sum, sumsq) partials the PRODUCER of x wrote (rowstat_out below)
+  const float* ln_colsum;
+  const float2* ln_partial;
+  int ln_chunks;
+  float ln_inv_c, ln_eps;
+  // producer side: per-row (sum, sumsq) of every 32-column chunk of the stored values
+  float2* rowstat_out;
+  int rowstat_chunks;
   int* abort_flag;
 };
 
@@ -120,6 +130,19 @@ __device__ __forceinline__ void add32_smem(float* v, const float* src) {
     v[q * 4 + 1] += f.y;
     v[q * 4 + 2] += f.z;
     v[q * 4 + 3] += f.w;
+  }
+}
+
+// folded LayerNorm: v = rstd * (v - mu * colsum), colsum broadcast from shared memory
+__device__ __forceinline__ void ln_apply32(float* v, const float* cs, float mu, float rstd) {
+  const float nm = -mu * rstd;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 f = *(reinterpret_cast<const float4*>(cs) + q);
+    v[q * 4 + 0] = fmaf(nm, f.x, rstd * v[q * 4 + 0]);
+    v[q * 4 + 1] = fmaf(nm, f.y, rstd * v[q * 4 + 1]);
+    v[q * 4 + 2] = fmaf(nm, f.z, rstd * v[q * 4 + 2]);
+    v[q * 4 + 3] = fmaf(nm, f.w, rstd * v[q * 4 + 3]);
   }
 }
 
@@ -307,7 +330,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
     const int ew = warp - 4;
     const int quad = warp & 3;       // TMEM lane quadrant this warp may touch
     const int cpar = ew >> 2;        // position of this warp among the EPI_PER_QUAD warps of its quadrant
-    float* wbias = sbias + ew * 64;
+    float* wbias = sbias + ew * 128;
     uint32_t chunk_rot = 0;          // chunks dealt so far (mod EPI_PER_QUAD): keeps the deal balanced across tiles
     const int r_own = quad * 32 + lane;
     uint8_t* stg = stg_base + ew * STG_WARP_BYTES;
@@ -397,10 +420,11 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int c_first = (cpar + EPI_PER_QUAD - (int)(chunk_rot % EPI_PER_QUAD)) % EPI_PER_QUAD;
       chunk_rot += (uint32_t)n_chunks;
       // bias slice of a chunk: one coalesced load per lane, issued early; broadcast through smem at use
-      float bias_h = 0.f, bias_g = 0.f;
+      const bool ln_fold = (p.flags & APTP_EPI_LN_FOLD) != 0;
+      float bias_h = 0.f, bias_g = 0.f, cs_h = 0.f, cs_g = 0.f;
       auto load_bias = [&](int c) {
         const int col0 = ocol_base + c * 32;
-        bias_h = bias_g = 0.f;
+        bias_h = bias_g = cs_h = cs_g = 0.f;
         if (p.bias && col0 + lane < seg.n_valid) {
           if (geglu) {  // packed bias follows the packed (interleaved [h | g]) weight rows
             bias_h = __ldg(p.bias + seg.vec_off + tile.n0 + c * 32 + lane);
@@ -409,7 +433,28 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
             bias_h = __ldg(p.bias + seg.vec_off + col0 + lane);
           }
         }
+        if (ln_fold && col0 + lane < seg.n_valid) {
+          if (geglu) {
+            cs_h = __ldg(p.ln_colsum + seg.vec_off + tile.n0 + c * 32 + lane);
+            cs_g = __ldg(p.ln_colsum + seg.vec_off + tile.n0 + p.bn / 2 + c * 32 + lane);
+          } else {
+            cs_h = __ldg(p.ln_colsum + seg.vec_off + col0 + lane);
+          }
+        }
       };
+      // folded LayerNorm: this row's mean / rstd from the producer's per-chunk partial sums (fixed order)
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      if (ln_fold && valid) {
+        const float2* pp = p.ln_partial + (size_t)row * p.ln_chunks;
+        float su = 0.f, sq = 0.f;
+        for (int i = 0; i < p.ln_chunks; i += 2) {  // ln_chunks is even (C is a multiple of 64)
+          const float4 q = *reinterpret_cast<const float4*>(pp + i);
+          su += q.x + q.z;
+          sq += q.y + q.w;
+        }
+        ln_mu = su * p.ln_inv_c;
+        ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_c - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
       if (c_first < n_chunks) {
         if (use_res && ocol_base + c_first * 32 < seg.n_store) load_res(ocol_base + c_first * 32);
         if (use_res32 && ocol_base + c_first * 32 < seg.n_store) load_res32(ocol_base + c_first * 32);
@@ -425,9 +470,13 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int col0 = ocol_base + c * 32;
         if (col0 >= seg.n_store) break;  // warp-uniform
         const int n_ok = seg.n_valid - col0;  // columns of this chunk that carry data (may be <= 0)
-        if (p.bias) {
+        if (p.bias || ln_fold) {
           wbias[lane] = bias_h;
           if (geglu) wbias[32 + lane] = bias_g;
+          if (ln_fold) {
+            wbias[64 + lane] = cs_h;
+            if (geglu) wbias[96 + lane] = cs_g;
+          }
           __syncwarp();
         }
         const bool more = (c + EPI_PER_QUAD < n_chunks) && (col0 + 32 * EPI_PER_QUAD < seg.n_store);
@@ -442,6 +491,10 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           for (int j = 0; j < 32; ++j) {
             v[j] = __uint_as_float(ra[j]);
             gv[j] = __uint_as_float(rb[j]);
+          }
+          if (ln_fold) {
+            ln_apply32(v, wbias + 64, ln_mu, ln_rstd);
+            ln_apply32(gv, wbias + 96, ln_mu, ln_rstd);
           }
           if (p.bias) {
             add32_smem(v, wbias);
@@ -460,7 +513,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_fast(gv[j]);
-          if (p.bias) {
+          if (p.bias || ln_fold) {
             __syncwarp();
             if (more) load_bias(c + EPI_PER_QUAD);
           }
@@ -470,8 +523,9 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-          if (p.bias) {
-            add32_smem(v, wbias);
+          if (ln_fold) ln_apply32(v, wbias + 64, ln_mu, ln_rstd);
+          if (p.bias) add32_smem(v, wbias);
+          if (p.bias || ln_fold) {
             __syncwarp();
             if (more) load_bias(c + EPI_PER_QUAD);
           }
@@ -523,6 +577,16 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j >= n_ok) v[j] = 0.f;
+          }
+          if (!kGeglu && p.rowstat_out && valid) {
+            // per-row (sum, sumsq) of this 32-column chunk, for the LayerNorm folded into the consumer GEMM
+            float su = 0.f, sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              su += v[j];
+              sq = fmaf(v[j], v[j], sq);
+            }
+            p.rowstat_out[(size_t)row * p.rowstat_chunks + ((seg.out_col_off + col0) >> 5)] = make_float2(su, sq);
           }
           // own row -> swizzled smem
 #pragma unroll
@@ -654,6 +718,16 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
                  "aptp_grouped_gemm_fwd: a bf16 residual needs a bf16 output and res_ld %% 8 == 0");
   APTP_REQUIRE(a->a_rows < (1ll << 31), "aptp_grouped_gemm_fwd: too many rows");
   APTP_REQUIRE(!(a->flags & APTP_EPI_GN_STATS), "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS not implemented yet");
+  if (a->flags & APTP_EPI_LN_FOLD) {
+    APTP_REQUIRE(a->ln_colsum && a->ln_partial && a->ln_chunks > 0 && a->ln_chunks % 2 == 0 && a->ln_width > 0 &&
+                     (reinterpret_cast<uintptr_t>(a->ln_partial) & 15) == 0,
+                 "aptp_grouped_gemm_fwd: APTP_EPI_LN_FOLD needs ln_colsum, ln_partial (16-byte aligned), an even ln_chunks and ln_width");
+    APTP_REQUIRE(a->a_mode == APTP_A_LINEAR, "aptp_grouped_gemm_fwd: APTP_EPI_LN_FOLD applies to linear layers");
+  }
+  if (a->rowstat_out) {
+    APTP_REQUIRE(a->out_mode == APTP_OUT_BF16 && !(a->flags & APTP_EPI_GEGLU) && a->rowstat_chunks > 0 && a->bn % 32 == 0,
+                 "aptp_grouped_gemm_fwd: rowstat_out needs a plain bf16 output");
+  }
   if (a->flags & APTP_EPI_GEGLU) {
     APTP_REQUIRE(a->bn % 64 == 0, "aptp_grouped_gemm_fwd: GEGLU needs bn %% 64 == 0");
     APTP_REQUIRE(a->out_mode == APTP_OUT_BF16 && !a->residual && !a->rowvec && !a->border_tab && !(a->flags & APTP_EPI_SILU),
@@ -736,6 +810,13 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   p.border_tab = a->border_tab;
   p.tab_ld = a->tab_ld;
   p.flags = a->flags;
+  p.ln_colsum = a->ln_colsum;
+  p.ln_partial = reinterpret_cast<const float2*>(a->ln_partial);
+  p.ln_chunks = a->ln_chunks;
+  p.ln_inv_c = a->ln_width > 0 ? 1.f / (float)a->ln_width : 0.f;
+  p.ln_eps = a->ln_eps;
+  p.rowstat_out = reinterpret_cast<float2*>(a->rowstat_out);
+  p.rowstat_chunks = a->rowstat_chunks;
   p.abort_flag = device_abort_flag();
   APTP_REQUIRE(p.abort_flag != nullptr, "aptp_grouped_gemm_fwd: could not allocate abort flag");
 

@@ -1061,7 +1061,7 @@ class _Engine:
 
     def linear(self, name: str, lin: nn.Module, x: torch.Tensor, rows: int, k: int, ld: int, out: torch.Tensor,
                out_ld: int, hw: int, *, residual=None, res_ld=0, flags=0, active=None, out_mode=OUT_BF16,
-               n_out: Optional[int] = None, out_col_off: int = 0):
+               n_out: Optional[int] = None, out_col_off: int = 0, rowstat_out=None):
         """Unpruned Linear / 1x1 conv over token rows (depth-dropped buckets skipped via `active`)."""
         d = self._dense_linear(name, lin)
         n = n_out if n_out is not None else lin.weight.shape[0]
@@ -1073,7 +1073,7 @@ class _Engine:
             return K.build_schedule(segs, bn, self.device)
         sched = self._sched(("lin", name, rows, hw), build)
         self._gemm(sched, x, d["w"], out, a_ld=ld, a_k=k, a_rows=rows, out_ld=out_ld, out_mode=out_mode, bias=d["b"],
-                   rows_per_sample=hw, residual=residual, res_ld=res_ld, flags=flags)
+                   rows_per_sample=hw, residual=residual, res_ld=res_ld, flags=flags, rowstat_out=rowstat_out)
 
     def conv3x3(self, name: str, conv: nn.Module, x: Act, out: torch.Tensor, out_ld: int, *, stride=1, out_mode=OUT_BF16,
                 n_pad_to=0):
@@ -1363,26 +1363,55 @@ class _Engine:
         return Act(None, B, H, W, r.cout, f=out)
 
     # ---- transformer -------------------------------------------------------------------------------
-    def _attn_pack(self, uid: str, attn: _Attention, gate_idx: int) -> Dict[str, Any]:
+    @staticmethod
+    def _pack_vec(vec: torch.Tensor, kept: List[np.ndarray], n_pad: int) -> torch.Tensor:
+        """Per-variant compaction of a per-output-row vector, laid out like P.pack_rows lays out the rows."""
+        out = torch.zeros(len(kept) * n_pad, device=vec.device, dtype=torch.float32)
+        for v, rows in enumerate(kept):
+            idx = torch.as_tensor(rows, device=vec.device, dtype=torch.long)
+            out[v * n_pad: v * n_pad + len(rows)] = vec.index_select(0, idx)
+        return out
+
+    def _attn_pack(self, uid: str, attn: _Attention, gate_idx: int, ln: nn.LayerNorm) -> Dict[str, Any]:
+        """Compacted q/k/v/out weights per kept-head variant. The LayerNorm in front of the attention
+        (BasicTransformerBlock.norm1 / norm2, blocks.py:782, :808-810) is FOLDED into the projections that read the
+        normalised tokens (q, k, v of self-attention; q of cross-attention): weights W*gamma, bias W@beta, plus the
+        column sums of the bf16 weights the epilogue needs (APTP_EPI_LN_FOLD)."""
         key = (("es", self._eid), uid)
         d = self.expert.get(key)
         if d is not None:
             return d
         C = attn.dim
+        is_cross = attn.ctx_dim is not None
         if self.compact:
             kept_h, vid = P.kept_variants(self.eset.width_bits(gate_idx))
         else:
             kept_h, vid = [np.arange(attn.heads)], np.zeros(1, dtype=np.int64)
         kept_c = [P.expand_groups(k, 64) for k in kept_h]
         d = {"vid": vid, "nh": np.asarray([len(k) for k in kept_h]), "V": len(kept_h)}
+        gam = ln.weight.detach().to(self.device, torch.float32)
+        bet = ln.bias.detach().to(self.device, torch.float32)
         for nm, lin in (("q", attn.to_q), ("k", attn.to_k), ("v", attn.to_v)):
-            d["w" + nm] = P.pack_rows(lin.weight.detach().to(self.device), kept_c, C)
+            w = lin.weight.detach().to(self.device, torch.float32)
+            if nm == "q" or not is_cross:
+                d["w" + nm] = P.pack_rows(w * gam[None, :], kept_c, C)
+                d["b" + nm] = self._pack_vec(w @ bet, kept_c, C)
+            else:
+                d["w" + nm] = P.pack_rows(w, kept_c, C)
+        if is_cross:
+            d["cq"] = d["wq"].float().sum(1).contiguous()
+            d["wkv"] = torch.cat([d["wk"], d["wv"]], 0).contiguous()
+        else:
+            d["wqkv"] = torch.cat([d["wq"], d["wk"], d["wv"]], 0).contiguous()
+            d["bqkv"] = torch.cat([d["bq"], d["bk"], d["bv"]], 0).contiguous()
+            d["cqkv"] = d["wqkv"].float().sum(1).contiguous()
         d["wo"] = P.pack_cols(attn.to_out[0].weight.detach().to(self.device, BF16), kept_c, 1)
         d["bo"] = attn.to_out[0].bias.detach().to(self.device, torch.float32).contiguous()
         self.expert[key] = d
         return d
 
-    def _ff_pack(self, uid: str, ff: _FeedForward, gate_idx: int) -> Dict[str, Any]:
+    def _ff_pack(self, uid: str, ff: _FeedForward, gate_idx: int, ln: nn.LayerNorm) -> Dict[str, Any]:
+        """GEGLU proj / net.2 per kept-FF-group variant; norm3 (blocks.py:821) is folded into the GEGLU projection."""
         key = (("es", self._eid), uid)
         d = self.expert.get(key)
         if d is not None:
@@ -1402,8 +1431,11 @@ class _Engine:
         half = bn // 2
         rows_pad = ((inner + half - 1) // half) * bn
         V = len(kept_c)
-        w = proj.weight.detach().to(self.device)
-        b = proj.bias.detach().to(self.device, torch.float32)
+        w = proj.weight.detach().to(self.device, torch.float32)
+        gam = ln.weight.detach().to(self.device, torch.float32)
+        bet = ln.bias.detach().to(self.device, torch.float32)
+        b = proj.bias.detach().to(self.device, torch.float32) + w @ bet
+        w = w * gam[None, :]
         wp = torch.zeros(V * rows_pad, C, device=self.device, dtype=BF16)
         bp = torch.zeros(V * rows_pad, device=self.device, dtype=torch.float32)
         for v, cols in enumerate(kept_c):
@@ -1424,16 +1456,19 @@ class _Engine:
             wp[v * rows_pad: v * rows_pad + nt * bn] = blk
             bp[v * rows_pad: v * rows_pad + nt * bn] = bblk
         d = {"vid": vid, "nf": nf, "V": V, "bn": bn, "rows_pad": rows_pad, "wp": wp, "bp": bp, "inner": inner,
-             "gs": gs}
+             "gs": gs, "sp": wp.float().sum(1).contiguous()}
         d["w2"] = P.pack_cols(ff.net[2].weight.detach().to(self.device, BF16), kept_c, 1)
         d["b2"] = ff.net[2].bias.detach().to(self.device, torch.float32).contiguous()
         self.expert[key] = d
         return d
 
-    def _attention(self, uid: str, attn: _Attention, gate_idx: int, xn: torch.Tensor, tok: torch.Tensor, B: int,
-                   hw: int, C: int, active: np.ndarray, ctx: Optional[torch.Tensor], n_ctx: int):
-        """GatedAttention + HeadGatedAttnProcessor2 (blocks.py:194-280); output accumulated into `tok`."""
-        pk = self._attn_pack(uid, attn, gate_idx)
+    def _attention(self, uid: str, attn: _Attention, gate_idx: int, ln: nn.LayerNorm, part: torch.Tensor,
+                   tok: torch.Tensor, B: int, hw: int, C: int, active: np.ndarray, ctx: Optional[torch.Tensor],
+                   n_ctx: int, want_stats: bool = True):
+        """LayerNorm + GatedAttention + HeadGatedAttnProcessor2 (blocks.py:782-806 / :808-819, :194-280); the output is
+        accumulated into `tok`. `part` holds the per-row LayerNorm partial sums of `tok` on entry (written by the GEMM
+        that produced it) and, with want_stats, those of the updated `tok` on exit."""
+        pk = self._attn_pack(uid, attn, gate_idx, ln)
         E = self.eset.n_experts if self.compact else 1
         vid, nh_e = pk["vid"], pk["nh"][pk["vid"]]
         M = B * hw
@@ -1451,8 +1486,8 @@ class _Engine:
             s = {}
             nv = [int(n) * 64 for n in nh_e]
             if is_cross:
-                s["q"] = K.build_schedule(self._segments(hw, nv, [(kq + 63) // 64] * E, vid * C, active=active), bn,
-                                          self.device)
+                s["q"] = K.build_schedule(self._segments(hw, nv, [(kq + 63) // 64] * E, vid * C, vec_off=vid * C,
+                                                         active=active), bn, self.device)
                 segs = []
                 for j in range(2):
                     segs += self._segments(n_kv, nv, [(kkv + 63) // 64] * E, vid * C + j * pk["V"] * C, active=active,
@@ -1461,7 +1496,8 @@ class _Engine:
             else:
                 segs = []
                 for j in range(3):
-                    segs += self._segments(hw, nv, [(kq + 63) // 64] * E, vid * C + j * pk["V"] * C, active=active,
+                    off = vid * C + j * pk["V"] * C
+                    segs += self._segments(hw, nv, [(kq + 63) // 64] * E, off, vec_off=off, active=active,
                                            out_col_off=j * C)
                 s["qkv"] = K.build_schedule(segs, bn, self.device)
             s["o"] = K.build_schedule(self._segments(hw, [C] * E, [int(n) for n in nh_e], vid * C, active=active),
@@ -1474,17 +1510,17 @@ class _Engine:
                 else float(attn.heads * B)
             return s
         s = self._sched(("attn", uid, hw, n_kv), build)
-        if "wqkv" not in pk:
-            pk["wqkv"] = torch.cat([pk["wq"], pk["wk"], pk["wv"]], 0).contiguous() if not is_cross else None
-            pk["wkv"] = torch.cat([pk["wk"], pk["wv"]], 0).contiguous() if is_cross else None
         gkw = dict(gate=gate, gate_ld=gate.stride(0), gate_group=64) if gate is not None else {}
+        lnkw = dict(ln_partial=part, ln_width=C, ln_eps=ln.eps)
         if is_cross:
-            self._gemm(s["q"], xn, pk["wq"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=C, rows_per_sample=hw, **gkw)
+            self._gemm(s["q"], tok, pk["wq"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=C, rows_per_sample=hw, bias=pk["bq"],
+                       ln_colsum=pk["cq"], **lnkw, **gkw)
             self._gemm(s["kv"], ctx, pk["wkv"], kvb, a_ld=kkv, a_k=kkv, a_rows=Mkv, out_ld=2 * C, rows_per_sample=n_kv,
                        **gkw)
             q, ldq, kk, vv, ldkv = qkv, C, kvb, kvb[:, C:], 2 * C
         else:
-            self._gemm(s["qkv"], xn, pk["wqkv"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=3 * C, rows_per_sample=hw, **gkw)
+            self._gemm(s["qkv"], tok, pk["wqkv"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=3 * C, rows_per_sample=hw,
+                       bias=pk["bqkv"], ln_colsum=pk["cqkv"], **lnkw, **gkw)
             q, ldq, kk, vv, ldkv = qkv, 3 * C, qkv[:, C:], qkv[:, 2 * C:], 3 * C
         o = self.buf("attn_o", M, C)
         if s["max_heads"] > 0:
@@ -1498,9 +1534,10 @@ class _Engine:
                 self.profile.append(("attn", e0, e1, fl, f"{uid} nq{hw} nkv{n_kv}"))
             self.launches += 1
             self.flops += fl
-        # to_out (K-compacted to the kept heads) + bias + residual, in place on the token stream
+        # to_out (K-compacted to the kept heads) + bias + residual, in place on the token stream; its epilogue also
+        # writes the LayerNorm partial sums of the updated rows for the next folded LayerNorm
         self._gemm(s["o"], o, pk["wo"], tok, a_ld=C, a_k=C, a_rows=M, out_ld=C, bias=pk["bo"], residual=tok, res_ld=C,
-                   rows_per_sample=hw)
+                   rows_per_sample=hw, rowstat_out=part if want_stats else None)
 
     def transformer(self, t: Transformer2DModelWidthGated, x: Act) -> Act:
         """Transformer2DModelWidth(Depth)Gated.forward (blocks.py:1139-1355) incl. the
@@ -1534,20 +1571,16 @@ class _Engine:
         self.groupnorm(x.f, C, C, B, hw, t.groups, gs, 1e-6, dn["g"], dn["b"], C, xn, C, False,
                        sample_channels=aux["ch"], alg_elems=n_act * hw * C)
         tok = self.buf("tok", M, C)
-        self.linear("pi." + t.uid, t.proj_in, xn, M, C, C, tok, C, hw, active=active)
-        # self-attention
-        self._hbm(n_act * hw * C * 4, f"layernorm C{C} hw{hw}",
-                  lambda: K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg0"], dn["lb0"], aux["act"], hw))
-        self._attention(t.uid + ".a1", tb.attn1, cidx["w"][0], xn, tok, B, hw, C, active, None, 0)
-        # cross-attention
-        self._hbm(n_act * hw * C * 4, f"layernorm C{C} hw{hw}",
-                  lambda: K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg1"], dn["lb1"], aux["act"], hw))
-        self._attention(t.uid + ".a2", tb.attn2, cidx["w"][1], xn, tok, B, hw, C, active, self.ctx, self.n_ctx)
-        # feed-forward: GEGLU (N-compacted, gated) then Linear (K-compacted) + residual
-        self._hbm(n_act * hw * C * 4, f"layernorm C{C} hw{hw}",
-                  lambda: K.layernorm(tok, C, xn, C, M, C, 1e-5, dn["lg2"], dn["lb2"], aux["act"], hw))
-        self.launches += 3
-        fk = self._ff_pack(t.uid + ".ff", tb.ff, cidx["w"][2])
+        # LayerNorm statistics travel with the token stream: every GEMM that writes `tok` also writes per-row
+        # (sum, sumsq) partials per 32-column chunk, and the three LayerNorms of the block (norm1/2/3, blocks.py:782,
+        # :808-810, :821) are folded into the GEMMs that consume them -- no LayerNorm pass over HBM at all
+        part = self.buf("ln_part", M, (C // 32) * 2, torch.float32).view(M, C // 32, 2)
+        self.linear("pi." + t.uid, t.proj_in, xn, M, C, C, tok, C, hw, active=active, rowstat_out=part)
+        # self-attention, cross-attention
+        self._attention(t.uid + ".a1", tb.attn1, cidx["w"][0], tb.norm1, part, tok, B, hw, C, active, None, 0)
+        self._attention(t.uid + ".a2", tb.attn2, cidx["w"][1], tb.norm2, part, tok, B, hw, C, active, self.ctx, self.n_ctx)
+        # feed-forward: norm3 folded into GEGLU (N-compacted, gated), then Linear (K-compacted) + residual
+        fk = self._ff_pack(t.uid + ".ff", tb.ff, cidx["w"][2], tb.norm3)
         vid, nf_e = fk["vid"], fk["nf"][fk["vid"]]
         inner = fk["inner"]
         ffb = self.buf("ff", M, inner)
@@ -1565,8 +1598,8 @@ class _Engine:
         s = self._sched(("ff", t.uid, hw), build_ff)
         gate = self._soft_gate(cidx["w"][2]) if not self.compact else None
         gkw = dict(gate=gate, gate_ld=gate.stride(0), gate_group=fk["gs"]) if gate is not None else {}
-        self._gemm(s["p"], xn, fk["wp"], ffb, a_ld=C, a_k=C, a_rows=M, out_ld=inner, bias=fk["bp"], flags=EPI_GEGLU,
-                   rows_per_sample=hw, **gkw)
+        self._gemm(s["p"], tok, fk["wp"], ffb, a_ld=C, a_k=C, a_rows=M, out_ld=inner, bias=fk["bp"], flags=EPI_GEGLU,
+                   rows_per_sample=hw, ln_colsum=fk["sp"], ln_partial=part, ln_width=C, ln_eps=tb.norm3.eps, **gkw)
         self._gemm(s["o"], ffb, fk["w2"], tok, a_ld=inner, a_k=inner, a_rows=M, out_ld=C, bias=fk["b2"], residual=tok,
                    res_ld=C, rows_per_sample=hw)
         # proj_out + residual: back onto the fp32 stream

@@ -74,7 +74,8 @@ enum {
   APTP_EPI_GEGLU = 1,      /* tile columns are [bn/2 h | bn/2 g]; out = h * gelu_erf(g)            */
   APTP_EPI_SILU = 2,       /* out = silu(out) (time-embedding MLP)                                 */
   APTP_EPI_GN_STATS = 4,   /* accumulate per-(sample,group) sum / sumsq of the stored values       */
-  APTP_EPI_RES_F32 = 8     /* `residual` holds fp32 rows (fp32 residual stream); needs APTP_OUT_F32 */
+  APTP_EPI_RES_F32 = 8,    /* `residual` holds fp32 rows (fp32 residual stream); needs APTP_OUT_F32 */
+  APTP_EPI_LN_FOLD = 16    /* LayerNorm of the A rows folded into this GEMM (see ln_* below)         */
 };
 
 typedef struct aptp_gemm_args {
@@ -119,6 +120,20 @@ typedef struct aptp_gemm_args {
   int32_t n_segs;
   const aptp_gemm_tile* tiles;
   int32_t n_tiles;
+  /* LayerNorm folded into the GEMM (APTP_EPI_LN_FOLD; replaces BasicTransformerBlock.norm1/2/3, blocks.py:782,:808-810,
+   * :821): `a` holds the RAW rows x, `w` holds W*gamma, `bias` holds W@beta (+ the layer's own bias) and
+   *   out[row, n] = rstd[row] * (acc[row, n] - mean[row] * ln_colsum[vec_off + n]) + bias[vec_off + n]
+   * where ln_colsum[n] = sum_k w[n, k] (of the bf16-rounded packed weights) and mean / rstd of a row come from
+   * ln_partial[row * ln_chunks + i] = (sum, sumsq) over the i-th 32-column chunk of x, ln_width = C columns in total.
+   * The partials are written by the GEMM that PRODUCED x: rowstat_out[row * rowstat_chunks + (out_col_off + col) / 32]
+   * (sum, sumsq of the values it stores, bf16 output only). Deterministic (no atomics). */
+  const float* ln_colsum;
+  const float* ln_partial;   /* float2 per (row, chunk) */
+  int32_t ln_chunks;
+  int32_t ln_width;
+  float ln_eps;
+  float* rowstat_out;        /* float2 per (row, chunk) */
+  int32_t rowstat_chunks;
 } aptp_gemm_args;
 
 int aptp_grouped_gemm_fwd(const aptp_gemm_args* args, void* stream);

@@ -80,6 +80,7 @@ def replay_pipeline(unet, hyper_net, quantizer, device, n_prompts=3, steps=3, gu
             latent_model_input = torch.cat([latents] * 2) if do_classifier_free_guidance else latents  # :792
             noise_pred = unet(latent_model_input, t.to(device), encoder_hidden_states=prompt_embeds,
                               cross_attention_kwargs=None, return_dict=False)[0]                   # :796-802
+            trace.append(noise_pred.clone())  # raw [uncond; cond] prediction of this step (test hook, not in the reference)
             if do_classifier_free_guidance:                                                        # :805-807
                 noise_pred_uncond, noise_pred_text = noise_pred.chunk(2)
                 noise_pred = noise_pred_uncond + guidance_scale * (noise_pred_text - noise_pred_uncond)
@@ -89,7 +90,6 @@ def replay_pipeline(unet, hyper_net, quantizer, device, n_prompts=3, steps=3, gu
             x0 = a_t.sqrt() * latents - (1 - a_t).sqrt() * noise_pred
             eps = a_t.sqrt() * noise_pred + (1 - a_t).sqrt() * latents
             latents = a_p.sqrt() * x0 + (1 - a_p).sqrt() * eps                                      # :814
-            trace.append(noise_pred)
     macs_dict = unet.calc_macs()                                                                   # :822
     resource_ratios = macs_dict['cur_prunable_macs'] / (unet.resource_info_dict['cur_prunable_macs'].squeeze())  # :823-824
     return latents, min_encoding_indices, resource_ratios, structure_vector_quantized, trace

@@ -50,7 +50,8 @@ def _check_tiles(sched: K.Schedule, mode, Ho, Wo, geglu):
 
 def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1, H=1, W=1, k_tap_pitch=0, out_ld,
                  out_mode=OUT_BF16, bias=None, rowvec=None, rowvec_ld=0, rows_per_sample=1, residual=None, res_ld=0,
-                 gate=None, gate_ld=0, gate_group=1, border_tab=None, tab_ld=0, flags=0):
+                 gate=None, gate_ld=0, gate_group=1, border_tab=None, tab_ld=0, flags=0, ln_colsum=None, ln_partial=None,
+                 ln_width=0, ln_eps=1e-5, rowstat_out=None):
     if sched.n_tiles == 0:
         return
     geglu = bool(flags & EPI_GEGLU)
@@ -77,6 +78,13 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
                 wh = blk[:, 0].reshape(nt * half, kk)
                 wg = blk[:, 1].reshape(nt * half, kk)
                 acc_h, acc_g = Ae @ wh.t(), Ae @ wg.t()
+                if ln_partial is not None:  # APTP_EPI_LN_FOLD: rstd * (acc - mean * colsum), per row
+                    ps = ln_partial[rb:re].sum(1)
+                    mu = ps[:, 0] / ln_width
+                    rstd = torch.rsqrt((ps[:, 1] / ln_width - mu * mu).clamp(min=0) + ln_eps)
+                    cs = ln_colsum[voff:voff + nt * sched.bn].reshape(nt, 2, half)
+                    acc_h = rstd[:, None] * (acc_h - mu[:, None] * cs[:, 0].reshape(-1)[None])
+                    acc_g = rstd[:, None] * (acc_g - mu[:, None] * cs[:, 1].reshape(-1)[None])
                 if bias is not None:
                     bb_ = bias[voff:voff + nt * sched.bn].reshape(nt, 2, half)
                     acc_h = acc_h + bb_[:, 0].reshape(-1)
@@ -102,6 +110,12 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
             acc = acc_h * F.gelu(acc_g)
         else:
             cols = torch.arange(acc.shape[1])
+            if ln_partial is not None:
+                ps = ln_partial[rb:re].sum(1)
+                mu = ps[:, 0] / ln_width
+                rstd = torch.rsqrt((ps[:, 1] / ln_width - mu * mu).clamp(min=0) + ln_eps)
+                nb = min(nv, acc.shape[1])
+                acc[:, :nb] = rstd[:, None] * (acc[:, :nb] - mu[:, None] * ln_colsum[voff:voff + nb][None])
             if bias is not None:
                 nb = min(nv, acc.shape[1])
                 acc[:, :nb] += bias[voff:voff + nb]
@@ -128,6 +142,11 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
         if out_mode == OUT_BF16:
             O = _view(out, re, out_ld, out_ld)
             O[rb:re, oco:oco + nst] = acc[:, :nst].to(torch.bfloat16)
+            if rowstat_out is not None:  # per-row (sum, sumsq) per 32-column chunk of the stored values
+                assert oco % 32 == 0 and nst % 32 == 0
+                a32 = acc[:, :nst].reshape(re - rb, nst // 32, 32)
+                rowstat_out[rb:re, oco // 32: oco // 32 + nst // 32, 0] = a32.sum(-1)
+                rowstat_out[rb:re, oco // 32: oco // 32 + nst // 32, 1] = (a32 * a32).sum(-1)
         elif out_mode == OUT_F32:
             O = _view(out, re, out_ld, out_ld)
             O[rb:re, oco:oco + nst] = acc[:, :nst]

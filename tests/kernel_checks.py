@@ -401,6 +401,58 @@ def check_gemm_res_f32(conv=False, seed=0):
     _close(out, ref, 2e-3, 1e-4, "gemm fp32 out + fp32 residual")
 
 
+def check_gemm_ln_fold(geglu=False, seed=0):
+    """LayerNorm folded into the consumer GEMM (APTP_EPI_LN_FOLD) with the row statistics written by the producer GEMM's
+    epilogue (rowstat_out): producer = Linear + residual -> x (bf16); consumer = Linear(LayerNorm(x)) [or GEGLU]."""
+    M, C, N = 1000, 320, 640
+    a0 = _rand(M, C, seed=seed).bfloat16()
+    w0 = _rand(C, C, scale=C ** -0.5, seed=seed + 1).bfloat16()
+    res = (_rand(M, C, seed=seed + 2) * 2 + 0.7).bfloat16()
+    x = res.clone()
+    part = torch.full((M, C // 32, 2), float("nan"), device=DEV)
+    sched = K.build_schedule([K.Segment(0, M, C, C // 64)], 160, DEV)
+    K.grouped_gemm(a0, w0, x, sched, a_ld=C, a_k=C, a_rows=M, out_ld=C, residual=x, res_ld=C, rowstat_out=part)
+    K.check_abort()
+    xr = (a0.float() @ w0.float().t() + res.float())
+    _close(x, xr, 3e-2, 1e-2, "producer output")
+    ref_p = torch.stack([xr.reshape(M, C // 32, 32).sum(-1), (xr ** 2).reshape(M, C // 32, 32).sum(-1)], -1)
+    _close(part, ref_p, 2e-2, 2e-3, "row-stat partials")
+    gamma = _rand(C, seed=seed + 3) * 0.2 + 1
+    beta = _rand(C, seed=seed + 4) * 0.2
+    xs = x.float()  # what the consumer reads
+    ln = F.layer_norm(xs, (C,), gamma, beta, 1e-5)
+    if not geglu:
+        w = _rand(N, C, scale=C ** -0.5, seed=seed + 5)
+        b = _rand(N, seed=seed + 6)
+        wf = (w * gamma[None]).bfloat16()
+        colsum = wf.float().sum(1).contiguous()
+        bias = (w @ beta + b).contiguous()
+        out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+        sched = K.build_schedule([K.Segment(0, M, N, C // 64)], 160, DEV)
+        K.grouped_gemm(x, wf, out, sched, a_ld=C, a_k=C, a_rows=M, out_ld=N, bias=bias, ln_colsum=colsum,
+                       ln_partial=part, ln_width=C, ln_eps=1e-5)
+        K.check_abort()
+        _close(out, ln @ w.t() + b, 4e-2, 2e-2, "ln-fold linear")
+    else:
+        inner, bn = 640, 256
+        half = bn // 2
+        w = _rand(2 * inner, C, scale=C ** -0.5, seed=seed + 5)
+        b = _rand(2 * inner, seed=seed + 6) * 0.1
+        nt = inner // half
+        wg = w * gamma[None]
+        wp = torch.stack([wg[:inner].reshape(nt, half, C), wg[inner:].reshape(nt, half, C)], 1).reshape(nt * bn, C).bfloat16()
+        bb = w @ beta + b
+        bp = torch.stack([bb[:inner].reshape(nt, half), bb[inner:].reshape(nt, half)], 1).reshape(nt * bn).contiguous()
+        colsum = wp.float().sum(1).contiguous()
+        out = torch.full((M, inner), float("nan"), device=DEV, dtype=torch.bfloat16)
+        sched = K.build_schedule([K.Segment(0, M, inner, C // 64)], bn, DEV, geglu=True)
+        K.grouped_gemm(x, wp, out, sched, a_ld=C, a_k=C, a_rows=M, out_ld=inner, bias=bp, flags=EPI_GEGLU,
+                       ln_colsum=colsum, ln_partial=part, ln_width=C, ln_eps=1e-5)
+        K.check_abort()
+        hg = ln @ w.t() + b
+        _close(out, hg[:, :inner] * F.gelu(hg[:, inner:]), 5e-2, 3e-2, "ln-fold geglu")
+
+
 def check_attention(B=2, heads=3, kept=(3, 1), Nq=256, Nkv=256, seed=0):
     C = heads * 64
     q = _rand(B * Nq, C, seed=seed).bfloat16()
@@ -473,6 +525,8 @@ ALL = [
     ("groupnorm_big", lambda: check_groupnorm(B=8, HW=4096, C0=320)),
     ("stream_f32", check_stream_f32),
     ("gemm_res_f32", check_gemm_res_f32),
+    ("gemm_ln_fold", check_gemm_ln_fold),
+    ("gemm_ln_fold_geglu", lambda: check_gemm_ln_fold(geglu=True)),
     ("conv_res_f32", lambda: check_gemm_res_f32(conv=True)),
     ("layernorm", lambda: check_layernorm()),
     ("layernorm_1280", lambda: check_layernorm(rows=77, C=1280)),

@@ -36,11 +36,15 @@ def test_count_macs_sequence_and_pipeline_loop_match_oracle():
     t0 = torch.tensor([(1000 // 3) * 2 + 1])
     with torch.no_grad():
         ref_pred = oracle(torch.cat([lat0] * 2), t0, torch.cat([neg, cond]))
-    u, c = ref_pred.chunk(2)
-    ref_pred = u + 7.5 * (c - u)
-    got = trace[0].float().cpu()
+    got = trace[0].float().cpu()                     # raw [uncond; cond] prediction of the first loop iteration
     cos = torch.nn.functional.cosine_similarity(got.flatten(), ref_pred.flatten(), dim=0).item()
-    assert cos >= 0.999, cos  # guidance 7.5 amplifies the bf16 difference of the two halves
+    err = (got - ref_pred).abs().max().item() / max(1.0, ref_pred.abs().max().item())
+    assert cos >= 0.9999 and err <= 2e-2, (cos, err)
+    # after guidance 7.5 the bf16 difference of the two halves is amplified 7.5x: looser, but the same direction
+    gu, gc = got.chunk(2)
+    ru, rc = ref_pred.chunk(2)
+    cosg = torch.nn.functional.cosine_similarity((gu + 7.5 * (gc - gu)).flatten(), (ru + 7.5 * (rc - ru)).flatten(), dim=0)
+    assert cosg.item() >= 0.995, cosg.item()
 
 
 def test_api_surface_the_callers_touch():
