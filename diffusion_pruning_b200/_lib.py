@@ -38,7 +38,8 @@ class GemmArgs(C.Structure):
         ("gn_stats", c_void_p), ("gn_group", c_int), ("gn_groups", c_int),
         ("flags", c_int),
         ("segs", c_void_p), ("n_segs", c_int), ("tiles", c_void_p), ("n_tiles", c_int),
-        ("ln_colsum", c_void_p), ("ln_partial", c_void_p), ("ln_chunks", c_int), ("ln_width", c_int), ("ln_eps", c_float),
+        ("ln_colsum", c_void_p), ("ln_rowstats", c_void_p), ("ln_reserved0", c_int), ("ln_reserved1", c_int),
+        ("ln_reserved2", c_float),
         ("rowstat_out", c_void_p), ("rowstat_chunks", c_int),
     ]
 
@@ -65,6 +66,7 @@ SIGNATURES = {
     "aptp_depth_lerp_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int,
                                     c_void_p]),
     "aptp_upsample2x_cvt": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "aptp_ln_rowstats": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "aptp_layernorm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p,
                                c_void_p, c_int, c_void_p]),
     "aptp_depth_lerp": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int,

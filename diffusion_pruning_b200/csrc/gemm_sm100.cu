@@ -64,9 +64,7 @@ struct GemmParams {
   //   out = rstd[row] * (acc - mu[row] * colsum[n]) + bias'[n]
   // with (mu, rstd) derived per row from the (sum, sumsq) partials the PRODUCER of x wrote (rowstat_out below)
   const float* ln_colsum;
-  const float2* ln_partial;
-  int ln_chunks;
-  float ln_inv_c, ln_eps;
+  const float2* ln_rowstats;
   // producer side: per-row (sum, sumsq) of every 32-column chunk of the stored values
   float2* rowstat_out;
   int rowstat_chunks;
@@ -133,16 +131,23 @@ __device__ __forceinline__ void add32_smem(float* v, const float* src) {
   }
 }
 
-// folded LayerNorm: v = rstd * (v - mu * colsum), colsum broadcast from shared memory
-__device__ __forceinline__ void ln_apply32(float* v, const float* cs, float mu, float rstd) {
+// folded LayerNorm + bias in two packed FFMA2 per column pair: v = rstd * v + bias' - mu * rstd * colsum
+// (bias' and colsum broadcast from shared memory; the epilogue of the K = 320 layers is issue-bound, so the
+// fold must cost next to nothing on top of the bias add it replaces)
+__device__ __forceinline__ void ln_bias_apply32(float* v, const float* bias, const float* cs, float mu, float rstd) {
+  const uint64_t r2 = pack_f32x2(rstd, rstd);
   const float nm = -mu * rstd;
+  const uint64_t n2 = pack_f32x2(nm, nm);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float4 f = *(reinterpret_cast<const float4*>(cs) + q);
-    v[q * 4 + 0] = fmaf(nm, f.x, rstd * v[q * 4 + 0]);
-    v[q * 4 + 1] = fmaf(nm, f.y, rstd * v[q * 4 + 1]);
-    v[q * 4 + 2] = fmaf(nm, f.z, rstd * v[q * 4 + 2]);
-    v[q * 4 + 3] = fmaf(nm, f.w, rstd * v[q * 4 + 3]);
+    const float4 b = *(reinterpret_cast<const float4*>(bias) + q);
+    const float4 c = *(reinterpret_cast<const float4*>(cs) + q);
+    uint64_t a0 = fma_f32x2(r2, pack_f32x2(v[q * 4 + 0], v[q * 4 + 1]), pack_f32x2(b.x, b.y));
+    uint64_t a1 = fma_f32x2(r2, pack_f32x2(v[q * 4 + 2], v[q * 4 + 3]), pack_f32x2(b.z, b.w));
+    a0 = fma_f32x2(n2, pack_f32x2(c.x, c.y), a0);
+    a1 = fma_f32x2(n2, pack_f32x2(c.z, c.w), a1);
+    unpack_f32x2(a0, v[q * 4 + 0], v[q * 4 + 1]);
+    unpack_f32x2(a1, v[q * 4 + 2], v[q * 4 + 3]);
   }
 }
 
@@ -442,18 +447,12 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         }
       };
-      // folded LayerNorm: this row's mean / rstd from the producer's per-chunk partial sums (fixed order)
+      // folded LayerNorm: this row's (mean, rstd), one 8-byte load per tile, in flight under the accumulator wait
       float ln_mu = 0.f, ln_rstd = 1.f;
       if (ln_fold && valid) {
-        const float2* pp = p.ln_partial + (size_t)row * p.ln_chunks;
-        float su = 0.f, sq = 0.f;
-        for (int i = 0; i < p.ln_chunks; i += 2) {  // ln_chunks is even (C is a multiple of 64)
-          const float4 q = *reinterpret_cast<const float4*>(pp + i);
-          su += q.x + q.z;
-          sq += q.y + q.w;
-        }
-        ln_mu = su * p.ln_inv_c;
-        ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_c - ln_mu * ln_mu, 0.f) + p.ln_eps);
+        const float2 ms = __ldg(p.ln_rowstats + row);
+        ln_mu = ms.x;
+        ln_rstd = ms.y;
       }
       if (c_first < n_chunks) {
         if (use_res && ocol_base + c_first * 32 < seg.n_store) load_res(ocol_base + c_first * 32);
@@ -492,11 +491,10 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
             v[j] = __uint_as_float(ra[j]);
             gv[j] = __uint_as_float(rb[j]);
           }
-          if (ln_fold) {
-            ln_apply32(v, wbias + 64, ln_mu, ln_rstd);
-            ln_apply32(gv, wbias + 96, ln_mu, ln_rstd);
-          }
-          if (p.bias) {
+          if (ln_fold) {  // (host: APTP_EPI_LN_FOLD always comes with a bias vector)
+            ln_bias_apply32(v, wbias, wbias + 64, ln_mu, ln_rstd);
+            ln_bias_apply32(gv, wbias + 32, wbias + 96, ln_mu, ln_rstd);
+          } else if (p.bias) {
             add32_smem(v, wbias);
             add32_smem(gv, wbias + 32);
           }
@@ -523,8 +521,8 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-          if (ln_fold) ln_apply32(v, wbias + 64, ln_mu, ln_rstd);
-          if (p.bias) add32_smem(v, wbias);
+          if (ln_fold) ln_bias_apply32(v, wbias, wbias + 64, ln_mu, ln_rstd);
+          else if (p.bias) add32_smem(v, wbias);
           if (p.bias || ln_fold) {
             __syncwarp();
             if (more) load_bias(c + EPI_PER_QUAD);
@@ -580,13 +578,18 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
           if (!kGeglu && p.rowstat_out && valid) {
             // per-row (sum, sumsq) of this 32-column chunk, for the LayerNorm folded into the consumer GEMM
-            float su = 0.f, sq = 0.f;
+            uint64_t su2 = pack_f32x2(0.f, 0.f), sq2 = su2;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              su += v[j];
-              sq = fmaf(v[j], v[j], sq);
+            for (int j = 0; j < 32; j += 2) {
+              const uint64_t x2 = pack_f32x2(v[j], v[j + 1]);
+              su2 = add_f32x2(su2, x2);
+              sq2 = fma_f32x2(x2, x2, sq2);
             }
-            p.rowstat_out[(size_t)row * p.rowstat_chunks + ((seg.out_col_off + col0) >> 5)] = make_float2(su, sq);
+            float s0, s1, q0, q1;
+            unpack_f32x2(su2, s0, s1);
+            unpack_f32x2(sq2, q0, q1);
+            p.rowstat_out[(size_t)row * p.rowstat_chunks + ((seg.out_col_off + col0) >> 5)] =
+                make_float2(s0 + s1, q0 + q1);
           }
           // own row -> swizzled smem
 #pragma unroll
@@ -719,9 +722,8 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   APTP_REQUIRE(a->a_rows < (1ll << 31), "aptp_grouped_gemm_fwd: too many rows");
   APTP_REQUIRE(!(a->flags & APTP_EPI_GN_STATS), "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS not implemented yet");
   if (a->flags & APTP_EPI_LN_FOLD) {
-    APTP_REQUIRE(a->ln_colsum && a->ln_partial && a->ln_chunks > 0 && a->ln_chunks % 2 == 0 && a->ln_width > 0 &&
-                     (reinterpret_cast<uintptr_t>(a->ln_partial) & 15) == 0,
-                 "aptp_grouped_gemm_fwd: APTP_EPI_LN_FOLD needs ln_colsum, ln_partial (16-byte aligned), an even ln_chunks and ln_width");
+    APTP_REQUIRE(a->ln_colsum && a->ln_rowstats && a->bias && (reinterpret_cast<uintptr_t>(a->ln_rowstats) & 7) == 0,
+                 "aptp_grouped_gemm_fwd: APTP_EPI_LN_FOLD needs ln_colsum, ln_rowstats and bias (= W @ beta + layer bias)");
     APTP_REQUIRE(a->a_mode == APTP_A_LINEAR, "aptp_grouped_gemm_fwd: APTP_EPI_LN_FOLD applies to linear layers");
   }
   if (a->rowstat_out) {
@@ -811,10 +813,7 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   p.tab_ld = a->tab_ld;
   p.flags = a->flags;
   p.ln_colsum = a->ln_colsum;
-  p.ln_partial = reinterpret_cast<const float2*>(a->ln_partial);
-  p.ln_chunks = a->ln_chunks;
-  p.ln_inv_c = a->ln_width > 0 ? 1.f / (float)a->ln_width : 0.f;
-  p.ln_eps = a->ln_eps;
+  p.ln_rowstats = reinterpret_cast<const float2*>(a->ln_rowstats);
   p.rowstat_out = reinterpret_cast<float2*>(a->rowstat_out);
   p.rowstat_chunks = a->rowstat_chunks;
   p.abort_flag = device_abort_flag();

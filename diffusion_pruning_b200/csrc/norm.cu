@@ -469,6 +469,25 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __
   }
 }
 
+// LayerNorm row statistics for the LN-fold GEMM epilogue: (mean, rstd) of every row from the per-chunk (sum, sumsq)
+// partials the producing GEMM wrote, summed in chunk order (deterministic). One thread per row.
+__global__ void __launch_bounds__(256) ln_rowstats_kernel(const float2* __restrict__ partial, int chunks, long long rows,
+                                                          float inv_c, float eps, float2* __restrict__ out,
+                                                          const uint8_t* __restrict__ sample_active, int rows_per_sample) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  if (sample_active && !sample_active[row / rows_per_sample]) return;
+  const float4* pp = reinterpret_cast<const float4*>(partial + row * chunks);
+  float su = 0.f, sq = 0.f;
+  for (int i = 0; i < chunks / 2; ++i) {
+    const float4 q = __ldg(pp + i);
+    su += q.x + q.z;
+    sq += q.y + q.w;
+  }
+  const float mu = su * inv_c;
+  out[row] = make_float2(mu, rsqrtf(fmaxf(sq * inv_c - mu * mu, 0.f) + eps));
+}
+
 static int pick_pix_per_cta(int hw, int batch) {
   // ~8 CTAs per SM across the grid (two waves at the register-limited occupancy), at least 16 pixels per CTA
   int target_ctas = 8 * sm_count();
@@ -556,6 +575,20 @@ extern "C" int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, con
     gn_apply_kernel<false><<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size,
                                                              eps, stats, stats_groups, gamma, beta, affine_ld, sample_seg,
                                                              sample_channels, gate, gate_ld, silu, ppc);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_ln_rowstats(const float* partial, int32_t chunks, int64_t rows, int32_t C, float eps, float* out,
+                                const uint8_t* sample_active, int32_t rows_per_sample, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(partial && out && chunks > 0 && chunks % 2 == 0 && C > 0 && rows_per_sample > 0 &&
+                   (reinterpret_cast<uintptr_t>(partial) & 15) == 0,
+               "aptp_ln_rowstats: bad arguments (chunks must be even, partial 16-byte aligned)");
+  if (rows == 0) return APTP_OK;
+  ln_rowstats_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float2*>(partial), chunks, rows, 1.f / (float)C, eps, reinterpret_cast<float2*>(out),
+      sample_active, rows_per_sample);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

@@ -138,8 +138,8 @@ def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Sch
                  rowvec: Optional[torch.Tensor] = None, rowvec_ld: int = 0, rows_per_sample: int = 1,
                  residual: Optional[torch.Tensor] = None, res_ld: int = 0, gate: Optional[torch.Tensor] = None,
                  gate_ld: int = 0, gate_group: int = 1, border_tab: Optional[torch.Tensor] = None, tab_ld: int = 0,
-                 flags: int = 0, ln_colsum: Optional[torch.Tensor] = None, ln_partial: Optional[torch.Tensor] = None,
-                 ln_width: int = 0, ln_eps: float = 1e-5, rowstat_out: Optional[torch.Tensor] = None) -> None:
+                 flags: int = 0, ln_colsum: Optional[torch.Tensor] = None, ln_rowstats: Optional[torch.Tensor] = None,
+                 rowstat_out: Optional[torch.Tensor] = None) -> None:
     """out = epilogue(A @ W^T) through aptp_grouped_gemm_fwd. `a`, `w`, `out` may be views: only
     data_ptr() and the explicit pitches are used."""
     if sched.n_tiles == 0:
@@ -157,11 +157,9 @@ def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Sch
     args.gate, args.gate_ld, args.gate_group = _ptr(gate), gate_ld, gate_group
     args.border_tab, args.tab_ld = _ptr(border_tab), tab_ld
     args.gn_stats, args.gn_group, args.gn_groups = None, 0, 0
-    args.flags = flags | (_lib.EPI_LN_FOLD if ln_partial is not None else 0)
-    args.ln_colsum, args.ln_partial = _ptr(ln_colsum), _ptr(ln_partial)
-    args.ln_chunks = ln_partial.shape[1] if ln_partial is not None else 0   # [rows, C/32, 2] fp32
-    args.ln_width, args.ln_eps = ln_width, float(ln_eps)
-    args.rowstat_out = _ptr(rowstat_out)
+    args.flags = flags | (_lib.EPI_LN_FOLD if ln_rowstats is not None else 0)
+    args.ln_colsum, args.ln_rowstats = _ptr(ln_colsum), _ptr(ln_rowstats)   # ln_rowstats: [rows, 2] fp32 (mean, rstd)
+    args.rowstat_out = _ptr(rowstat_out)                                     # [rows, C/32, 2] fp32 (sum, sumsq)
     args.rowstat_chunks = rowstat_out.shape[1] if rowstat_out is not None else 0
     args.segs, args.n_segs = sched.segs.data_ptr(), sched.n_segs
     args.tiles, args.n_tiles = sched.tiles.data_ptr(), sched.n_tiles
@@ -205,6 +203,12 @@ def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps
                                       group_size, float(eps), _ptr(stats), stats_groups, _ptr(gamma), _ptr(beta),
                                       affine_ld, _ptr(sample_seg), _ptr(sample_channels), _ptr(gate), gate_ld,
                                       int(silu), _stream()), "aptp_groupnorm_apply")
+
+
+def ln_rowstats(partial, rows, C_, eps, out, sample_active=None, rows_per_sample=1):
+    """partial [rows, C/32, 2] (sum, sumsq per 32-column chunk, from a GEMM's rowstat_out) -> out [rows, 2] (mean, rstd)."""
+    check(load().aptp_ln_rowstats(_ptr(partial), partial.shape[1], rows, C_, float(eps), _ptr(out), _ptr(sample_active),
+                                  rows_per_sample, _stream()), "aptp_ln_rowstats")
 
 
 def layernorm(x, ldx, y, ldy, rows, C_, eps, gamma, beta, sample_active=None, rows_per_sample=1):

@@ -813,6 +813,8 @@ class _Engine:
         # sampling run walks through many prompt -> expert assignments): schedules / layouts are kept for the
         # MAX_STATES most recently used (batch, code set, assignment) states, compacted weight packs for the MAX_ESETS
         # most recently used code sets; older entries are dropped together with their device buffers.
+        # APTP_LN_FOLD=0 keeps the three LayerNorms of a transformer block as separate HBM passes (A/B measurements)
+        self.ln_fold = os.environ.get("APTP_LN_FOLD", "1") != "0"
         self._states: "OrderedDict[Any, int]" = OrderedDict()
         self._esets: "OrderedDict[Any, int]" = OrderedDict()
         self._next_id = 0
@@ -1391,6 +1393,8 @@ class _Engine:
         d = {"vid": vid, "nh": np.asarray([len(k) for k in kept_h]), "V": len(kept_h)}
         gam = ln.weight.detach().to(self.device, torch.float32)
         bet = ln.bias.detach().to(self.device, torch.float32)
+        if not self.ln_fold:
+            gam, bet = torch.ones_like(gam), torch.zeros_like(bet)
         for nm, lin in (("q", attn.to_q), ("k", attn.to_k), ("v", attn.to_v)):
             w = lin.weight.detach().to(self.device, torch.float32)
             if nm == "q" or not is_cross:
@@ -1434,6 +1438,8 @@ class _Engine:
         w = proj.weight.detach().to(self.device, torch.float32)
         gam = ln.weight.detach().to(self.device, torch.float32)
         bet = ln.bias.detach().to(self.device, torch.float32)
+        if not self.ln_fold:
+            gam, bet = torch.ones_like(gam), torch.zeros_like(bet)
         b = proj.bias.detach().to(self.device, torch.float32) + w @ bet
         w = w * gam[None, :]
         wp = torch.zeros(V * rows_pad, C, device=self.device, dtype=BF16)
@@ -1461,6 +1467,32 @@ class _Engine:
         d["b2"] = ff.net[2].bias.detach().to(self.device, torch.float32).contiguous()
         self.expert[key] = d
         return d
+
+    def _layernorm(self, tok: torch.Tensor, ln: nn.LayerNorm, M: int, C: int, hw: int, active: np.ndarray) -> torch.Tensor:
+        """Un-folded LayerNorm pass (APTP_LN_FOLD=0 only): tok -> normalised bf16 rows."""
+        key = ("ln_affine", id(ln))
+        d = self.dense.get(key)
+        if d is None:
+            d = (ln.weight.detach().to(self.device, torch.float32).contiguous(),
+                 ln.bias.detach().to(self.device, torch.float32).contiguous())
+            self.dense[key] = d
+        xn = self.buf("ln", M, C)
+        act = self._sched(("ln_act", id(ln)), lambda: self._per_pos(active.astype(np.uint8), torch.uint8)
+                          if (self.compact and (~active).any()) else None)
+        n_act = float(active[self.layout.expert_of_pos].sum()) if self.compact else float(self.B)
+        self._hbm(n_act * hw * C * 4, f"layernorm C{C} hw{hw}",
+                  lambda: K.layernorm(tok, C, xn, C, M, C, ln.eps, d[0], d[1], act, hw))
+        self.launches += 1
+        return xn
+
+    def _ln_rowstats(self, part: torch.Tensor, M: int, C: int, eps: float, hw: int) -> torch.Tensor:
+        """(mean, rstd) per token row from the partial sums the producing GEMM wrote: 8 bytes per row for the LN-fold
+        epilogue (a 4-byte-per-element pass over `tok` in the reference's three LayerNorms becomes this)."""
+        rs = self.buf("ln_rs", M, 2, torch.float32)
+        self._hbm(float(M) * (part.shape[1] * 8 + 8), f"ln_rowstats C{C} hw{hw}",
+                  lambda: K.ln_rowstats(part, M, C, eps, rs))
+        self.launches += 1
+        return rs
 
     def _attention(self, uid: str, attn: _Attention, gate_idx: int, ln: nn.LayerNorm, part: torch.Tensor,
                    tok: torch.Tensor, B: int, hw: int, C: int, active: np.ndarray, ctx: Optional[torch.Tensor],
@@ -1511,16 +1543,22 @@ class _Engine:
             return s
         s = self._sched(("attn", uid, hw, n_kv), build)
         gkw = dict(gate=gate, gate_ld=gate.stride(0), gate_group=64) if gate is not None else {}
-        lnkw = dict(ln_partial=part, ln_width=C, ln_eps=ln.eps)
+        if self.ln_fold:
+            a_in = tok
+            lnkw = dict(ln_rowstats=self._ln_rowstats(part, M, C, ln.eps, hw))
+            lq = dict(bias=pk["bq"], ln_colsum=pk["cq"]) if is_cross else dict(bias=pk["bqkv"], ln_colsum=pk["cqkv"])
+        else:
+            a_in = self._layernorm(tok, ln, M, C, hw, active)
+            lnkw, lq, want_stats = {}, {}, False
         if is_cross:
-            self._gemm(s["q"], tok, pk["wq"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=C, rows_per_sample=hw, bias=pk["bq"],
-                       ln_colsum=pk["cq"], **lnkw, **gkw)
+            self._gemm(s["q"], a_in, pk["wq"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=C, rows_per_sample=hw,
+                       **lq, **lnkw, **gkw)
             self._gemm(s["kv"], ctx, pk["wkv"], kvb, a_ld=kkv, a_k=kkv, a_rows=Mkv, out_ld=2 * C, rows_per_sample=n_kv,
                        **gkw)
             q, ldq, kk, vv, ldkv = qkv, C, kvb, kvb[:, C:], 2 * C
         else:
-            self._gemm(s["qkv"], tok, pk["wqkv"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=3 * C, rows_per_sample=hw,
-                       bias=pk["bqkv"], ln_colsum=pk["cqkv"], **lnkw, **gkw)
+            self._gemm(s["qkv"], a_in, pk["wqkv"], qkv, a_ld=C, a_k=C, a_rows=M, out_ld=3 * C, rows_per_sample=hw,
+                       **lq, **lnkw, **gkw)
             q, ldq, kk, vv, ldkv = qkv, 3 * C, qkv[:, C:], qkv[:, 2 * C:], 3 * C
         o = self.buf("attn_o", M, C)
         if s["max_heads"] > 0:
@@ -1575,7 +1613,8 @@ class _Engine:
         # (sum, sumsq) partials per 32-column chunk, and the three LayerNorms of the block (norm1/2/3, blocks.py:782,
         # :808-810, :821) are folded into the GEMMs that consume them -- no LayerNorm pass over HBM at all
         part = self.buf("ln_part", M, (C // 32) * 2, torch.float32).view(M, C // 32, 2)
-        self.linear("pi." + t.uid, t.proj_in, xn, M, C, C, tok, C, hw, active=active, rowstat_out=part)
+        self.linear("pi." + t.uid, t.proj_in, xn, M, C, C, tok, C, hw, active=active,
+                    rowstat_out=part if self.ln_fold else None)
         # self-attention, cross-attention
         self._attention(t.uid + ".a1", tb.attn1, cidx["w"][0], tb.norm1, part, tok, B, hw, C, active, None, 0)
         self._attention(t.uid + ".a2", tb.attn2, cidx["w"][1], tb.norm2, part, tok, B, hw, C, active, self.ctx, self.n_ctx)
@@ -1598,8 +1637,13 @@ class _Engine:
         s = self._sched(("ff", t.uid, hw), build_ff)
         gate = self._soft_gate(cidx["w"][2]) if not self.compact else None
         gkw = dict(gate=gate, gate_ld=gate.stride(0), gate_group=fk["gs"]) if gate is not None else {}
-        self._gemm(s["p"], tok, fk["wp"], ffb, a_ld=C, a_k=C, a_rows=M, out_ld=inner, bias=fk["bp"], flags=EPI_GEGLU,
-                   rows_per_sample=hw, ln_colsum=fk["sp"], ln_partial=part, ln_width=C, ln_eps=tb.norm3.eps, **gkw)
+        if self.ln_fold:
+            self._gemm(s["p"], tok, fk["wp"], ffb, a_ld=C, a_k=C, a_rows=M, out_ld=inner, bias=fk["bp"], flags=EPI_GEGLU,
+                       rows_per_sample=hw, ln_colsum=fk["sp"],
+                       ln_rowstats=self._ln_rowstats(part, M, C, tb.norm3.eps, hw), **gkw)
+        else:
+            self._gemm(s["p"], self._layernorm(tok, tb.norm3, M, C, hw, active), fk["wp"], ffb, a_ld=C, a_k=C, a_rows=M,
+                       out_ld=inner, bias=fk["bp"], flags=EPI_GEGLU, rows_per_sample=hw, **gkw)
         self._gemm(s["o"], ffb, fk["w2"], tok, a_ld=inner, a_k=inner, a_rows=M, out_ld=C, bias=fk["b2"], residual=tok,
                    res_ld=C, rows_per_sample=hw)
         # proj_out + residual: back onto the fp32 stream

@@ -123,15 +123,15 @@ typedef struct aptp_gemm_args {
   /* LayerNorm folded into the GEMM (APTP_EPI_LN_FOLD; replaces BasicTransformerBlock.norm1/2/3, blocks.py:782,:808-810,
    * :821): `a` holds the RAW rows x, `w` holds W*gamma, `bias` holds W@beta (+ the layer's own bias) and
    *   out[row, n] = rstd[row] * (acc[row, n] - mean[row] * ln_colsum[vec_off + n]) + bias[vec_off + n]
-   * where ln_colsum[n] = sum_k w[n, k] (of the bf16-rounded packed weights) and mean / rstd of a row come from
-   * ln_partial[row * ln_chunks + i] = (sum, sumsq) over the i-th 32-column chunk of x, ln_width = C columns in total.
-   * The partials are written by the GEMM that PRODUCED x: rowstat_out[row * rowstat_chunks + (out_col_off + col) / 32]
-   * (sum, sumsq of the values it stores, bf16 output only). Deterministic (no atomics). */
+   * where ln_colsum[n] = sum_k w[n, k] (of the bf16-rounded packed weights) and ln_rowstats[row] = (mean, rstd) of the
+   * row (float2, from aptp_ln_rowstats). The (sum, sumsq) partials behind them are written by the GEMM that PRODUCED x:
+   * rowstat_out[row * rowstat_chunks + (out_col_off + col) / 32] (of the values it stores, bf16 output only).
+   * Deterministic (no atomics). */
   const float* ln_colsum;
-  const float* ln_partial;   /* float2 per (row, chunk) */
-  int32_t ln_chunks;
-  int32_t ln_width;
-  float ln_eps;
+  const float* ln_rowstats;  /* float2 per row: (mean, rstd) */
+  int32_t ln_reserved0;
+  int32_t ln_reserved1;
+  float ln_reserved2;
   float* rowstat_out;        /* float2 per (row, chunk) */
   int32_t rowstat_chunks;
 } aptp_gemm_args;
@@ -171,6 +171,10 @@ int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, const void* x1
 int aptp_layernorm(const void* x, int32_t ldx, void* y, int32_t ldy, int64_t rows, int32_t C, float eps,
                    const float* gamma, const float* beta, const uint8_t* sample_active,
                    int32_t rows_per_sample, void* stream);
+/* (mean, rstd) per row [rows] float2 from the per-chunk (sum, sumsq) partials a GEMM epilogue wrote (rowstat_out of
+ * aptp_gemm_args): the row statistics of the LayerNorm that APTP_EPI_LN_FOLD folds into the consuming GEMM. */
+int aptp_ln_rowstats(const float* partial, int32_t chunks, int64_t rows, int32_t C, float eps, float* out,
+                     const uint8_t* sample_active, int32_t rows_per_sample, void* stream);
 /* out = (1-d)*x + d*y per sample (DepthGate.forward, pdm/models/unet/gates.py:36-42), bf16 rows. */
 int aptp_depth_lerp(const void* x, int32_t ldx, const void* y, int32_t ldy, void* out, int32_t ldo,
                     int64_t rows, int32_t C, const float* d, int32_t rows_per_sample, void* stream);

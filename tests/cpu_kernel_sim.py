@@ -50,8 +50,8 @@ def _check_tiles(sched: K.Schedule, mode, Ho, Wo, geglu):
 
 def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1, H=1, W=1, k_tap_pitch=0, out_ld,
                  out_mode=OUT_BF16, bias=None, rowvec=None, rowvec_ld=0, rows_per_sample=1, residual=None, res_ld=0,
-                 gate=None, gate_ld=0, gate_group=1, border_tab=None, tab_ld=0, flags=0, ln_colsum=None, ln_partial=None,
-                 ln_width=0, ln_eps=1e-5, rowstat_out=None):
+                 gate=None, gate_ld=0, gate_group=1, border_tab=None, tab_ld=0, flags=0, ln_colsum=None, ln_rowstats=None,
+                 rowstat_out=None):
     if sched.n_tiles == 0:
         return
     geglu = bool(flags & EPI_GEGLU)
@@ -78,10 +78,8 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
                 wh = blk[:, 0].reshape(nt * half, kk)
                 wg = blk[:, 1].reshape(nt * half, kk)
                 acc_h, acc_g = Ae @ wh.t(), Ae @ wg.t()
-                if ln_partial is not None:  # APTP_EPI_LN_FOLD: rstd * (acc - mean * colsum), per row
-                    ps = ln_partial[rb:re].sum(1)
-                    mu = ps[:, 0] / ln_width
-                    rstd = torch.rsqrt((ps[:, 1] / ln_width - mu * mu).clamp(min=0) + ln_eps)
+                if ln_rowstats is not None:  # APTP_EPI_LN_FOLD: rstd * (acc - mean * colsum), per row
+                    mu, rstd = ln_rowstats[rb:re, 0], ln_rowstats[rb:re, 1]
                     cs = ln_colsum[voff:voff + nt * sched.bn].reshape(nt, 2, half)
                     acc_h = rstd[:, None] * (acc_h - mu[:, None] * cs[:, 0].reshape(-1)[None])
                     acc_g = rstd[:, None] * (acc_g - mu[:, None] * cs[:, 1].reshape(-1)[None])
@@ -110,10 +108,8 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
             acc = acc_h * F.gelu(acc_g)
         else:
             cols = torch.arange(acc.shape[1])
-            if ln_partial is not None:
-                ps = ln_partial[rb:re].sum(1)
-                mu = ps[:, 0] / ln_width
-                rstd = torch.rsqrt((ps[:, 1] / ln_width - mu * mu).clamp(min=0) + ln_eps)
+            if ln_rowstats is not None:
+                mu, rstd = ln_rowstats[rb:re, 0], ln_rowstats[rb:re, 1]
                 nb = min(nv, acc.shape[1])
                 acc[:, :nb] = rstd[:, None] * (acc[:, :nb] - mu[:, None] * ln_colsum[voff:voff + nb][None])
             if bias is not None:
@@ -202,6 +198,13 @@ def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps
         cs = min((ct + 63) // 64 * 64, ldy)
         Y[b * hw:(b + 1) * hw, :ct] = o.to(torch.bfloat16)
         Y[b * hw:(b + 1) * hw, ct:cs] = 0
+
+
+def ln_rowstats(partial, rows, C_, eps, out, sample_active=None, rows_per_sample=1):
+    ps = partial[:rows].sum(1)
+    mu = ps[:, 0] / C_
+    out[:rows, 0] = mu
+    out[:rows, 1] = torch.rsqrt((ps[:, 1] / C_ - mu * mu).clamp(min=0) + eps)
 
 
 def layernorm(x, ldx, y, ldy, rows, C_, eps, gamma, beta, sample_active=None, rows_per_sample=1):
@@ -297,7 +300,7 @@ def check_abort():
 
 
 def install(monkeypatch):
-    for name in ("grouped_gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "depth_lerp", "copy_rows",
+    for name in ("grouped_gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "ln_rowstats", "depth_lerp", "copy_rows",
                  "copy_rows_cvt", "depth_lerp_f32", "upsample2x_cvt",
                  "upsample2x", "im2col_input", "timestep_embedding", "cast_f32_bf16", "silu_bf16", "attention",
                  "check_abort"):

@@ -419,6 +419,10 @@ def check_gemm_ln_fold(geglu=False, seed=0):
     _close(part, ref_p, 2e-2, 2e-3, "row-stat partials")
     gamma = _rand(C, seed=seed + 3) * 0.2 + 1
     beta = _rand(C, seed=seed + 4) * 0.2
+    rs = torch.full((M, 2), float("nan"), device=DEV)
+    K.ln_rowstats(part, M, C, 1e-5, rs)
+    _close(rs[:, 0], xr.mean(1), 1e-3, 1e-3, "ln mean")
+    _close(rs[:, 1], torch.rsqrt(xr.var(1, unbiased=False) + 1e-5), 1e-3, 2e-3, "ln rstd")
     xs = x.float()  # what the consumer reads
     ln = F.layer_norm(xs, (C,), gamma, beta, 1e-5)
     if not geglu:
@@ -430,7 +434,7 @@ def check_gemm_ln_fold(geglu=False, seed=0):
         out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
         sched = K.build_schedule([K.Segment(0, M, N, C // 64)], 160, DEV)
         K.grouped_gemm(x, wf, out, sched, a_ld=C, a_k=C, a_rows=M, out_ld=N, bias=bias, ln_colsum=colsum,
-                       ln_partial=part, ln_width=C, ln_eps=1e-5)
+                       ln_rowstats=rs)
         K.check_abort()
         _close(out, ln @ w.t() + b, 4e-2, 2e-2, "ln-fold linear")
     else:
@@ -447,7 +451,7 @@ def check_gemm_ln_fold(geglu=False, seed=0):
         out = torch.full((M, inner), float("nan"), device=DEV, dtype=torch.bfloat16)
         sched = K.build_schedule([K.Segment(0, M, inner, C // 64)], bn, DEV, geglu=True)
         K.grouped_gemm(x, wp, out, sched, a_ld=C, a_k=C, a_rows=M, out_ld=inner, bias=bp, flags=EPI_GEGLU,
-                       ln_colsum=colsum, ln_partial=part, ln_width=C, ln_eps=1e-5)
+                       ln_colsum=colsum, ln_rowstats=rs)
         K.check_abort()
         hg = ln @ w.t() + b
         _close(out, hg[:, :inner] * F.gelu(hg[:, inner:]), 5e-2, 3e-2, "ln-fold geglu")
