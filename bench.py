@@ -294,6 +294,40 @@ def run_ours(args):
                      "step_frac_of_peak_kept_work": round(kept_flops / (ms_step / 1e3) / 1e12 / peaks["tflops"], 4),
                      "dense_equivalent_tflops": round(BATCH * DENSE_TFLOP_PER_SAMPLE / (ms_step / 1e3), 1)},
     }
+    # Re-structuring cost (the reference calls set_structure for every prompt batch, pruning_pipelines.py:757-759): a
+    # FRESH random prompt -> expert assignment of the same 8 codes, set_structure, first forward, host-timed with a
+    # synchronize on both sides; and the throughput when EVERY step brings a new assignment (no CUDA-graph reuse unless
+    # the engine can key its cached state on something coarser than the exact assignment).
+    from diffusion_pruning_b200.synthetic import split_arch as _split
+    st_ = model.get_structure()
+    gr = torch.Generator().manual_seed(99 + rank)
+
+    def fresh_arch():
+        a = torch.randint(0, N_CODES, (BATCH,), generator=gr)
+        return codes[a].to(device)
+    restruct = []
+    for _ in range(3):
+        arch_new = fresh_arch()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.set_structure(_split(arch_new, st_))
+        step_resident()
+        torch.cuda.synchronize()
+        restruct.append((time.perf_counter() - t0) * 1e3)
+    n_fresh = max(4, min(args.steps, 10))
+    archs = [fresh_arch() for _ in range(n_fresh)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for a in archs:
+        model.set_structure(_split(a, st_))
+        step_resident()
+    torch.cuda.synchronize()
+    fresh_ms = (time.perf_counter() - t0) * 1e3 / n_fresh
+    out["restructure_ms"] = round(sorted(restruct)[1], 2)
+    out["restructure_note"] = ("host-timed median of 3: fresh random assignment of the same codes -> set_structure -> first "
+                               "forward -> synchronize (bucketing, schedule builds for new bucket sizes, eager forward)")
+    out["value_fresh_assignment"] = round(BATCH * world / (fresh_ms / 1e3), 2)
+    out["ms_per_step_fresh_assignment"] = round(fresh_ms, 3)
     # flat copies of the per-kernel-class numbers (the nested dict above is kept for continuity with round 1)
     out.update({
         "attention_tflops": round(a_fl / (a_ms / 1e3) / 1e12, 1) if a_ms else None, "attention_ms": round(a_ms, 3),

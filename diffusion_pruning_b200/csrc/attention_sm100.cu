@@ -29,9 +29,10 @@ constexpr int ATT_BN = 128;   // keys per tile
 constexpr int ATT_D = 64;
 constexpr int ATT_KV_STAGES = 4;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
-// smem map (from 1024-aligned base): Q0 | Q1 | (K,V) x stages | barriers
+// smem map (from 1024-aligned base): 2 slots x (Q0 | Q1) | (K,V) x stages | barriers
 constexpr int ATT_SMEM_Q = 0;
-constexpr int ATT_SMEM_KV = 2 * ATT_TILE_BYTES;
+constexpr int ATT_Q_SLOT_BYTES = 2 * ATT_TILE_BYTES;
+constexpr int ATT_SMEM_KV = 2 * ATT_Q_SLOT_BYTES;
 constexpr int ATT_SMEM_BAR = ATT_SMEM_KV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;
 constexpr int ATT_SMEM_BYTES = ATT_SMEM_BAR + 256 + 1024;
 constexpr int ATT_TMEM_COLS = 512;
@@ -68,9 +69,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
-  uint64_t* q_full = bars;                       // 1
-  uint64_t* q_empty = bars + 1;                  // 1
-  uint64_t* kv_full = bars + 2;                  // stages
+  uint64_t* q_full = bars;                       // 2 (Q is double-buffered: the next query pair loads under this one)
+  uint64_t* q_empty = bars + 2;                  // 2
+  uint64_t* kv_full = bars + 4;                  // stages
   uint64_t* kv_empty = kv_full + ATT_KV_STAGES;  // stages
   uint64_t* s_full = kv_empty + ATT_KV_STAGES;   // 2
   uint64_t* s_free = s_full + 2;                 // 2: softmax holds S in registers, S columns reusable
@@ -81,6 +82,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.n_kv + ATT_BN - 1) / ATT_BN;
+  // Short KV (cross-attention over 77 text tokens, or the 8x8 level): ONE key tile. K / V stay resident in stage 0 for
+  // every query pair of the CTA, the MMA warp looks one query pair ahead (S of the next pair is issued as soon as the
+  // softmax warps hold the current S in registers), the softmax skips fully masked 32-key chunks and PV runs over
+  // ceil(n_kv / 16) key steps only.
+  const bool single = (n_tiles == 1);
+  const int pv_steps_last = (p.n_kv - (n_tiles - 1) * ATT_BN + 15) / 16;  // K steps of PV for the last key tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_q);
@@ -89,8 +96,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   }
   if (warp == 1) {
     if (lane == 0) {
-      mbar_init(q_full, 1);
-      mbar_init(q_empty, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1);
+        mbar_init(&q_empty[i], 1);
+      }
       for (int s = 0; s < ATT_KV_STAGES; ++s) {
         mbar_init(&kv_full[s], 1);
         mbar_init(&kv_empty[s], 1);
@@ -126,14 +135,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       for (int qp = blockIdx.x; qp < p.n_qpairs && ok; qp += gridDim.x, ++it) {
         const int q0 = qp * 2 * ATT_BM;
         const bool act1 = q0 + ATT_BM < p.n_q;
-        if (!mbar_wait(q_empty, (it & 1) ^ 1, p.abort_flag)) break;
+        const int slot = it & 1;
+        if (!mbar_wait(&q_empty[slot], ((it >> 1) & 1) ^ 1, p.abort_flag)) break;
         if (elect_one()) {
-          mbar_expect_tx(q_full, act1 ? 2 * ATT_TILE_BYTES : ATT_TILE_BYTES);
-          tma_load_2d(smem + ATT_SMEM_Q, &p.tmap_q, q_full, head * ATT_D, b * p.n_q + q0);
-          if (act1)
-            tma_load_2d(smem + ATT_SMEM_Q + ATT_TILE_BYTES, &p.tmap_q, q_full, head * ATT_D, b * p.n_q + q0 + ATT_BM);
+          uint8_t* sq = smem + ATT_SMEM_Q + slot * ATT_Q_SLOT_BYTES;
+          mbar_expect_tx(&q_full[slot], act1 ? 2 * ATT_TILE_BYTES : ATT_TILE_BYTES);
+          tma_load_2d(sq, &p.tmap_q, &q_full[slot], head * ATT_D, b * p.n_q + q0);
+          if (act1) tma_load_2d(sq + ATT_TILE_BYTES, &p.tmap_q, &q_full[slot], head * ATT_D, b * p.n_q + q0 + ATT_BM);
         }
         __syncwarp();
+        if (single && it > 0) continue;  // K / V of this (sample, head) are already resident in stage 0
         for (int j = 0; j < n_tiles; ++j) {
           if (!mbar_wait(&kv_empty[stage], phase ^ 1, p.abort_flag)) {
             ok = false;
@@ -164,8 +175,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
       uint32_t it = 0;
       uint32_t gp[2] = {0, 0};  // tiles consumed per Q tile (phase of s_free / p_full)
       bool ok = true;
-      auto issue_s = [&](int w, int kv_stage) {
-        const uint64_t dq = make_desc_kmajor_sw128(smem_base + ATT_SMEM_Q + w * ATT_TILE_BYTES);
+      auto issue_s = [&](int w, int kv_stage, int q_slot) {
+        const uint64_t dq =
+            make_desc_kmajor_sw128(smem_base + ATT_SMEM_Q + q_slot * ATT_Q_SLOT_BYTES + w * ATT_TILE_BYTES);
         const uint64_t dk = make_desc_kmajor_sw128(smem_base + ATT_SMEM_KV + kv_stage * 2 * ATT_TILE_BYTES);
         const uint32_t s_tmem = tmem_base + ATT_TMEM_S + w * ATT_BN;
         if (elect_one()) {
@@ -176,13 +188,69 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         }
         __syncwarp();
       };
+      auto issue_pv = [&](int w, int kv_stage, int j, int ksteps) {
+        // O_w (+)= P_w V_j. V: 16 keys = 2 swizzle atoms (2048 B) per step = +128 in the descriptor address field
+        const uint64_t dv = make_desc_mnmajor_sw128(
+            smem_base + ATT_SMEM_KV + kv_stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, ATT_TILE_BYTES);
+        const uint32_t p_tmem = tmem_base + ATT_TMEM_P + w * (ATT_BN / 2);
+        const uint32_t o_tmem = tmem_base + ATT_TMEM_O + w * ATT_D;
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k)  // P: 16 keys = 8 packed 32-bit TMEM columns per step
+            umma_bf16_ts(o_tmem, p_tmem + k * 8, dv + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
+          umma_commit(&pv_done[w]);
+        }
+        __syncwarp();
+      };
+      if (single) {
+        // one key tile per query pair, K / V resident: pipeline ACROSS query pairs
+        if (blockIdx.x < p.n_qpairs) {
+          ok = mbar_wait(&kv_full[0], 0, p.abort_flag) && mbar_wait(&q_full[0], 0, p.abort_flag);
+          if (ok) {
+            tc_fence_after();
+            const int n_w0 = (blockIdx.x * 2 * ATT_BM + ATT_BM < p.n_q) ? 2 : 1;
+            for (int w = 0; w < n_w0; ++w) issue_s(w, 0, 0);
+          }
+        }
+        for (int qp = blockIdx.x; qp < p.n_qpairs && ok; qp += gridDim.x, ++it) {
+          const int slot = it & 1;
+          const int n_w = (qp * 2 * ATT_BM + ATT_BM < p.n_q) ? 2 : 1;
+          const int qn = qp + gridDim.x;
+          const bool has_next = qn < p.n_qpairs;
+          const int n_wn = has_next ? ((qn * 2 * ATT_BM + ATT_BM < p.n_q) ? 2 : 1) : 0;
+          if (has_next && !mbar_wait(&q_full[slot ^ 1], ((it + 1) >> 1) & 1, p.abort_flag)) {
+            ok = false;
+            break;
+          }
+          for (int w = 0; w < n_w && ok; ++w) {
+            ok = mbar_wait(&s_free[w], gp[w] & 1, p.abort_flag);
+            if (ok && w < n_wn) {
+              tc_fence_after();
+              issue_s(w, 0, slot ^ 1);
+            }
+          }
+          if (!ok) break;
+          for (int w = 0; w < n_w; ++w) {
+            if (!mbar_wait(&p_full[w], gp[w] & 1, p.abort_flag)) {
+              ok = false;
+              break;
+            }
+            ++gp[w];
+            tc_fence_after();
+            issue_pv(w, 0, 0, pv_steps_last);
+          }
+          if (!ok) break;
+          if (elect_one()) umma_commit(&q_empty[slot]);
+          __syncwarp();
+        }
+      } else
       for (int qp = blockIdx.x; qp < p.n_qpairs && ok; qp += gridDim.x, ++it) {
         const int q0 = qp * 2 * ATT_BM;
         const int n_w = (q0 + ATT_BM < p.n_q) ? 2 : 1;
-        if (!mbar_wait(q_full, it & 1, p.abort_flag)) break;
+        const int slot = it & 1;
+        if (!mbar_wait(&q_full[slot], (it >> 1) & 1, p.abort_flag)) break;
         if (!mbar_wait(&kv_full[stage], phase, p.abort_flag)) break;
         tc_fence_after();
-        for (int w = 0; w < n_w; ++w) issue_s(w, stage);
+        for (int w = 0; w < n_w; ++w) issue_s(w, stage, slot);
         for (int j = 0; j < n_tiles && ok; ++j) {
           int ns = stage + 1;
           uint32_t nphase = phase;
@@ -200,14 +268,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             ok = mbar_wait(&s_free[w], gp[w] & 1, p.abort_flag);
             if (ok && more) {
               tc_fence_after();
-              issue_s(w, ns);
+              issue_s(w, ns, slot);
             }
           }
           if (!ok) break;
           // O_w (+)= P_w V_j once P_w is in tensor memory
-          // V: 16 keys = 2 swizzle atoms (2048 B) per step = +128 in the descriptor address field
-          const uint64_t dv = make_desc_mnmajor_sw128(
-              smem_base + ATT_SMEM_KV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, ATT_TILE_BYTES);
           for (int w = 0; w < n_w; ++w) {
             if (!mbar_wait(&p_full[w], gp[w] & 1, p.abort_flag)) {
               ok = false;
@@ -215,15 +280,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             }
             ++gp[w];
             tc_fence_after();
-            const uint32_t p_tmem = tmem_base + ATT_TMEM_P + w * (ATT_BN / 2);
-            const uint32_t o_tmem = tmem_base + ATT_TMEM_O + w * ATT_D;
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < ATT_BN / 16; ++k)  // P: 16 keys = 8 packed 32-bit TMEM columns per step
-                umma_bf16_ts(o_tmem, p_tmem + k * 8, dv + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
-              umma_commit(&pv_done[w]);
-            }
-            __syncwarp();
+            issue_pv(w, stage, j, more ? ATT_BN / 16 : pv_steps_last);
           }
           if (!ok) break;
           if (elect_one()) umma_commit(&kv_empty[stage]);
@@ -231,7 +288,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           stage = ns;
           phase = nphase;
         }
-        if (elect_one()) umma_commit(q_empty);
+        if (elect_one()) umma_commit(&q_empty[slot]);
         __syncwarp();
       }
     }
@@ -266,6 +323,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         tmem_ld_32x32(s_addr + 64, s + 64);
         tmem_ld_32x32(s_addr + 96, s + 96);
         const int kv_left = p.n_kv - j * ATT_BN;  // keys valid in this tile (>= 1)
+        // 32-key chunks that hold at least one valid key: fully masked chunks of a ragged tile are skipped (their P
+        // columns stay unwritten; PV of this tile only runs over ceil(kv_left / 16) key steps)
+        int nch = ATT_BN / 32;
+        if constexpr (decltype(ragged)::value) nch = (kv_left + 31) >> 5;
         const bool optimistic = (j > 0);          // exponentials against the STALE max (checked afterwards)
         float mx0 = -INFINITY, mx1 = -INFINITY;
         uint64_t lsum = 0ull;                     // packed (l0, l1) partial row sums of this tile
@@ -316,8 +377,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[w]);
-        max_chunk(1);
-        if (optimistic) exp_chunk(1, pk1);
+        if (nch > 1) {
+          max_chunk(1);
+          if (optimistic) exp_chunk(1, pk1);
+        }
         if (j > 0) {  // PV of the previous tile must be complete before P is overwritten / O rescaled
           const bool done = mbar_wait(&pv_done[w], gd & 1, p.abort_flag);
           ++gd;
@@ -326,14 +389,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         }
         if (optimistic) {
           tmem_st_32x16(p_addr, pk0);
-          tmem_st_32x16(p_addr + 16, pk1);
+          if (nch > 1) tmem_st_32x16(p_addr + 16, pk1);
         }
 #pragma unroll
         for (int c = 2; c < ATT_BN / 32; ++c) {
-          max_chunk(c);
-          if (optimistic) {
-            exp_chunk(c, pk0);
-            tmem_st_32x16(p_addr + c * 16, pk0);
+          if (c < nch) {
+            max_chunk(c);
+            if (optimistic) {
+              exp_chunk(c, pk0);
+              tmem_st_32x16(p_addr + c * 16, pk0);
+            }
           }
         }
         const float m_cand = fmaxf(mx0, mx1) * p.scale_log2;
@@ -359,8 +424,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
           lsum = 0ull;
 #pragma unroll
           for (int c = 0; c < ATT_BN / 32; ++c) {
-            exp_chunk(c, pk0);
-            tmem_st_32x16(p_addr + c * 16, pk0);
+            if (c < nch) {
+              exp_chunk(c, pk0);
+              tmem_st_32x16(p_addr + c * 16, pk0);
+            }
           }
         }
         {

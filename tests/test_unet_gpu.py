@@ -102,3 +102,25 @@ def test_engine_caches_stay_bounded_over_many_assignments():
     assert len(eng._states) <= eng.MAX_STATES and len(eng._esets) <= eng.MAX_ESETS
     assert max(s[0] for s in sizes[20:]) <= max(s[0] for s in sizes[:20]) * 1.5 + 50, sizes[-1]
     assert sizes[-1][2] <= 4
+
+
+def test_new_assignment_with_same_bucket_sizes_reuses_the_cached_graph():
+    """Cached schedules / CUDA graph are keyed on bucket SIZES: a different prompt -> expert assignment with the same sizes
+    must only rewrite the permutation buffers and still match the oracle (and the graph must really be reused)."""
+    import unet_checks as U
+    from diffusion_pruning_b200.synthetic import split_arch, synthetic_codes
+    model, oracle = U.build_pair(True, beta_std=0.1)
+    st = model.get_structure()
+    codes = synthetic_codes(st, 8)
+    sample, t, ctx = U.inputs(4, 16, model.config["cross_attention_dim"])
+    for it, assign in enumerate(([0, 3, 3, 7], [0, 3, 3, 7], [0, 3, 3, 7], [3, 0, 7, 3], [7, 3, 0, 3], [3, 3, 7, 0])):
+        arch = codes[assign]
+        model.set_structure(split_arch(arch.clone().cuda(), st))
+        with torch.no_grad():
+            got = model(sample.cuda(), t.cuda(), ctx.cuda()).sample
+        oracle.set_structure(split_arch(arch.clone(), st))
+        with torch.no_grad():
+            ref = oracle(sample, t, ctx)
+        _assert(U.metrics(got, ref))
+    eng = model._engine
+    assert len(eng.graphs) == 1 and len(eng._states) == 1, (len(eng.graphs), len(eng._states))
