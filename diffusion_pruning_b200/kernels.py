@@ -73,6 +73,43 @@ class Schedule:
     out_elems: float = 0.0  # output elements written (x2 / x4 bytes by output type; same count for a residual read)
 
 
+class _Stager:
+    """Pinned staging ring for the small host -> device uploads of schedule / table arrays: one asynchronous copy per
+    array instead of a synchronous pageable copy (a forward for a NEW prompt -> expert assignment uploads ~500 of them)."""
+
+    def __init__(self, nbytes: int = 32 << 20):
+        self.buf = None
+        self.cap = nbytes
+        self.off = 0
+
+    def upload(self, arr: np.ndarray, device) -> torch.Tensor:
+        device = torch.device(device)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if device.type != "cuda" or torch.cuda.is_current_stream_capturing() or t.numel() == 0:
+            return t.to(device)
+        n = (t.numel() * t.element_size() + 63) // 64 * 64
+        if n > self.cap // 4:
+            return t.to(device)
+        if self.buf is None:
+            self.buf = torch.empty(self.cap, dtype=torch.uint8).pin_memory()
+        if self.off + n > self.cap:  # ring wrap: every copy issued so far must have left the staging area
+            torch.cuda.synchronize()
+            self.off = 0
+        view = self.buf[self.off:self.off + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+        self.off += n
+        view.copy_(t)
+        dev = torch.empty(t.shape, dtype=t.dtype, device=device)
+        dev.copy_(view, non_blocking=True)
+        return dev
+
+
+_STAGER = _Stager()
+
+
+def upload(arr: np.ndarray, device) -> torch.Tensor:
+    return _STAGER.upload(arr, device)
+
+
 def conv_box(W: int, H: int) -> tuple:
     """Pick the 128-pixel output box (bw, bh, bb) that tiles a W x H image."""
     for bw in (128, 64, 32, 16, 8, 4, 2, 1):
@@ -88,7 +125,7 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
                    geglu: bool = False, taps: Optional[int] = None) -> Schedule:
     """Enumerate tiles (m outer, n inner so concurrently running CTAs share the A tile in L2)."""
     segs = np.zeros((max(len(segments), 1), 12), dtype=np.int32)
-    tiles: List[tuple] = []
+    tiles: List[np.ndarray] = []
     box = (BM, 1, 1) if mode == A_LINEAR else conv_box(Wo, Ho)
     bw, bh, bb = box
     hw = Ho * Wo
@@ -110,25 +147,36 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
         bytes_in += 2.0 * rows * s.k_chunks * BK + 2.0 * s.n_valid * (2 if geglu else 1) * s.k_chunks * BK * taps
         out_elems += float(rows) * n_store
         if mode == A_LINEAR:
-            m_bases = range(s.row_begin, s.row_end, BM)
+            m_bases = np.arange(s.row_begin, s.row_end, BM, dtype=np.int64)
         else:
             assert s.row_begin % hw == 0 and s.row_end % hw == 0, "conv segments must cover whole samples"
-            m_bases = [(img * Ho + oy) * Wo + ox
-                       for img in range(s.row_begin // hw, s.row_end // hw, bb)
-                       for oy in range(0, Ho, bh) for ox in range(0, Wo, bw)]
+            img = np.arange(s.row_begin // hw, s.row_end // hw, bb, dtype=np.int64)
+            oy = np.arange(0, Ho, bh, dtype=np.int64)
+            ox = np.arange(0, Wo, bw, dtype=np.int64)
+            m_bases = ((img[:, None, None] * Ho + oy[None, :, None]) * Wo + ox[None, None, :]).reshape(-1)
         # tiles go in PAIRS (2i, 2i+1) = two row tiles that share the weight tile: a cluster of two CTAs
         # multicasts it. An odd row-tile count is padded with a placeholder that repeats its partner.
-        m_bases = list(m_bases)
-        for i in range(0, len(m_bases), 2):
-            m0 = m_bases[i]
-            has1 = i + 1 < len(m_bases)
-            m1 = m_bases[i + 1] if has1 else m0
-            for nt in range(n_tiles_n):
-                tiles.append((si, m0, nt * bn, 0))
-                tiles.append((si, m1, nt * bn, 0 if has1 else TILE_PLACEHOLDER))
-    tl = np.asarray(tiles, dtype=np.int32).reshape(-1, 4) if tiles else np.zeros((0, 4), dtype=np.int32)
-    return Schedule(segs=torch.from_numpy(segs).to(device), tiles=torch.from_numpy(tl).to(device),
-                    n_segs=len(segments), n_tiles=len(tiles), bn=bn, box=box, flops=flops, bytes_in=bytes_in,
+        # (vectorised: a level-0 launch has 10-20 k tiles and a forward ~250 schedules; Python loops over them
+        # dominated the cost of re-structuring for a new prompt -> expert assignment)
+        nm = len(m_bases)
+        if nm == 0:
+            continue
+        odd = nm % 2
+        mb = np.concatenate([m_bases, m_bases[-1:]]) if odd else m_bases
+        n_pairs = len(mb) // 2
+        m_pair = mb.reshape(n_pairs, 2)                                        # [pair, which]
+        n0 = (np.arange(n_tiles_n, dtype=np.int64) * bn)                       # [nt]
+        blk = np.empty((n_pairs, n_tiles_n, 2, 4), dtype=np.int32)
+        blk[..., 0] = si
+        blk[..., 1] = m_pair[:, None, :]
+        blk[..., 2] = n0[None, :, None]
+        blk[..., 3] = 0
+        if odd:
+            blk[n_pairs - 1, :, 1, 3] = TILE_PLACEHOLDER
+        tiles.append(blk.reshape(-1, 4))
+    tl = np.concatenate(tiles, 0) if tiles else np.zeros((0, 4), dtype=np.int32)
+    return Schedule(segs=upload(segs, device), tiles=upload(tl, device),
+                    n_segs=len(segments), n_tiles=int(tl.shape[0]), bn=bn, box=box, flops=flops, bytes_in=bytes_in,
                     out_elems=out_elems)
 
 

@@ -977,7 +977,8 @@ class _Engine:
 
     def _per_pos(self, per_expert: Sequence[int], dtype=torch.int32) -> torch.Tensor:
         arr = np.asarray(per_expert)[self.layout.expert_of_pos]
-        return torch.as_tensor(arr, device=self.device).to(dtype)
+        np_dt = {torch.int32: np.int32, torch.uint8: np.uint8, torch.int64: np.int64}[dtype]
+        return K.upload(arr.astype(np_dt), self.device)
 
     def _soft_gate(self, gate_idx: int) -> torch.Tensor:
         """Columns of one width gate as a VIEW of the [B, 1620] gate matrix: the kernels take the row pitch
