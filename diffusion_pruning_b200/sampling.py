@@ -69,6 +69,39 @@ def denoise(unet, hyper_net, arch_vectors: torch.Tensor, latents: torch.Tensor, 
     return x
 
 
+def plan_dispatch(idx: torch.Tensor, n_experts: int, policy: str = "balanced") -> torch.Tensor:
+    """Destination rank of every local prompt.
+
+    "expert_mod": expert e lives on rank e % world (round 1). Eval routing is an unbalanced cosine argmax
+    (pdm/models/vq/quantizer.py:264-271; SURVEY section 7 measured 47 ... 1212 of 4096 prompts per code), so this leaves
+    most GPUs idle behind the one that owns the hot expert.
+    "balanced" (default): the GLOBAL prompt list is sorted by expert and cut into `world` contiguous chunks of equal
+    size. A hot expert spans several ranks (replicas), cold experts share one, every rank still sees few distinct
+    experts (its compacted weight packs stay cached), and no rank gets more than ceil(total / world) prompts. Every
+    rank holds the full dense U-Net, so any rank can serve any expert. Needs one all-gather of the per-expert counts."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return torch.zeros_like(idx)
+    if policy == "expert_mod":
+        return idx % world
+    assert policy == "balanced", policy
+    rank = dist.get_rank()
+    counts = torch.bincount(idx, minlength=n_experts).to(torch.int64)
+    all_counts = torch.empty(world, n_experts, dtype=torch.int64, device=idx.device)
+    dist.all_gather_into_tensor(all_counts, counts.reshape(1, n_experts))
+    tot_e = all_counts.sum(0)
+    start_e = torch.cumsum(tot_e, 0) - tot_e                  # first global position of each expert's block
+    before = all_counts[:rank].sum(0)                          # this expert's prompts held by lower ranks
+    order = torch.argsort(idx, stable=True)
+    first = torch.cumsum(counts, 0) - counts                   # first local sorted position of each expert
+    within = torch.empty_like(idx)
+    within[order] = torch.arange(idx.numel(), device=idx.device) - first[idx[order]]
+    gpos = start_e[idx] + before[idx] + within
+    total = int(tot_e.sum().item())
+    chunk = max(1, (total + world - 1) // world)
+    return torch.clamp(gpos // chunk, max=world - 1)
+
+
 def _all_to_all_rows(t: torch.Tensor, send_counts: List[int], recv_counts: List[int]) -> torch.Tensor:
     out = torch.empty(sum(recv_counts), *t.shape[1:], device=t.device, dtype=t.dtype)
     dist.all_to_all_single(out, t.contiguous(), output_split_sizes=recv_counts, input_split_sizes=send_counts)
@@ -78,14 +111,15 @@ def _all_to_all_rows(t: torch.Tensor, send_counts: List[int], recv_counts: List[
 @torch.no_grad()
 def routed_sampling(unet, hyper_net, quantizer, prompt_embeddings: torch.Tensor, latents: torch.Tensor,
                     cond: torch.Tensor, uncond: torch.Tensor, num_inference_steps: int = 25,
-                    guidance_scale: float = 7.5, acp: Optional[torch.Tensor] = None):
-    """BASELINE configs[3]: route local prompts, dispatch them to the GPU that owns their expert (all-to-all over
-    NVLink), denoise there, return the final latents to the rank that asked. Returns (latents, code index)."""
+                    guidance_scale: float = 7.5, acp: Optional[torch.Tensor] = None, dispatch: str = "balanced"):
+    """BASELINE configs[3]: route local prompts, dispatch them (all-to-all over NVLink) to the GPU chosen by
+    plan_dispatch -- the rank(s) serving their expert, load-balanced --, denoise there, return the final latents to
+    the rank that asked. Returns (latents, code index)."""
     arch, idx = route_prompts(hyper_net, quantizer, prompt_embeddings)
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
         return denoise(unet, hyper_net, arch, latents, cond, uncond, num_inference_steps, guidance_scale, acp), idx
-    owner = idx % world
+    owner = plan_dispatch(idx, quantizer.n_e, dispatch)
     order = torch.argsort(owner, stable=True)
     send = torch.bincount(owner, minlength=world)
     recv = torch.empty_like(send)

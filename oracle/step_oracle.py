@@ -52,8 +52,13 @@ def split(arch: torch.Tensor, layout: R.ArchLayout) -> Dict[str, list]:
 
 
 def pruning_step(unet, hyper_w: torch.Tensor, hyper_b: torch.Tensor, codebook: torch.Tensor, layout: R.ArchLayout,
-                 batch: Dict[str, torch.Tensor], cfg, p_actual: float, temperature=0.4, base=3.0):
-    """unet: GatedUNetOracle with count_macs() done and `ones_prunable` = cur_prunable at all-ones gates."""
+                 batch: Dict[str, torch.Tensor], cfg, p_actual: float, temperature=0.4, base=3.0, ddp=None):
+    """unet: GatedUNetOracle with count_macs() done and `ones_prunable` = cur_prunable at all-ones gates.
+
+    ddp (data-parallel emulation in ONE process, for the 2-rank NCCL test): "collect" returns this rank's router
+    tensors before the U-Net runs; a dict(idx, text_all, arch_all, rank) replaces the local Sinkhorn assignment by this
+    rank's slice of the GLOBAL one (quantizer.py:278-300: marginals all-reduced over ranks) and evaluates the contrastive
+    loss on the all-gathered batch in which only the local rows carry gradient (trainer.py:1153-1160)."""
     noisy, timesteps, target = batch["noisy_latents"], batch["timesteps"], batch["target"]
     enc, text = batch["encoder_hidden_states"], batch["mpnet_embeddings"]
     B, K = text.shape[0], codebook.shape[0]
@@ -61,12 +66,23 @@ def pruning_step(unet, hyper_w: torch.Tensor, hyper_b: torch.Tensor, codebook: t
     # quantizer.forward, train mode (quantizer.py:140-151)
     codes_gs = R.gumbel_sigmoid_trick(codebook, R.draw_uniforms(layout, K, False), layout, temperature, base)
     z_gs = R.gumbel_sigmoid_trick(arch.detach(), R.draw_uniforms(layout, B, False), layout, temperature, base)
-    idx, _, _ = R.ot_indices(z_gs, codes_gs.detach(), layout)
+    if isinstance(ddp, dict):
+        idx = ddp["idx"]
+    else:
+        idx, _, _ = R.ot_indices(z_gs, codes_gs.detach(), layout)
     arch_q = codes_gs[idx]
     arch_gs = R.gumbel_sigmoid_trick(arch, R.draw_uniforms(layout, B, False), layout, temperature, base)  # :1132
     arch_norm = R.width_depth_normalize(arch_gs, layout)                             # :1138
     _ = R.draw_uniforms(layout, K, False)                                            # :1140 (similarity, no grad)
-    c_loss = R.contrastive_loss(text, arch_norm, cfg.arch_vector_temperature, cfg.prompt_embedding_temperature)
+    if ddp == "collect":
+        return {"z_gs": z_gs.detach(), "codes_gs": codes_gs.detach(), "arch_norm": arch_norm.detach()}
+    if isinstance(ddp, dict):
+        r, Bl = ddp["rank"], text.shape[0]
+        arch_all = torch.cat([ddp["arch_all"][:r * Bl], arch_norm, ddp["arch_all"][(r + 1) * Bl:]], 0)
+        c_loss = R.contrastive_loss(ddp["text_all"], arch_all, cfg.arch_vector_temperature,
+                                    cfg.prompt_embedding_temperature)
+    else:
+        c_loss = R.contrastive_loss(text, arch_norm, cfg.arch_vector_temperature, cfg.prompt_embedding_temperature)
     with torch.no_grad():                                                            # :1185-1190
         unet.set_structure(split(torch.ones_like(arch_gs), layout))
         full_pred, t_taps = unet(noisy, timesteps, enc, return_blocks=True)

@@ -124,7 +124,9 @@ def _sampling_worker(rank, world, port, out_path, P):
         return lat * 2.0 + tag[:, None, None, None] + 1000.0 * rank + 10.0 * codes[:, None, None, None].float()
 
     S.route_prompts, S.denoise = fake_route, fake_denoise
-    out, got_idx = S.routed_sampling(None, None, None, prompt, latents, cond, uncond)
+    import types
+    out, got_idx = S.routed_sampling(None, None, types.SimpleNamespace(n_e=8), prompt, latents, cond, uncond,
+                                     dispatch="expert_mod")
     tag = cond.mean(dim=(1, 2)) + 2.0 * uncond.mean(dim=(1, 2))
     want = latents * 2.0 + tag[:, None, None, None] + 1000.0 * (idx % world)[:, None, None, None].float() + \
         10.0 * idx[:, None, None, None].float()
@@ -143,3 +145,57 @@ def test_routed_sampling_dispatch_and_return_over_all_to_all(tmp_path, world):
     mp.spawn(_sampling_worker, args=(world, _free_port(), out, 11), nprocs=world, join=True)
     res = [torch.load(f"{out}.{r}") for r in range(world)]
     assert all(r["ok"] for r in res) and all(r["idx_ok"] for r in res), res
+
+
+def _balanced_worker(rank, world, port, out_path, P):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import types
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diffusion_pruning_b200 import sampling as S
+    g = torch.Generator().manual_seed(70 + rank)
+    latents = torch.randn(P, 4, 6, 6, generator=g)
+    cond = torch.randn(P, 5, 16, generator=g)
+    uncond = torch.randn(P, 5, 16, generator=g)
+    # skewed routing (eval cosine argmax is unbalanced): ~70 % of the prompts hit expert 2
+    idx = torch.where(torch.rand(P, generator=g) < 0.7, torch.full((P,), 2), torch.randint(0, 8, (P,), generator=g))
+    arch = torch.nn.functional.one_hot(idx, 8).float()
+    load = {}
+
+    def fake_route(hyper_net, quantizer, prompt_embeddings):
+        return arch, idx
+
+    def fake_denoise(unet, hyper_net, arch_vectors, lat, c, u, num_inference_steps=25, guidance_scale=7.5, acp=None,
+                     prediction_type="v_prediction"):
+        codes = arch_vectors.argmax(dim=1)
+        load["n"], load["experts"] = lat.shape[0], sorted(set(codes.tolist()))
+        tag = c.mean(dim=(1, 2)) + 2.0 * u.mean(dim=(1, 2))
+        return lat * 2.0 + tag[:, None, None, None] + 10.0 * codes[:, None, None, None].float()
+
+    S.route_prompts, S.denoise = fake_route, fake_denoise
+    out, got_idx = S.routed_sampling(None, None, types.SimpleNamespace(n_e=8), torch.zeros(P, 8), latents, cond, uncond)
+    tag = cond.mean(dim=(1, 2)) + 2.0 * uncond.mean(dim=(1, 2))
+    want = latents * 2.0 + tag[:, None, None, None] + 10.0 * idx[:, None, None, None].float()
+    mod_load = torch.bincount(idx % world, minlength=world)
+    torch.save({"ok": bool(torch.allclose(out, want, rtol=0, atol=1e-5)), "load": load.get("n", 0),
+                "experts": load.get("experts", []), "mod_load": mod_load}, f"{out_path}.{rank}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 4])
+def test_balanced_dispatch_under_skewed_routing(tmp_path, world):
+    """sampling.plan_dispatch("balanced"): with ~70 % of the prompts on one expert no rank serves more than
+    ceil(total / world) prompts (the hot expert is replicated over several ranks), results still come back to the asking
+    rank in the caller's order; the round-1 rule (expert % world) would have piled them on one rank."""
+    P = 23
+    out = str(tmp_path / "res")
+    mp.spawn(_balanced_worker, args=(world, _free_port(), out, P), nprocs=world, join=True)
+    res = [torch.load(f"{out}.{r}") for r in range(world)]
+    assert all(r["ok"] for r in res), res
+    total = P * world
+    cap = (total + world - 1) // world
+    assert sum(r["load"] for r in res) == total and max(r["load"] for r in res) <= cap, [r["load"] for r in res]
+    mod = sum(r["mod_load"] for r in res)
+    assert int(mod.max()) > cap, "the case must really be skewed for expert % world"

@@ -69,3 +69,215 @@ def test_sharded_router_nccl_matches_single_process(tmp_path):
     z_gs = R.gumbel_sigmoid_trick(z_all, u_all, layout, 0.4, 3.0)
     ref_idx, _, ref_Q = R.ot_indices(z_gs, codes, layout)
     RC._assert_assignments(got, ref_idx, ref_Q, "sharded Sinkhorn (2 ranks, NCCL)", amplification=1.0 / 0.05)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pruning train step over 2 NCCL ranks: Sinkhorn marginals all-reduced, contrastive all-gather, gradient all-reduce
+# ----------------------------------------------------------------------------------------------------------------
+TRAIN = dict(B_local=2, H=16, n_codes=4, input_dim=64, seed=21)
+
+
+def _train_setup(device):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import unet_checks as U
+    from diffusion_pruning_b200 import HyperStructure, StructureVectorQuantizer
+    from diffusion_pruning_b200.synthetic import DEPTH_ORDER
+    model, oracle = U.build_pair(True, beta_std=0.1) if device != "cpu" else (None, None)
+    if device == "cpu":
+        from oracle.unet_oracle import GatedUNetOracle, UNetConfig, seeded_init
+        oracle = GatedUNetOracle(UNetConfig.tiny()).eval()
+        seeded_init(oracle, 0, 0.1)
+        st = oracle.get_structure()
+    else:
+        st = model.get_structure()
+    torch.manual_seed(TRAIN["seed"])
+    hyper = HyperStructure(structure=st, input_dim=TRAIN["input_dim"], wn_flag=False, linear_bias=True)
+    quant = StructureVectorQuantizer(n_e=TRAIN["n_codes"], structure=st, beta=0.25, temperature=0.4, base=3,
+                                     depth_order=list(DEPTH_ORDER), non_zero_width=True,
+                                     resource_aware_normalization=False, optimal_transport=True)
+    with torch.no_grad():
+        for l in hyper.mh_fc:
+            l.bias.copy_(0.1 * torch.randn_like(l.bias))
+        quant.embedding.weight.copy_(torch.randn_like(quant.embedding.weight) * 1.5 - 2.8)
+    return model, oracle, st, hyper, quant
+
+
+def _train_batch(rank, cd):
+    g = torch.Generator().manual_seed(TRAIN["seed"] + 1 + 100 * rank)
+    B, H = TRAIN["B_local"], TRAIN["H"]
+    ts = [[981, 661], [341, 21]][rank % 2]
+    return {"noisy_latents": torch.randn(B, 4, H, H, generator=g), "timesteps": torch.tensor(ts[:B]),
+            "target": torch.randn(B, 4, H, H, generator=g), "encoder_hidden_states": torch.randn(B, 77, cd, generator=g),
+            "mpnet_embeddings": torch.randn(B, TRAIN["input_dim"], generator=g)}
+
+
+def _train_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    model, _, st, hyper, quant = _train_setup("cuda")
+    from diffusion_pruning_b200 import pruning_step as PS
+    hyper, quant = hyper.cuda(), quant.cuda()
+    quant.train()
+    H = TRAIN["H"]
+    cfg = PS.PruningLossConfig()
+    model.count_macs(H, H)
+    p_got = PS.actual_pruning_target(model, cfg.pruning_target)
+    taps = PS.BlockTaps(model)
+    batch = {k: v.cuda() for k, v in _train_batch(rank, model.config["cross_attention_dim"]).items()}
+    params = [p for p in list(hyper.parameters()) + list(quant.parameters()) if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for p in params), device="cuda")
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    torch.manual_seed(TRAIN["seed"] + 2)      # every rank draws the same Gumbel uniforms (as in the oracle emulation)
+    got = PS.pruning_step(model, hyper, quant, batch, cfg, taps, p_got)
+    got["loss"].backward()
+    local = flat.clone()
+    dist.all_reduce(flat)
+    flat.div_(world)
+    torch.cuda.synchronize()
+    names = ["loss", "diff_loss", "distillation_loss", "block_loss", "contrastive_loss", "resource_loss"]
+    torch.save({"losses": {k: float(got[k].detach()) for k in names}, "grad": flat.cpu(), "local_grad": local.cpu(),
+                "names": [n for n, p in list(hyper.named_parameters()) + list(quant.named_parameters()) if p.requires_grad]},
+               f"{out_path}.{rank}")
+    taps.remove()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_train_step_matches_single_process_oracle(tmp_path):
+    """SURVEY 8(d) config 3 parity: losses and the all-reduced gradients of hypernet + codebook of a 2-rank NCCL pruning
+    train step vs the fp32 CPU oracle emulating the same data-parallel step in one process (rel 2e-2 on the losses,
+    relative L2 <= 6e-2 / cosine >= 0.995 on the gradients, the single-GPU gradient tolerance of tests/train_checks.py)."""
+    import torch.multiprocessing as mp
+    world = 2
+    out = str(tmp_path / "tr")
+    mp.spawn(_train_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = [torch.load(f"{out}.{r}") for r in range(world)]
+    assert torch.equal(res[0]["grad"], res[1]["grad"]), "all-reduced gradients must be identical on both ranks"
+    # ---- oracle emulation of the 2-rank step ----
+    from diffusion_pruning_b200 import pruning_step as PS
+    from diffusion_pruning_b200.synthetic import DEPTH_ORDER
+    from oracle import router_oracle as R
+    from oracle import step_oracle as SO
+    _, oracle, st, hyper, quant = _train_setup("cpu")
+    layout = R.ArchLayout(st, DEPTH_ORDER)
+    cfg = PS.PruningLossConfig()
+    H = TRAIN["H"]
+    hw_ = torch.cat([l.weight.detach() for l in hyper.mh_fc], 0).clone().requires_grad_(True)
+    hb_ = torch.cat([l.bias.detach() for l in hyper.mh_fc], 0).clone().requires_grad_(True)
+    cb_ = quant.embedding.weight.detach().clone().requires_grad_(True)
+    oracle.count_macs(H, H)
+    oracle.set_all_ones(1)
+    ones = oracle.calc_macs()
+    oracle.ones_prunable = ones["cur_prunable_macs"].squeeze()
+    p_ref = float(1 - (1 - cfg.pruning_target) * ones["total_macs"] / ones["cur_prunable_macs"])
+    cd = oracle.cfg.cross_attention_dim
+    batches = [_train_batch(r, cd) for r in range(world)]
+    pre = []
+    for r in range(world):
+        torch.manual_seed(TRAIN["seed"] + 2)
+        pre.append(SO.pruning_step(oracle, hw_, hb_, cb_, layout, batches[r], cfg, p_ref, ddp="collect"))
+    idx_all, _, _ = R.ot_indices(torch.cat([p["z_gs"] for p in pre]), pre[0]["codes_gs"], layout)
+    text_all = torch.cat([b["mpnet_embeddings"] for b in batches])
+    arch_all = torch.cat([p["arch_norm"] for p in pre])
+    Bl = TRAIN["B_local"]
+    ref_losses = []
+    for r in range(world):
+        torch.manual_seed(TRAIN["seed"] + 2)
+        ref = SO.pruning_step(oracle, hw_, hb_, cb_, layout, batches[r], cfg, p_ref,
+                              ddp={"idx": idx_all[r * Bl:(r + 1) * Bl], "text_all": text_all, "arch_all": arch_all, "rank": r})
+        ref["loss"].backward()      # gradients of both ranks accumulate in the shared leaves
+        ref_losses.append({k: float(ref[k].detach()) for k in res[r]["losses"]})
+    for r in range(world):
+        for k, v in res[r]["losses"].items():
+            tol = 2e-2 * max(abs(ref_losses[r][k]), 1e-3) + (2e-3 if k in ("distillation_loss", "block_loss", "loss") else 0)
+            assert abs(v - ref_losses[r][k]) <= tol, (r, k, v, ref_losses[r][k])
+    # flat layout of the product: hypernet parameters in module order (per Linear: weight, bias), then the codebook
+    got = res[0]["grad"]
+    ref_parts = []
+    off_w = off_b = 0
+    for l in hyper.mh_fc:
+        n_out = l.weight.shape[0]
+        ref_parts += [hw_.grad[off_w:off_w + n_out].reshape(-1), hb_.grad[off_b:off_b + n_out]]
+        off_w += n_out
+        off_b += n_out
+    ref_flat = torch.cat(ref_parts + [cb_.grad.reshape(-1)]) / world
+    assert got.numel() == ref_flat.numel(), (got.numel(), ref_flat.numel())
+    n_h = ref_flat.numel() - cb_.numel()
+    for name, a, b in (("hypernet", got[:n_h], ref_flat[:n_h]), ("codebook", got[n_h:], ref_flat[n_h:])):
+        rel = ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+        cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+        assert rel <= 6e-2 and cos >= 0.995, (name, rel, cos)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# routed sampling over 2 NCCL ranks (all-to-all dispatch + return) on the tiny model
+# ----------------------------------------------------------------------------------------------------------------
+def _sample_inputs(rank, cd, P=3, H=16):
+    g = torch.Generator().manual_seed(300 + rank)
+    return (torch.randn(P, 16, generator=g), torch.randn(P, 4, H, H, generator=g), torch.randn(P, 77, cd, generator=g),
+            torch.randn(P, 77, cd, generator=g))
+
+
+def _sample_models():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import unet_checks as U
+    from diffusion_pruning_b200 import HyperStructure, StructureVectorQuantizer
+    from diffusion_pruning_b200.synthetic import DEPTH_ORDER, synthetic_codes
+    model, oracle = U.build_pair(True, beta_std=0.1)
+    st = model.get_structure()
+    torch.manual_seed(9)
+    hyper = HyperStructure(structure=st, input_dim=16, wn_flag=False, linear_bias=True).cuda().eval()
+    quant = StructureVectorQuantizer(n_e=8, structure=st, beta=0.25, temperature=0.4, base=3,
+                                     depth_order=list(DEPTH_ORDER), non_zero_width=True,
+                                     resource_aware_normalization=False, optimal_transport=True).cuda().eval()
+    quant.embedding_gs.data = (synthetic_codes(st, 8).float() * 0.9 + 0.05).cuda()
+    return model, oracle, hyper, quant
+
+
+def _sample_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    model, _, hyper, quant = _sample_models()
+    from diffusion_pruning_b200 import sampling as S
+    prompt, lat, cond, unc = [t.cuda() for t in _sample_inputs(rank, model.config["cross_attention_dim"])]
+    out, idx = S.routed_sampling(model, hyper, quant, prompt, lat, cond, unc, num_inference_steps=3, guidance_scale=7.5)
+    torch.cuda.synchronize()
+    torch.save({"out": out.cpu(), "idx": idx.cpu()}, f"{out_path}.{rank}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_routed_sampling_matches_local_denoise_and_oracle(tmp_path):
+    """configs[3] end to end on the tiny model: prompts routed on 2 ranks, dispatched over NCCL all-to-all, denoised on
+    the serving rank and returned -- equal to denoising the same prompts locally in one process, and within the sampling
+    tolerance of the fp32 oracle loop."""
+    import torch.multiprocessing as mp
+    world = 2
+    out = str(tmp_path / "sm")
+    mp.spawn(_sample_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    res = [torch.load(f"{out}.{r}") for r in range(world)]
+    model, oracle, hyper, quant = _sample_models()
+    from diffusion_pruning_b200 import sampling as S
+    from diffusion_pruning_b200.synthetic import DEPTH_ORDER
+    from oracle import router_oracle as R
+    from oracle import sampling_oracle as SO
+    import unet_checks as U
+    layout = R.ArchLayout(model.get_structure(), DEPTH_ORDER)
+    for r in range(world):
+        prompt, lat, cond, unc = _sample_inputs(r, model.config["cross_attention_dim"])
+        arch, idx = S.route_prompts(hyper, quant, prompt.cuda())
+        assert torch.equal(idx.cpu(), res[r]["idx"])
+        local = S.denoise(model, hyper, arch, lat.cuda(), cond.cuda(), unc.cuda(), num_inference_steps=3, guidance_scale=7.5)
+        assert torch.allclose(local.cpu(), res[r]["out"], rtol=0, atol=1e-4), (local.cpu() - res[r]["out"]).abs().max()
+        ref = SO.denoise(oracle, layout, arch.float().cpu(), lat, cond, unc, steps=3, guidance=7.5)
+        max_abs, cos = U.metrics(res[r]["out"], ref)
+        assert cos >= 0.998 and max_abs <= 6e-2, (max_abs, cos)
