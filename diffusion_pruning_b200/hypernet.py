@@ -16,6 +16,42 @@ from ._mixin import ConfigModelMixin
 from .quantizer import hard_concrete
 
 
+class _PackedLinear(torch.autograd.Function):
+    """y = x W^T + b over the row-concatenated Linears on the fp32 K9 kernels (csrc/smallops.cu): no cuBLAS, fixed
+    summation order; backward gives dW / db (split back to the 71 Linears by autograd's cat) and dx."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        from . import kernels as K
+        x32 = x.detach().to(torch.float32).contiguous()
+        W32 = W.detach().to(torch.float32).contiguous()
+        b32 = b.detach().to(torch.float32).contiguous() if b is not None else None
+        B, Kd = x32.shape
+        N = W32.shape[0]
+        y = torch.empty(B, N, device=x32.device, dtype=torch.float32)
+        K.linear_f32_fwd(x32, W32, b32, y, B, Kd, N)
+        ctx.save_for_backward(x32, W32)
+        ctx.has_bias, ctx.x_dtype, ctx.w_dtype = b is not None, x.dtype, W.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import kernels as K
+        x32, W32 = ctx.saved_tensors
+        B, Kd = x32.shape
+        N = W32.shape[0]
+        dy = dy.to(torch.float32).contiguous()
+        dW = torch.empty_like(W32) if ctx.needs_input_grad[1] else None
+        db = torch.empty(N, device=dy.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dx = torch.empty_like(x32) if ctx.needs_input_grad[0] else None
+        if B > 0 and (dW is not None or dx is not None):
+            if dW is None and db is not None:
+                dW = torch.empty_like(W32)
+            K.linear_f32_bwd(x32, W32, dy, dx, dW, db, B, Kd, N)
+        return (dx.to(ctx.x_dtype) if dx is not None else None,
+                dW.to(ctx.w_dtype) if (dW is not None and ctx.needs_input_grad[1]) else None, db)
+
+
 class HyperStructure(ConfigModelMixin, nn.Module):
     def __init__(self, structure, input_dim=768, wn_flag=True, linear_bias=False, single_arch_param=False):
         super().__init__()
@@ -56,7 +92,10 @@ class HyperStructure(ConfigModelMixin, nn.Module):
         # one fused product instead of 71 (autograd splits the gradient back to the per-Linear parameters)
         W = torch.cat([l.weight for l in self.mh_fc], dim=0)
         b = torch.cat([l.bias for l in self.mh_fc], dim=0) if self.linear_bias else None
-        return F.linear(x, W, b)
+        if not W.is_cuda:
+            raise RuntimeError("HyperStructure runs on the sm_100a CUDA path only: move the module to a CUDA device "
+                               "(there is no CPU fallback)")
+        return _PackedLinear.apply(x, W, b)
 
     def transform_structure_vector(self, inputs):
         """hypernet.py:86-101."""

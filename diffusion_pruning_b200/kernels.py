@@ -514,3 +514,29 @@ def groupnorm_bwd_affine(x, ldx, da, ldda, dx, lddx, accumulate, batch, hw, C_, 
 def layernorm_affine_bwd(x, ldx, dy, lddy, rows, C_, eps, daffine):
     check(load().aptp_layernorm_affine_bwd(_ptr(x), ldx, _ptr(dy), lddy, rows, C_, eps, _ptr(daffine), _stream()),
           "aptp_layernorm_affine_bwd")
+
+
+# --------------------------------------------------------------------------------------------
+# K9: fp32 hypernet linear, contrastive loss
+# --------------------------------------------------------------------------------------------
+def linear_f32_fwd(x, w, bias, y, B, K_, N):
+    check(load().aptp_linear_f32_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), B, K_, N, _stream()), "aptp_linear_f32_fwd")
+
+
+def linear_f32_bwd(x, w, dy, dx, dw, db, B, K_, N):
+    check(load().aptp_linear_f32_bwd(_ptr(x), _ptr(w), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), B, K_, N, _stream()),
+          "aptp_linear_f32_bwd")
+
+
+def contrastive_fwd(arch, prompt, arch_temp, prompt_temp, inv_a, inv_p, Sa, Sp, row_loss, loss):
+    M = arch.shape[0]
+    check(load().aptp_contrastive_fwd(_ptr(arch), arch.shape[1], _ptr(prompt), prompt.shape[1], M, float(arch_temp),
+                                      float(prompt_temp), _ptr(inv_a), _ptr(inv_p), _ptr(Sa), _ptr(Sp), _ptr(row_loss),
+                                      _ptr(loss), _stream()), "aptp_contrastive_fwd")
+
+
+def contrastive_bwd(arch, arch_temp, inv_a, Sa, Sp, grad_loss, dG, dhat, darch):
+    M = arch.shape[0]
+    check(load().aptp_contrastive_bwd(_ptr(arch), arch.shape[1], M, float(arch_temp), _ptr(inv_a), _ptr(Sa), _ptr(Sp),
+                                      _ptr(grad_loss), _ptr(dG), _ptr(dhat), _ptr(darch), _stream()),
+          "aptp_contrastive_bwd")

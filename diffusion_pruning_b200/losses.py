@@ -144,3 +144,42 @@ def add_noise_and_target(tables: NoiseTables, latents: torch.Tensor, noise: torc
     K.add_noise_velocity(x, n, t, tables.sqrt_acp, tables.sqrt_1m_acp, noisy, target, x.shape[0], x[0].numel(),
                          v_prediction)
     return noisy, target
+
+
+class _Contrastive(torch.autograd.Function):
+    """ContrastiveLoss.forward (pdm/losses/contrastive_loss.py:11-22) on the K9 kernels: gradient to the architecture
+    vectors only (the prompt embeddings come from the frozen MPNet encoder)."""
+
+    @staticmethod
+    def forward(ctx, prompt, arch, t_arch, t_prompt):
+        if not arch.is_cuda:
+            raise RuntimeError("diffusion_pruning_b200.losses runs on the sm_100a CUDA path only (no CPU fallback)")
+        a = arch.detach().to(torch.float32).contiguous()
+        p = prompt.detach().to(device=a.device, dtype=torch.float32).contiguous()
+        M = a.shape[0]
+        assert p.shape[0] == M
+        dev = a.device
+        inv_a, inv_p = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        Sa, Sp = torch.empty(M, M, device=dev), torch.empty(M, M, device=dev)
+        row_loss, loss = torch.empty(M, device=dev), torch.empty(1, device=dev)
+        K.contrastive_fwd(a, p, t_arch, t_prompt, inv_a, inv_p, Sa, Sp, row_loss, loss)
+        ctx.save_for_backward(a, inv_a, Sa, Sp)
+        ctx.t_arch, ctx.dtype = float(t_arch), arch.dtype
+        return loss.reshape(()), Sa
+
+    @staticmethod
+    def backward(ctx, g, _g_sa):
+        a, inv_a, Sa, Sp = ctx.saved_tensors
+        M, D = a.shape
+        dG = torch.empty(M, M, device=a.device)
+        dhat = torch.empty(M, D, device=a.device)
+        da = torch.empty(M, D, device=a.device)
+        K.contrastive_bwd(a, ctx.t_arch, inv_a, Sa, Sp, g.reshape(1).to(torch.float32).contiguous(), dG, dhat, da)
+        return None, da.to(ctx.dtype), None, None
+
+
+def contrastive_loss(prompt_embeddings: torch.Tensor, arch_vectors: torch.Tensor, arch_vector_temperature: float,
+                     prompt_embedding_temperature: float):
+    """(loss, softmax(arch similarity).detach()) as ContrastiveLoss.forward returns them (contrastive_loss.py:21-22)."""
+    loss, sa = _Contrastive.apply(prompt_embeddings, arch_vectors, arch_vector_temperature, prompt_embedding_temperature)
+    return loss, sa.detach()

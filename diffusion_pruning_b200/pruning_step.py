@@ -55,7 +55,11 @@ def compute_snr(acp: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
 
 
 def contrastive_loss(prompt_embeddings, arch_vectors, t_arch: float, t_prompt: float):
-    """pdm/losses/contrastive_loss.py:11-22."""
+    """pdm/losses/contrastive_loss.py:11-22: the fused K9 kernels on CUDA tensors (csrc/smallops.cu); the torch-op
+    form below only serves CPU tensors (host-side checks of the loss algebra in the GPU-less container)."""
+    if arch_vectors.is_cuda:
+        from .losses import contrastive_loss as _cl
+        return _cl(prompt_embeddings, arch_vectors, t_arch, t_prompt)
     a = arch_vectors / arch_vectors.norm(dim=1, keepdim=True)
     p = prompt_embeddings / prompt_embeddings.norm(dim=1, keepdim=True)
     sa = F.softmax((a @ a.T) / t_arch, dim=-1)

@@ -396,6 +396,26 @@ int aptp_groupnorm_bwd_affine(const void* x, int32_t ldx, const void* da, int32_
 int aptp_layernorm_affine_bwd(const void* x, int32_t ldx, const void* dy, int32_t lddy, int64_t rows, int32_t C, float eps,
                               float* daffine, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K9  small fp32 operators of the pruning train step (no cuBLAS / eager PyTorch left on the path).
+ * ---------------------------------------------------------------------------------------------- */
+/* HyperStructure._forward (pdm/models/hypernet/hypernet.py:72-79) over the row-concatenated 71 Linears:
+ * y[B,N] = x[B,K] w[N,K]^T + bias[N]; backward: dw[N,K], db[N] (NULL to skip), dx[B,K] (NULL to skip). fp32 SIMT,
+ * fixed summation order (the logits feed the router, whose assignments must be reproducible). */
+int aptp_linear_f32_fwd(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t K, int32_t N,
+                        void* stream);
+int aptp_linear_f32_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db, int32_t B,
+                        int32_t K, int32_t N, void* stream);
+/* ContrastiveLoss.forward (pdm/losses/contrastive_loss.py:11-22) over the all-gathered batch of M rows:
+ * loss = BCE(softmax(A A^T / arch_temp)^T, softmax(P P^T / prompt_temp)^T), A / P = row-normalised arch / prompt rows.
+ * Workspaces (device, fp32): inv_a[M], inv_p[M], Sa[M*M], Sp[M*M] (kept for the backward), row_loss[M]; loss[1].
+ * Backward: darch[M,Da] = d loss / d arch * grad_loss[0]; workspaces dG[M*M], dhat[M*Da]. */
+int aptp_contrastive_fwd(const float* arch, int32_t Da, const float* prompt, int32_t Dp, int32_t M, float arch_temp,
+                         float prompt_temp, float* inv_a, float* inv_p, float* Sa, float* Sp, float* row_loss, float* loss,
+                         void* stream);
+int aptp_contrastive_bwd(const float* arch, int32_t Da, int32_t M, float arch_temp, const float* inv_a, const float* Sa,
+                         const float* Sp, const float* grad_loss, float* dG, float* dhat, float* darch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

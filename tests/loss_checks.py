@@ -113,3 +113,80 @@ def check_macs_kernel(B=6, H=16, seed=8):
                       abs(k[2] - o[2]) / o[2], abs(k[3] - o[3]) / o[3],
                       ((grads["kernel"] - grads[other]).abs().max() / grads[other].abs().max()).item())
     return out
+
+
+def check_hypernet_product_vs_reference_golden():
+    """The PRODUCT HyperStructure (fp32 K9 linear kernel, no cuBLAS) against tests/golden/hypernet.npz, which was produced by
+    executing the reference's own hypernet.py: forward values, the split into gate tensors, and the backward vs autograd of
+    the same product in torch ops."""
+    import os
+    import numpy as np
+    from diffusion_pruning_b200 import HyperStructure
+    from oracle.structure import sd21_gate_structure
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hypernet.npz"))
+    structure = sd21_gate_structure()
+    hn = HyperStructure(structure=structure, input_dim=32, wn_flag=False, linear_bias=True).cuda()
+    W, b = torch.from_numpy(g["weight"]), torch.from_numpy(g["bias"])
+    off = 0
+    with torch.no_grad():
+        for l in hn.mh_fc:
+            n = l.weight.shape[0]
+            l.weight.copy_(W[off:off + n])
+            l.bias.copy_(b[off:off + n])
+            off += n
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    y = hn(x)
+    assert torch.allclose(y.detach().cpu(), torch.from_numpy(g["y"]), atol=2e-6, rtol=1e-6), \
+        (y.detach().cpu() - torch.from_numpy(g["y"])).abs().max()
+    sv = hn.transform_structure_vector(y.detach())
+    assert len(sv["width"]) == int(g["n_width"]) and len(sv["depth"]) == int(g["n_depth"])
+    assert torch.allclose(sv["width"][3].cpu(), torch.from_numpy(g["width_3"]), atol=2e-6)
+    assert torch.allclose(sv["depth"][5].cpu(), torch.from_numpy(g["depth_5"]), atol=2e-6)
+    # backward: dW / db / dx vs torch autograd of x W^T + b
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    Wt, bt = W.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    xt = x.detach().clone().requires_grad_(True)
+    (torch.nn.functional.linear(xt, Wt, bt) * gy).sum().backward()
+    gw = torch.cat([l.weight.grad for l in hn.mh_fc], 0)
+    gb = torch.cat([l.bias.grad for l in hn.mh_fc], 0)
+    assert torch.allclose(gw, Wt.grad, atol=1e-5, rtol=1e-5) and torch.allclose(gb, bt.grad, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(x.grad, xt.grad, atol=1e-5, rtol=1e-5)
+
+
+def check_contrastive_kernel_vs_reference_golden():
+    """Fused contrastive-loss kernels vs the value the reference's own ContrastiveLoss produced (golden) and vs torch
+    autograd of the same formula for the gradient."""
+    import os
+    import numpy as np
+    from diffusion_pruning_b200.losses import contrastive_loss
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses_gates.npz"))
+    p = torch.from_numpy(g["prompt"]).cuda()
+    a = torch.from_numpy(g["arch"]).cuda().requires_grad_(True)
+    loss, sa = contrastive_loss(p, a, 0.03, 0.03)
+    assert abs(float(loss) - float(g["contrastive"])) <= 1e-5 * max(1.0, abs(float(g["contrastive"]))), (float(loss), float(g["contrastive"]))
+    loss.backward()
+    a2 = a.detach().clone().requires_grad_(True)
+    an = a2 / a2.norm(dim=1, keepdim=True)
+    pn = p / p.norm(dim=1, keepdim=True)
+    s_a = torch.softmax(an @ an.T / 0.03, dim=-1)
+    s_p = torch.softmax(pn @ pn.T / 0.03, dim=-1)
+    ref = torch.nn.functional.binary_cross_entropy(s_a.T, s_p.T)
+    ref.backward()
+    assert torch.allclose(sa, s_a.detach(), atol=1e-6)
+    rel = ((a.grad - a2.grad).norm() / a2.grad.norm()).item()
+    assert rel <= 1e-4, rel
+    # a larger, all-gathered-size batch (8 ranks x 32)
+    gen = torch.Generator().manual_seed(3)
+    p = torch.randn(256, 768, generator=gen).cuda()
+    a = torch.rand(256, 1620, generator=gen).cuda().requires_grad_(True)
+    loss, _ = contrastive_loss(p, a, 0.03, 0.03)
+    (loss * 100.0).backward()
+    a2 = a.detach().clone().requires_grad_(True)
+    an = a2 / a2.norm(dim=1, keepdim=True)
+    pn = p / p.norm(dim=1, keepdim=True)
+    ref = torch.nn.functional.binary_cross_entropy(torch.softmax(an @ an.T / 0.03, -1).T, torch.softmax(pn @ pn.T / 0.03, -1).T)
+    (ref * 100.0).backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+    rel = ((a.grad - a2.grad).norm() / a2.grad.norm()).item()
+    assert rel <= 1e-3, rel

@@ -27,3 +27,13 @@ def test_macs_kernel_matches_closed_form_and_oracle():
     for other, errs in LC.check_macs_kernel().items():
         # fp64 accumulation in the kernel vs fp32 torch sums of ~1e9..1e11 MAC terms
         assert all(e <= 2e-6 for e in errs), (other, errs)
+
+
+def test_hypernet_product_matches_reference_golden_and_autograd():
+    import loss_checks as LC
+    LC.check_hypernet_product_vs_reference_golden()
+
+
+def test_contrastive_kernels_match_reference_golden_and_autograd():
+    import loss_checks as LC
+    LC.check_contrastive_kernel_vs_reference_golden()
