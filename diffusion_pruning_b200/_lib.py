@@ -35,12 +35,13 @@ class GemmArgs(C.Structure):
         ("residual", c_void_p), ("res_ld", c_int),
         ("gate", c_void_p), ("gate_ld", c_int), ("gate_group", c_int),
         ("border_tab", c_void_p), ("tab_ld", c_int),
-        ("gn_stats", c_void_p), ("gn_group", c_int), ("gn_groups", c_int),
+        ("gn_stats", c_void_p), ("gn_ld", c_int), ("gn_blocks", c_int),
         ("flags", c_int),
         ("segs", c_void_p), ("n_segs", c_int), ("tiles", c_void_p), ("n_tiles", c_int),
         ("ln_colsum", c_void_p), ("ln_rowstats", c_void_p), ("ln_reserved0", c_int), ("ln_reserved1", c_int),
         ("ln_reserved2", c_float),
         ("rowstat_out", c_void_p), ("rowstat_chunks", c_int),
+        ("gn_stats_sq", c_void_p),
     ]
 
 
@@ -58,6 +59,8 @@ SIGNATURES = {
     "aptp_groupnorm_stats_workspace": (c_int64, [c_int, c_int, c_int]),
     "aptp_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "aptp_groupnorm_stats_from_partials": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                                   c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "aptp_groupnorm_apply": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                      c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                      c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -68,6 +68,10 @@ struct GemmParams {
   // producer side: per-row (sum, sumsq) of every 32-column chunk of the stored values
   float2* rowstat_out;
   int rowstat_chunks;
+  // APTP_EPI_GN_STATS: per-channel column sums / sums of squares of every 32-row quadrant of the fp32 output
+  float* gn_sum;
+  float* gn_sq;
+  int gn_ld, gn_blocks;
   int* abort_flag;
 };
 
@@ -387,6 +391,20 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         co_row[it] = rr;
       }
       const int ocol_base = geglu ? tile.n0 / 2 : tile.n0;  // first OUTPUT column of this tile
+      // GroupNorm partial statistics: row of the partial planes this (tile, quadrant) owns
+      long long gn_row = -1;
+      if (!kGeglu && p.gn_sum != nullptr && !placeholder) {
+        const int smp = tile.m_base / p.rows_per_sample;
+        const int rem = tile.m_base - smp * p.rows_per_sample;
+        int t_in_s;
+        if (g.linear) {
+          t_in_s = rem >> 7;
+        } else {
+          const int oy0 = rem / p.Wo, ox0 = rem - oy0 * p.Wo;
+          t_in_s = (oy0 >> p.lbh) * (p.Wo >> p.lbw) + (ox0 >> p.lbw);
+        }
+        gn_row = ((long long)smp * p.gn_blocks + t_in_s * 4 + quad) * p.gn_ld;
+      }
 
       // residual of the first chunk goes in flight before we wait for the accumulator
       uint4 rres[4];
@@ -658,6 +676,34 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int it = 0; it < 4; ++it)
               if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o4[it];
+            if (gn_row >= 0) {
+              // column sums of the 32 rows of this quadrant over the lane's 4 columns: 4 rows in registers, then a
+              // fixed butterfly over the 8 lanes that share the column unit (lane bits 2..4)
+              float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                if (co_ok[it]) {
+                  const float f0 = __uint_as_float(o4[it].x), f1 = __uint_as_float(o4[it].y);
+                  const float f2 = __uint_as_float(o4[it].z), f3 = __uint_as_float(o4[it].w);
+                  cs[0] += f0; cs[1] += f1; cs[2] += f2; cs[3] += f3;
+                  cq[0] = fmaf(f0, f0, cq[0]); cq[1] = fmaf(f1, f1, cq[1]);
+                  cq[2] = fmaf(f2, f2, cq[2]); cq[3] = fmaf(f3, f3, cq[3]);
+                }
+              }
+#pragma unroll
+              for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
+                  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], o);
+                }
+              }
+              if (lane < 4 && col_ok) {
+                const long long gi = gn_row + seg.out_col_off + col0 + h * 16 + co_q * 4;
+                *reinterpret_cast<float4*>(p.gn_sum + gi) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+                *reinterpret_cast<float4*>(p.gn_sq + gi) = make_float4(cq[0], cq[1], cq[2], cq[3]);
+              }
+            }
             __syncwarp();
           }
           if (use_res32 && more) load_res32(col0 + 32 * EPI_PER_QUAD);  // after the stores: `residual` may alias `out`
@@ -720,7 +766,15 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
     APTP_REQUIRE(a->residual == nullptr || (a->out_mode == APTP_OUT_BF16 && a->res_ld % 8 == 0),
                  "aptp_grouped_gemm_fwd: a bf16 residual needs a bf16 output and res_ld %% 8 == 0");
   APTP_REQUIRE(a->a_rows < (1ll << 31), "aptp_grouped_gemm_fwd: too many rows");
-  APTP_REQUIRE(!(a->flags & APTP_EPI_GN_STATS), "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS not implemented yet");
+  if (a->flags & APTP_EPI_GN_STATS) {
+    APTP_REQUIRE(a->gn_stats && a->gn_stats_sq && a->out_mode == APTP_OUT_F32 && !(a->flags & APTP_EPI_GEGLU),
+                 "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS needs both partial planes and an fp32 row output");
+    APTP_REQUIRE(a->rows_per_sample % 128 == 0 && a->gn_blocks == a->rows_per_sample / 32 && a->gn_ld % 4 == 0,
+                 "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS needs rows_per_sample %% 128 == 0, gn_blocks = rows_per_sample / 32");
+    APTP_REQUIRE(a->a_mode == APTP_A_LINEAR || a->bb == 1, "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS needs conv boxes inside one image");
+    APTP_REQUIRE((reinterpret_cast<uintptr_t>(a->gn_stats) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->gn_stats_sq) & 15) == 0,
+                 "aptp_grouped_gemm_fwd: partial planes must be 16-byte aligned");
+  }
   if (a->flags & APTP_EPI_LN_FOLD) {
     APTP_REQUIRE(a->ln_colsum && a->ln_rowstats && a->bias && (reinterpret_cast<uintptr_t>(a->ln_rowstats) & 7) == 0,
                  "aptp_grouped_gemm_fwd: APTP_EPI_LN_FOLD needs ln_colsum, ln_rowstats and bias (= W @ beta + layer bias)");
@@ -816,6 +870,11 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   p.ln_rowstats = reinterpret_cast<const float2*>(a->ln_rowstats);
   p.rowstat_out = reinterpret_cast<float2*>(a->rowstat_out);
   p.rowstat_chunks = a->rowstat_chunks;
+  const bool gn = (a->flags & APTP_EPI_GN_STATS) != 0;
+  p.gn_sum = gn ? a->gn_stats : nullptr;
+  p.gn_sq = gn ? a->gn_stats_sq : nullptr;
+  p.gn_ld = a->gn_ld;
+  p.gn_blocks = a->gn_blocks;
   p.abort_flag = device_abort_flag();
   APTP_REQUIRE(p.abort_flag != nullptr, "aptp_grouped_gemm_fwd: could not allocate abort flag");
 

@@ -469,6 +469,46 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __
   }
 }
 
+// GroupNorm statistics from the per-channel partials written by GEMM epilogues (APTP_EPI_GN_STATS): one warp per
+// (sample, group) adds the group's (32-row block, channel) cells in a fixed order + a fixed shuffle tree. The partial
+// planes are 1/8 (fp32 stream: 1/16 per plane) of the tensor itself, so this replaces a full statistics pass over HBM.
+__global__ void __launch_bounds__(256)
+    gn_partials_finalize_kernel(const float* __restrict__ sum0, const float* __restrict__ sq0, int c0, int ld0,
+                                const float* __restrict__ sum1, const float* __restrict__ sq1, int ld1, int ctot_all,
+                                int blocks, int gs, const int* __restrict__ sample_channels, float* __restrict__ stats,
+                                int stats_groups) {
+  const int b = blockIdx.x;
+  const int ctot = sample_channels ? sample_channels[b] : ctot_all;
+  if (ctot <= 0) return;
+  const int groups = (ctot + gs - 1) / gs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.y * 8 + warp;
+  if (g >= groups) return;
+  const int c_lo = g * gs, width = min(ctot, c_lo + gs) - c_lo;
+  const int n_cells = blocks * width;
+  float a = 0.f, q = 0.f;
+  for (int i = lane; i < n_cells; i += 32) {
+    const int blk = i / width, c = c_lo + (i - blk * width);
+    const size_t row = (size_t)b * blocks + blk;
+    if (c < c0) {
+      a += __ldg(sum0 + row * ld0 + c);
+      q += __ldg(sq0 + row * ld0 + c);
+    } else {
+      a += __ldg(sum1 + row * ld1 + (c - c0));
+      q += __ldg(sq1 + row * ld1 + (c - c0));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    stats[((size_t)b * stats_groups + g) * 2] = a;
+    stats[((size_t)b * stats_groups + g) * 2 + 1] = q;
+  }
+}
+
 // LayerNorm row statistics for the LN-fold GEMM epilogue: (mean, rstd) of every row from the per-chunk (sum, sumsq)
 // partials the producing GEMM wrote, summed in chunk order (deterministic). One thread per row.
 __global__ void __launch_bounds__(256) ln_rowstats_kernel(const float2* __restrict__ partial, int chunks, long long rows,
@@ -550,6 +590,23 @@ extern "C" int aptp_groupnorm_stats(const void* x0, int32_t c0, int32_t ld0, con
   else
     gn_stats_kernel<false><<<grid, NORM_THREADS, smem, stream>>>(s, hw, group_size, sample_channels, stats,
                                                                 stats_groups, ppc, tickets, partial);
+  APTP_CUDA_CHECK(cudaGetLastError());
+  return APTP_OK;
+}
+
+extern "C" int aptp_groupnorm_stats_from_partials(const float* sum0, const float* sq0, int32_t c0, int32_t ld0,
+                                                  const float* sum1, const float* sq1, int32_t c1, int32_t ld1,
+                                                  int32_t blocks, int32_t batch, int32_t group_size,
+                                                  const int32_t* sample_channels, float* stats, int32_t stats_groups,
+                                                  void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(sum0 && sq0 && c0 > 0 && ld0 >= c0 && stats && blocks > 0 && batch > 0 && group_size > 0,
+               "aptp_groupnorm_stats_from_partials: bad arguments");
+  APTP_REQUIRE(c1 == 0 || (sum1 && sq1 && ld1 >= c1), "aptp_groupnorm_stats_from_partials: bad second source");
+  const int groups = (c0 + c1 + group_size - 1) / group_size;
+  APTP_REQUIRE(groups <= stats_groups, "aptp_groupnorm_stats_from_partials: stats_groups too small");
+  gn_partials_finalize_kernel<<<dim3(batch, (groups + 7) / 8), 256, 0, stream>>>(
+      sum0, sq0, c0, ld0, sum1, sq1, ld1, c0 + c1, blocks, group_size, sample_channels, stats, stats_groups);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

@@ -187,7 +187,7 @@ def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Sch
                  residual: Optional[torch.Tensor] = None, res_ld: int = 0, gate: Optional[torch.Tensor] = None,
                  gate_ld: int = 0, gate_group: int = 1, border_tab: Optional[torch.Tensor] = None, tab_ld: int = 0,
                  flags: int = 0, ln_colsum: Optional[torch.Tensor] = None, ln_rowstats: Optional[torch.Tensor] = None,
-                 rowstat_out: Optional[torch.Tensor] = None) -> None:
+                 rowstat_out: Optional[torch.Tensor] = None, colstat=None) -> None:
     """out = epilogue(A @ W^T) through aptp_grouped_gemm_fwd. `a`, `w`, `out` may be views: only
     data_ptr() and the explicit pitches are used."""
     if sched.n_tiles == 0:
@@ -204,7 +204,13 @@ def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Sch
     args.residual, args.res_ld = _ptr(residual), res_ld
     args.gate, args.gate_ld, args.gate_group = _ptr(gate), gate_ld, gate_group
     args.border_tab, args.tab_ld = _ptr(border_tab), tab_ld
-    args.gn_stats, args.gn_group, args.gn_groups = None, 0, 0
+    if colstat is not None:   # (sum plane, sumsq plane) [batch * blocks, ld] fp32, blocks = rows_per_sample / 32
+        cs_sum, cs_sq = colstat
+        args.gn_stats, args.gn_stats_sq = cs_sum.data_ptr(), cs_sq.data_ptr()
+        args.gn_ld, args.gn_blocks = cs_sum.shape[1], rows_per_sample // 32
+        flags |= _lib.EPI_GN_STATS
+    else:
+        args.gn_stats, args.gn_stats_sq, args.gn_ld, args.gn_blocks = None, None, 0, 0
     args.flags = flags | (_lib.EPI_LN_FOLD if ln_rowstats is not None else 0)
     args.ln_colsum, args.ln_rowstats = _ptr(ln_colsum), _ptr(ln_rowstats)   # ln_rowstats: [rows, 2] fp32 (mean, rstd)
     args.rowstat_out = _ptr(rowstat_out)                                     # [rows, C/32, 2] fp32 (sum, sumsq)
@@ -243,6 +249,14 @@ def groupnorm_stats(x0, c0, ld0, x1, c1, ld1, batch, hw, group_size, sample_chan
     check(lib.aptp_groupnorm_stats(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, int(x_f32), batch, hw, group_size,
                                    _ptr(sample_channels), _ptr(stats), stats_groups, ws.data_ptr(), ws.numel(),
                                    _stream()), "aptp_groupnorm_stats")
+
+
+def groupnorm_stats_from_partials(cs0, c0, cs1, c1, blocks, batch, group_size, sample_channels, stats, stats_groups):
+    """cs0 / cs1: (sum plane, sumsq plane) written by GEMM epilogues (grouped_gemm(colstat=...)); cs1 None = one source."""
+    check(load().aptp_groupnorm_stats_from_partials(
+        _ptr(cs0[0]), _ptr(cs0[1]), c0, cs0[0].shape[1], _ptr(cs1[0]) if cs1 else None, _ptr(cs1[1]) if cs1 else None,
+        c1, cs1[0].shape[1] if cs1 else 0, blocks, batch, group_size, _ptr(sample_channels), _ptr(stats), stats_groups,
+        _stream()), "aptp_groupnorm_stats_from_partials")
 
 
 def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps, stats, stats_groups, gamma, beta,

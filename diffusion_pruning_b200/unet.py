@@ -271,11 +271,14 @@ class Act:
     the residual stream of unet_2d_conditional.py:1629-1715) are kept in fp32 by the inference engine so the running
     residual sum is not re-rounded to bf16 at every block; a bf16 copy is made only where a GEMM
     reads the tensor directly. The training engine keeps bf16 rows throughout."""
-    __slots__ = ("t", "f", "B", "H", "W", "C", "ld")
+    __slots__ = ("t", "f", "B", "H", "W", "C", "ld", "cs")
 
-    def __init__(self, t, B, H, W, C, ld=None, f=None):
+    def __init__(self, t, B, H, W, C, ld=None, f=None, cs=None):
         self.t, self.f, self.B, self.H, self.W, self.C = t, f, B, H, W, C
         self.ld = ld if ld is not None else C
+        # (sum plane, sumsq plane) [B * H*W/32, C] fp32: per-channel GroupNorm partials written by the epilogue of the
+        # GEMM that produced `f` (APTP_EPI_GN_STATS), or None when the shape is not eligible
+        self.cs = cs
 
     @property
     def hw(self):
@@ -815,6 +818,8 @@ class _Engine:
         # most recently used code sets; older entries are dropped together with their device buffers.
         # APTP_LN_FOLD=0 keeps the three LayerNorms of a transformer block as separate HBM passes (A/B measurements)
         self.ln_fold = os.environ.get("APTP_LN_FOLD", "1") != "0"
+        # APTP_GN_EPI=0: GroupNorm statistics by the separate pass over HBM instead of the producing GEMM's epilogue
+        self.gn_epi = os.environ.get("APTP_GN_EPI", "1") != "0"
         self._states: "OrderedDict[Any, int]" = OrderedDict()
         self._esets: "OrderedDict[Any, int]" = OrderedDict()
         self._next_id = 0
@@ -1081,7 +1086,7 @@ class _Engine:
 
     def linear(self, name: str, lin: nn.Module, x: torch.Tensor, rows: int, k: int, ld: int, out: torch.Tensor,
                out_ld: int, hw: int, *, residual=None, res_ld=0, flags=0, active=None, out_mode=OUT_BF16,
-               n_out: Optional[int] = None, out_col_off: int = 0, rowstat_out=None):
+               n_out: Optional[int] = None, out_col_off: int = 0, rowstat_out=None, colstat=None):
         """Unpruned Linear / 1x1 conv over token rows (depth-dropped buckets skipped via `active`)."""
         d = self._dense_linear(name, lin)
         n = n_out if n_out is not None else lin.weight.shape[0]
@@ -1093,10 +1098,11 @@ class _Engine:
             return K.build_schedule(segs, bn, self.device)
         sched = self._sched(("lin", name, rows, hw), build)
         self._gemm(sched, x, d["w"], out, a_ld=ld, a_k=k, a_rows=rows, out_ld=out_ld, out_mode=out_mode, bias=d["b"],
-                   rows_per_sample=hw, residual=residual, res_ld=res_ld, flags=flags, rowstat_out=rowstat_out)
+                   rows_per_sample=hw, residual=residual, res_ld=res_ld, flags=flags, rowstat_out=rowstat_out,
+                   colstat=colstat)
 
     def conv3x3(self, name: str, conv: nn.Module, x: Act, out: torch.Tensor, out_ld: int, *, stride=1, out_mode=OUT_BF16,
-                n_pad_to=0):
+                n_pad_to=0, colstat=None):
         d = self._dense_linear(name, conv, n_pad_to=n_pad_to)
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
         Ho, Wo = x.H // stride, x.W // stride
@@ -1109,13 +1115,14 @@ class _Engine:
             return K.build_schedule(segs, bn, self.device, mode=mode, Ho=Ho, Wo=Wo)
         sched = self._sched(("conv", name, x.B, x.H, x.W), build)
         self._gemm(sched, x.t, d["w"], out, a_ld=x.ld, a_k=x.C, a_rows=x.rows, mode=mode, batch=x.B, H=x.H, W=x.W,
-                   k_tap_pitch=cin, out_ld=out_ld, out_mode=out_mode, bias=d["b"], rows_per_sample=Ho * Wo)
+                   k_tap_pitch=cin, out_ld=out_ld, out_mode=out_mode, bias=d["b"], rows_per_sample=Ho * Wo,
+                   colstat=colstat)
 
     # ---- group norm ------------------------------------------------------------------------------
     def groupnorm(self, x: torch.Tensor, C: int, ld: int, B: int, hw: int, groups_full: int, gs: int, eps: float,
                   gamma: torch.Tensor, beta: torch.Tensor, affine_ld: int, out: torch.Tensor, out_ld: int, silu: bool,
                   sample_seg=None, sample_channels=None, gate=None, x1: Optional[torch.Tensor] = None, c1: int = 0,
-                  ld1: int = 0, alg_elems: Optional[float] = None):
+                  ld1: int = 0, alg_elems: Optional[float] = None, cs0=None, cs1=None):
         """GroupNorm [+ soft width gate] [+ SiLU] -> bf16 rows. `x` (and the optional second source `x1` = the skip half
         of an up-block torch.cat) are bf16 or fp32 rows (dtype decides). Statistics: deterministic two-stage reduction
         (no atomics), see csrc/norm.cu."""
@@ -1123,14 +1130,43 @@ class _Engine:
         assert x1 is None or (x1.dtype == torch.float32) == f32
         stats = self.buf("gnstats", B, groups_full * 2, torch.float32)
         elems = float(alg_elems) if alg_elems is not None else float(B) * hw * (C + c1)
-        self._hbm(elems * (4 if f32 else 2), f"gn_stats C{C + c1} hw{hw} {'f32' if f32 else 'bf16'}",
-                  lambda: K.groupnorm_stats(x, C, ld, x1, c1, ld1, B, hw, gs, sample_channels, stats, groups_full,
-                                            x_f32=f32))
+        if cs0 is not None and (x1 is None or cs1 is not None):
+            # statistics from the partials the producing GEMMs' epilogues wrote: 1/4 of the tensor's bytes (two fp32
+            # planes of 1/32 of its rows) instead of a full pass
+            self._hbm(elems / 32 * 8, f"gn_stats_partials C{C + c1} hw{hw}",
+                      lambda: K.groupnorm_stats_from_partials(cs0, C, cs1, c1, hw // 32, B, gs, sample_channels, stats,
+                                                              groups_full))
+        else:
+            self._hbm(elems * (4 if f32 else 2), f"gn_stats C{C + c1} hw{hw} {'f32' if f32 else 'bf16'}",
+                      lambda: K.groupnorm_stats(x, C, ld, x1, c1, ld1, B, hw, gs, sample_channels, stats, groups_full,
+                                                x_f32=f32))
         self._hbm(elems * ((4 if f32 else 2) + 2), f"gn_apply C{C + c1} hw{hw} {'f32' if f32 else 'bf16'} silu{int(silu)}",
                   lambda: K.groupnorm_apply(x, C, ld, x1, c1, ld1, out, out_ld, B, hw, gs, eps, stats, groups_full, gamma,
                                             beta, affine_ld, sample_seg, sample_channels, gate,
                                             gate.stride(0) if gate is not None else groups_full, silu, x_f32=f32))
         self.launches += 2
+
+    def _colstat_new(self, B: int, H: int, W: int, C: int):
+        """Partial planes for a block output of shape [B, H, W, C] if its GroupNorm statistics can be gathered in the
+        producing GEMM's epilogue: every 128-row tile inside one sample."""
+        hw = H * W
+        if not self.gn_epi or hw % 128 != 0 or K.conv_box(W, H)[2] != 1:
+            return None
+        return (torch.empty(B * (hw // 32), C, device=self.device, dtype=torch.float32),
+                torch.empty(B * (hw // 32), C, device=self.device, dtype=torch.float32))
+
+    def _colstat_identity(self, cs_out, x: Act, keep_c: int, drop_mask, hw: int):
+        """Depth-dropped samples take the identity path (a row copy, no GEMM epilogue): their partial rows are copied from
+        the input's. Returns the planes, or None if the input has none."""
+        if cs_out is None or drop_mask is None:
+            return cs_out
+        if x.cs is None:
+            return None
+        nblk = hw // 32
+        for src, dst in zip(x.cs, cs_out):
+            K.copy_rows_cvt(src, src.shape[1], dst, dst.shape[1], src.shape[0], keep_c, drop_mask, nblk)
+        self.launches += 2
+        return cs_out
 
     def _bf16(self, x: Act) -> torch.Tensor:
         """bf16 rows of an fp32 stream tensor, for a GEMM that reads it directly (shortcut 1x1 conv, down-sampler)."""
@@ -1319,10 +1355,11 @@ class _Engine:
         a1 = self.buf("gn_a", M, r.cin)
         if skip is not None:
             self.groupnorm(x.f, x.C, x.C, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
-                           sample_channels=aux.get("ch_in"), x1=skip.f, c1=skip.C, ld1=skip.C, alg_elems=el_in)
+                           sample_channels=aux.get("ch_in"), x1=skip.f, c1=skip.C, ld1=skip.C, alg_elems=el_in,
+                           cs0=x.cs, cs1=skip.cs)
         else:
             self.groupnorm(x.f, x.C, x.C, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
-                           sample_channels=aux.get("ch_in"), alg_elems=el_in)
+                           sample_channels=aux.get("ch_in"), alg_elems=el_in, cs0=x.cs)
         # conv1 (N-compacted) + time embedding (+ conv1/time biases, folded into the row vector)
         h1 = self.buf("res_h1", M, r.cout)
 
@@ -1367,9 +1404,12 @@ class _Engine:
                                   tab_off=tab_off, active=active)
             return K.build_schedule(segs, bn, self.device, mode=A_CONV3X3, Ho=H, Wo=W)
         sched = self._sched(("res_c2", r.uid, H, W), build_c2)
+        cs_out = self._colstat_new(B, H, W, r.cout)
+        if cs_out is not None and self.compact and aux["drop_mask"] is not None and x.cs is None:
+            cs_out = None  # dropped samples would need the input's partial rows
         self._gemm(sched, a2, pk["w2"], out, a_ld=r.cout, a_k=r.cout, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W,
                    k_tap_pitch=r.cout, out_ld=r.cout, out_mode=OUT_F32, bias=pk["b2"], residual=res, res_ld=res_ld,
-                   flags=EPI_RES_F32, rows_per_sample=hw, border_tab=pk["tab"], tab_ld=r.cout)
+                   flags=EPI_RES_F32, rows_per_sample=hw, border_tab=pk["tab"], tab_ld=r.cout, colstat=cs_out)
         # depth gate: the non-skip part of the input is the identity branch (blocks.py:485-495)
         if r.depth_gate is not None:
             keep_c = x.C if skip is not None else x.C - (r.skip_connection_dim or 0)
@@ -1377,10 +1417,12 @@ class _Engine:
                 if aux["drop_mask"] is not None:  # dropped experts: identity on the (non-skip) input
                     K.copy_rows_cvt(x.f, x.C, out, r.cout, M, keep_c, aux["drop_mask"], hw)
                     self.launches += 1
+                    cs_out = self._colstat_identity(cs_out, x, keep_c, aux["drop_mask"], hw)
             else:
                 K.depth_lerp_f32(x.f, x.C, out, r.cout, out, r.cout, M, keep_c, self._soft_depth(cidx["d"]), hw)
                 self.launches += 1
-        return Act(None, B, H, W, r.cout, f=out)
+                cs_out = None  # the lerp changes the stored values after the epilogue gathered its statistics
+        return Act(None, B, H, W, r.cout, f=out, cs=cs_out)
 
     # ---- transformer -------------------------------------------------------------------------------
     @staticmethod
@@ -1625,7 +1667,7 @@ class _Engine:
         xn = self.buf("ln", M, C)
         n_act = float(active[self.layout.expert_of_pos].sum()) if self.compact else float(B)
         self.groupnorm(x.f, C, C, B, hw, t.groups, gs, 1e-6, dn["g"], dn["b"], C, xn, C, False,
-                       sample_channels=aux["ch"], alg_elems=n_act * hw * C)
+                       sample_channels=aux["ch"], alg_elems=n_act * hw * C, cs0=x.cs)
         tok = self.buf("tok", M, C)
         # LayerNorm statistics travel with the token stream: every GEMM that writes `tok` also writes per-row
         # (sum, sumsq) partials per 32-column chunk, and the three LayerNorms of the block (norm1/2/3, blocks.py:782,
@@ -1666,24 +1708,30 @@ class _Engine:
                    res_ld=C, rows_per_sample=hw)
         # proj_out + residual: back onto the fp32 stream
         out = torch.empty(M, C, device=self.device, dtype=torch.float32)
+        cs_out = self._colstat_new(B, H, W, C)
+        if cs_out is not None and self.compact and aux["drop"] is not None and x.cs is None:
+            cs_out = None
         self.linear("po." + t.uid, t.proj_out, tok, M, C, C, out, C, hw, residual=x.f, res_ld=C, active=active,
-                    out_mode=OUT_F32, flags=EPI_RES_F32)
+                    out_mode=OUT_F32, flags=EPI_RES_F32, colstat=cs_out)
         if t.depth_gate is not None:
             if self.compact:
                 if aux["drop"] is not None:
                     K.copy_rows_cvt(x.f, C, out, C, M, C, aux["drop"], hw)
                     self.launches += 1
+                    cs_out = self._colstat_identity(cs_out, x, C, aux["drop"], hw)
             else:
                 K.depth_lerp_f32(x.f, C, out, C, out, C, M, C, self._soft_depth(cidx["d"]), hw)
                 self.launches += 1
-        return Act(None, B, H, W, C, f=out)
+                cs_out = None
+        return Act(None, B, H, W, C, f=out, cs=cs_out)
 
     # ---- samplers ----------------------------------------------------------------------------------
     def downsample(self, s: _Sampler, x: Act) -> Act:
         out = torch.empty(x.rows // 4, x.C, device=self.device, dtype=torch.float32)
         x16 = Act(self._bf16(x), x.B, x.H, x.W, x.C)
-        self.conv3x3("ds.%d" % id(s), s.conv, x16, out, x.C, stride=2, out_mode=OUT_F32)
-        return Act(None, x.B, x.H // 2, x.W // 2, x.C, f=out)
+        cs = self._colstat_new(x.B, x.H // 2, x.W // 2, x.C)
+        self.conv3x3("ds.%d" % id(s), s.conv, x16, out, x.C, stride=2, out_mode=OUT_F32, colstat=cs)
+        return Act(None, x.B, x.H // 2, x.W // 2, x.C, f=out, cs=cs)
 
     def upsample(self, s: _Sampler, x: Act) -> Act:
         up = self.buf("up", x.rows * 4, x.C)
@@ -1691,8 +1739,9 @@ class _Engine:
         self.launches += 1
         xu = Act(up, x.B, x.H * 2, x.W * 2, x.C)
         out = torch.empty(xu.rows, x.C, device=self.device, dtype=torch.float32)
-        self.conv3x3("us.%d" % id(s), s.conv, xu, out, x.C, out_mode=OUT_F32)
-        return Act(None, xu.B, xu.H, xu.W, x.C, f=out)
+        cs = self._colstat_new(xu.B, xu.H, xu.W, x.C)
+        self.conv3x3("us.%d" % id(s), s.conv, xu, out, x.C, out_mode=OUT_F32, colstat=cs)
+        return Act(None, xu.B, xu.H, xu.W, x.C, f=out, cs=cs)
 
     # ---- CUDA-graph replay of the hard-gate forward -------------------------------------------------
     def run_graphed(self, sample: torch.Tensor, timestep, ctx: torch.Tensor, want_taps: bool = False):
@@ -1783,9 +1832,10 @@ class _Engine:
         x0 = torch.empty(B * H * W, c0, device=self.device, dtype=torch.float32)
         sched = self._sched(("conv_in", H, W), lambda: K.build_schedule(
             [K.Segment(0, B * H * W, c0, 1)], P.choose_bn([c0]), self.device))
+        cs0 = self._colstat_new(B, H, W, c0)
         self._gemm(sched, col, d["w"], x0, a_ld=64, a_k=64, a_rows=B * H * W, out_ld=c0, out_mode=OUT_F32, bias=d["b"],
-                   rows_per_sample=H * W)
-        x = Act(None, B, H, W, c0, f=x0)
+                   rows_per_sample=H * W, colstat=cs0)
+        x = Act(None, B, H, W, c0, f=x0, cs=cs0)
         skips = [x]
         tap_acts = []
         for blk in m.down_blocks:
@@ -1807,7 +1857,7 @@ class _Engine:
         groups = m.config["norm_num_groups"]
         a = self.buf("gn_a", x.rows, x.C)
         self.groupnorm(x.f, x.C, x.C, B, x.hw, groups, x.C // groups, m.config["norm_eps"], dn["g"], dn["b"], x.C, a,
-                       x.C, True)
+                       x.C, True, cs0=x.cs)
         cout = m.config["out_channels"]
         y = torch.empty(B, cout, x.H, x.W, device=self.device, dtype=torch.float32)
         dco = self._dense_linear("conv_out", m.conv_out, n_pad_to=32)

@@ -73,7 +73,7 @@ enum { APTP_OUT_BF16 = 0, APTP_OUT_F32 = 1, APTP_OUT_F32_NCHW = 2 };
 enum {
   APTP_EPI_GEGLU = 1,      /* tile columns are [bn/2 h | bn/2 g]; out = h * gelu_erf(g)            */
   APTP_EPI_SILU = 2,       /* out = silu(out) (time-embedding MLP)                                 */
-  APTP_EPI_GN_STATS = 4,   /* accumulate per-(sample,group) sum / sumsq of the stored values       */
+  APTP_EPI_GN_STATS = 4,   /* per-channel (sum, sumsq) partials of the stored fp32 rows, see gn_stats */
   APTP_EPI_RES_F32 = 8,    /* `residual` holds fp32 rows (fp32 residual stream); needs APTP_OUT_F32 */
   APTP_EPI_LN_FOLD = 16    /* LayerNorm of the A rows folded into this GEMM (see ln_* below)         */
 };
@@ -111,9 +111,17 @@ typedef struct aptp_gemm_args {
                               channels, which the *gated* reference still feeds as silu(beta_c)
                               (SURVEY Appendix D-1); [tab_off + (ycls*3+xcls)*tab_ld + col]        */
   int32_t tab_ld;
-  float* gn_stats;        /* APTP_EPI_GN_STATS: [sample][group][2] fp32 (sum, sumsq), atomics      */
-  int32_t gn_group;       /* channels per group                                                   */
-  int32_t gn_groups;      /* groups per sample in gn_stats                                        */
+  /* APTP_EPI_GN_STATS (needs APTP_OUT_F32): GroupNorm statistics of the tensor this GEMM writes, gathered in its
+   * epilogue so the consumer's statistics pass over HBM disappears. Every (tile, 32-row quadrant) writes the column
+   * sums / sums of squares of its 32 rows x N columns:
+   *   gn_stats   [ (sample * gn_blocks + blk) * gn_ld + out_col_off + col ] = sum over the 32 rows
+   *   gn_stats_sq[ same index ]                                              = sum of squares
+   * blk = (tile index inside the sample) * 4 + quadrant, gn_blocks = rows_per_sample / 32. Requires
+   * rows_per_sample % 128 == 0 and, for conv tiles, a box inside one image (bb == 1). No atomics: every entry has
+   * one writer; aptp_groupnorm_stats_from_partials reduces them per (sample, group) in a fixed order. */
+  float* gn_stats;
+  int32_t gn_ld;          /* floats per partial row (>= channels of the output tensor)              */
+  int32_t gn_blocks;      /* 32-row blocks per sample                                             */
   int32_t flags;          /* APTP_EPI_*                                                            */
   /* schedule (device memory) */
   const aptp_gemm_seg* segs;
@@ -134,6 +142,7 @@ typedef struct aptp_gemm_args {
   float ln_reserved2;
   float* rowstat_out;        /* float2 per (row, chunk) */
   int32_t rowstat_chunks;
+  float* gn_stats_sq;        /* APTP_EPI_GN_STATS: the sum-of-squares plane (same indexing as gn_stats) */
 } aptp_gemm_args;
 
 int aptp_grouped_gemm_fwd(const aptp_gemm_args* args, void* stream);
@@ -154,6 +163,13 @@ int aptp_groupnorm_stats(const void* x0, int32_t c0, int32_t ld0, const void* x1
                          int32_t x_f32, int32_t batch, int32_t hw, int32_t group_size,
                          const int32_t* sample_channels, float* stats, int32_t stats_groups, void* workspace,
                          int64_t workspace_bytes, void* stream);
+/* stats[sample][group] = (sum, sumsq) from the per-channel partials that GEMM epilogues wrote (APTP_EPI_GN_STATS):
+ * up to two sources (the halves of an up-block torch.cat) with their own partial planes [batch][blocks][ld]; group g
+ * covers concatenated channels [g*group_size, (g+1)*group_size). Fixed summation order (deterministic). */
+int aptp_groupnorm_stats_from_partials(const float* sum0, const float* sq0, int32_t c0, int32_t ld0, const float* sum1,
+                                       const float* sq1, int32_t c1, int32_t ld1, int32_t blocks, int32_t batch,
+                                       int32_t group_size, const int32_t* sample_channels, float* stats,
+                                       int32_t stats_groups, void* stream);
 /* y = [silu]( (x*g - mean)*rstd*gamma + beta ) written bf16 with row pitch ldy; channels in
  * [c_valid, c_store) are written as zeros. `sample_seg[b]` selects the per-expert compacted
  * gamma/beta block (offset sample_seg[b]*affine_ld) and c_valid (sample_channels[b]).

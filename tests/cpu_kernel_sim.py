@@ -51,7 +51,7 @@ def _check_tiles(sched: K.Schedule, mode, Ho, Wo, geglu):
 def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1, H=1, W=1, k_tap_pitch=0, out_ld,
                  out_mode=OUT_BF16, bias=None, rowvec=None, rowvec_ld=0, rows_per_sample=1, residual=None, res_ld=0,
                  gate=None, gate_ld=0, gate_group=1, border_tab=None, tab_ld=0, flags=0, ln_colsum=None, ln_rowstats=None,
-                 rowstat_out=None):
+                 rowstat_out=None, colstat=None):
     if sched.n_tiles == 0:
         return
     geglu = bool(flags & EPI_GEGLU)
@@ -146,6 +146,12 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
         elif out_mode == OUT_F32:
             O = _view(out, re, out_ld, out_ld)
             O[rb:re, oco:oco + nst] = acc[:, :nst]
+            if colstat is not None:  # per-channel partial sums of every 32-row block (block order differs from the
+                # device's tile / quadrant order for conv boxes; the consumer only sums over the blocks of a sample)
+                assert rows_per_sample % 128 == 0 and rb % rows_per_sample == 0
+                a32 = acc[:, :nst].reshape((re - rb) // 32, 32, nst)
+                colstat[0][rb // 32: re // 32, oco:oco + nst] = a32.sum(1)
+                colstat[1][rb // 32: re // 32, oco:oco + nst] = (a32 * a32).sum(1)
         else:
             nb = re // rows_per_sample
             O = torch.as_strided(out, (nb, out_ld, rows_per_sample), (out_ld * rows_per_sample, rows_per_sample, 1),
@@ -168,6 +174,22 @@ def groupnorm_stats(x0, c0, ld0, x1, c1, ld1, batch, hw, group_size, sample_chan
         xg = xb.reshape(hw, g, group_size)
         st[b, :g, 0] = xg.sum((0, 2))  # overwritten, not accumulated (deterministic two-stage reduction)
         st[b, :g, 1] = (xg * xg).sum((0, 2))
+
+
+def groupnorm_stats_from_partials(cs0, c0, cs1, c1, blocks, batch, group_size, sample_channels, stats, stats_groups):
+    S = cs0[0].view(batch, blocks, -1)[:, :, :c0].sum(1)
+    Q = cs0[1].view(batch, blocks, -1)[:, :, :c0].sum(1)
+    if cs1 is not None:
+        S = torch.cat([S, cs1[0].view(batch, blocks, -1)[:, :, :c1].sum(1)], 1)
+        Q = torch.cat([Q, cs1[1].view(batch, blocks, -1)[:, :, :c1].sum(1)], 1)
+    st = stats.view(batch, stats_groups, 2)
+    for b in range(batch):
+        ct = int(sample_channels[b]) if sample_channels is not None else S.shape[1]
+        if ct <= 0:
+            continue
+        g = (ct + group_size - 1) // group_size
+        st[b, :g, 0] = S[b, :ct].reshape(g, group_size).sum(1)
+        st[b, :g, 1] = Q[b, :ct].reshape(g, group_size).sum(1)
 
 
 def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps, stats, stats_groups, gamma, beta,
@@ -300,7 +322,7 @@ def check_abort():
 
 
 def install(monkeypatch):
-    for name in ("grouped_gemm", "groupnorm_stats", "groupnorm_apply", "layernorm", "ln_rowstats", "depth_lerp", "copy_rows",
+    for name in ("grouped_gemm", "groupnorm_stats", "groupnorm_stats_from_partials", "groupnorm_apply", "layernorm", "ln_rowstats", "depth_lerp", "copy_rows",
                  "copy_rows_cvt", "depth_lerp_f32", "upsample2x_cvt",
                  "upsample2x", "im2col_input", "timestep_embedding", "cast_f32_bf16", "silu_bf16", "attention",
                  "check_abort"):

@@ -457,6 +457,55 @@ def check_gemm_ln_fold(geglu=False, seed=0):
         _close(out, hg[:, :inner] * F.gelu(hg[:, inner:]), 5e-2, 3e-2, "ln-fold geglu")
 
 
+def check_gemm_colstat(conv=False, seed=0):
+    """APTP_EPI_GN_STATS: per-channel (sum, sumsq) partials of the fp32 output gathered in the GEMM epilogue, then reduced
+    per (sample, group) by aptp_groupnorm_stats_from_partials -- vs torch on the stored output (two-source cat case too)."""
+    B, H, W, Cin, Cout, bn = 3, 16, 16, 128, 320, 160
+    hw, M = H * W, 3 * 16 * 16
+    x = _rand(B, Cin, H, W, seed=seed).bfloat16()
+    a = x.permute(0, 2, 3, 1).reshape(M, Cin).contiguous()
+    res = _rand(M, Cout, seed=seed + 3) + 0.3
+    out = res.clone()
+    cs = (torch.full((B * hw // 32, Cout), float("nan"), device=DEV), torch.full((B * hw // 32, Cout), float("nan"), device=DEV))
+    b = _rand(Cout, seed=seed + 2)
+    if conv:
+        w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=seed + 1).bfloat16()
+        wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+        sched = K.build_schedule([K.Segment(0, M, Cout, Cin // 64)], bn, DEV, mode=A_CONV3X3, Ho=H, Wo=W)
+        K.grouped_gemm(a, wp, out, sched, a_ld=Cin, a_k=Cin, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W, k_tap_pitch=Cin,
+                       out_ld=Cout, out_mode=OUT_F32, bias=b, residual=out, res_ld=Cout, flags=EPI_RES_F32,
+                       rows_per_sample=hw, colstat=cs)
+    else:
+        w = _rand(Cout, Cin, scale=Cin ** -0.5, seed=seed + 1).bfloat16()
+        # two expert buckets with different kept widths are not needed here: the planes are per output column
+        sched = K.build_schedule([K.Segment(0, 2 * hw, Cout, Cin // 64), K.Segment(2 * hw, M, Cout, Cin // 64)], bn, DEV)
+        K.grouped_gemm(a, w, out, sched, a_ld=Cin, a_k=Cin, a_rows=M, out_ld=Cout, out_mode=OUT_F32, bias=b, residual=out,
+                       res_ld=Cout, flags=EPI_RES_F32, rows_per_sample=hw, colstat=cs)
+    K.check_abort()
+    o3 = out.reshape(B, hw, Cout)
+    _close(cs[0].reshape(B, hw // 32, Cout).sum(1), o3.sum(1), 2e-3, 1e-5, "column sums")
+    _close(cs[1].reshape(B, hw // 32, Cout).sum(1), (o3 * o3).sum(1), 2e-3, 1e-5, "column sums of squares")
+    # consumer side: one source, then [out | skip] as an up-block cat with groups straddling the boundary
+    groups = 32
+    stats = torch.full((B, groups, 2), float("nan"), device=DEV)
+    K.groupnorm_stats_from_partials(cs, Cout, None, 0, hw // 32, B, Cout // groups, None, stats, groups)
+    ref = torch.stack([o3.reshape(B, hw, groups, -1).sum((1, 3)), (o3 * o3).reshape(B, hw, groups, -1).sum((1, 3))], -1)
+    _close(stats, ref, 1e-2, 1e-5, "group statistics from partials")
+    skip = _rand(M, 160, seed=seed + 9)
+    s3 = skip.reshape(B, hw, 160)
+    cs1 = (s3.reshape(B, hw // 32, 32, 160).sum(2).reshape(-1, 160).contiguous(),
+           (s3 * s3).reshape(B, hw // 32, 32, 160).sum(2).reshape(-1, 160).contiguous())
+    gs = (Cout + 160) // groups   # 15: groups straddle the 320 | 160 boundary
+    ch = torch.tensor([Cout + 160, 0, Cout + 160], device=DEV, dtype=torch.int32)
+    stats2 = torch.full((B, groups, 2), -7.0, device=DEV)
+    K.groupnorm_stats_from_partials(cs, Cout, cs1, 160, hw // 32, B, gs, ch, stats2, groups)
+    cat = torch.cat([o3, s3], 2)
+    ref2 = torch.stack([cat.reshape(B, hw, groups, gs).sum((1, 3)), (cat * cat).reshape(B, hw, groups, gs).sum((1, 3))], -1)
+    _close(stats2[0], ref2[0], 1e-2, 1e-5, "two-source group statistics")
+    _close(stats2[2], ref2[2], 1e-2, 1e-5, "two-source group statistics")
+    assert (stats2[1] == -7.0).all(), "samples with zero channels are skipped"
+
+
 def check_attention(B=2, heads=3, kept=(3, 1), Nq=256, Nkv=256, seed=0):
     C = heads * 64
     q = _rand(B * Nq, C, seed=seed).bfloat16()
@@ -529,6 +578,8 @@ ALL = [
     ("groupnorm_big", lambda: check_groupnorm(B=8, HW=4096, C0=320)),
     ("stream_f32", check_stream_f32),
     ("gemm_res_f32", check_gemm_res_f32),
+    ("gemm_colstat", check_gemm_colstat),
+    ("conv_colstat", lambda: check_gemm_colstat(conv=True)),
     ("gemm_ln_fold", check_gemm_ln_fold),
     ("gemm_ln_fold_geglu", lambda: check_gemm_ln_fold(geglu=True)),
     ("conv_res_f32", lambda: check_gemm_res_f32(conv=True)),
