@@ -41,7 +41,7 @@ class GemmArgs(C.Structure):
         ("ln_colsum", c_void_p), ("ln_rowstats", c_void_p), ("ln_reserved0", c_int), ("ln_reserved1", c_int),
         ("ln_reserved2", c_float),
         ("rowstat_out", c_void_p), ("rowstat_chunks", c_int),
-        ("gn_stats_sq", c_void_p),
+        ("gn_stats_sq", c_void_p), ("a_stat_chunks", c_int), ("a_stat_pairs", c_int),
     ]
 
 
@@ -56,6 +56,7 @@ SIGNATURES = {
     "aptp_check_abort": (c_int, [c_void_p]),
     "aptp_poll_abort": (c_int, [c_void_p]),
     "aptp_grouped_gemm_fwd": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "aptp_gemm_max_pairs": (c_int, []),
     "aptp_groupnorm_stats_workspace": (c_int64, [c_int, c_int, c_int]),
     "aptp_groupnorm_stats": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p]),

@@ -72,8 +72,15 @@ struct GemmParams {
   float* gn_sum;
   float* gn_sq;
   int gn_ld, gn_blocks;
+  // A-stationary mode (linear layers with K <= 6 chunks, i.e. the K = 320 projections of the 64x64 level, which are
+  // bound by the L2 -> shared-memory fill, not by the tensor pipe): the host lays the tile list out so that every CTA
+  // pair walks all N tiles of one pair of row tiles back to back; the A row tile (128 x K) is loaded ONCE per run
+  // (tile flag APTP_TILE_A_FIRST) into a resident region, only the weight tiles stream through the stage ring
+  int a_stat;        // 0, or the number of resident A chunk slots
   int* abort_flag;
 };
+
+constexpr int A_STAT_MAX_CHUNKS = 6;
 
 __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int stages) {
   if (++stage == stages) {
@@ -164,15 +171,19 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
-  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.bn * 128u;
-  uint8_t* stg_base = smem + (size_t)stages * stage_bytes;
+  // normal mode: ring of (A tile | B tile) stages; A-stationary: a_stat resident A chunk slots, then a ring of B tiles
+  const uint32_t stage_bytes = (p.a_stat ? 0u : (uint32_t)A_STAGE_BYTES) + (uint32_t)p.bn * 128u;
+  const uint32_t ring_off = (uint32_t)p.a_stat * A_STAGE_BYTES;
+  uint8_t* stg_base = smem + ring_off + (size_t)stages * stage_bytes;
   float* sbias = reinterpret_cast<float*>(stg_base + STG_BYTES);
   aptp_gemm_seg* ssegs = reinterpret_cast<aptp_gemm_seg*>(stg_base + STG_BYTES + SBIAS_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES + SBIAS_BYTES + SSEG_BYTES);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* afull_bar = tempty_bar + 2;                   // A-stationary: one pair of barriers per resident A chunk
+  uint64_t* aempty_bar = afull_bar + A_STAT_MAX_CHUNKS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + A_STAT_MAX_CHUNKS);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -201,6 +212,10 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
         mbar_init(&tempty_bar[a], EPI_WARPS);
+      }
+      for (int a = 0; a < A_STAT_MAX_CHUNKS; ++a) {
+        mbar_init(&afull_bar[a], 1);
+        mbar_init(&aempty_bar[a], 1);
       }
       fence_barrier_init();
     }
@@ -233,10 +248,45 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int taps = (p.a_mode == APTP_A_LINEAR) ? 1 : 9;
       aptp_gemm_tile tile_next = p.tiles[2 * pair0 + cta_rank];  // grid/2 <= n_pairs
       const uint32_t b_half_bytes = (uint32_t)p.bn * 64u;          // bn/2 weight rows x 128 B
+      uint32_t a_bits = 0;  // A-stationary: bit kc = parity of the uses of resident chunk kc (runs may differ in K)
       for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride) {
         const aptp_gemm_tile tile = tile_next;
         if (pr + pair_stride < n_pairs) tile_next = p.tiles[2 * (pr + pair_stride) + cta_rank];  // in flight
+        if (tile.flags & APTP_TILE_SKIP) continue;
         const aptp_gemm_seg seg = segs[tile.seg];
+        if (p.a_stat) {
+          const int b_row = seg.w_row_off + tile.n0 + (int)cta_rank * (p.bn >> 1);
+          if (tile.flags & APTP_TILE_A_FIRST) {
+            // the A row tile of this run: chunk kc may be overwritten as soon as the previous run's last N tile has
+            // consumed it (per-chunk barriers, so the refill trails the tensor pipe chunk by chunk)
+            for (int kc = 0; kc < seg.k_chunks && ok; ++kc) {
+              if (!mbar_wait(&aempty_bar[kc], ((a_bits >> kc) & 1u) ^ 1u, p.abort_flag)) {
+                ok = false;
+                break;
+              }
+              a_bits ^= 1u << kc;
+              if (elect_one()) {
+                mbar_expect_tx(&afull_bar[kc], A_STAGE_BYTES);
+                tma_load_2d(smem + (size_t)kc * A_STAGE_BYTES, &p.tmap_a, &afull_bar[kc], kc * BK, tile.m_base);
+              }
+              __syncwarp();
+            }
+          }
+          for (int kc = 0; kc < seg.k_chunks && ok; ++kc) {
+            if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.abort_flag)) {
+              ok = false;
+              break;
+            }
+            if (elect_one()) {
+              uint8_t* sb = smem + ring_off + (size_t)stage * stage_bytes;
+              mbar_expect_tx(&full_bar[stage], stage_bytes);
+              tma_load_2d_mc(sb + cta_rank * b_half_bytes, &p.tmap_b, &full_bar[stage], kc * BK, b_row, (uint16_t)0x3);
+            }
+            __syncwarp();
+            advance(stage, phase, stages);
+          }
+          continue;
+        }
         int img = 0, oy0 = 0, ox0 = 0;
         if (p.a_mode != APTP_A_LINEAR) {
           const int hw = p.Ho * p.Wo;
@@ -293,14 +343,55 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       uint32_t acc_phase = 0;
       bool ok = true;
       int seg_next = p.tiles[2 * pair0 + cta_rank].seg;
+      int flags_next = p.tiles[2 * pair0 + cta_rank].flags;
+      uint32_t a_bits = 0;
       for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride) {
         const int seg_id = __shfl_sync(0xffffffffu, seg_next, 0);
-        if (pr + pair_stride < n_pairs) seg_next = p.tiles[2 * (pr + pair_stride) + cta_rank].seg;
+        const int tflags = __shfl_sync(0xffffffffu, flags_next, 0);
+        if (pr + pair_stride < n_pairs) {
+          seg_next = p.tiles[2 * (pr + pair_stride) + cta_rank].seg;
+          flags_next = p.tiles[2 * (pr + pair_stride) + cta_rank].flags;
+        }
+        if (tflags & APTP_TILE_SKIP) continue;
         const int k_chunks = __shfl_sync(0xffffffffu, segs[seg_id].k_chunks, 0);
         const int kblocks = ((p.a_mode == APTP_A_LINEAR) ? 1 : 9) * k_chunks;
         if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
+        if (p.a_stat) {
+          const bool first = (tflags & APTP_TILE_A_FIRST) != 0, last = (tflags & APTP_TILE_A_LAST) != 0;
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            if (first) {
+              if (!mbar_wait(&afull_bar[kc], (a_bits >> kc) & 1u, p.abort_flag)) {
+                ok = false;
+                break;
+              }
+              a_bits ^= 1u << kc;
+            }
+            if (!mbar_wait(&full_bar[stage], phase, p.abort_flag)) {
+              ok = false;
+              break;
+            }
+            tc_fence_after();
+            const uint64_t da = make_desc_kmajor_sw128(smem_base + (uint32_t)kc * A_STAGE_BYTES);
+            const uint64_t db = make_desc_kmajor_sw128(smem_base + ring_off + (uint32_t)stage * stage_bytes);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);
+              if (last) umma_commit(&aempty_bar[kc]);  // the run's last N tile: chunk kc may be refilled
+            }
+            __syncwarp();
+            advance(stage, phase, stages);
+          }
+          if (!ok) break;
+          if (elect_one()) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          continue;
+        }
         for (int kb = 0; kb < kblocks; ++kb) {
           if (!mbar_wait(&full_bar[stage], phase, p.abort_flag)) {
             ok = false;
@@ -356,6 +447,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
     for (int pr = pair0; pr < n_pairs; pr += pair_stride) {
       const aptp_gemm_tile tile = tile_next;
       if (pr + pair_stride < n_pairs) tile_next = p.tiles[2 * (pr + pair_stride) + cta_rank];
+      if (tile.flags & APTP_TILE_SKIP) continue;  // padding entry of an A-stationary tile list
       const aptp_gemm_seg seg = segs[tile.seg];
       const bool placeholder = (tile.flags & APTP_TILE_PLACEHOLDER) != 0;  // odd tile count of a bucket: no stores
       TileGeom g;
@@ -745,6 +837,36 @@ static int g_gemm_max_clusters = 0;
 
 using namespace aptp;
 
+static int gemm_max_clusters() {
+  if (!g_gemm_smem_set) {
+    if (cudaFuncSetAttribute(grouped_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(grouped_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return 0;
+    g_gemm_smem_set = 1;
+  }
+  if (!g_gemm_max_clusters) {
+    // CTA pairs must land on one GPC: the number of co-resident pairs can be below sm_count()/2
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(sm_count() & ~1, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 227 * 1024;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, grouped_gemm_kernel<false>, &cfg) != cudaSuccess || n <= 0) return 0;
+    g_gemm_max_clusters = n;
+  }
+  return g_gemm_max_clusters;
+}
+
+extern "C" int aptp_gemm_max_pairs(void) { return gemm_max_clusters(); }
+
 extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   APTP_REQUIRE(a != nullptr, "aptp_grouped_gemm_fwd: null args");
@@ -878,39 +1000,29 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   p.abort_flag = device_abort_flag();
   APTP_REQUIRE(p.abort_flag != nullptr, "aptp_grouped_gemm_fwd: could not allocate abort flag");
 
-  const int stage_bytes = A_STAGE_BYTES + a->bn * 128;
-  const int budget = 225 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - STG_BYTES /*epilogue staging*/ - SBIAS_BYTES - SSEG_BYTES;
+  p.a_stat = 0;
+  if (a->a_stat_chunks > 0) {
+    APTP_REQUIRE(a->a_mode == APTP_A_LINEAR && a->a_stat_chunks <= A_STAT_MAX_CHUNKS,
+                 "aptp_grouped_gemm_fwd: A-stationary mode needs a linear layer with at most %d K chunks", A_STAT_MAX_CHUNKS);
+    p.a_stat = a->a_stat_chunks;
+  }
+  const int stage_bytes = (p.a_stat ? 0 : A_STAGE_BYTES) + a->bn * 128;
+  const int budget = 225 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STG_BYTES /*epilogue staging*/ - SBIAS_BYTES -
+                     SSEG_BYTES - p.a_stat * A_STAGE_BYTES;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   APTP_REQUIRE(stages >= 2, "aptp_grouped_gemm_fwd: tile too large for shared memory");
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + STG_BYTES + SBIAS_BYTES + SSEG_BYTES + 1024 + 256;
-  if (!g_gemm_smem_set) {
-    APTP_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    APTP_CUDA_CHECK(cudaFuncSetAttribute(grouped_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    g_gemm_smem_set = 1;
-  }
-  if (!g_gemm_max_clusters) {
-    // CTA pairs must land on one GPC: the number of co-resident pairs can be below sm_count()/2
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(sm_count() & ~1, 1, 1);
-    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = 227 * 1024;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    APTP_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, grouped_gemm_kernel<false>, &cfg));
-    APTP_REQUIRE(n > 0, "aptp_grouped_gemm_fwd: no CTA pair fits on this device");
-    g_gemm_max_clusters = n;
-  }
+  const size_t smem_bytes = (size_t)p.a_stat * A_STAGE_BYTES + (size_t)stages * stage_bytes + STG_BYTES + SBIAS_BYTES +
+                            SSEG_BYTES + 1024 + 512;
+  APTP_REQUIRE(gemm_max_clusters() > 0, "aptp_grouped_gemm_fwd: no CTA pair fits on this device");
   const int n_pairs = a->n_tiles / 2;
-  const int grid = 2 * (n_pairs < g_gemm_max_clusters ? n_pairs : g_gemm_max_clusters);
+  int grid = 2 * (n_pairs < g_gemm_max_clusters ? n_pairs : g_gemm_max_clusters);
+  if (p.a_stat) {  // the tile list was laid out for exactly a_stat_pairs CTA pairs (entry c + j * pairs belongs to pair c)
+    APTP_REQUIRE(a->a_stat_pairs > 0 && a->a_stat_pairs <= g_gemm_max_clusters && n_pairs % a->a_stat_pairs == 0,
+                 "aptp_grouped_gemm_fwd: A-stationary tile list needs 0 < a_stat_pairs <= %d dividing the pair count", g_gemm_max_clusters);
+    grid = 2 * a->a_stat_pairs;
+  }
   if (a->flags & APTP_EPI_GEGLU)
     grouped_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
   else

@@ -475,37 +475,45 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __
 __global__ void __launch_bounds__(256)
     gn_partials_finalize_kernel(const float* __restrict__ sum0, const float* __restrict__ sq0, int c0, int ld0,
                                 const float* __restrict__ sum1, const float* __restrict__ sq1, int ld1, int ctot_all,
-                                int blocks, int gs, const int* __restrict__ sample_channels, float* __restrict__ stats,
-                                int stats_groups) {
+                                int blocks, int gs, int groups_per_cta, const int* __restrict__ sample_channels,
+                                float* __restrict__ stats, int stats_groups) {
+  // thread = one channel (coalesced walks down the 32-row blocks), then one thread per group adds its gs channel
+  // totals in channel order: every sum has a fixed order
+  __shared__ float ssum[256], ssq[256];
   const int b = blockIdx.x;
   const int ctot = sample_channels ? sample_channels[b] : ctot_all;
   if (ctot <= 0) return;
   const int groups = (ctot + gs - 1) / gs;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.y * 8 + warp;
-  if (g >= groups) return;
-  const int c_lo = g * gs, width = min(ctot, c_lo + gs) - c_lo;
-  const int n_cells = blocks * width;
+  const int g0 = blockIdx.y * groups_per_cta;
+  if (g0 >= groups) return;
+  const int c = g0 * gs + threadIdx.x;
   float a = 0.f, q = 0.f;
-  for (int i = lane; i < n_cells; i += 32) {
-    const int blk = i / width, c = c_lo + (i - blk * width);
-    const size_t row = (size_t)b * blocks + blk;
+  if (threadIdx.x < groups_per_cta * gs && c < ctot) {
+    const float* ps;
+    const float* pq;
+    int ld;
     if (c < c0) {
-      a += __ldg(sum0 + row * ld0 + c);
-      q += __ldg(sq0 + row * ld0 + c);
+      ps = sum0 + c; pq = sq0 + c; ld = ld0;
     } else {
-      a += __ldg(sum1 + row * ld1 + (c - c0));
-      q += __ldg(sq1 + row * ld1 + (c - c0));
+      ps = sum1 + (c - c0); pq = sq1 + (c - c0); ld = ld1;
+    }
+    const size_t row0 = (size_t)b * blocks;
+    for (int blk = 0; blk < blocks; ++blk) {
+      a += __ldg(ps + (row0 + blk) * ld);
+      q += __ldg(pq + (row0 + blk) * ld);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-  if (lane == 0) {
-    stats[((size_t)b * stats_groups + g) * 2] = a;
-    stats[((size_t)b * stats_groups + g) * 2 + 1] = q;
+  ssum[threadIdx.x] = a;
+  ssq[threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < groups_per_cta && g0 + threadIdx.x < groups) {
+    float ga = 0.f, gq = 0.f;
+    for (int e = 0; e < gs; ++e) {
+      ga += ssum[threadIdx.x * gs + e];
+      gq += ssq[threadIdx.x * gs + e];
+    }
+    stats[((size_t)b * stats_groups + g0 + threadIdx.x) * 2] = ga;
+    stats[((size_t)b * stats_groups + g0 + threadIdx.x) * 2 + 1] = gq;
   }
 }
 
@@ -605,8 +613,10 @@ extern "C" int aptp_groupnorm_stats_from_partials(const float* sum0, const float
   APTP_REQUIRE(c1 == 0 || (sum1 && sq1 && ld1 >= c1), "aptp_groupnorm_stats_from_partials: bad second source");
   const int groups = (c0 + c1 + group_size - 1) / group_size;
   APTP_REQUIRE(groups <= stats_groups, "aptp_groupnorm_stats_from_partials: stats_groups too small");
-  gn_partials_finalize_kernel<<<dim3(batch, (groups + 7) / 8), 256, 0, stream>>>(
-      sum0, sq0, c0, ld0, sum1, sq1, ld1, c0 + c1, blocks, group_size, sample_channels, stats, stats_groups);
+  APTP_REQUIRE(group_size <= 256, "aptp_groupnorm_stats_from_partials: group_size %d > 256", group_size);
+  const int gpc = 256 / group_size;  // whole groups per CTA
+  gn_partials_finalize_kernel<<<dim3(batch, (groups + gpc - 1) / gpc), 256, 0, stream>>>(
+      sum0, sq0, c0, ld0, sum1, sq1, ld1, c0 + c1, blocks, group_size, gpc, sample_channels, stats, stats_groups);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

@@ -6,6 +6,7 @@ hand-written kernel from libaptp_sm100.so and raises if the library is missing.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -18,7 +19,19 @@ from ._lib import (A_CONV3X3, A_CONV3X3_S2, A_LINEAR, EPI_GEGLU, EPI_SILU, OUT_B
 
 BM = 128
 BK = 64
-TILE_PLACEHOLDER = 1  # APTP_TILE_PLACEHOLDER
+TILE_PLACEHOLDER, TILE_A_FIRST, TILE_A_LAST, TILE_SKIP = 1, 2, 4, 8  # APTP_TILE_*
+A_STAT_MAX_CHUNKS = 6
+_MAX_PAIRS = {}
+
+
+def gemm_max_pairs() -> int:
+    """Co-resident CTA pairs of the GEMM kernel on the current device (aptp_gemm_max_pairs), cached."""
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    v = _MAX_PAIRS.get(dev)
+    if v is None:
+        v = int(load().aptp_gemm_max_pairs()) if dev >= 0 else 74
+        _MAX_PAIRS[dev] = v
+    return v
 
 
 def _stream() -> int:
@@ -68,6 +81,8 @@ class Schedule:
     n_tiles: int
     bn: int
     box: tuple           # (bw, bh, bb)
+    a_stat: int = 0      # > 0: A-stationary tile list (resident A chunk slots = max k_chunks), see build_schedule
+    a_pairs: int = 0     # CTA pairs that list was laid out for
     flops: float = 0.0   # 2 * kept MACs of this launch (for roofline accounting)
     bytes_in: float = 0.0   # algorithmic operand bytes: kept A rows x kept K + kept weight block (bf16), read once
     out_elems: float = 0.0  # output elements written (x2 / x4 bytes by output type; same count for a residual read)
@@ -125,7 +140,9 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
                    geglu: bool = False, taps: Optional[int] = None) -> Schedule:
     """Enumerate tiles (m outer, n inner so concurrently running CTAs share the A tile in L2)."""
     segs = np.zeros((max(len(segments), 1), 12), dtype=np.int32)
-    tiles: List[np.ndarray] = []
+    runs: List[np.ndarray] = []
+    by_rows = {}
+    kc_max = 0
     box = (BM, 1, 1) if mode == A_LINEAR else conv_box(Wo, Ho)
     bw, bh, bb = box
     hw = Ho * Wo
@@ -173,11 +190,50 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
         blk[..., 3] = 0
         if odd:
             blk[n_pairs - 1, :, 1, 3] = TILE_PLACEHOLDER
-        tiles.append(blk.reshape(-1, 4))
-    tl = np.concatenate(tiles, 0) if tiles else np.zeros((0, 4), dtype=np.int32)
+        # segments over the SAME rows (the q | k | v blocks of one expert bucket) share their A row tiles: their N tiles
+        # are walked back to back per pair of row tiles, so A is fetched from DRAM once instead of once per block
+        key = (s.row_begin, s.row_end) if mode == A_LINEAR else None
+        prev = by_rows.get(key) if key is not None else None
+        if prev is not None and runs[prev].shape[0] == blk.shape[0]:
+            runs[prev] = np.concatenate([runs[prev], blk], axis=1)
+        else:
+            if key is not None:
+                by_rows[key] = len(runs)
+            runs.append(blk)
+        kc_max = max(kc_max, s.k_chunks)
+    a_stat = a_pairs = 0
+    # (opt-in: measured neutral on B200 -- 53.6 ms per step either way, profiles/README.md round 2: the K = 320 layers
+    # are bound by the per-tile hand-offs of the issuing warp, not by the L2 -> shared-memory fill)
+    if (mode == A_LINEAR and runs and 0 < kc_max <= A_STAT_MAX_CHUNKS and os.environ.get("APTP_A_STAT", "0") != "0"
+            and max(r.shape[1] for r in runs) >= 2
+            and (torch.device(device).type == "cuda" or os.environ.get("APTP_A_STAT") == "force")):
+        # A-stationary layout: the K <= 384 projections are bound by the L2 -> shared-memory fill, so every CTA pair
+        # walks ALL N tiles of one pair of row tiles back to back and keeps the A row tile resident. Runs are dealt
+        # round-robin to the S pairs of the grid; pair c consumes entries c, c + S, c + 2S, ...
+        n_n = np.concatenate([np.full(r.shape[0], r.shape[1], dtype=np.int64) for r in runs])   # N tiles per run
+        n_runs = len(n_n)
+        S = min(n_runs, gemm_max_pairs())
+        R = (n_runs + S - 1) // S
+        nn_pad = np.zeros(R * S, dtype=np.int64)
+        nn_pad[:n_runs] = n_n
+        off = (np.cumsum(nn_pad.reshape(R, S), axis=0) - nn_pad.reshape(R, S)).reshape(-1)[:n_runs]  # entries before it
+        max_len = int((np.cumsum(nn_pad.reshape(R, S), axis=0)[-1]).max())
+        ent = np.concatenate([r.reshape(-1, 2, 4) for r in runs], 0)            # [entries, 2, 4] in run-major order
+        run_of = np.repeat(np.arange(n_runs), n_n)
+        first_ent = np.cumsum(n_n) - n_n
+        nt = np.arange(len(run_of)) - first_ent[run_of]
+        ent[nt == 0, :, 3] |= TILE_A_FIRST
+        ent[nt == n_n[run_of] - 1, :, 3] |= TILE_A_LAST
+        out_t = np.zeros((max_len * S, 2, 4), dtype=np.int32)
+        out_t[:, :, 3] = TILE_SKIP
+        out_t[(off[run_of] + nt) * S + (run_of % S)] = ent
+        tl = out_t.reshape(-1, 4)
+        a_stat, a_pairs = int(kc_max), int(S)
+    else:
+        tl = np.concatenate([r.reshape(-1, 4) for r in runs], 0) if runs else np.zeros((0, 4), dtype=np.int32)
     return Schedule(segs=upload(segs, device), tiles=upload(tl, device),
-                    n_segs=len(segments), n_tiles=int(tl.shape[0]), bn=bn, box=box, flops=flops, bytes_in=bytes_in,
-                    out_elems=out_elems)
+                    n_segs=len(segments), n_tiles=int(tl.shape[0]), bn=bn, box=box, a_stat=a_stat, a_pairs=a_pairs,
+                    flops=flops, bytes_in=bytes_in, out_elems=out_elems)
 
 
 def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Schedule, *, a_ld: int, a_k: int,
@@ -215,6 +271,7 @@ def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Sch
     args.ln_colsum, args.ln_rowstats = _ptr(ln_colsum), _ptr(ln_rowstats)   # ln_rowstats: [rows, 2] fp32 (mean, rstd)
     args.rowstat_out = _ptr(rowstat_out)                                     # [rows, C/32, 2] fp32 (sum, sumsq)
     args.rowstat_chunks = rowstat_out.shape[1] if rowstat_out is not None else 0
+    args.a_stat_chunks, args.a_stat_pairs = sched.a_stat, sched.a_pairs
     args.segs, args.n_segs = sched.segs.data_ptr(), sched.n_segs
     args.tiles, args.n_tiles = sched.tiles.data_ptr(), sched.n_tiles
     check(load().aptp_grouped_gemm_fwd(C.byref(args), _stream()), "aptp_grouped_gemm_fwd")

@@ -29,17 +29,31 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
-def choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False) -> int:
-    """Accumulator width minimising padded MMA work over the experts' kept widths; narrow tiles are
-    penalised because A is re-read from shared memory once per tile column block."""
+def choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False, k: int = 0) -> int:
+    """Accumulator width for one launch: the candidate with the fewest padded MMA columns, small widths penalised for
+    their worse operand reuse. An alternative model that also charges a fixed per-tile cost of the issuing warp (so
+    short-K layers get few, wide tiles; `k` = reduction length) is kept behind APTP_BN_MODEL=1 for experiments only: a
+    same-box A/B on the headline step measured it SLOWER (55.9 / 56.1 ms vs 53.7 / 53.4 ms, GEMM time 38.8 vs 34.6 ms)
+    -- wide tiles halve the tile count of the short launches, and the load imbalance over 74 CTA pairs costs more than
+    the per-tile overhead saved (profiles/README.md, round 2)."""
+    import os
     cands = [256, 224, 192, 160, 128, 96, 64]
     if geglu:
         cands = [256, 192, 128]
+    if k <= 0 or os.environ.get("APTP_BN_MODEL", "0") != "1":
+        best, best_cost = None, None
+        for bn in cands:
+            cols = bn // 2 if geglu else bn
+            pen = 1.0 if bn >= 160 else (1.08 if bn >= 128 else (1.25 if bn >= 96 else 1.5))
+            cost = sum(((n + cols - 1) // cols) * cols for n in n_values if n > 0) * pen
+            if best_cost is None or cost < best_cost - 1e-9:
+                best, best_cost = bn, cost
+        return best or 128
+    overhead_cols = 2000.0 * 32.0 / max(k, 32)
     best, best_cost = None, None
     for bn in cands:
         cols = bn // 2 if geglu else bn
-        pen = 1.0 if bn >= 160 else (1.08 if bn >= 128 else (1.25 if bn >= 96 else 1.5))
-        cost = sum(((n + cols - 1) // cols) * cols for n in n_values if n > 0) * pen
+        cost = sum(((n + cols - 1) // cols) * (bn + overhead_cols) for n in n_values if n > 0)
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = bn, cost
     return best or 128

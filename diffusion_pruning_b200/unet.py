@@ -1093,7 +1093,7 @@ class _Engine:
         E = self.eset.n_experts if self.compact else 1
 
         def build():
-            bn = P.choose_bn([n])
+            bn = P.choose_bn([n], k=k)
             segs = self._segments(hw, [n] * E, [(k + 63) // 64] * E, [0] * E, active=active, out_col_off=out_col_off)
             return K.build_schedule(segs, bn, self.device)
         sched = self._sched(("lin", name, rows, hw), build)
@@ -1110,7 +1110,7 @@ class _Engine:
         E = self.eset.n_experts if self.compact else 1
 
         def build():
-            bn = P.choose_bn([max(cout, 32)])
+            bn = P.choose_bn([max(cout, 32)], k=9 * cin)
             segs = self._segments(Ho * Wo, [cout] * E, [(cin + 63) // 64] * E, [0] * E)
             return K.build_schedule(segs, bn, self.device, mode=mode, Ho=Ho, Wo=Wo)
         sched = self._sched(("conv", name, x.B, x.H, x.W), build)
@@ -1364,7 +1364,7 @@ class _Engine:
         h1 = self.buf("res_h1", M, r.cout)
 
         def build_c1():
-            bn = P.choose_bn(list(pk["n1"]))
+            bn = P.choose_bn(list(pk["n1"]), k=9 * r.cin)
             segs = self._segments(hw, n1_e, [(r.cin + 63) // 64] * E, vid * r.cout, active=active,
                                   n_store=[min(P.round_up(int(n), 64), r.cout) for n in n1_e])
             return K.build_schedule(segs, bn, self.device, mode=A_CONV3X3, Ho=H, Wo=W)
@@ -1398,7 +1398,7 @@ class _Engine:
         # conv2 (K-compacted) + bias + border table + fp32 residual -> fp32 stream
 
         def build_c2():
-            bn = P.choose_bn([r.cout])
+            bn = P.choose_bn([r.cout], k=9 * int(max(pk["n1"])))
             tab_off = vid * 9 * r.cout
             segs = self._segments(hw, [r.cout] * E, [(int(n) + 63) // 64 for n in n1_e], vid * r.cout,
                                   tab_off=tab_off, active=active)
@@ -1491,7 +1491,7 @@ class _Engine:
             kept_g, vid = [np.arange(gw)], np.zeros(1, dtype=np.int64)
         kept_c = [P.expand_groups(k, gs) for k in kept_g]
         nf = np.asarray([len(k) for k in kept_c])
-        bn = P.choose_bn(list(nf), geglu=True)
+        bn = P.choose_bn(list(nf), geglu=True, k=C)
         half = bn // 2
         rows_pad = ((inner + half - 1) // half) * bn
         V = len(kept_c)
@@ -1574,7 +1574,7 @@ class _Engine:
         kvb = self.buf("qkv_kv", Mkv, 2 * C) if is_cross else None
 
         def build():
-            bn = P.choose_bn([int(n) * 64 for n in pk["nh"]])
+            bn = P.choose_bn([int(n) * 64 for n in pk["nh"]], k=C)
             s = {}
             nv = [int(n) * 64 for n in nh_e]
             if is_cross:
@@ -1593,7 +1593,7 @@ class _Engine:
                                            out_col_off=j * C)
                 s["qkv"] = K.build_schedule(segs, bn, self.device)
             s["o"] = K.build_schedule(self._segments(hw, [C] * E, [int(n) for n in nh_e], vid * C, active=active),
-                                      P.choose_bn([C]), self.device)
+                                      P.choose_bn([C], k=64 * int(max(pk["nh"]))), self.device)
             heads = np.where(active, nh_e, 0) if self.compact else np.asarray([attn.heads])
             s["heads"] = self._per_pos(heads) if self.compact else torch.full((B,), attn.heads, device=self.device,
                                                                              dtype=torch.int32)
@@ -1692,7 +1692,7 @@ class _Engine:
                 fk["bn"], self.device, geglu=True)
             s["o"] = K.build_schedule(
                 self._segments(hw, [C] * E, [(int(n) + 63) // 64 for n in nf_e], vid * C, active=active),
-                P.choose_bn([C]), self.device)
+                P.choose_bn([C], k=int(max(fk["nf"]))), self.device)
             return s
         s = self._sched(("ff", t.uid, hw), build_ff)
         gate = self._soft_gate(cidx["w"][2]) if not self.compact else None

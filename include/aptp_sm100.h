@@ -66,7 +66,16 @@ typedef struct aptp_gemm_tile {
 /* Tiles are consumed in PAIRS by a cluster of two CTAs that share (multicast) the weight tile: n_tiles is
  * even and tiles[2i], tiles[2i+1] have the same seg and n0 and different m_base. A bucket with an odd
  * number of row tiles is padded with a placeholder that repeats its partner's m_base and stores nothing. */
-enum { APTP_TILE_PLACEHOLDER = 1 };
+enum {
+  APTP_TILE_PLACEHOLDER = 1,
+  /* A-stationary tile lists (a_stat_chunks > 0): CTA pair c of the S = min(runs, aptp_gemm_max_pairs()) pairs in the
+   * grid consumes entries c, c + S, c + 2S, ...; the host orders them so that every pair sees all N tiles of one pair
+   * of row tiles back to back. The first entry of such a run loads the A row tile (A_FIRST), the last one releases it
+   * (A_LAST); SKIP entries pad the shorter sequences and do nothing. */
+  APTP_TILE_A_FIRST = 2,
+  APTP_TILE_A_LAST = 4,
+  APTP_TILE_SKIP = 8
+};
 
 enum { APTP_A_LINEAR = 0, APTP_A_CONV3X3 = 1, APTP_A_CONV3X3_S2 = 2 };
 enum { APTP_OUT_BF16 = 0, APTP_OUT_F32 = 1, APTP_OUT_F32_NCHW = 2 };
@@ -143,9 +152,14 @@ typedef struct aptp_gemm_args {
   float* rowstat_out;        /* float2 per (row, chunk) */
   int32_t rowstat_chunks;
   float* gn_stats_sq;        /* APTP_EPI_GN_STATS: the sum-of-squares plane (same indexing as gn_stats) */
+  int32_t a_stat_chunks;     /* > 0: A-stationary tile list (see APTP_TILE_A_FIRST); = max k_chunks over the segments,
+                                at most 6 (K <= 384), linear layers only                                          */
+  int32_t a_stat_pairs;      /* the number S of CTA pairs the A-stationary tile list was laid out for              */
 } aptp_gemm_args;
 
 int aptp_grouped_gemm_fwd(const aptp_gemm_args* args, void* stream);
+/* CTA pairs of the GEMM kernel that are co-resident on this device (the grid is 2 * min(pairs of tiles, this)). */
+int aptp_gemm_max_pairs(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K2  HBM-bound fused normalisation / gate / residual kernels.

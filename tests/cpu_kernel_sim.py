@@ -23,6 +23,7 @@ def _check_tiles(sched: K.Schedule, mode, Ho, Wo, geglu):
     """Every active segment must be exactly covered by its tiles."""
     segs = sched.segs.numpy()
     tiles = sched.tiles.numpy()
+    tiles = tiles[(tiles[:, 3] & 8) == 0]  # APTP_TILE_SKIP: padding entries of an A-stationary list
     bw, bh, bb = sched.box
     cols = sched.bn // 2 if geglu else sched.bn
     for si in range(sched.n_segs):
@@ -60,6 +61,7 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
     _check_tiles(sched, mode, Ho, Wo, geglu)
     segs = sched.segs.numpy()
     tiles = sched.tiles.numpy()
+    tiles = tiles[(tiles[:, 3] & 8) == 0]
     A = _view(a, a_rows, a_ld, a_ld).float()
     A[:, a_k:] = 0  # reads beyond the tensor-map extent are zero-filled
     Wm = w.float()

