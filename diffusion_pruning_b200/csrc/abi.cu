@@ -95,6 +95,31 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return APTP_OK;
 }
 
+// Output tensor map of the GEMM epilogue's bulk stores: rows x cols row-major, box = 32 rows x 64 bytes (32 bf16 or 16
+// fp32 columns), 64-byte swizzle -- the layout the epilogue warps already write their staging tile in (16-byte units
+// XORed with (row >> 1) & 3).
+int make_tmap_store64(CUtensorMap* out, const void* base, bool f32, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return APTP_ERR_CUDA;
+  cuuint64_t gdims[2] = {cols, rows};
+  cuuint64_t gstrides[1] = {row_stride_bytes};
+  cuuint32_t gbox[2] = {f32 ? 16u : 32u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  if (row_stride_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("store tensor map: base / row pitch not 16-byte aligned");
+    return APTP_ERR_INVALID;
+  }
+  CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                   gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (store map) failed with CUresult %d (cols %llu rows %llu pitch %llu)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes);
+    return APTP_ERR_CUDA;
+  }
+  return APTP_OK;
+}
+
 }  // namespace aptp
 
 extern "C" int aptp_version(void) { return APTP_ABI_VERSION; }

@@ -46,6 +46,8 @@ PFN_encodeTiled get_encode_tiled();
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true);
 
+int make_tmap_store64(CUtensorMap* out, const void* base, bool f32, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes);
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------
 // device-side PTX wrappers
@@ -96,14 +98,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // (aptp_poll_abort, called from UNet2DConditionModelGated.forward) and at its own sync points (aptp_check_abort).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* abort_flag) {
   if (mbar_try_wait(bar, parity)) return true;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL || *((volatile int*)abort_flag) != 0) {
-      atomicExch(abort_flag, 1);
-      return false;
+  // The poll loop itself touches nothing but the barrier (try_wait suspends the thread for a hardware-bounded time):
+  // a global read of the abort flag on EVERY failed poll made each blocked hand-off cost a ~1 us memory round trip
+  // (ncu, round 2: 21 polls per tile in the MMA issuer of the K = 320 layers). Clock and flag are looked at every 64 polls.
+  const long long t0 = clock64();
+#ifndef APTP_MBAR_POLLS
+#define APTP_MBAR_POLLS 64
+#endif
+#pragma unroll 1
+  for (uint32_t spin = 1;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return true;
+#ifdef APTP_MBAR_SLEEP
+    __nanosleep(APTP_MBAR_SLEEP);
+#endif
+    if ((spin & (uint32_t)(APTP_MBAR_POLLS - 1)) == 0u) {
+      if (clock64() - t0 > 4000000000LL || *((volatile int*)abort_flag) != 0) {
+        atomicExch(abort_flag, 1);
+        return false;
+      }
     }
   }
-  return true;
 }
 
 // ---- TMA loads (tile mode), completion signalled on an mbarrier ----
@@ -140,6 +154,17 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- TMA stores (bulk async-group completion): shared -> global, issued by one thread ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source (the buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- thread-block clusters ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -166,6 +191,69 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
                    smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
+}
+
+// ---- CTA-pair ("2-SM") forms: one tcgen05.mma.cta_group::2 of M = 256 spans both CTAs of a cluster of two ----
+// Each CTA stages its own 128 rows of A and HALF of the B tile; the tensor cores of both SMs read both halves, so the
+// shared-memory operand traffic per SM drops from (A + B) to (A + B/2) per MMA and B is never duplicated.
+// TMA load whose completion bytes are signalled on the LEADER CTA's mbarrier (peer bit 24 of the shared::cluster
+// address cleared), data into the executing CTA's own shared memory.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {  // one warp of EACH CTA, same slot
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N columns: N/2 per CTA]; issued by ONE thread of the leader.
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at the same offset in every CTA of cta_mask once all prior MMAs of the pair complete
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 
 // ---- tcgen05 / TMEM ----
@@ -430,6 +518,33 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   float Phi, e;
   gelu_erf_fast_parts(x, Phi, e);
   return x * Phi;
+}
+// GEGLU value for TWO columns, h * gelu(g), with ONE MUFU op per element and packed FFMA2 for the rest (the K = 320
+// GEGLU epilogue is issue- and XU-bound: 12 288 outputs per tile against ~1900 tensor-pipe cycles). Uses
+//   gelu(x) = x Phi(x) = relu(x) - |x| (1 - Phi(|x|)),   1 - Phi(a) = 2^q(a),
+// q = degree-6 fit of log2 of the Gaussian tail on [0, 6], weighted for the ABSOLUTE error of a 2^q(a): <= 9e-8 in
+// fp32 including ex2.approx (tools/fit_gelu_tail.py; the Abramowitz-Stegun form above has 1.5e-7 |x|). Beyond a = 6
+// the tail is < 1e-9 and q is clamped there.
+__device__ __forceinline__ void geglu_pair(float& h0, float& h1, float g0, float g1) {
+  // n = -min(|g|, 6): one FMNMX with source modifiers; the polynomial is written in n (odd coefficients negated) so the
+  // last step is a single FFMA2, relu(g) + n * tail
+  const uint64_t n2 = pack_f32x2(fmaxf(-fabsf(g0), -6.f), fmaxf(-fabsf(g1), -6.f));
+#define APTP_C2(c) pack_f32x2(c, c)
+  uint64_t q = fma_f32x2(n2, APTP_C2(3.309331805212423e-05f), APTP_C2(0.0007692242506891489f));
+  q = fma_f32x2(q, n2, APTP_C2(0.008080732077360153f));
+  q = fma_f32x2(q, n2, APTP_C2(0.05341212823987007f));
+  q = fma_f32x2(q, n2, APTP_C2(-0.4587709605693817f));
+  q = fma_f32x2(q, n2, APTP_C2(1.1512017250061035f));
+  q = fma_f32x2(q, n2, APTP_C2(-0.999993085861206f));
+#undef APTP_C2
+  float q0, q1, e0, e1;
+  unpack_f32x2(q, q0, q1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  const uint64_t gl = fma_f32x2(n2, pack_f32x2(e0, e1), pack_f32x2(fmaxf(g0, 0.f), fmaxf(g1, 0.f)));
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(gl), "l"(pack_f32x2(h0, h1)));
+  unpack_f32x2(r, h0, h1);
 }
 __device__ __forceinline__ void gelu_erf_fast_grad(float x, float& value, float& grad) {
   float Phi, e;

@@ -33,11 +33,15 @@ constexpr int STG_WARP_BYTES = 32 * 64;            // per-warp staging: 32 rows 
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 constexpr int MAX_SMEM_SEGS = 96;                   // expert-bucket records cached in shared memory (else read from global)
 constexpr int SSEG_BYTES = MAX_SMEM_SEGS * 48;
+constexpr int TILE_CACHE = 160;                     // tile records of this CTA staged in shared memory at kernel start
+constexpr int STILE_BYTES = TILE_CACHE * 16;
 constexpr int SBIAS_BYTES = EPI_WARPS * 128 * 4;    // per epilogue warp: bias slice of its current chunk (32, or 2 x 32 for GEGLU) + the LN-fold column sums
 
 struct GemmParams {
   CUtensorMap tmap_a;
   CUtensorMap tmap_b;
+  CUtensorMap tmap_out;  // out_tma: rows x out_ld, box 32 rows x 64 B, 64-byte swizzle (bulk stores of full chunks)
+  int out_tma;
   const aptp_gemm_seg* segs;
   const aptp_gemm_tile* tiles;
   int n_tiles;
@@ -165,19 +169,46 @@ __device__ __forceinline__ void ln_bias_apply32(float* v, const float* bias, con
 // kGeglu selects the GEGLU epilogue (two accumulator halves per output column, erf-GELU) and compiles out the
 // residual / row-vector / border-table / fp32 paths it never uses, so neither instantiation pays for the other's
 // registers.
-template <bool kGeglu>
+//
+// kEpi selects the whole output side at compile time -- EPI_BF16 (bf16 rows; bf16 residual, LayerNorm row partials),
+// EPI_GEGLU, EPI_F32 (fp32 rows of the residual stream; fp32 residual, GroupNorm column partials), EPI_NCHW (the fp32
+// NCHW prediction of conv_out) -- so that no instantiation carries the prefetch registers of another one: with all of
+// them in one body the epilogue warps spilled inside the chunk loop (ncu source page, round 2).
+enum { EPI_BF16 = 0, EPI_GEGLU = 1, EPI_F32 = 2, EPI_NCHW = 3 };
+#ifdef APTP_GEMM_TRACE
+// kernel-tuning builds only: cycles each role spends blocked on each barrier, per CTA (tools/gemm_trace.py)
+__device__ long long g_gemm_trace[512][16];
+#define TRACE_T0() const long long _t0 = clock64(); long long _tw[2] = {0, 0}
+#define TRACE_ADD(slot) if (lane == 0) { g_gemm_trace[blockIdx.x][slot] += clock64() - _t0; g_gemm_trace[blockIdx.x][slot + 1] += _tw[1]; if (slot == 2) g_gemm_trace[blockIdx.x][4] += _tw[0]; }
+#define TRACE_WAIT(slot, expr) [&]() { const long long _w0 = clock64(); const bool _r = (expr); _tw[slot & 1] += clock64() - _w0; return _r; }()
+#else
+#define TRACE_T0()
+#define TRACE_ADD(slot)
+#define TRACE_WAIT(slot, expr) (expr)
+#endif
+//
+// k2Sm: the CTA pair issues ONE tcgen05.mma.cta_group::2 of M = 256 per K step instead of two independent M = 128 MMAs
+// over a multicast B tile. Each CTA stages its own A rows and only HALF of the B tile (nothing is duplicated, so the
+// ring holds ~1.4x more stages), the leader CTA's full barrier collects the bytes of both CTAs, the leader issues the
+// MMAs and multicasts the commits, and the epilogue warps of both CTAs release the accumulator on the leader's
+// barrier. Per MMA an SM reads A + B/2 instead of A + B from shared memory -- the operand fetch of a 128 x 160 tile
+// alone took 115 of the 128 B/clk of shared-memory bandwidth and left nothing for the TMA writes and the epilogue's
+// staging (round-2 analysis).
+template <int kEpi, bool k2Sm>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr bool kGeglu = (kEpi == EPI_GEGLU);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
   // normal mode: ring of (A tile | B tile) stages; A-stationary: a_stat resident A chunk slots, then a ring of B tiles
-  const uint32_t stage_bytes = (p.a_stat ? 0u : (uint32_t)A_STAGE_BYTES) + (uint32_t)p.bn * 128u;
+  const uint32_t stage_bytes = (p.a_stat ? 0u : (uint32_t)A_STAGE_BYTES) + (uint32_t)p.bn * (k2Sm ? 64u : 128u);
   const uint32_t ring_off = (uint32_t)p.a_stat * A_STAGE_BYTES;
   uint8_t* stg_base = smem + ring_off + (size_t)stages * stage_bytes;
   float* sbias = reinterpret_cast<float*>(stg_base + STG_BYTES);
   aptp_gemm_seg* ssegs = reinterpret_cast<aptp_gemm_seg*>(stg_base + STG_BYTES + SBIAS_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES + SBIAS_BYTES + SSEG_BYTES);
+  aptp_gemm_tile* stiles = reinterpret_cast<aptp_gemm_tile*>(stg_base + STG_BYTES + SBIAS_BYTES + SSEG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + STG_BYTES + SBIAS_BYTES + SSEG_BYTES + STILE_BYTES);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tfull_bar = empty_bar + stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -187,6 +218,9 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+#ifdef APTP_GEMM_TRACE
+  const long long _t0_epi = clock64();
+#endif
   // CTA pair (cluster of 2): the pair works on tiles (2i, 2i+1) of the list, which share the expert bucket and
   // the weight rows (n0) and differ in their 128 output rows; each CTA fetches HALF of the weight tile of every
   // stage and multicasts it to both, so the L2 -> shared-memory traffic for B is halved.
@@ -202,16 +236,17 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
+    if (p.out_tma) tma_prefetch_desc(&p.tmap_out);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], 2);  // one tcgen05.commit from each CTA of the pair
+        mbar_init(&empty_bar[s], k2Sm ? 1 : 2);  // one tcgen05.commit from each CTA of the pair (2-SM: the leader's)
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], EPI_WARPS);
+        mbar_init(&tempty_bar[a], k2Sm ? 2 * EPI_WARPS : EPI_WARPS);  // 2-SM: both CTAs' warps, on the leader
       }
       for (int a = 0; a < A_STAT_MAX_CHUNKS; ++a) {
         mbar_init(&afull_bar[a], 1);
@@ -220,8 +255,13 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (k2Sm) {
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   // expert-bucket records -> shared memory (every role reads one per tile; a dependent global load per tile
   // is a ~1 us bubble on the short K=320 tiles)
@@ -230,6 +270,19 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
     const int4* src = reinterpret_cast<const int4*>(p.segs);
     int4* dst = reinterpret_cast<int4*>(ssegs);
     for (int i = threadIdx.x; i < p.n_segs * 3; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  // ... and so are this CTA's first TILE_CACHE tile records: each role used to prefetch its next record into
+  // registers, but in the register-starved epilogue warps ptxas spilled that prefetch to local memory, which turns it
+  // into a blocking ~1 us load per tile (ncu source page, round 2). Records beyond the cache are read from global.
+  {
+    const int pair0_ = blockIdx.x >> 1, pair_stride_ = gridDim.x >> 1, n_pairs_ = p.n_tiles >> 1;
+    const uint32_t rank_ = cluster_ctarank();
+    const int4* src = reinterpret_cast<const int4*>(p.tiles);
+    int4* dst = reinterpret_cast<int4*>(stiles);
+    for (int i = threadIdx.x; i < TILE_CACHE; i += blockDim.x) {
+      const int pr = pair0_ + i * pair_stride_;
+      if (pr < n_pairs_) dst[i] = __ldg(src + 2 * pr + rank_);
+    }
   }
   tc_fence_before();
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before any multicast load / remote arrive
@@ -246,15 +299,15 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       uint32_t phase = 0;
       bool ok = true;
       const int taps = (p.a_mode == APTP_A_LINEAR) ? 1 : 9;
-      aptp_gemm_tile tile_next = p.tiles[2 * pair0 + cta_rank];  // grid/2 <= n_pairs
       const uint32_t b_half_bytes = (uint32_t)p.bn * 64u;          // bn/2 weight rows x 128 B
       uint32_t a_bits = 0;  // A-stationary: bit kc = parity of the uses of resident chunk kc (runs may differ in K)
-      for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride) {
-        const aptp_gemm_tile tile = tile_next;
-        if (pr + pair_stride < n_pairs) tile_next = p.tiles[2 * (pr + pair_stride) + cta_rank];  // in flight
+      int ti = 0;
+      TRACE_T0();
+      for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride, ++ti) {
+        const aptp_gemm_tile tile = (ti < TILE_CACHE) ? stiles[ti] : p.tiles[2 * pr + cta_rank];
         if (tile.flags & APTP_TILE_SKIP) continue;
         const aptp_gemm_seg seg = segs[tile.seg];
-        if (p.a_stat) {
+        if (!k2Sm && p.a_stat) {
           const int b_row = seg.w_row_off + tile.n0 + (int)cta_rank * (p.bn >> 1);
           if (tile.flags & APTP_TILE_A_FIRST) {
             // the A row tile of this run: chunk kc may be overwritten as soon as the previous run's last N tile has
@@ -299,66 +352,81 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         for (int tap = 0; tap < taps && ok; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
           for (int kc = 0; kc < seg.k_chunks; ++kc) {
-            if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.abort_flag)) {
+            if (!TRACE_WAIT(1, mbar_wait(&empty_bar[stage], phase ^ 1, p.abort_flag))) {
               ok = false;
               break;
             }
             if (elect_one()) {
               uint8_t* sa = smem + (size_t)stage * stage_bytes;
               uint8_t* sb = sa + A_STAGE_BYTES;
-              mbar_expect_tx(&full_bar[stage], stage_bytes);
-              if (p.a_mode == APTP_A_LINEAR) {
-                tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kc * BK, tile.m_base);
-              } else if (p.a_mode == APTP_A_CONV3X3) {
-                tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * BK, ox0 + dx - 1, oy0 + dy - 1, img);
+              // input y = 2*oy + dy - 1: dy=0 -> (parity 1, shift -1); dy=1 -> (0, 0); dy=2 -> (1, 0)
+              const int py = (dy == 1) ? 0 : 1, sy = (dy == 0) ? -1 : 0;
+              const int px = (dx == 1) ? 0 : 1, sx = (dx == 0) ? -1 : 0;
+              if constexpr (k2Sm) {
+                // the LEADER's barrier counts the bytes both CTAs deliver for this stage (its own expect_tx may come
+                // after the peer's bytes: the transaction count is signed and the phase cannot complete before the
+                // leader's arrival)
+                if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+                if (p.a_mode == APTP_A_LINEAR) {
+                  tma_load_2d_2sm(sa, &p.tmap_a, &full_bar[stage], kc * BK, tile.m_base);
+                } else if (p.a_mode == APTP_A_CONV3X3) {
+                  tma_load_4d_2sm(sa, &p.tmap_a, &full_bar[stage], kc * BK, ox0 + dx - 1, oy0 + dy - 1, img);
+                } else {
+                  tma_load_5d_2sm(sa, &p.tmap_a, &full_bar[stage], px * p.k_tap_pitch + kc * BK, ox0 + sx, py, oy0 + sy,
+                                  img);
+                }
+                tma_load_2d_2sm(sb, &p.tmap_b, &full_bar[stage], tap * p.k_tap_pitch + kc * BK, b_row);
               } else {
-                // input y = 2*oy + dy - 1: dy=0 -> (parity 1, shift -1); dy=1 -> (0, 0); dy=2 -> (1, 0)
-                const int py = (dy == 1) ? 0 : 1, sy = (dy == 0) ? -1 : 0;
-                const int px = (dx == 1) ? 0 : 1, sx = (dx == 0) ? -1 : 0;
-                tma_load_5d(sa, &p.tmap_a, &full_bar[stage], px * p.k_tap_pitch + kc * BK, ox0 + sx, py, oy0 + sy,
-                            img);
+                mbar_expect_tx(&full_bar[stage], stage_bytes);
+                if (p.a_mode == APTP_A_LINEAR) {
+                  tma_load_2d(sa, &p.tmap_a, &full_bar[stage], kc * BK, tile.m_base);
+                } else if (p.a_mode == APTP_A_CONV3X3) {
+                  tma_load_4d(sa, &p.tmap_a, &full_bar[stage], kc * BK, ox0 + dx - 1, oy0 + dy - 1, img);
+                } else {
+                  tma_load_5d(sa, &p.tmap_a, &full_bar[stage], px * p.k_tap_pitch + kc * BK, ox0 + sx, py, oy0 + sy,
+                              img);
+                }
+                tma_load_2d_mc(sb + cta_rank * b_half_bytes, &p.tmap_b, &full_bar[stage],
+                               tap * p.k_tap_pitch + kc * BK, b_row, (uint16_t)0x3);
               }
-              tma_load_2d_mc(sb + cta_rank * b_half_bytes, &p.tmap_b, &full_bar[stage], tap * p.k_tap_pitch + kc * BK,
-                             b_row, (uint16_t)0x3);
             }
             __syncwarp();
             advance(stage, phase, stages);
           }
         }
       }
+      TRACE_ADD(0);
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (!k2Sm || cluster_ctarank() == 0)) {
     // ------------------------------- MMA issuer ---------------------------------
+    // (2-SM: the leader CTA issues for the pair; the peer's warp 1 only allocates and frees tensor memory)
     // The WHOLE warp walks the tile list in uniform control flow (so descriptors, barrier addresses and
     // loop counters live in uniform registers) and one elected lane issues the tcgen05 instructions.
     // A loop nested under `if (lane == 0)` instead makes ptxas wrap every UTCHMMA in a per-lane
     // R2UR "waterfall" loop, which capped the issue rate at ~140 cycles per MMA (ncu, round 1).
     {
       GEMM_ROLE_PROLOGUE();
-      const uint32_t idesc = make_idesc_bf16(BM, (uint32_t)p.bn, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(k2Sm ? 2 * BM : BM, (uint32_t)p.bn, 0, 0);
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       bool ok = true;
-      int seg_next = p.tiles[2 * pair0 + cta_rank].seg;
-      int flags_next = p.tiles[2 * pair0 + cta_rank].flags;
       uint32_t a_bits = 0;
-      for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride) {
-        const int seg_id = __shfl_sync(0xffffffffu, seg_next, 0);
-        const int tflags = __shfl_sync(0xffffffffu, flags_next, 0);
-        if (pr + pair_stride < n_pairs) {
-          seg_next = p.tiles[2 * (pr + pair_stride) + cta_rank].seg;
-          flags_next = p.tiles[2 * (pr + pair_stride) + cta_rank].flags;
-        }
+      int ti = 0;
+      TRACE_T0();
+      for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride, ++ti) {
+        const aptp_gemm_tile* trec = (ti < TILE_CACHE) ? &stiles[ti] : &p.tiles[2 * pr + cta_rank];
+        const int seg_id = __shfl_sync(0xffffffffu, trec->seg, 0);
+        const int tflags = __shfl_sync(0xffffffffu, trec->flags, 0);
         if (tflags & APTP_TILE_SKIP) continue;
         const int k_chunks = __shfl_sync(0xffffffffu, segs[seg_id].k_chunks, 0);
         const int kblocks = ((p.a_mode == APTP_A_LINEAR) ? 1 : 9) * k_chunks;
-        if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.abort_flag)) break;
+        if (!TRACE_WAIT(3, mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.abort_flag))) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn);
-        if (p.a_stat) {
+        if (!k2Sm && p.a_stat) {
           const bool first = (tflags & APTP_TILE_A_FIRST) != 0, last = (tflags & APTP_TILE_A_LAST) != 0;
           for (int kc = 0; kc < k_chunks; ++kc) {
             if (first) {
@@ -393,7 +461,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           continue;
         }
         for (int kb = 0; kb < kblocks; ++kb) {
-          if (!mbar_wait(&full_bar[stage], phase, p.abort_flag)) {
+          if (!TRACE_WAIT(4, mbar_wait(&full_bar[stage], phase, p.abort_flag))) {
             ok = false;
             break;
           }
@@ -405,19 +473,28 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // +32 bytes per K=16 step inside the 128B-swizzled row: +2 in the (addr >> 4) field
-              umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              if constexpr (k2Sm)
+                umma_bf16_ss_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                umma_bf16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);  // the stage is free once BOTH CTAs have read it
+            // the stage is free once BOTH CTAs have read it (2-SM: one commit covers the pair's MMAs)
+            if constexpr (k2Sm) umma_commit_2sm(&empty_bar[stage], (uint16_t)0x3);
+            else umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);
           }
           __syncwarp();
           advance(stage, phase, stages);
         }
         if (!ok) break;
-        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if constexpr (k2Sm) umma_commit_2sm(&tfull_bar[acc], (uint16_t)0x3);  // both CTAs' epilogues
+          else umma_commit(&tfull_bar[acc]);
+        }
         __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      TRACE_ADD(2);
     }
   }
   } else {
@@ -442,11 +519,14 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint32_t acc_phase = 0;
     constexpr bool geglu = kGeglu;
     const int out_cols_per_tile = geglu ? p.bn / 2 : p.bn;
-    const bool bf16_out = kGeglu || (p.out_mode == APTP_OUT_BF16);
-    aptp_gemm_tile tile_next = p.tiles[2 * pair0 + cta_rank];
-    for (int pr = pair0; pr < n_pairs; pr += pair_stride) {
-      const aptp_gemm_tile tile = tile_next;
-      if (pr + pair_stride < n_pairs) tile_next = p.tiles[2 * (pr + pair_stride) + cta_rank];
+    constexpr bool bf16_out = (kEpi == EPI_BF16 || kEpi == EPI_GEGLU);
+    int ti = 0;
+    bool st_pending = false;
+#ifdef APTP_GEMM_TRACE
+    long long _tr_ld = 0, _tr_math = 0, _tr_st = 0, _tr_tfull = 0, _tr_busy = 0, _tr_tiles = 0;
+#endif
+    for (int pr = pair0; pr < n_pairs; pr += pair_stride, ++ti) {
+      const aptp_gemm_tile tile = (ti < TILE_CACHE) ? stiles[ti] : p.tiles[2 * pr + cta_rank];
       if (tile.flags & APTP_TILE_SKIP) continue;  // padding entry of an A-stationary tile list
       const aptp_gemm_seg seg = segs[tile.seg];
       const bool placeholder = (tile.flags & APTP_TILE_PLACEHOLDER) != 0;  // odd tile count of a bucket: no stores
@@ -483,9 +563,13 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         co_row[it] = rr;
       }
       const int ocol_base = geglu ? tile.n0 / 2 : tile.n0;  // first OUTPUT column of this tile
+      // bulk (TMA) store of a chunk: all 32 rows of this quadrant lie inside the bucket (linear layers; ragged bucket
+      // ends, placeholders and partial column chunks take the per-lane store path)
+      const int row0_q = tile.m_base + quad * 32;
+      const bool rows_full = bf16_out && p.out_tma && !placeholder && row0_q >= seg.row_begin && row0_q + 32 <= seg.row_end;
       // GroupNorm partial statistics: row of the partial planes this (tile, quadrant) owns
       long long gn_row = -1;
-      if (!kGeglu && p.gn_sum != nullptr && !placeholder) {
+      if (kEpi == EPI_F32 && p.gn_sum != nullptr && !placeholder) {
         const int smp = tile.m_base / p.rows_per_sample;
         const int rem = tile.m_base - smp * p.rows_per_sample;
         int t_in_s;
@@ -499,35 +583,39 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
 
       // residual of the first chunk goes in flight before we wait for the accumulator
-      uint4 rres[4];
-      const bool use_res = !kGeglu && (p.residual != nullptr) && bf16_out;
+      uint4 rres[kEpi == EPI_BF16 ? 4 : 1];
+      const bool use_res = (kEpi == EPI_BF16) && (p.residual != nullptr);
       auto load_res = [&](int col0) {
+        if constexpr (kEpi == EPI_BF16) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          rres[it] = make_uint4(0u, 0u, 0u, 0u);
-          if (co_ok[it] && col0 + co_q * 8 < seg.n_valid)
-            rres[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                       (size_t)co_row[it] * p.res_ld + seg.out_col_off + col0 +
-                                                       co_q * 8);  // may alias `out`
+          for (int it = 0; it < 4; ++it) {
+            rres[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (co_ok[it] && col0 + co_q * 8 < seg.n_valid)
+              rres[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                         (size_t)co_row[it] * p.res_ld + seg.out_col_off + col0 +
+                                                         co_q * 8);  // may alias `out`
+          }
         }
       };
       // fp32 residual stream (block outputs): same coalesced shape as the bf16 path -- one
       // instruction moves 8 rows x 64 contiguous bytes -- but 64 B are 16 fp32 columns, so a 32-column chunk goes
       // through the per-warp staging tile as two halves. The chunk's residual is loaded one chunk ahead.
-      const bool f32_rows = !kGeglu && (p.out_mode == APTP_OUT_F32);
+      constexpr bool f32_rows = (kEpi == EPI_F32);
       const bool use_res32 = f32_rows && (p.residual != nullptr) && (p.flags & APTP_EPI_RES_F32) != 0;
-      uint4 rres32[2][4];
+      uint4 rres32[f32_rows ? 2 : 1][f32_rows ? 4 : 1];
       auto load_res32 = [&](int col0) {
+        if constexpr (f32_rows) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            rres32[h][it] = make_uint4(0u, 0u, 0u, 0u);
-            if (co_ok[it] && col0 + h * 16 + co_q * 4 < seg.n_valid)
-              rres32[h][it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) +
-                                                              (size_t)co_row[it] * p.res_ld + seg.out_col_off + col0 +
-                                                              h * 16 + co_q * 4);  // may alias `out`
-          }
+            for (int it = 0; it < 4; ++it) {
+              rres32[h][it] = make_uint4(0u, 0u, 0u, 0u);
+              if (co_ok[it] && col0 + h * 16 + co_q * 4 < seg.n_valid)
+                rres32[h][it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) +
+                                                                (size_t)co_row[it] * p.res_ld + seg.out_col_off + col0 +
+                                                                h * 16 + co_q * 4);  // may alias `out`
+            }
+        }
       };
       // this tile's chunks are dealt round-robin to the EPI_PER_QUAD warps of the quadrant, continuing where the
       // previous tile stopped, so tiles whose chunk count is not a multiple of EPI_PER_QUAD still balance
@@ -570,15 +658,46 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         load_bias(c_first);
       }
 
+#ifdef APTP_GEMM_TRACE
+      const long long _e0 = clock64();
       const bool got = mbar_wait(&tfull_bar[acc], acc_phase, p.abort_flag);
+      const long long _e1 = clock64();
+      _tr_tfull += _e1 - _e0;
+#else
+      const bool got = mbar_wait(&tfull_bar[acc], acc_phase, p.abort_flag);
+#endif
       if (!got) break;
       tc_fence_after();
+      // first use of the prefetched row statistics stays BEHIND the wait (ptxas otherwise hoists -mu * rstd above it and
+      // the warp blocks on the load before it ever looks at the barrier)
+      asm volatile("" : "+f"(ln_mu), "+f"(ln_rstd));
+      // this warp's arrive on tempty_bar[acc]. Releasing right after the warp's LAST TMEM read of the tile
+      // (-DAPTP_EARLY_RELEASE) instead of after its stores was measured SLOWER on the K = 320 layers (the MMA running
+      // further ahead only adds operand traffic to a shared-memory pipe the epilogue staging also needs), so the
+      // release stays at the end of the tile.
+      bool released = false;
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (k2Sm) mbar_arrive_rank(&tempty_bar[acc], 0u);  // the leader's MMA warp waits for both CTAs
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+      };
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
 
+#ifdef APTP_DBG_NOEPI
+      if (p.n_tiles < 0)
+#endif
       for (int c = c_first; c < n_chunks; c += EPI_PER_QUAD) {
         const int col0 = ocol_base + c * 32;
         if (col0 >= seg.n_store) break;  // warp-uniform
         const int n_ok = seg.n_valid - col0;  // columns of this chunk that carry data (may be <= 0)
+        if (st_pending) {  // the previous chunk's bulk store must have read the staging tile before it is rewritten
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          st_pending = false;
+        }
         if (p.bias || ln_fold) {
           wbias[lane] = bias_h;
           if (geglu) wbias[32 + lane] = bias_g;
@@ -590,11 +709,25 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
         const bool more = (c + EPI_PER_QUAD < n_chunks) && (col0 + 32 * EPI_PER_QUAD < seg.n_store);
         float v[32];
+#ifdef APTP_GEMM_TRACE
+        const long long _c0 = clock64();
+        long long _c1 = 0;
+#define TRACE_LD_DONE() _c1 = clock64(); _tr_ld += _c1 - _c0
+#else
+#define TRACE_LD_DONE()
+#endif
         if constexpr (kGeglu) {
           uint32_t ra[32], rb[32];
           tmem_ld_32x32(t_addr + c * 32, ra);
           tmem_ld_32x32(t_addr + p.bn / 2 + c * 32, rb);
           tmem_ld_wait();
+          TRACE_LD_DONE();
+#ifdef APTP_EARLY_RELEASE
+          if (!more) {
+            release_acc();
+            released = true;
+          }
+#endif
           float gv[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -619,8 +752,13 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
               }
             }
           }
+#ifdef APTP_GEGLU_AS
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_fast(gv[j]);
+#else
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) geglu_pair(v[j], v[j + 1], gv[j], gv[j + 1]);
+#endif
           if (p.bias || ln_fold) {
             __syncwarp();
             if (more) load_bias(c + EPI_PER_QUAD);
@@ -629,6 +767,13 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           uint32_t ra[32];
           tmem_ld_32x32(t_addr + c * 32, ra);
           tmem_ld_wait();
+          TRACE_LD_DONE();
+#ifdef APTP_EARLY_RELEASE
+          if (!more) {
+            release_acc();
+            released = true;
+          }
+#endif
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
           if (ln_fold) ln_bias_apply32(v, wbias, wbias + 64, ln_mu, ln_rstd);
@@ -651,11 +796,15 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         }
 
-        if (bf16_out) {
+#ifdef APTP_GEMM_TRACE
+        const long long _c2 = clock64();
+        _tr_math += _c2 - _c1;
+#endif
+        if constexpr (bf16_out) {
           // per-warp staging tile: 32 rows x 64 B, 16-byte units XOR-swizzled by (row >> 1) & 3. Plain C++ accesses
           // (ordered by __syncwarp) so the compiler can batch the four loads / stores of each phase.
           uint4* stg4 = reinterpret_cast<uint4*>(stg);
-          if (use_res) {
+          if (kEpi == EPI_BF16 && use_res) {
             // residual: coalesced registers -> swizzled smem -> own row
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
@@ -686,7 +835,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < 32; ++j)
               if (j >= n_ok) v[j] = 0.f;
           }
-          if (!kGeglu && p.rowstat_out && valid) {
+          if (kEpi == EPI_BF16 && p.rowstat_out && valid) {
             // per-row (sum, sumsq) of this 32-column chunk, for the LayerNorm folded into the consumer GEMM
             uint64_t su2 = pack_f32x2(0.f, 0.f), sq2 = su2;
 #pragma unroll
@@ -702,11 +851,27 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
                 make_float2(s0 + s1, q0 + q1);
           }
           // own row -> swizzled smem
+#ifdef APTP_DBG_NOSTAGE
+          if (v[0] == 1.2345e30f) p.abort_flag[1] = 1;
+          if (p.n_tiles >= 0) continue;
+#endif
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             stg4[lane * 4 + (q ^ own_sw)] =
                 make_uint4(pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
                            pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+          if (rows_full && col0 + 32 <= seg.n_store) {
+            // the staging tile IS the 64-byte-swizzled TMA box: one bulk store per chunk, nothing held in registers
+            // and no per-lane store instructions queueing in the LSU
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tmap_out, stg, seg.out_col_off + col0, row0_q);
+              bulk_commit();
+            }
+            st_pending = true;
+            continue;
+          }
           __syncwarp();
           // coalesced side: 8 rows x 64 B per instruction
           __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + seg.out_col_off + col0 + co_q * 8;
@@ -717,11 +882,14 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
             const int rl = it * 8 + (lane >> 2);
             o4[it] = stg4[rl * 4 + (co_q ^ ((rl >> 1) & 3))];
           }
+#ifdef APTP_DBG_NOSTORE
+          if (o4[0].x == 0x12345678u && o4[1].y == 0x9abcdef0u && o4[2].z == 0x0fedcba9u && o4[3].w == 0x87654321u)
+#endif
 #pragma unroll
           for (int it = 0; it < 4; ++it)
             if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o4[it];
           __syncwarp();
-        } else if (f32_rows) {
+        } else if constexpr (f32_rows) {
           uint4* stg4 = reinterpret_cast<uint4*>(stg);
           if (n_ok < 32) {
 #pragma unroll
@@ -813,25 +981,64 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
               if (j < n_ok) op[((size_t)sample * p.out_ld + col0 + j) * p.rows_per_sample + pix] = v[j];
           }
         }
+#ifdef APTP_GEMM_TRACE
+        _tr_st += clock64() - _c2;
+#endif
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (!released) release_acc();  // no chunk of this tile fell to this warp
+#ifdef APTP_GEMM_TRACE
+      _tr_busy += clock64() - _e1;
+      _tr_tiles += 1;
+#endif
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait0();  // outstanding bulk stores (their shared-memory source dies with the CTA)
+#ifdef APTP_GEMM_TRACE
+    if (lane == 0 && ew < 2) {
+      g_gemm_trace[blockIdx.x][6 + 3 * ew] += _tr_tfull;
+      g_gemm_trace[blockIdx.x][7 + 3 * ew] += _tr_busy;
+      g_gemm_trace[blockIdx.x][8 + 3 * ew] += _tr_tiles;
+      if (ew == 0) {
+        g_gemm_trace[blockIdx.x][12] += _tr_ld;
+        g_gemm_trace[blockIdx.x][13] += _tr_math;
+        g_gemm_trace[blockIdx.x][14] += _tr_st;
+      }
+    }
+#endif
   }
 
+#ifdef APTP_GEMM_TRACE
+  if (warp == 4 && lane == 0) g_gemm_trace[blockIdx.x][5] += clock64() - _t0_epi;
+#endif
   tc_fence_before();
   cluster_sync_all();  // the peer may still multicast into this CTA's smem / arrive on its barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(*tmem_slot, TMEM_COLS);
+    if constexpr (k2Sm) tmem_dealloc_2sm(*tmem_slot, TMEM_COLS);
+    else tmem_dealloc(*tmem_slot, TMEM_COLS);
   }
 }
 
+#ifdef APTP_GEMM_TRACE
+}  // namespace aptp
+extern "C" int aptp_debug_gemm_trace(long long* host_out, int reset) {  // [512][16]
+  if (host_out && cudaMemcpyFromSymbol(host_out, aptp::g_gemm_trace, sizeof(long long) * 512 * 16) != cudaSuccess) return -1;
+  if (reset) {
+    static long long zeros[512 * 16];
+    if (cudaMemcpyToSymbol(aptp::g_gemm_trace, zeros, sizeof(zeros)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+namespace aptp {
+#endif
 static int g_gemm_smem_set = 0;
 static int g_gemm_max_clusters = 0;
+static int g_gemm_2sm = 1;
+// Measured on B200 (tools/gemm_bench.py, same box): 3x3 convs +8..17 %, K = N = 1280 linear +13 %, 8192^3 +8 % with the
+// 2-SM scheme, but the K = 320 / 640 projections LOSE 10..25 % (their tiles are 5-10 K steps long and every tile
+// hand-off crosses the CTA pair), so short reductions keep the two independent M = 128 MMAs.
+static int g_gemm_2sm_mink = 1280;
 
 }  // namespace aptp
 
@@ -839,9 +1046,18 @@ using namespace aptp;
 
 static int gemm_max_clusters() {
   if (!g_gemm_smem_set) {
-    if (cudaFuncSetAttribute(grouped_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(grouped_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return 0;
+    const void* fns[8] = {(const void*)grouped_gemm_kernel<EPI_BF16, false>, (const void*)grouped_gemm_kernel<EPI_GEGLU, false>,
+                          (const void*)grouped_gemm_kernel<EPI_F32, false>,  (const void*)grouped_gemm_kernel<EPI_NCHW, false>,
+                          (const void*)grouped_gemm_kernel<EPI_BF16, true>,  (const void*)grouped_gemm_kernel<EPI_GEGLU, true>,
+                          (const void*)grouped_gemm_kernel<EPI_F32, true>,   (const void*)grouped_gemm_kernel<EPI_NCHW, true>};
+    for (int i = 0; i < 8; ++i)
+      if (cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return 0;
+    // APTP_GEMM_1SM=1: the round-1 scheme (two M = 128 MMAs per pair over a multicast B tile) everywhere, for A/B runs;
+    // APTP_GEMM_2SM_MINK: shortest reduction length (K, times 9 for the convs) that takes the 2-SM scheme
+    const char* e = getenv("APTP_GEMM_1SM");
+    g_gemm_2sm = !(e && e[0] == '1');
+    const char* mk = getenv("APTP_GEMM_2SM_MINK");
+    if (mk && atoi(mk) > 0) g_gemm_2sm_mink = atoi(mk);
     g_gemm_smem_set = 1;
   }
   if (!g_gemm_max_clusters) {
@@ -859,7 +1075,7 @@ static int gemm_max_clusters() {
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, grouped_gemm_kernel<false>, &cfg) != cudaSuccess || n <= 0) return 0;
+    if (cudaOccupancyMaxActiveClusters(&n, grouped_gemm_kernel<EPI_BF16, true>, &cfg) != cudaSuccess || n <= 0) return 0;
     g_gemm_max_clusters = n;
   }
   return g_gemm_max_clusters;
@@ -976,6 +1192,21 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   p.out = a->out;
   p.out_ld = a->out_ld;
   p.out_mode = a->out_mode;
+  p.out_tma = 0;
+  {
+    static int tma_store = -1;  // APTP_GEMM_TMA_STORE=0: per-lane stores everywhere (A/B runs)
+    if (tma_store < 0) {
+      const char* e = getenv("APTP_GEMM_TMA_STORE");
+      tma_store = !(e && e[0] == '0');
+    }
+    if (tma_store && a->a_mode == APTP_A_LINEAR && a->out_mode == APTP_OUT_BF16 &&
+        (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) {
+      const uint64_t out_cols = (uint64_t)a->out_ld;  // columns addressable in a row (segments write disjoint column ranges)
+      int rc = make_tmap_store64(&p.tmap_out, a->out, false, out_cols, (uint64_t)a->a_rows, (uint64_t)a->out_ld * 2);
+      if (rc) return rc;
+      p.out_tma = 1;
+    }
+  }
   p.bias = a->bias;
   p.rowvec = a->rowvec;
   p.rowvec_ld = a->rowvec_ld;
@@ -1006,16 +1237,18 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
                  "aptp_grouped_gemm_fwd: A-stationary mode needs a linear layer with at most %d K chunks", A_STAT_MAX_CHUNKS);
     p.a_stat = a->a_stat_chunks;
   }
-  const int stage_bytes = (p.a_stat ? 0 : A_STAGE_BYTES) + a->bn * 128;
+  APTP_REQUIRE(gemm_max_clusters() > 0, "aptp_grouped_gemm_fwd: no CTA pair fits on this device");
+  // (the opt-in A-stationary layout exists in the 1-SM scheme only)
+  const bool two_sm = g_gemm_2sm && !p.a_stat && (a->a_mode == APTP_A_LINEAR ? 1 : 9) * a->a_k >= g_gemm_2sm_mink;
+  const int stage_bytes = (p.a_stat ? 0 : A_STAGE_BYTES) + a->bn * (two_sm ? 64 : 128);
   const int budget = 225 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STG_BYTES /*epilogue staging*/ - SBIAS_BYTES -
-                     SSEG_BYTES - p.a_stat * A_STAGE_BYTES;
+                     SSEG_BYTES - STILE_BYTES - p.a_stat * A_STAGE_BYTES;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   APTP_REQUIRE(stages >= 2, "aptp_grouped_gemm_fwd: tile too large for shared memory");
   p.stages = stages;
   const size_t smem_bytes = (size_t)p.a_stat * A_STAGE_BYTES + (size_t)stages * stage_bytes + STG_BYTES + SBIAS_BYTES +
-                            SSEG_BYTES + 1024 + 512;
-  APTP_REQUIRE(gemm_max_clusters() > 0, "aptp_grouped_gemm_fwd: no CTA pair fits on this device");
+                            SSEG_BYTES + STILE_BYTES + 1024 + 512;
   const int n_pairs = a->n_tiles / 2;
   int grid = 2 * (n_pairs < g_gemm_max_clusters ? n_pairs : g_gemm_max_clusters);
   if (p.a_stat) {  // the tile list was laid out for exactly a_stat_pairs CTA pairs (entry c + j * pairs belongs to pair c)
@@ -1023,10 +1256,16 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
                  "aptp_grouped_gemm_fwd: A-stationary tile list needs 0 < a_stat_pairs <= %d dividing the pair count", g_gemm_max_clusters);
     grid = 2 * a->a_stat_pairs;
   }
-  if (a->flags & APTP_EPI_GEGLU)
-    grouped_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
-  else
-    grouped_gemm_kernel<false><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+#define APTP_LAUNCH_GEMM(EPI)                                                                  \
+  do {                                                                                         \
+    if (two_sm) grouped_gemm_kernel<EPI, true><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p); \
+    else grouped_gemm_kernel<EPI, false><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);       \
+  } while (0)
+  if (a->flags & APTP_EPI_GEGLU) APTP_LAUNCH_GEMM(EPI_GEGLU);
+  else if (a->out_mode == APTP_OUT_BF16) APTP_LAUNCH_GEMM(EPI_BF16);
+  else if (a->out_mode == APTP_OUT_F32) APTP_LAUNCH_GEMM(EPI_F32);
+  else APTP_LAUNCH_GEMM(EPI_NCHW);
+#undef APTP_LAUNCH_GEMM
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }
