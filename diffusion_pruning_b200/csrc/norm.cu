@@ -472,23 +472,26 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(const __nv_bfloat16* __
 // GroupNorm statistics from the per-channel partials written by GEMM epilogues (APTP_EPI_GN_STATS): one warp per
 // (sample, group) adds the group's (32-row block, channel) cells in a fixed order + a fixed shuffle tree. The partial
 // planes are 1/8 (fp32 stream: 1/16 per plane) of the tensor itself, so this replaces a full statistics pass over HBM.
-__global__ void __launch_bounds__(256)
+constexpr int GNF_SLICES = 4;  // threads per channel: each walks every 4th 32-row block (more loads in flight)
+__global__ void __launch_bounds__(256 * GNF_SLICES)
     gn_partials_finalize_kernel(const float* __restrict__ sum0, const float* __restrict__ sq0, int c0, int ld0,
                                 const float* __restrict__ sum1, const float* __restrict__ sq1, int ld1, int ctot_all,
                                 int blocks, int gs, int groups_per_cta, const int* __restrict__ sample_channels,
                                 float* __restrict__ stats, int stats_groups) {
-  // thread = one channel (coalesced walks down the 32-row blocks), then one thread per group adds its gs channel
-  // totals in channel order: every sum has a fixed order
-  __shared__ float ssum[256], ssq[256];
+  // thread (x, y) = channel x, block slice y (coalesced walks down the 32-row blocks y, y + 4, ...: four independent
+  // accumulators each, so 16 loads per plane are in flight per channel); then one thread per group adds the slices and
+  // its gs channel totals in a fixed order: every sum has a fixed order
+  __shared__ float ssum[GNF_SLICES][256], ssq[GNF_SLICES][256];
   const int b = blockIdx.x;
   const int ctot = sample_channels ? sample_channels[b] : ctot_all;
   if (ctot <= 0) return;
   const int groups = (ctot + gs - 1) / gs;
   const int g0 = blockIdx.y * groups_per_cta;
   if (g0 >= groups) return;
-  const int c = g0 * gs + threadIdx.x;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = g0 * gs + tx;
   float a = 0.f, q = 0.f;
-  if (threadIdx.x < groups_per_cta * gs && c < ctot) {
+  if (tx < groups_per_cta * gs && c < ctot) {
     const float* ps;
     const float* pq;
     int ld;
@@ -498,22 +501,36 @@ __global__ void __launch_bounds__(256)
       ps = sum1 + (c - c0); pq = sq1 + (c - c0); ld = ld1;
     }
     const size_t row0 = (size_t)b * blocks;
-    for (int blk = 0; blk < blocks; ++blk) {
-      a += __ldg(ps + (row0 + blk) * ld);
-      q += __ldg(pq + (row0 + blk) * ld);
+    float a4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+    int blk = ty;
+    for (; blk + 3 * GNF_SLICES < blocks; blk += 4 * GNF_SLICES) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a4[u] += __ldg(ps + (row0 + blk + u * GNF_SLICES) * ld);
+        q4[u] += __ldg(pq + (row0 + blk + u * GNF_SLICES) * ld);
+      }
     }
+    for (; blk < blocks; blk += GNF_SLICES) {
+      a4[0] += __ldg(ps + (row0 + blk) * ld);
+      q4[0] += __ldg(pq + (row0 + blk) * ld);
+    }
+    a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
   }
-  ssum[threadIdx.x] = a;
-  ssq[threadIdx.x] = q;
+  ssum[ty][tx] = a;
+  ssq[ty][tx] = q;
   __syncthreads();
-  if (threadIdx.x < groups_per_cta && g0 + threadIdx.x < groups) {
+  if (ty == 0 && tx < groups_per_cta && g0 + tx < groups) {
     float ga = 0.f, gq = 0.f;
     for (int e = 0; e < gs; ++e) {
-      ga += ssum[threadIdx.x * gs + e];
-      gq += ssq[threadIdx.x * gs + e];
+#pragma unroll
+      for (int y = 0; y < GNF_SLICES; ++y) {
+        ga += ssum[y][tx * gs + e];
+        gq += ssq[y][tx * gs + e];
+      }
     }
-    stats[((size_t)b * stats_groups + g0 + threadIdx.x) * 2] = ga;
-    stats[((size_t)b * stats_groups + g0 + threadIdx.x) * 2 + 1] = gq;
+    stats[((size_t)b * stats_groups + g0 + tx) * 2] = ga;
+    stats[((size_t)b * stats_groups + g0 + tx) * 2 + 1] = gq;
   }
 }
 
@@ -615,7 +632,7 @@ extern "C" int aptp_groupnorm_stats_from_partials(const float* sum0, const float
   APTP_REQUIRE(groups <= stats_groups, "aptp_groupnorm_stats_from_partials: stats_groups too small");
   APTP_REQUIRE(group_size <= 256, "aptp_groupnorm_stats_from_partials: group_size %d > 256", group_size);
   const int gpc = 256 / group_size;  // whole groups per CTA
-  gn_partials_finalize_kernel<<<dim3(batch, (groups + gpc - 1) / gpc), 256, 0, stream>>>(
+  gn_partials_finalize_kernel<<<dim3(batch, (groups + gpc - 1) / gpc), dim3(256, GNF_SLICES), 0, stream>>>(
       sum0, sq0, c0, ld0, sum1, sq1, ld1, c0 + c1, blocks, group_size, gpc, sample_channels, stats, stats_groups);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;

@@ -40,7 +40,7 @@ def choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False, 
     cands = [256, 224, 192, 160, 128, 96, 64]
     if geglu:
         cands = [256, 192, 128]
-    if k <= 0 or os.environ.get("APTP_BN_MODEL", "0") != "1":
+    if k <= 0 or os.environ.get("APTP_BN_MODEL", "1") != "1":
         best, best_cost = None, None
         for bn in cands:
             cols = bn // 2 if geglu else bn
@@ -49,7 +49,9 @@ def choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False, 
             if best_cost is None or cost < best_cost - 1e-9:
                 best, best_cost = bn, cost
         return best or 128
-    overhead_cols = 2000.0 * 32.0 / max(k, 32)
+    # shared-memory traffic model (round 2): a K step of a 128 x bn tile moves A (16 KB) + B (bn / 8 KB) in and out of
+    # shared memory, i.e. costs ~ (A_cols + bn) with A_cols = 128 (1-SM) .. 171 (2-SM scheme, B written once)
+    overhead_cols = float(os.environ.get("APTP_BN_OVERHEAD", "171" if k >= 1280 else "128"))
     best, best_cost = None, None
     for bn in cands:
         cols = bn // 2 if geglu else bn
