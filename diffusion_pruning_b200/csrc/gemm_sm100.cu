@@ -898,27 +898,9 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            if (use_res32) {
-              // residual half: coalesced registers -> swizzled smem -> own row (columns beyond n_valid read as 0)
-#pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int rl = it * 8 + (lane >> 2);
-                stg4[rl * 4 + (co_q ^ ((rl >> 1) & 3))] = rres32[h][it];
-              }
-              __syncwarp();
-              uint4 w4[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) w4[q] = stg4[lane * 4 + (q ^ own_sw)];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[h * 16 + q * 4 + 0] += __uint_as_float(w4[q].x);
-                v[h * 16 + q * 4 + 1] += __uint_as_float(w4[q].y);
-                v[h * 16 + q * 4 + 2] += __uint_as_float(w4[q].z);
-                v[h * 16 + q * 4 + 3] += __uint_as_float(w4[q].w);
-              }
-              __syncwarp();
-            }
-            // own row -> swizzled smem -> 8 rows x 64 B per store instruction
+            // own row -> swizzled smem -> coalesced side (8 rows x 64 B per instruction). The fp32 residual was loaded
+            // in the coalesced layout and is added THERE (same fp32 add, no second trip of the residual through shared
+            // memory: the transposes of this epilogue moved as many shared-memory bytes as the K = 320 main loop).
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               stg4[lane * 4 + (q ^ own_sw)] =
@@ -932,6 +914,15 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
             for (int it = 0; it < 4; ++it) {
               const int rl = it * 8 + (lane >> 2);
               o4[it] = stg4[rl * 4 + (co_q ^ ((rl >> 1) & 3))];
+            }
+            if (use_res32) {
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                o4[it].x = __float_as_uint(__uint_as_float(o4[it].x) + __uint_as_float(rres32[h][it].x));
+                o4[it].y = __float_as_uint(__uint_as_float(o4[it].y) + __uint_as_float(rres32[h][it].y));
+                o4[it].z = __float_as_uint(__uint_as_float(o4[it].z) + __uint_as_float(rres32[h][it].z));
+                o4[it].w = __float_as_uint(__uint_as_float(o4[it].w) + __uint_as_float(rres32[h][it].w));
+              }
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it)
