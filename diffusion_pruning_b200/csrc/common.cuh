@@ -383,6 +383,20 @@ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same with an explicit stride between 8-row groups and a start that is NOT aligned to the 1024-byte swizzle
+// pattern (rows of a larger tile picked out by moving the start address: the conv halo tile). Measured on B200: the
+// tensor core applies the 128B swizzle to the ABSOLUTE shared-memory address (bits 4-6 ^= bits 7-9), exactly as TMA wrote
+// the tile, so the descriptor's base-offset field stays 0 for any 128-byte-aligned start (setting it to the row phase
+// (start >> 7) & 7 gives wrong products).
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128_ex(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // MN-major operand, 128B swizzle: 64 contiguous bf16 along MN per row (128 B), 8 k-rows per 1024 B
 // atom (SBO between k-groups of 8), LBO = byte stride between 64-element MN atoms.
 __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {

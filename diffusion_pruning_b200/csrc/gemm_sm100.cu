@@ -81,10 +81,17 @@ struct GemmParams {
   // pair walks all N tiles of one pair of row tiles back to back; the A row tile (128 x K) is loaded ONCE per run
   // (tile flag APTP_TILE_A_FIRST) into a resident region, only the weight tiles stream through the stage ring
   int a_stat;        // 0, or the number of resident A chunk slots
+  // Halo mode (2-SM 3x3 stride-1 convs over 8 x 16 pixel boxes): ONE TMA box of 18 rows x 16 pixels x 64 channels per K
+  // chunk lands in an A slot and the nine taps are nine MMA groups whose A descriptors start (dy * 16 + dx) pixel rows into
+  // it (8-pixel box rows = the 8-row groups of the operand, 16 pixel rows = 2048 B apart); only the weight tiles stream
+  // through the ring. A is written to shared memory once per chunk instead of once per tap.
+  int halo;          // 0, or the number of A (halo) slots
   int* abort_flag;
 };
 
 constexpr int A_STAT_MAX_CHUNKS = 6;
+constexpr int HALO_W = 16, HALO_H = 18;                   // halo box in pixels (10 needed across; 16 keeps the 8-row groups regular)
+constexpr int HALO_BYTES = HALO_W * HALO_H * 128;         // 36 KB per 64-channel chunk (9 boxes of 16 KB before)
 
 __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int stages) {
   if (++stage == stages) {
@@ -202,8 +209,8 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
   // normal mode: ring of (A tile | B tile) stages; A-stationary: a_stat resident A chunk slots, then a ring of B tiles
-  const uint32_t stage_bytes = (p.a_stat ? 0u : (uint32_t)A_STAGE_BYTES) + (uint32_t)p.bn * (k2Sm ? 64u : 128u);
-  const uint32_t ring_off = (uint32_t)p.a_stat * A_STAGE_BYTES;
+  const uint32_t stage_bytes = ((p.a_stat || p.halo) ? 0u : (uint32_t)A_STAGE_BYTES) + (uint32_t)p.bn * (k2Sm ? 64u : 128u);
+  const uint32_t ring_off = p.halo ? (uint32_t)p.halo * HALO_BYTES : (uint32_t)p.a_stat * A_STAGE_BYTES;
   uint8_t* stg_base = smem + ring_off + (size_t)stages * stage_bytes;
   float* sbias = reinterpret_cast<float*>(stg_base + STG_BYTES);
   aptp_gemm_seg* ssegs = reinterpret_cast<aptp_gemm_seg*>(stg_base + STG_BYTES + SBIAS_BYTES);
@@ -301,6 +308,8 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int taps = (p.a_mode == APTP_A_LINEAR) ? 1 : 9;
       const uint32_t b_half_bytes = (uint32_t)p.bn * 64u;          // bn/2 weight rows x 128 B
       uint32_t a_bits = 0;  // A-stationary: bit kc = parity of the uses of resident chunk kc (runs may differ in K)
+      int aslot = 0;        // halo mode: A slot ring
+      uint32_t aphase = 0;
       int ti = 0;
       TRACE_T0();
       for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride, ++ti) {
@@ -349,6 +358,39 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           ox0 = rem - oy0 * p.Wo;
         }
         const int b_row = seg.w_row_off + tile.n0 + (int)cta_rank * (p.bn >> 1);  // this CTA's half of the weight tile
+        if constexpr (k2Sm) {
+          if (p.halo) {
+            for (int kc = 0; kc < seg.k_chunks && ok; ++kc) {
+              if (!mbar_wait(&aempty_bar[aslot], aphase ^ 1, p.abort_flag)) {
+                ok = false;
+                break;
+              }
+              if (elect_one()) {
+                if (cta_rank == 0) mbar_expect_tx(&afull_bar[aslot], 2u * HALO_BYTES);
+                tma_load_4d_2sm(smem + (size_t)aslot * HALO_BYTES, &p.tmap_a, &afull_bar[aslot], kc * BK, ox0 - 1, oy0 - 1, img);
+              }
+              __syncwarp();
+              for (int tap = 0; tap < 9; ++tap) {
+                if (!mbar_wait(&empty_bar[stage], phase ^ 1, p.abort_flag)) {
+                  ok = false;
+                  break;
+                }
+                if (elect_one()) {
+                  if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+                  tma_load_2d_2sm(smem + ring_off + (size_t)stage * stage_bytes, &p.tmap_b, &full_bar[stage],
+                                  tap * p.k_tap_pitch + kc * BK, b_row);
+                }
+                __syncwarp();
+                advance(stage, phase, stages);
+              }
+              if (++aslot == p.halo) {
+                aslot = 0;
+                aphase ^= 1;
+              }
+            }
+            continue;
+          }
+        }
         for (int tap = 0; tap < taps && ok; ++tap) {
           const int dy = tap / 3, dx = tap - dy * 3;
           for (int kc = 0; kc < seg.k_chunks; ++kc) {
@@ -414,6 +456,8 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       uint32_t acc_phase = 0;
       bool ok = true;
       uint32_t a_bits = 0;
+      int aslot = 0;
+      uint32_t aphase = 0;
       int ti = 0;
       TRACE_T0();
       for (int pr = pair0; pr < n_pairs && ok; pr += pair_stride, ++ti) {
@@ -459,6 +503,49 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
           continue;
+        }
+        if constexpr (k2Sm) {
+          if (p.halo) {
+            for (int kc = 0; kc < k_chunks && ok; ++kc) {
+              if (!mbar_wait(&afull_bar[aslot], aphase, p.abort_flag)) {
+                ok = false;
+                break;
+              }
+              for (int tap = 0; tap < 9; ++tap) {
+                if (!TRACE_WAIT(4, mbar_wait(&full_bar[stage], phase, p.abort_flag))) {
+                  ok = false;
+                  break;
+                }
+                tc_fence_after();
+                const int dy = tap / 3, dx = tap - dy * 3;
+                // output pixel (y, x) of the 8 x 16 box reads halo pixel (y + dy, x + dx): rows of 16 pixels = 2048 B
+                const uint64_t da = make_desc_kmajor_sw128_ex(
+                    smem_base + (uint32_t)aslot * HALO_BYTES + (uint32_t)(dy * HALO_W + dx) * 128u, HALO_W * 128u);
+                const uint64_t db = make_desc_kmajor_sw128(smem_base + ring_off + (uint32_t)stage * stage_bytes);
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16_ss_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                  umma_commit_2sm(&empty_bar[stage], (uint16_t)0x3);
+                }
+                __syncwarp();
+                advance(stage, phase, stages);
+              }
+              if (!ok) break;
+              if (elect_one()) umma_commit_2sm(&aempty_bar[aslot], (uint16_t)0x3);  // both CTAs' halo slot may be refilled
+              __syncwarp();
+              if (++aslot == p.halo) {
+                aslot = 0;
+                aphase ^= 1;
+              }
+            }
+            if (!ok) break;
+            if (elect_one()) umma_commit_2sm(&tfull_bar[acc], (uint16_t)0x3);
+            __syncwarp();
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+            continue;
+          }
         }
         for (int kb = 0; kb < kblocks; ++kb) {
           if (!TRACE_WAIT(4, mbar_wait(&full_bar[stage], phase, p.abort_flag))) {
@@ -1030,6 +1117,7 @@ static int g_gemm_2sm = 1;
 // 2-SM scheme, but the K = 320 / 640 projections LOSE 10..25 % (their tiles are 5-10 K steps long and every tile
 // hand-off crosses the CTA pair), so short reductions keep the two independent M = 128 MMAs.
 static int g_gemm_2sm_mink = 1280;
+static int g_conv_halo = 1;  // APTP_CONV_HALO=0: nine shifted boxes per K chunk (round-1 scheme) for A/B runs
 
 }  // namespace aptp
 
@@ -1047,6 +1135,8 @@ static int gemm_max_clusters() {
     // APTP_GEMM_2SM_MINK: shortest reduction length (K, times 9 for the convs) that takes the 2-SM scheme
     const char* e = getenv("APTP_GEMM_1SM");
     g_gemm_2sm = !(e && e[0] == '1');
+    const char* hl = getenv("APTP_CONV_HALO");
+    if (hl && hl[0] == '0') g_conv_halo = 0;
     const char* mk = getenv("APTP_GEMM_2SM_MINK");
     if (mk && atoi(mk) > 0) g_gemm_2sm_mink = atoi(mk);
     g_gemm_smem_set = 1;
@@ -1122,6 +1212,11 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int Ho = 1, Wo = 1;
+  APTP_REQUIRE(gemm_max_clusters() > 0, "aptp_grouped_gemm_fwd: no CTA pair fits on this device");
+  // (the opt-in A-stationary layout exists in the 1-SM scheme only)
+  const bool two_sm = g_gemm_2sm && a->a_stat_chunks <= 0 && (a->a_mode == APTP_A_LINEAR ? 1 : 9) * a->a_k >= g_gemm_2sm_mink;
+  // halo tile instead of nine shifted boxes: 2-SM stride-1 3x3 convs whose schedule uses 8 x 16 pixel boxes
+  const bool halo = two_sm && g_conv_halo && a->a_mode == APTP_A_CONV3X3 && a->bw == 8 && a->bh == 16 && a->bb == 1;
   if (a->a_mode == APTP_A_LINEAR) {
     uint64_t dims[2] = {(uint64_t)a->a_k, (uint64_t)a->a_rows};
     uint64_t strides[1] = {(uint64_t)a->a_ld * 2};
@@ -1136,6 +1231,10 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
     uint64_t dims[4] = {(uint64_t)a->a_k, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->batch};
     uint64_t strides[3] = {(uint64_t)a->a_ld * 2, (uint64_t)a->W * a->a_ld * 2, (uint64_t)a->H * a->W * a->a_ld * 2};
     uint32_t box[4] = {BK, (uint32_t)a->bw, (uint32_t)a->bh, (uint32_t)a->bb};
+    if (halo) {
+      box[1] = HALO_W;
+      box[2] = HALO_H;
+    }
     int rc = make_tmap_bf16(&p.tmap_a, a->a, 4, dims, strides, box);
     if (rc) return rc;
   } else if (a->a_mode == APTP_A_CONV3X3_S2) {
@@ -1228,17 +1327,21 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
                  "aptp_grouped_gemm_fwd: A-stationary mode needs a linear layer with at most %d K chunks", A_STAT_MAX_CHUNKS);
     p.a_stat = a->a_stat_chunks;
   }
-  APTP_REQUIRE(gemm_max_clusters() > 0, "aptp_grouped_gemm_fwd: no CTA pair fits on this device");
-  // (the opt-in A-stationary layout exists in the 1-SM scheme only)
-  const bool two_sm = g_gemm_2sm && !p.a_stat && (a->a_mode == APTP_A_LINEAR ? 1 : 9) * a->a_k >= g_gemm_2sm_mink;
-  const int stage_bytes = (p.a_stat ? 0 : A_STAGE_BYTES) + a->bn * (two_sm ? 64 : 128);
+  const int stage_bytes = ((p.a_stat || halo) ? 0 : A_STAGE_BYTES) + a->bn * (two_sm ? 64 : 128);
+  p.halo = 0;
+  if (halo) {  // 2 halo slots, a third one when the weight ring still gets 8 stages
+    p.halo = 2;
+    const int b8 = 8 * stage_bytes;
+    if (225 * 1024 - 1024 - 512 - STG_BYTES - SBIAS_BYTES - SSEG_BYTES - STILE_BYTES - 3 * HALO_BYTES >= b8) p.halo = 3;
+  }
+  const int a_region = p.halo ? p.halo * HALO_BYTES : p.a_stat * A_STAGE_BYTES;
   const int budget = 225 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STG_BYTES /*epilogue staging*/ - SBIAS_BYTES -
-                     SSEG_BYTES - STILE_BYTES - p.a_stat * A_STAGE_BYTES;
+                     SSEG_BYTES - STILE_BYTES - a_region;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   APTP_REQUIRE(stages >= 2, "aptp_grouped_gemm_fwd: tile too large for shared memory");
   p.stages = stages;
-  const size_t smem_bytes = (size_t)p.a_stat * A_STAGE_BYTES + (size_t)stages * stage_bytes + STG_BYTES + SBIAS_BYTES +
+  const size_t smem_bytes = (size_t)a_region + (size_t)stages * stage_bytes + STG_BYTES + SBIAS_BYTES +
                             SSEG_BYTES + STILE_BYTES + 1024 + 512;
   const int n_pairs = a->n_tiles / 2;
   int grid = 2 * (n_pairs < g_gemm_max_clusters ? n_pairs : g_gemm_max_clusters);

@@ -144,6 +144,10 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
     by_rows = {}
     kc_max = 0
     box = (BM, 1, 1) if mode == A_LINEAR else conv_box(Wo, Ho)
+    if mode == _lib.A_CONV3X3 and Wo % 8 == 0 and Ho % 16 == 0 and os.environ.get("APTP_CONV_HALO", "1") != "0":
+        # 8 x 16 pixel boxes: the kernel then loads ONE 18 x 16 halo tile per K chunk and derives the nine taps from it
+        # (aptp_grouped_gemm_fwd, halo mode) instead of nine shifted boxes
+        box = (8, 16, 1)
     bw, bh, bb = box
     hw = Ho * Wo
     cols_per_tile = bn // 2 if geglu else bn
