@@ -93,6 +93,20 @@ constexpr int A_STAT_MAX_CHUNKS = 6;
 constexpr int HALO_W = 16, HALO_H = 18;                   // halo box in pixels (10 needed across; 16 keeps the 8-row groups regular)
 constexpr int HALO_BYTES = HALO_W * HALO_H * 128;         // 36 KB per 64-channel chunk (9 boxes of 16 KB before)
 
+// Accumulator columns the MMAs of a tile compute: the LAST column tile of a bucket is ragged (kept widths are not
+// multiples of bn), so its MMAs run with N = the 32-column-rounded remainder instead of bn -- tensor time and operand reads
+// shrink with it (the weight box is still loaded whole). GEGLU tiles keep bn (their [h | g] halves sit at fixed columns).
+__device__ __forceinline__ int tile_mma_n(const aptp_gemm_seg& seg, int n0, int bn, bool geglu) {
+#ifdef APTP_NO_RAGGED_N
+  return bn;
+#else
+  if (geglu) return bn;
+  const int n_cols = seg.n_valid > seg.n_store ? seg.n_valid : seg.n_store;
+  const int left = (n_cols - n0 + 31) & ~31;
+  return left < bn ? (left < 32 ? 32 : left) : bn;
+#endif
+}
+
 __device__ __forceinline__ void advance(int& stage, uint32_t& phase, int stages) {
   if (++stage == stages) {
     stage = 0;
@@ -357,7 +371,9 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
           oy0 = rem / p.Wo;
           ox0 = rem - oy0 * p.Wo;
         }
-        const int b_row = seg.w_row_off + tile.n0 + (int)cta_rank * (p.bn >> 1);  // this CTA's half of the weight tile
+        // this CTA's half of the weight tile (2-SM: half of the columns the tile's MMAs really compute)
+        const int b_row = seg.w_row_off + tile.n0 +
+                          (int)cta_rank * ((k2Sm ? tile_mma_n(seg, tile.n0, p.bn, kGeglu) : p.bn) >> 1);
         if constexpr (k2Sm) {
           if (p.halo) {
             for (int kc = 0; kc < seg.k_chunks && ok; ++kc) {
@@ -448,7 +464,6 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
     // R2UR "waterfall" loop, which capped the issue rate at ~140 cycles per MMA (ncu, round 1).
     {
       GEMM_ROLE_PROLOGUE();
-      const uint32_t idesc = make_idesc_bf16(k2Sm ? 2 * BM : BM, (uint32_t)p.bn, 0, 0);
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
@@ -466,6 +481,8 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int tflags = __shfl_sync(0xffffffffu, trec->flags, 0);
         if (tflags & APTP_TILE_SKIP) continue;
         const int k_chunks = __shfl_sync(0xffffffffu, segs[seg_id].k_chunks, 0);
+        const int n_mma = __shfl_sync(0xffffffffu, tile_mma_n(segs[seg_id], trec->n0, p.bn, kGeglu), 0);
+        const uint32_t idesc = make_idesc_bf16(k2Sm ? 2 * BM : BM, (uint32_t)n_mma, 0, 0);
         const int kblocks = ((p.a_mode == APTP_A_LINEAR) ? 1 : 9) * k_chunks;
         if (!TRACE_WAIT(3, mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.abort_flag))) break;
         tc_fence_after();

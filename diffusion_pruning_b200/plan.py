@@ -30,17 +30,18 @@ def round_up(x: int, m: int) -> int:
 
 
 def choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False, k: int = 0) -> int:
-    """Accumulator width for one launch: the candidate with the fewest padded MMA columns, small widths penalised for
-    their worse operand reuse. An alternative model that also charges a fixed per-tile cost of the issuing warp (so
-    short-K layers get few, wide tiles; `k` = reduction length) is kept behind APTP_BN_MODEL=1 for experiments only: a
-    same-box A/B on the headline step measured it SLOWER (55.9 / 56.1 ms vs 53.7 / 53.4 ms, GEMM time 38.8 vs 34.6 ms)
-    -- wide tiles halve the tile count of the short launches, and the load imbalance over 74 CTA pairs costs more than
-    the per-tile overhead saved (profiles/README.md, round 2)."""
+    """Accumulator width for one launch from the shared-memory traffic of its tiles (the GEMM main
+    loop is bound by the ~128 B/clk the TMA writes and the tensor core's operand reads share). Per K step a 128-row
+    tile writes A + the weight box (bn rows; half of it per CTA in the 2-SM scheme, K*taps >= 1280; a quarter of A with
+    the conv halo tile) and reads A + the weight rows its MMAs really use -- the last column tile of a bucket is ragged
+    and runs with N = its 32-column-rounded remainder (`tile_mma_n` in gemm_sm100.cu), so wide tiles cost little padding.
+    Units: rows of 128 B. `k` = reduction length incl. taps (0: unknown, 1-SM assumed). APTP_BN_MODEL=0 restores the
+    round-1 rule (fewest padded columns)."""
     import os
     cands = [256, 224, 192, 160, 128, 96, 64]
     if geglu:
         cands = [256, 192, 128]
-    if k <= 0 or os.environ.get("APTP_BN_MODEL", "1") != "1":
+    if os.environ.get("APTP_BN_MODEL", "1") != "1":
         best, best_cost = None, None
         for bn in cands:
             cols = bn // 2 if geglu else bn
@@ -49,13 +50,22 @@ def choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False, 
             if best_cost is None or cost < best_cost - 1e-9:
                 best, best_cost = bn, cost
         return best or 128
-    # shared-memory traffic model (round 2): a K step of a 128 x bn tile moves A (16 KB) + B (bn / 8 KB) in and out of
-    # shared memory, i.e. costs ~ (A_cols + bn) with A_cols = 128 (1-SM) .. 171 (2-SM scheme, B written once)
-    overhead_cols = float(os.environ.get("APTP_BN_OVERHEAD", "171" if k >= 1280 else "128"))
+    two_sm = k >= 1280
+    a_write = 128.0 if k < 2880 else 40.0          # 3x3 convs: one halo tile per 9 taps (36 KB / 9 = 4 KB per K step)
+    a_write = float(os.environ.get("APTP_BN_OVERHEAD", a_write))
     best, best_cost = None, None
     for bn in cands:
         cols = bn // 2 if geglu else bn
-        cost = sum(((n + cols - 1) // cols) * (bn + overhead_cols) for n in n_values if n > 0)
+        cost = 0.0
+        for n in n_values:
+            if n <= 0:
+                continue
+            full, rem = divmod(n, cols)
+            w_box = bn / 2.0 if two_sm else float(bn)
+            cost += full * (a_write + w_box + 128.0 + bn)
+            if rem:
+                n_mma = bn if geglu else min(bn, (rem + 31) // 32 * 32)
+                cost += a_write + w_box + 128.0 + n_mma
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = bn, cost
     return best or 128
