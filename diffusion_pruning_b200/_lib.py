@@ -65,6 +65,9 @@ SIGNATURES = {
     "aptp_groupnorm_apply": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                      c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                      c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "aptp_groupnorm_apply_raw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                         c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                         c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "aptp_copy_rows_cvt": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_int,
                                    c_void_p]),
     "aptp_depth_lerp_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int,

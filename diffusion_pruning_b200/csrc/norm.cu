@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(NORM_THREADS)
                     const float* __restrict__ stats, int stats_groups, const float* __restrict__ gamma,
                     const float* __restrict__ beta, int affine_ld, const int* __restrict__ sample_seg,
                     const int* __restrict__ sample_channels, const float* __restrict__ gate, int gate_ld, int silu,
-                    int pix_per_cta) {
+                    int pix_per_cta, __nv_bfloat16* __restrict__ raw, int ld_raw) {
   const int b = blockIdx.y;
   const int ctot = sample_channels ? sample_channels[b] : (s.c0 + s.c1);
   if (ctot <= 0) return;
@@ -286,6 +286,14 @@ __global__ void __launch_bounds__(NORM_THREADS)
         out.z = pack_bf16(o[4], o[5]);
         out.w = pack_bf16(o[6], o[7]);
         *reinterpret_cast<uint4*>(y + ((long long)b * hw + pp) * ldy + v * 8) = out;
+        if (raw != nullptr) {  // bf16 copy of the UN-normalised input (the 1x1 shortcut's A operand), same pass
+          uint4 rw;
+          rw.x = pack_bf16(v * 8 + 0 < ctot ? f[0] : 0.f, v * 8 + 1 < ctot ? f[1] : 0.f);
+          rw.y = pack_bf16(v * 8 + 2 < ctot ? f[2] : 0.f, v * 8 + 3 < ctot ? f[3] : 0.f);
+          rw.z = pack_bf16(v * 8 + 4 < ctot ? f[4] : 0.f, v * 8 + 5 < ctot ? f[5] : 0.f);
+          rw.w = pack_bf16(v * 8 + 6 < ctot ? f[6] : 0.f, v * 8 + 7 < ctot ? f[7] : 0.f);
+          *reinterpret_cast<uint4*>(raw + ((long long)b * hw + pp) * ld_raw + v * 8) = rw;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
@@ -644,7 +652,19 @@ extern "C" int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, con
                                     const float* gamma, const float* beta, int32_t affine_ld,
                                     const int32_t* sample_seg, const int32_t* sample_channels, const float* gate,
                                     int32_t gate_ld, int32_t silu, void* stream_) {
+  return aptp_groupnorm_apply_raw(x0, c0, ld0, x1, c1, ld1, x_f32, y, ldy, batch, hw, group_size, eps, stats, stats_groups,
+                                  gamma, beta, affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, nullptr, 0,
+                                  stream_);
+}
+
+extern "C" int aptp_groupnorm_apply_raw(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
+                                        int32_t x_f32, void* y, int32_t ldy, int32_t batch, int32_t hw,
+                                        int32_t group_size, float eps, const float* stats, int32_t stats_groups,
+                                        const float* gamma, const float* beta, int32_t affine_ld,
+                                        const int32_t* sample_seg, const int32_t* sample_channels, const float* gate,
+                                        int32_t gate_ld, int32_t silu, void* raw_out, int32_t raw_ld, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  APTP_REQUIRE(raw_out == nullptr || (raw_ld % 8 == 0 && raw_ld >= c0 + c1), "aptp_groupnorm_apply_raw: bad raw_ld");
   int rc = check_src(x0, c0, ld0, x1, c1, ld1, "aptp_groupnorm_apply");
   if (rc) return rc;
   APTP_REQUIRE(y && stats && gamma && beta && ldy % 8 == 0, "aptp_groupnorm_apply: bad arguments");
@@ -654,11 +674,13 @@ extern "C" int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, con
   if (x_f32)
     gn_apply_kernel<true><<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size,
                                                             eps, stats, stats_groups, gamma, beta, affine_ld, sample_seg,
-                                                            sample_channels, gate, gate_ld, silu, ppc);
+                                                            sample_channels, gate, gate_ld, silu, ppc,
+                                                            reinterpret_cast<__nv_bfloat16*>(raw_out), raw_ld);
   else
     gn_apply_kernel<false><<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size,
                                                              eps, stats, stats_groups, gamma, beta, affine_ld, sample_seg,
-                                                             sample_channels, gate, gate_ld, silu, ppc);
+                                                             sample_channels, gate, gate_ld, silu, ppc,
+                                                             reinterpret_cast<__nv_bfloat16*>(raw_out), raw_ld);
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

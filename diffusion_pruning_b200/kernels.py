@@ -321,11 +321,13 @@ def groupnorm_stats_from_partials(cs0, c0, cs1, c1, blocks, batch, group_size, s
 
 
 def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps, stats, stats_groups, gamma, beta,
-                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, x_f32: bool = False):
-    check(load().aptp_groupnorm_apply(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, int(x_f32), _ptr(y), ldy, batch, hw,
-                                      group_size, float(eps), _ptr(stats), stats_groups, _ptr(gamma), _ptr(beta),
-                                      affine_ld, _ptr(sample_seg), _ptr(sample_channels), _ptr(gate), gate_ld,
-                                      int(silu), _stream()), "aptp_groupnorm_apply")
+                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, x_f32: bool = False, raw_out=None,
+                    raw_ld: int = 0):
+    """`raw_out` (optional bf16 [rows, raw_ld]): also write the un-normalised input (both sources) as bf16 rows."""
+    check(load().aptp_groupnorm_apply_raw(_ptr(x0), c0, ld0, _ptr(x1), c1, ld1, int(x_f32), _ptr(y), ldy, batch, hw,
+                                          group_size, float(eps), _ptr(stats), stats_groups, _ptr(gamma), _ptr(beta),
+                                          affine_ld, _ptr(sample_seg), _ptr(sample_channels), _ptr(gate), gate_ld,
+                                          int(silu), _ptr(raw_out), raw_ld, _stream()), "aptp_groupnorm_apply_raw")
 
 
 def ln_rowstats(partial, rows, C_, eps, out, sample_active=None, rows_per_sample=1):

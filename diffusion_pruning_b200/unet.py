@@ -1122,7 +1122,7 @@ class _Engine:
     def groupnorm(self, x: torch.Tensor, C: int, ld: int, B: int, hw: int, groups_full: int, gs: int, eps: float,
                   gamma: torch.Tensor, beta: torch.Tensor, affine_ld: int, out: torch.Tensor, out_ld: int, silu: bool,
                   sample_seg=None, sample_channels=None, gate=None, x1: Optional[torch.Tensor] = None, c1: int = 0,
-                  ld1: int = 0, alg_elems: Optional[float] = None, cs0=None, cs1=None):
+                  ld1: int = 0, alg_elems: Optional[float] = None, cs0=None, cs1=None, raw_out=None):
         """GroupNorm [+ soft width gate] [+ SiLU] -> bf16 rows. `x` (and the optional second source `x1` = the skip half
         of an up-block torch.cat) are bf16 or fp32 rows (dtype decides). Statistics: deterministic two-stage reduction
         (no atomics), see csrc/norm.cu."""
@@ -1140,10 +1140,12 @@ class _Engine:
             self._hbm(elems * (4 if f32 else 2), f"gn_stats C{C + c1} hw{hw} {'f32' if f32 else 'bf16'}",
                       lambda: K.groupnorm_stats(x, C, ld, x1, c1, ld1, B, hw, gs, sample_channels, stats, groups_full,
                                                 x_f32=f32))
-        self._hbm(elems * ((4 if f32 else 2) + 2), f"gn_apply C{C + c1} hw{hw} {'f32' if f32 else 'bf16'} silu{int(silu)}",
+        self._hbm(elems * ((4 if f32 else 2) + 2 + (2 if raw_out is not None else 0)),
+                  f"gn_apply C{C + c1} hw{hw} {'f32' if f32 else 'bf16'} silu{int(silu)}{' +raw' if raw_out is not None else ''}",
                   lambda: K.groupnorm_apply(x, C, ld, x1, c1, ld1, out, out_ld, B, hw, gs, eps, stats, groups_full, gamma,
                                             beta, affine_ld, sample_seg, sample_channels, gate,
-                                            gate.stride(0) if gate is not None else groups_full, silu, x_f32=f32))
+                                            gate.stride(0) if gate is not None else groups_full, silu, x_f32=f32,
+                                            raw_out=raw_out, raw_ld=raw_out.shape[1] if raw_out is not None else 0))
         self.launches += 2
 
     def _colstat_new(self, B: int, H: int, W: int, C: int):
@@ -1353,13 +1355,15 @@ class _Engine:
         # norm1 + SiLU straight from the fp32 stream; an up block's torch.cat([hidden_states, res_hidden_states], 1)
         # (blocks.py: inherited UpBlock2D.forward) is read as two sources, never materialised in fp32
         a1 = self.buf("gn_a", M, r.cin)
+        # the 1x1 shortcut's bf16 A operand (the concatenated, un-normalised input) is written by the same pass
+        xin16 = self.buf("cat", M, r.cin) if r.conv_shortcut is not None else None
         if skip is not None:
             self.groupnorm(x.f, x.C, x.C, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
                            sample_channels=aux.get("ch_in"), x1=skip.f, c1=skip.C, ld1=skip.C, alg_elems=el_in,
-                           cs0=x.cs, cs1=skip.cs)
+                           cs0=x.cs, cs1=skip.cs, raw_out=xin16)
         else:
             self.groupnorm(x.f, x.C, x.C, B, hw, r.groups, gs_in, r.eps, pk["g1"], pk["b1"], r.cin, a1, r.cin, True,
-                           sample_channels=aux.get("ch_in"), alg_elems=el_in, cs0=x.cs)
+                           sample_channels=aux.get("ch_in"), alg_elems=el_in, cs0=x.cs, raw_out=xin16)
         # conv1 (N-compacted) + time embedding (+ conv1/time biases, folded into the row vector)
         h1 = self.buf("res_h1", M, r.cout)
 
@@ -1381,14 +1385,7 @@ class _Engine:
         # shortcut: 1x1 conv over the bf16 copy of the (concatenated) input, written fp32 and added in place by conv2
         out = torch.empty(M, r.cout, device=self.device, dtype=torch.float32)
         if r.conv_shortcut is not None:
-            if skip is not None:
-                xin16 = self.buf("cat", M, r.cin)
-                K.copy_rows_cvt(x.f, x.C, xin16, r.cin, M, x.C)
-                K.copy_rows_cvt(skip.f, skip.C, xin16[:, x.C:], r.cin, M, skip.C)
-                self.launches += 2
-                xin_ld = r.cin
-            else:
-                xin16, xin_ld = self._bf16(x), x.ld
+            xin_ld = r.cin
             self.linear("sc." + r.uid, r.conv_shortcut, xin16, M, r.cin, xin_ld, out, r.cout, hw, active=active,
                         out_mode=OUT_F32)
             res, res_ld = out, r.cout

@@ -195,6 +195,15 @@ int aptp_groupnorm_apply(const void* x0, int32_t c0, int32_t ld0, const void* x1
                          const float* beta, int32_t affine_ld, const int32_t* sample_seg,
                          const int32_t* sample_channels, const float* gate, int32_t gate_ld, int32_t silu,
                          void* stream);
+/* The same pass additionally writes `raw_out` (bf16 rows, pitch raw_ld, may be NULL): the UN-normalised input converted
+ * to bf16 with both sources concatenated -- the A operand of ResnetBlock2D's 1x1 conv_shortcut over
+ * torch.cat([hidden_states, res_hidden_states], 1) (blocks.py:367-369) -- so the fp32 stream is read once for both. */
+int aptp_groupnorm_apply_raw(const void* x0, int32_t c0, int32_t ld0, const void* x1, int32_t c1, int32_t ld1,
+                             int32_t x_f32, void* y, int32_t ldy, int32_t batch, int32_t hw, int32_t group_size,
+                             float eps, const float* stats, int32_t stats_groups, const float* gamma,
+                             const float* beta, int32_t affine_ld, const int32_t* sample_seg,
+                             const int32_t* sample_channels, const float* gate, int32_t gate_ld, int32_t silu,
+                             void* raw_out, int32_t raw_ld, void* stream);
 /* LayerNorm over the channel dim of [rows, C] bf16 (eps 1e-5, affine); replaces
  * BasicTransformerBlock.norm1/2/3 (blocks.py:782,:808-810,:821). row_active (optional, per sample)
  * skips depth-dropped samples. */

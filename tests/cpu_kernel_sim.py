@@ -195,10 +195,16 @@ def groupnorm_stats_from_partials(cs0, c0, cs1, c1, blocks, batch, group_size, s
 
 
 def groupnorm_apply(x0, c0, ld0, x1, c1, ld1, y, ldy, batch, hw, group_size, eps, stats, stats_groups, gamma, beta,
-                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, x_f32=False):
+                    affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, x_f32=False, raw_out=None, raw_ld=0):
     X = _view(x0, batch * hw, c0, ld0).float()
     if c1:
         X = torch.cat([X, _view(x1, batch * hw, c1, ld1).float()], 1)
+    if raw_out is not None:
+        R = _view(raw_out, batch * hw, raw_ld, raw_ld)
+        for b in range(batch):
+            ct = int(sample_channels[b]) if sample_channels is not None else c0 + c1
+            if ct > 0:
+                R[b * hw:(b + 1) * hw, :ct] = X[b * hw:(b + 1) * hw, :ct].to(torch.bfloat16)
     Y = _view(y, batch * hw, ldy, ldy)
     st = stats.view(batch, stats_groups, 2)
     G = gamma.reshape(-1, affine_ld)
