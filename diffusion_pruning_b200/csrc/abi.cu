@@ -1,4 +1,5 @@
 // Library plumbing for libaptp_sm100.so: error slot, device abort flag, tensor-map encoding.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/aptp_sm100.h"
 #include <stdarg.h>
@@ -118,6 +119,15 @@ int make_tmap_store64(CUtensorMap* out, const void* base, bool f32, uint64_t col
     return APTP_ERR_CUDA;
   }
   return APTP_OK;
+}
+
+int pdl_level() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("APTP_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
 }
 
 }  // namespace aptp

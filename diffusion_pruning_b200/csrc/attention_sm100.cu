@@ -64,7 +64,10 @@ struct AttnParams {
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   const int head = blockIdx.y, b = blockIdx.z;
-  if (head >= p.sample_heads[b]) return;  // pruned head / depth-dropped sample: no work at all
+  if (head >= p.sample_heads[b]) {  // pruned head / depth-dropped sample: no work at all
+    pdl_wait();  // (a grid none of whose CTAs waited would "complete" before its predecessors and unchain its successors)
+    return;
+  }
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -120,6 +123,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch();
+  pdl_wait();  // q / k / v come from the projection GEMMs before us
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -544,7 +549,7 @@ extern "C" int aptp_attention_fwd(const void* q, int32_t ldq, const void* k, int
     if (want < gx) gx = (int)want;
   }
   dim3 grid(gx, max_heads, batch);
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(p);
+  APTP_CUDA_CHECK(launch_pdl(attention_kernel, grid, dim3(ATT_THREADS), (size_t)ATT_SMEM_BYTES, stream, p));
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }

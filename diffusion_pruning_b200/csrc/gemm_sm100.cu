@@ -308,6 +308,8 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
   tc_fence_before();
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before any multicast load / remote arrive
   tc_fence_after();
+  pdl_launch();  // the next kernel's CTAs may take over SMs as ours exit and run their prologue
+  pdl_wait();    // everything above touched only launch-time data; from here on we read what predecessors wrote
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 " GEMM_CTRL_REGS ";");
@@ -1369,8 +1371,8 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
   }
 #define APTP_LAUNCH_GEMM(EPI)                                                                  \
   do {                                                                                         \
-    if (two_sm) grouped_gemm_kernel<EPI, true><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p); \
-    else grouped_gemm_kernel<EPI, false><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);       \
+    if (two_sm) APTP_CUDA_CHECK(launch_pdl(grouped_gemm_kernel<EPI, true>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, p)); \
+    else APTP_CUDA_CHECK(launch_pdl(grouped_gemm_kernel<EPI, false>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, p));       \
   } while (0)
   if (a->flags & APTP_EPI_GEGLU) APTP_LAUNCH_GEMM(EPI_GEGLU);
   else if (a->out_mode == APTP_OUT_BF16) APTP_LAUNCH_GEMM(EPI_BF16);

@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(NORM_THREADS)
                     int stats_groups, int pix_per_cta, unsigned int* __restrict__ tickets, float* __restrict__ partial) {
   extern __shared__ float cells[];  // [2][rows_per_iter][cv * 8]  (sum plane, then sum-of-squares plane)
   __shared__ int s_last;
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.y;
   const int ctot = sample_channels ? sample_channels[b] : (s.c0 + s.c1);
   if (ctot <= 0) return;  // uniform over the sample's CTAs
@@ -211,6 +213,8 @@ __global__ void __launch_bounds__(NORM_THREADS)
                     const float* __restrict__ beta, int affine_ld, const int* __restrict__ sample_seg,
                     const int* __restrict__ sample_channels, const float* __restrict__ gate, int gate_ld, int silu,
                     int pix_per_cta, __nv_bfloat16* __restrict__ raw, int ld_raw) {
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.y;
   const int ctot = sample_channels ? sample_channels[b] : (s.c0 + s.c1);
   if (ctot <= 0) return;
@@ -490,6 +494,8 @@ __global__ void __launch_bounds__(256 * GNF_SLICES)
   // accumulators each, so 16 loads per plane are in flight per channel); then one thread per group adds the slices and
   // its gs channel totals in a fixed order: every sum has a fixed order
   __shared__ float ssum[GNF_SLICES][256], ssq[GNF_SLICES][256];
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.x;
   const int ctot = sample_channels ? sample_channels[b] : ctot_all;
   if (ctot <= 0) return;
@@ -547,6 +553,8 @@ __global__ void __launch_bounds__(256 * GNF_SLICES)
 __global__ void __launch_bounds__(256) ln_rowstats_kernel(const float2* __restrict__ partial, int chunks, long long rows,
                                                           float inv_c, float eps, float2* __restrict__ out,
                                                           const uint8_t* __restrict__ sample_active, int rows_per_sample) {
+  pdl_launch();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   if (sample_active && !sample_active[row / rows_per_sample]) return;
@@ -618,11 +626,11 @@ extern "C" int aptp_groupnorm_stats(const void* x0, int32_t c0, int32_t ld0, con
   const int C = c0 + c1;
   const size_t smem = (size_t)2 * (C > NORM_THREADS * 8 ? C : NORM_THREADS * 8) * sizeof(float);
   if (x_f32)
-    gn_stats_kernel<true><<<grid, NORM_THREADS, smem, stream>>>(s, hw, group_size, sample_channels, stats,
-                                                               stats_groups, ppc, tickets, partial);
+    APTP_CUDA_CHECK(launch_pdl_at(2, gn_stats_kernel<true>, grid, dim3(NORM_THREADS), smem, stream, s, hw, group_size,
+                               sample_channels, stats, stats_groups, ppc, tickets, partial));
   else
-    gn_stats_kernel<false><<<grid, NORM_THREADS, smem, stream>>>(s, hw, group_size, sample_channels, stats,
-                                                                stats_groups, ppc, tickets, partial);
+    APTP_CUDA_CHECK(launch_pdl_at(2, gn_stats_kernel<false>, grid, dim3(NORM_THREADS), smem, stream, s, hw, group_size,
+                               sample_channels, stats, stats_groups, ppc, tickets, partial));
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }
@@ -640,8 +648,9 @@ extern "C" int aptp_groupnorm_stats_from_partials(const float* sum0, const float
   APTP_REQUIRE(groups <= stats_groups, "aptp_groupnorm_stats_from_partials: stats_groups too small");
   APTP_REQUIRE(group_size <= 256, "aptp_groupnorm_stats_from_partials: group_size %d > 256", group_size);
   const int gpc = 256 / group_size;  // whole groups per CTA
-  gn_partials_finalize_kernel<<<dim3(batch, (groups + gpc - 1) / gpc), dim3(256, GNF_SLICES), 0, stream>>>(
-      sum0, sq0, c0, ld0, sum1, sq1, ld1, c0 + c1, blocks, group_size, gpc, sample_channels, stats, stats_groups);
+  APTP_CUDA_CHECK(launch_pdl_at(2, gn_partials_finalize_kernel, dim3(batch, (groups + gpc - 1) / gpc), dim3(256, GNF_SLICES),
+                             (size_t)0, stream, sum0, sq0, c0, ld0, sum1, sq1, ld1, c0 + c1, blocks, group_size, gpc,
+                             sample_channels, stats, stats_groups));
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }
@@ -672,15 +681,15 @@ extern "C" int aptp_groupnorm_apply_raw(const void* x0, int32_t c0, int32_t ld0,
   const int ppc = pick_pix_per_cta(hw, batch);
   dim3 grid((hw + ppc - 1) / ppc, batch);
   if (x_f32)
-    gn_apply_kernel<true><<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size,
-                                                            eps, stats, stats_groups, gamma, beta, affine_ld, sample_seg,
-                                                            sample_channels, gate, gate_ld, silu, ppc,
-                                                            reinterpret_cast<__nv_bfloat16*>(raw_out), raw_ld);
+    APTP_CUDA_CHECK(launch_pdl_at(2, gn_apply_kernel<true>, grid, dim3(NORM_THREADS), (size_t)0, stream, s,
+                               reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size, eps, stats, stats_groups, gamma, beta,
+                               affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, ppc,
+                               reinterpret_cast<__nv_bfloat16*>(raw_out), raw_ld));
   else
-    gn_apply_kernel<false><<<grid, NORM_THREADS, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size,
-                                                             eps, stats, stats_groups, gamma, beta, affine_ld, sample_seg,
-                                                             sample_channels, gate, gate_ld, silu, ppc,
-                                                             reinterpret_cast<__nv_bfloat16*>(raw_out), raw_ld);
+    APTP_CUDA_CHECK(launch_pdl_at(2, gn_apply_kernel<false>, grid, dim3(NORM_THREADS), (size_t)0, stream, s,
+                               reinterpret_cast<__nv_bfloat16*>(y), ldy, hw, group_size, eps, stats, stats_groups, gamma, beta,
+                               affine_ld, sample_seg, sample_channels, gate, gate_ld, silu, ppc,
+                               reinterpret_cast<__nv_bfloat16*>(raw_out), raw_ld));
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }
@@ -692,9 +701,9 @@ extern "C" int aptp_ln_rowstats(const float* partial, int32_t chunks, int64_t ro
                    (reinterpret_cast<uintptr_t>(partial) & 15) == 0,
                "aptp_ln_rowstats: bad arguments (chunks must be even, partial 16-byte aligned)");
   if (rows == 0) return APTP_OK;
-  ln_rowstats_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const float2*>(partial), chunks, rows, 1.f / (float)C, eps, reinterpret_cast<float2*>(out),
-      sample_active, rows_per_sample);
+  APTP_CUDA_CHECK(launch_pdl_at(2, ln_rowstats_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), (size_t)0, stream,
+                             reinterpret_cast<const float2*>(partial), chunks, (long long)rows, 1.f / (float)C, eps,
+                             reinterpret_cast<float2*>(out), sample_active, rows_per_sample));
   APTP_CUDA_CHECK(cudaGetLastError());
   return APTP_OK;
 }
