@@ -757,7 +757,7 @@ def secondary_workloads(args):
     import torch
     sec = {}
     a = copy.copy(args)
-    a.steps, a.warmup = args.secondary_train_steps, 3
+    a.steps, a.warmup = args.secondary_train_steps, 6  # (the allocator re-grows its pools after the library-baseline leg)
     try:
         tr = measure_train(a)
         sec.update(train_samples_steps_per_s=tr["value"], train_ms=tr["ms_per_step"], train_batch_per_gpu=a.train_batch,
@@ -833,7 +833,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU library bar (N=1)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2] / configs[3] numbers")
-    ap.add_argument("--secondary-train-steps", type=int, default=4)
+    ap.add_argument("--secondary-train-steps", type=int, default=6)
     ap.add_argument("--workload", default="forward", choices=["forward", "train", "sample", "finetune"])
     ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--prompts", type=int, default=16, help="--workload sample: prompts per GPU")

@@ -42,6 +42,7 @@ class GemmArgs(C.Structure):
         ("ln_reserved2", c_float),
         ("rowstat_out", c_void_p), ("rowstat_chunks", c_int),
         ("gn_stats_sq", c_void_p), ("a_stat_chunks", c_int), ("a_stat_pairs", c_int),
+        ("a2", c_void_p), ("a2_ld", c_int), ("a2_k", c_int), ("w2", c_void_p), ("w2_rows", c_int64), ("w2_ld", c_int),
     ]
 
 

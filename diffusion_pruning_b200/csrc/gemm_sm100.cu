@@ -86,6 +86,11 @@ struct GemmParams {
   // it (8-pixel box rows = the 8-row groups of the operand, 16 pixel rows = 2048 B apart); only the weight tiles stream
   // through the ring. A is written to shared memory once per chunk instead of once per tap.
   int halo;          // 0, or the number of A (halo) slots
+  // second operand pair of a halo-mode conv (the ResNet's 1x1 shortcut): k2_chunks more K steps per tile whose A tile is
+  // the plain 8 x 16-pixel box of a second tensor and whose weights are indexed by the output column
+  CUtensorMap tmap_a2;
+  CUtensorMap tmap_b2;
+  int k2_chunks;
   int* abort_flag;
 };
 
@@ -258,6 +263,10 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
     if (p.out_tma) tma_prefetch_desc(&p.tmap_out);
+    if (p.k2_chunks) {
+      tma_prefetch_desc(&p.tmap_a2);
+      tma_prefetch_desc(&p.tmap_b2);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -401,6 +410,29 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
                 __syncwarp();
                 advance(stage, phase, stages);
               }
+              if (++aslot == p.halo) {
+                aslot = 0;
+                aphase ^= 1;
+              }
+            }
+            // the 1x1 shortcut's K steps: plain box of the second tensor into the next A slot, W2 rows = output columns
+            const int b2_row = tile.n0 + (int)cta_rank * (tile_mma_n(seg, tile.n0, p.bn, kGeglu) >> 1);
+            for (int kc = 0; kc < p.k2_chunks && ok; ++kc) {
+              if (!mbar_wait(&aempty_bar[aslot], aphase ^ 1, p.abort_flag) ||
+                  !mbar_wait(&empty_bar[stage], phase ^ 1, p.abort_flag)) {
+                ok = false;
+                break;
+              }
+              if (elect_one()) {
+                if (cta_rank == 0) {
+                  mbar_expect_tx(&afull_bar[aslot], 2u * A_STAGE_BYTES);
+                  mbar_expect_tx(&full_bar[stage], 2u * stage_bytes);
+                }
+                tma_load_4d_2sm(smem + (size_t)aslot * HALO_BYTES, &p.tmap_a2, &afull_bar[aslot], kc * BK, ox0, oy0, img);
+                tma_load_2d_2sm(smem + ring_off + (size_t)stage * stage_bytes, &p.tmap_b2, &full_bar[stage], kc * BK, b2_row);
+              }
+              __syncwarp();
+              advance(stage, phase, stages);
               if (++aslot == p.halo) {
                 aslot = 0;
                 aphase ^= 1;
@@ -553,6 +585,29 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
               if (!ok) break;
               if (elect_one()) umma_commit_2sm(&aempty_bar[aslot], (uint16_t)0x3);  // both CTAs' halo slot may be refilled
               __syncwarp();
+              if (++aslot == p.halo) {
+                aslot = 0;
+                aphase ^= 1;
+              }
+            }
+            for (int kc = 0; kc < p.k2_chunks && ok; ++kc) {  // the 1x1 shortcut accumulates into the same tile
+              if (!mbar_wait(&afull_bar[aslot], aphase, p.abort_flag) ||
+                  !TRACE_WAIT(4, mbar_wait(&full_bar[stage], phase, p.abort_flag))) {
+                ok = false;
+                break;
+              }
+              tc_fence_after();
+              const uint64_t da = make_desc_kmajor_sw128(smem_base + (uint32_t)aslot * HALO_BYTES);
+              const uint64_t db = make_desc_kmajor_sw128(smem_base + ring_off + (uint32_t)stage * stage_bytes);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_bf16_ss_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+                umma_commit_2sm(&empty_bar[stage], (uint16_t)0x3);
+                umma_commit_2sm(&aempty_bar[aslot], (uint16_t)0x3);
+              }
+              __syncwarp();
+              advance(stage, phase, stages);
               if (++aslot == p.halo) {
                 aslot = 0;
                 aphase ^= 1;
@@ -1279,6 +1334,27 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
     uint32_t box[2] = {BK, (uint32_t)a->bn / 2};  // each CTA of a pair loads (and multicasts) half of the weight tile
     int rc = make_tmap_bf16(&p.tmap_b, a->w, 2, dims, strides, box);
     if (rc) return rc;
+  }
+  p.k2_chunks = 0;
+  if (a->a2 != nullptr) {
+    if (!halo) {
+      set_error("aptp_grouped_gemm_fwd: the second operand pair (a2 / w2) needs the halo-tile conv scheme");
+      return APTP_ERR_UNSUPPORTED;
+    }
+    APTP_REQUIRE(a->w2 && a->a2_k > 0 && a->a2_k % 8 == 0 && a->a2_ld % 8 == 0 && a->w2_ld % 8 == 0 && a->w2_rows > 0 &&
+                     !(a->flags & APTP_EPI_GEGLU),
+                 "aptp_grouped_gemm_fwd: bad second operand pair");
+    uint64_t dims[4] = {(uint64_t)a->a2_k, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->batch};
+    uint64_t strides[3] = {(uint64_t)a->a2_ld * 2, (uint64_t)a->W * a->a2_ld * 2, (uint64_t)a->H * a->W * a->a2_ld * 2};
+    uint32_t box[4] = {BK, 8, 16, 1};
+    int rc = make_tmap_bf16(&p.tmap_a2, a->a2, 4, dims, strides, box);
+    if (rc) return rc;
+    uint64_t wdims[2] = {(uint64_t)a->w2_ld, (uint64_t)a->w2_rows};
+    uint64_t wstrides[1] = {(uint64_t)a->w2_ld * 2};
+    uint32_t wbox[2] = {BK, (uint32_t)a->bn / 2};
+    rc = make_tmap_bf16(&p.tmap_b2, a->w2, 2, wdims, wstrides, wbox);
+    if (rc) return rc;
+    p.k2_chunks = (a->a2_k + BK - 1) / BK;
   }
   p.segs = a->segs;
   p.tiles = a->tiles;

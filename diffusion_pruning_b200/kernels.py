@@ -247,7 +247,8 @@ def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Sch
                  residual: Optional[torch.Tensor] = None, res_ld: int = 0, gate: Optional[torch.Tensor] = None,
                  gate_ld: int = 0, gate_group: int = 1, border_tab: Optional[torch.Tensor] = None, tab_ld: int = 0,
                  flags: int = 0, ln_colsum: Optional[torch.Tensor] = None, ln_rowstats: Optional[torch.Tensor] = None,
-                 rowstat_out: Optional[torch.Tensor] = None, colstat=None) -> None:
+                 rowstat_out: Optional[torch.Tensor] = None, colstat=None, a2: Optional[torch.Tensor] = None,
+                 a2_ld: int = 0, a2_k: int = 0, w2: Optional[torch.Tensor] = None) -> None:
     """out = epilogue(A @ W^T) through aptp_grouped_gemm_fwd. `a`, `w`, `out` may be views: only
     data_ptr() and the explicit pitches are used."""
     if sched.n_tiles == 0:
@@ -276,6 +277,9 @@ def grouped_gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, sched: Sch
     args.rowstat_out = _ptr(rowstat_out)                                     # [rows, C/32, 2] fp32 (sum, sumsq)
     args.rowstat_chunks = rowstat_out.shape[1] if rowstat_out is not None else 0
     args.a_stat_chunks, args.a_stat_pairs = sched.a_stat, sched.a_pairs
+    # second operand pair accumulated into the same tiles (the ResNet's 1x1 shortcut inside conv2; halo-mode convs only)
+    args.a2, args.a2_ld, args.a2_k = _ptr(a2), a2_ld, a2_k
+    args.w2, args.w2_rows, args.w2_ld = _ptr(w2), (w2.shape[0] if w2 is not None else 0), (w2.shape[1] if w2 is not None else 0)
     args.segs, args.n_segs = sched.segs.data_ptr(), sched.n_segs
     args.tiles, args.n_tiles = sched.tiles.data_ptr(), sched.n_tiles
     check(load().aptp_grouped_gemm_fwd(C.byref(args), _stream()), "aptp_grouped_gemm_fwd")

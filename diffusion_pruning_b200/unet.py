@@ -1057,16 +1057,18 @@ class _Engine:
             fn()
 
     def _gemm(self, sched: K.Schedule, a, w, out, **kw):
+        extra_flops = kw.pop("extra_flops", 0.0)  # work of a fused second operand pair (not in the schedule's count)
         if self.profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             K.grouped_gemm(a, w, out, sched, **kw)
             e1.record()
-            self.profile.append(("gemm", e0, e1, sched.flops, f"{self._label} bn{sched.bn} tiles{sched.n_tiles} mode{kw.get('mode', 0)}"))
+            self.profile.append(("gemm", e0, e1, sched.flops + extra_flops,
+                                 f"{self._label} bn{sched.bn} tiles{sched.n_tiles} mode{kw.get('mode', 0)}"))
         else:
             K.grouped_gemm(a, w, out, sched, **kw)
         self.launches += 1
-        self.flops += sched.flops
+        self.flops += sched.flops + extra_flops
         res_bytes = 0 if kw.get('residual') is None else (4 if kw.get('flags', 0) & EPI_RES_F32 else 2)
         self.gemm_bytes += sched.bytes_in + sched.out_elems * ((2 if kw.get('out_mode', OUT_BF16) == OUT_BF16 else 4)
                                                                + res_bytes)
@@ -1384,7 +1386,21 @@ class _Engine:
                        sample_channels=aux.get("ch_mid"), gate=gate, alg_elems=el_mid)
         # shortcut: 1x1 conv over the bf16 copy of the (concatenated) input, written fp32 and added in place by conv2
         out = torch.empty(M, r.cout, device=self.device, dtype=torch.float32)
-        if r.conv_shortcut is not None:
+        # ... unless conv2 can take it as extra K steps of its own tiles (halo-mode convs: 8 x 16-pixel boxes, 2-SM scheme)
+        fuse_sc = (r.conv_shortcut is not None and W % 8 == 0 and H % 16 == 0 and 9 * r.cout >= 1280
+                   and os.environ.get("APTP_SC_FUSE", "1") != "0" and os.environ.get("APTP_CONV_HALO", "1") != "0"
+                   and os.environ.get("APTP_GEMM_1SM", "0") != "1")
+        sc_kw = {}
+        if fuse_sc:
+            dsc = self._dense_linear("sc." + r.uid, r.conv_shortcut)
+            bkey = ("b2sc", r.uid)
+            b2sc = self.dense.get(bkey)
+            if b2sc is None:
+                b2sc = self._pack(self.dense, bkey, lambda: (pk["b2"] + dsc["b"]).contiguous())
+            rows_act = float(active[self.layout.expert_of_pos].sum()) * hw if self.compact else float(M)
+            sc_kw = dict(a2=xin16, a2_ld=r.cin, a2_k=r.cin, w2=dsc["w"], extra_flops=2.0 * rows_act * r.cin * r.cout)
+            res, res_ld = None, 0
+        elif r.conv_shortcut is not None:
             xin_ld = r.cin
             self.linear("sc." + r.uid, r.conv_shortcut, xin16, M, r.cin, xin_ld, out, r.cout, hw, active=active,
                         out_mode=OUT_F32)
@@ -1405,8 +1421,9 @@ class _Engine:
         if cs_out is not None and self.compact and aux["drop_mask"] is not None and x.cs is None:
             cs_out = None  # dropped samples would need the input's partial rows
         self._gemm(sched, a2, pk["w2"], out, a_ld=r.cout, a_k=r.cout, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W,
-                   k_tap_pitch=r.cout, out_ld=r.cout, out_mode=OUT_F32, bias=pk["b2"], residual=res, res_ld=res_ld,
-                   flags=EPI_RES_F32, rows_per_sample=hw, border_tab=pk["tab"], tab_ld=r.cout, colstat=cs_out)
+                   k_tap_pitch=r.cout, out_ld=r.cout, out_mode=OUT_F32, bias=b2sc if fuse_sc else pk["b2"], residual=res,
+                   res_ld=res_ld, flags=EPI_RES_F32 if res is not None else 0, rows_per_sample=hw, border_tab=pk["tab"],
+                   tab_ld=r.cout, colstat=cs_out, **sc_kw)
         # depth gate: the non-skip part of the input is the identity branch (blocks.py:485-495)
         if r.depth_gate is not None:
             keep_c = x.C if skip is not None else x.C - (r.skip_connection_dim or 0)

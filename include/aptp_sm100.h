@@ -155,6 +155,18 @@ typedef struct aptp_gemm_args {
   int32_t a_stat_chunks;     /* > 0: A-stationary tile list (see APTP_TILE_A_FIRST); = max k_chunks over the segments,
                                 at most 6 (K <= 384), linear layers only                                          */
   int32_t a_stat_pairs;      /* the number S of CTA pairs the A-stationary tile list was laid out for              */
+  /* Second operand pair accumulated into the SAME tiles (APTP_A_CONV3X3 only): out += A2[pixel, :] * W2[n, :]^T, a 1x1
+   * conv over a second NHWC tensor of the same batch / H / W -- ResnetBlock2D.conv_shortcut over the (concatenated)
+   * block input (blocks.py:367-369), so the shortcut costs no launch, no fp32 round trip and no residual read. W2 is
+   * [>= n, a2_k] bf16 with row pitch w2_ld, indexed by the output column (not compacted); its bias is expected in
+   * `bias`. NULL a2: none. Honoured by the halo-tile scheme (8 x 16-pixel boxes, reductions >= 1280); otherwise
+   * aptp_grouped_gemm_fwd returns APTP_ERR_UNSUPPORTED and the caller launches the 1x1 conv itself. */
+  const void* a2;
+  int32_t a2_ld;
+  int32_t a2_k;
+  const void* w2;
+  int64_t w2_rows;
+  int32_t w2_ld;
 } aptp_gemm_args;
 
 int aptp_grouped_gemm_fwd(const aptp_gemm_args* args, void* stream);

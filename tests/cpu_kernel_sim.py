@@ -52,7 +52,7 @@ def _check_tiles(sched: K.Schedule, mode, Ho, Wo, geglu):
 def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1, H=1, W=1, k_tap_pitch=0, out_ld,
                  out_mode=OUT_BF16, bias=None, rowvec=None, rowvec_ld=0, rows_per_sample=1, residual=None, res_ld=0,
                  gate=None, gate_ld=0, gate_group=1, border_tab=None, tab_ld=0, flags=0, ln_colsum=None, ln_rowstats=None,
-                 rowstat_out=None, colstat=None):
+                 rowstat_out=None, colstat=None, a2=None, a2_ld=0, a2_k=0, w2=None):
     if sched.n_tiles == 0:
         return
     geglu = bool(flags & EPI_GEGLU)
@@ -100,6 +100,10 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
             ncols = max(nv, ns)
             wk = Wm[wro:wro + ncols].reshape(ncols, 9, k_tap_pitch)[:, :, :kk].reshape(ncols, 3, 3, kk).permute(0, 3, 1, 2)
             acc = F.conv2d(x, wk, None, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, ncols)
+            if a2 is not None:  # second operand pair: 1x1 conv over a second tensor into the same tiles
+                assert mode == A_CONV3X3
+                A2 = _view(a2, a_rows, a2_k, a2_ld).float()
+                acc = acc + A2[rb:re] @ w2.float()[:ncols, :a2_k].t()
         rows = torch.arange(rb, re)
         sample = rows // rows_per_sample
         if geglu:

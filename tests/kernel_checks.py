@@ -130,6 +130,27 @@ def check_conv3x3(B=3, H=16, W=16, Cin=128, Cout=96, bn=96, stride=1, border=Fal
     _close(out, ref, 2e-2, 1e-2, f"conv3x3 s{stride} B{B} {H}x{W} {Cin}->{Cout}")
 
 
+def check_conv3x3_fused_shortcut(B=2, H=32, W=32, Cin=320, Cout=320, C2=448, bn=160, seed=0):
+    """3x3 conv (halo-tile scheme: 8 x 16 boxes, 2-SM) with the ResNet's 1x1 conv_shortcut over a second tensor accumulated
+    into the same tiles (aptp_gemm_args.a2 / w2), fp32 rows out with the border table and both biases."""
+    x = _rand(B, Cin, H, W, seed=seed).bfloat16()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=seed + 1).bfloat16()
+    b = _rand(Cout, seed=seed + 2)
+    x2 = _rand(B * H * W, C2, seed=seed + 3).bfloat16()
+    w2 = _rand(Cout, C2, scale=C2 ** -0.5, seed=seed + 4).bfloat16()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_packed = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = torch.full((B * H * W, Cout), float("nan"), device=DEV, dtype=torch.float32)
+    sched = K.build_schedule([K.Segment(0, B * H * W, Cout, (Cin + 63) // 64)], bn, DEV, mode=A_CONV3X3, Ho=H, Wo=W)
+    assert sched.box == (8, 16, 1)
+    K.grouped_gemm(x_nhwc, w_packed, out, sched, a_ld=Cin, a_k=Cin, a_rows=B * H * W, mode=A_CONV3X3, batch=B, H=H, W=W,
+                   k_tap_pitch=Cin, out_ld=Cout, out_mode=OUT_F32, bias=b, rows_per_sample=H * W, a2=x2, a2_ld=C2, a2_k=C2,
+                   w2=w2)
+    K.check_abort()
+    ref = _conv_ref(x.float(), w.float(), b, 1).permute(0, 2, 3, 1).reshape(B * H * W, Cout) + x2.float() @ w2.float().t()
+    _close(out, ref, 2e-2, 1e-2, "conv3x3 + fused 1x1 shortcut")
+
+
 def check_geglu(M=512, Kd=320, inner=1280, n_keep=1000, bn=256, seed=0):
     """Packed rows interleave [bn/2 h | bn/2 g] per tile; output = h * gelu(g) compacted."""
     a = _rand(M, Kd, seed=seed).bfloat16()
@@ -558,6 +579,8 @@ ALL = [
     ("conv3x3_64", lambda: check_conv3x3(B=2, H=64, W=64, Cin=64, Cout=64, bn=64)),
     ("conv3x3_8_border", lambda: check_conv3x3(B=5, H=8, W=8, Cin=192, Cout=160, bn=160, border=True)),
     ("conv3x3_32", lambda: check_conv3x3(B=1, H=32, W=32, Cin=320, Cout=320, bn=160)),
+    ("conv3x3_fused_shortcut", check_conv3x3_fused_shortcut),
+    ("conv3x3_fused_shortcut_ragged", lambda: check_conv3x3_fused_shortcut(B=1, H=16, W=16, Cin=640, Cout=608, C2=1920, bn=224)),
     ("conv3x3_s2_16", lambda: check_conv3x3(stride=2, temb=False)),
     ("conv3x3_s2_64", lambda: check_conv3x3(B=2, H=64, W=64, Cin=64, Cout=64, bn=64, stride=2, temb=False)),
     ("geglu", check_geglu),
