@@ -362,17 +362,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             pk[i >> 1] = pack_bf16(p0, p1);
           }
         };
-        auto max_chunk = [&](int c) {
+        // After the first key tile the row max itself is NOT tracked per tile: the exponentials run against the stale max
+        // and the tile's own row sum tells whether that was safe -- sum(p) <= 2^8 implies every p <= 2^8, the same bound
+        // the explicit max test gave. Only when the sum exceeds it (or is not finite) is the max computed (S is still in
+        // registers) and the tile redone. This takes 64 FMNMX3 per row and tile out of a loop whose XU pipe idles
+        // whenever both softmax warps of a scheduler are outside their exponentials.
+        auto mask_chunk = [&](int c) {
           if constexpr (decltype(ragged)::value) {  // ragged last key tile: -inf -> p = 0
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= kv_left) s[c * 32 + i] = 0xff800000u;
           }
+        };
+        auto max_only = [&](int c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             mx0 = fmaxf(mx0, __uint_as_float(s[c * 32 + i]));
             mx1 = fmaxf(mx1, __uint_as_float(s[c * 32 + i + 1]));
           }
+        };
+        auto max_chunk = [&](int c) {
+          mask_chunk(c);
+#ifdef ATT_TRACK_MAX
+          max_only(c);
+#else
+          if (!optimistic) max_only(c);
+#endif
         };
         uint32_t pk0[16], pk1[16];
         max_chunk(0);
@@ -406,12 +421,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
             }
           }
         }
-        const float m_cand = fmaxf(mx0, mx1) * p.scale_log2;
-        const bool need = m_cand > m_used + ATT_RESCALE_LOG2;  // first tile: m_used = -inf
+#ifdef ATT_TRACK_MAX
+        const bool need = fmaxf(mx0, mx1) * p.scale_log2 > m_used + ATT_RESCALE_LOG2;  // first tile: m_used = -inf
+#else
+        bool need = true;  // first tile: the max is known, nothing has been exponentiated yet
+        if (optimistic) {
+          float l0, l1;
+          unpack_f32x2(lsum, l0, l1);
+          need = !(l0 + l1 <= 256.f);  // (also true for inf / nan)
+        }
+#endif
         if (__any_sync(0xffffffffu, need)) {
           // rare after the first tile: the running max grew by more than 2^8. Rescale O and redo this tile's
           // exponentials against the new max (S is still in registers, P has not been handed to the MMA yet).
-          const float m_new = need ? m_cand : m_used;
+#ifndef ATT_TRACK_MAX
+          if (optimistic) {
+#pragma unroll
+            for (int c = 0; c < ATT_BN / 32; ++c)
+              if (c < nch) max_only(c);
+          }
+#endif
+          const float m_cand = fmaxf(mx0, mx1) * p.scale_log2;
+          const float m_new = need ? fmaxf(m_cand, m_used) : m_used;
           if (j > 0) {
             const float factor = need ? ex2_approx(m_used - m_new) : 1.f;
             uint32_t o[ATT_D];
