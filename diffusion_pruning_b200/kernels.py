@@ -96,6 +96,7 @@ class _Stager:
         self.buf = None
         self.cap = nbytes
         self.off = 0
+        self.slabs = {}
 
     def upload(self, arr: np.ndarray, device) -> torch.Tensor:
         device = torch.device(device)
@@ -113,9 +114,23 @@ class _Stager:
         view = self.buf[self.off:self.off + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
         self.off += n
         view.copy_(t)
-        dev = torch.empty(t.shape, dtype=t.dtype, device=device)
+        dev = self._device_view(t, n, device)
         dev.copy_(view, non_blocking=True)
         return dev
+
+    def _device_view(self, t: torch.Tensor, n: int, device) -> torch.Tensor:
+        """Device memory for one uploaded array, carved out of a 4 MB slab: a forward for a new assignment uploads ~500
+        arrays of a few hundred bytes, and 500 separate allocations mean cudaMalloc calls of new small-pool segments in
+        the middle of an asynchronously queued forward (each waits for the GPU: 3 - 250 ms per re-structuring, measured).
+        The views keep their slab alive; it is freed when the schedules of an evicted state die."""
+        key = (device.type, device.index)
+        slab = self.slabs.get(key)
+        if slab is None or slab[1] + n > slab[0].numel():
+            slab = [torch.empty(4 << 20, dtype=torch.uint8, device=device), 0]
+            self.slabs[key] = slab
+        off = slab[1]
+        slab[1] = off + (n + 255) // 256 * 256
+        return slab[0][off:off + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
 
 
 _STAGER = _Stager()
