@@ -847,7 +847,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       };
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.bn);
 
-#ifdef APTP_DBG_NOEPI
+#ifdef APTP_DBG_NOEPI  // kernel-tuning build (tools/build_variant.sh): main loop alone, no epilogue work at all
       if (p.n_tiles < 0)
 #endif
       for (int c = c_first; c < n_chunks; c += EPI_PER_QUAD) {
@@ -1012,7 +1012,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
                 make_float2(s0 + s1, q0 + q1);
           }
           // own row -> swizzled smem
-#ifdef APTP_DBG_NOSTAGE
+#ifdef APTP_DBG_NOSTAGE  // kernel-tuning build: TMEM reads + epilogue math, but no staging and no stores
           if (v[0] == 1.2345e30f) p.abort_flag[1] = 1;
           if (p.n_tiles >= 0) continue;
 #endif
@@ -1043,7 +1043,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
             const int rl = it * 8 + (lane >> 2);
             o4[it] = stg4[rl * 4 + (co_q ^ ((rl >> 1) & 3))];
           }
-#ifdef APTP_DBG_NOSTORE
+#ifdef APTP_DBG_NOSTORE  // kernel-tuning build: everything but the global stores of the bf16 path
           if (o4[0].x == 0x12345678u && o4[1].y == 0x9abcdef0u && o4[2].z == 0x0fedcba9u && o4[3].w == 0x87654321u)
 #endif
 #pragma unroll
