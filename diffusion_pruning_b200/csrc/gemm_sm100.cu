@@ -730,7 +730,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       const bool rows_full = bf16_out && p.out_tma && !placeholder && row0_q >= seg.row_begin && row0_q + 32 <= seg.row_end;
       // GroupNorm partial statistics: row of the partial planes this (tile, quadrant) owns
       long long gn_row = -1;
-      if (kEpi == EPI_F32 && p.gn_sum != nullptr && !placeholder) {
+      if ((kEpi == EPI_F32 || kEpi == EPI_BF16) && p.gn_sum != nullptr && !placeholder) {
         const int smp = tile.m_base / p.rows_per_sample;
         const int rem = tile.m_base - smp * p.rows_per_sample;
         int t_in_s;
@@ -1049,6 +1049,44 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int it = 0; it < 4; ++it)
             if (co_ok[it] && col_ok) *reinterpret_cast<uint4*>(obase + (size_t)co_row[it] * p.out_ld) = o4[it];
+          if constexpr (kEpi == EPI_BF16) {
+            if (gn_row >= 0) {
+              // column sums of the STORED (bf16-rounded) values over the 32 rows of this quadrant: 4 rows x 8 columns in
+              // registers, then a fixed butterfly over the 8 lanes that share the column unit (lane bits 2..4)
+              float cs[8], cq[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) cs[e] = cq[e] = 0.f;
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                if (co_ok[it]) {
+                  const uint32_t wds[4] = {o4[it].x, o4[it].y, o4[it].z, o4[it].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float f0 = bf16_lo(wds[e]), f1 = bf16_hi(wds[e]);
+                    cs[2 * e] += f0;
+                    cs[2 * e + 1] += f1;
+                    cq[2 * e] = fmaf(f0, f0, cq[2 * e]);
+                    cq[2 * e + 1] = fmaf(f1, f1, cq[2 * e + 1]);
+                  }
+                }
+              }
+#pragma unroll
+              for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], o);
+                  cq[e] += __shfl_xor_sync(0xffffffffu, cq[e], o);
+                }
+              }
+              if (lane < 4 && col_ok) {
+                const long long gi = gn_row + seg.out_col_off + col0 + co_q * 8;
+                *reinterpret_cast<float4*>(p.gn_sum + gi) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+                *reinterpret_cast<float4*>(p.gn_sum + gi + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+                *reinterpret_cast<float4*>(p.gn_sq + gi) = make_float4(cq[0], cq[1], cq[2], cq[3]);
+                *reinterpret_cast<float4*>(p.gn_sq + gi + 4) = make_float4(cq[4], cq[5], cq[6], cq[7]);
+              }
+            }
+          }
           __syncwarp();
         } else if constexpr (f32_rows) {
           uint4* stg4 = reinterpret_cast<uint4*>(stg);
@@ -1260,8 +1298,9 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
                  "aptp_grouped_gemm_fwd: a bf16 residual needs a bf16 output and res_ld %% 8 == 0");
   APTP_REQUIRE(a->a_rows < (1ll << 31), "aptp_grouped_gemm_fwd: too many rows");
   if (a->flags & APTP_EPI_GN_STATS) {
-    APTP_REQUIRE(a->gn_stats && a->gn_stats_sq && a->out_mode == APTP_OUT_F32 && !(a->flags & APTP_EPI_GEGLU),
-                 "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS needs both partial planes and an fp32 row output");
+    APTP_REQUIRE(a->gn_stats && a->gn_stats_sq && (a->out_mode == APTP_OUT_F32 || a->out_mode == APTP_OUT_BF16) &&
+                     !(a->flags & APTP_EPI_GEGLU),
+                 "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS needs both partial planes and a row output (fp32 or bf16)");
     APTP_REQUIRE(a->rows_per_sample % 128 == 0 && a->gn_blocks == a->rows_per_sample / 32 && a->gn_ld % 4 == 0,
                  "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS needs rows_per_sample %% 128 == 0, gn_blocks = rows_per_sample / 32");
     APTP_REQUIRE(a->a_mode == APTP_A_LINEAR || a->bb == 1, "aptp_grouped_gemm_fwd: APTP_EPI_GN_STATS needs conv boxes inside one image");
@@ -1384,7 +1423,7 @@ extern "C" int aptp_grouped_gemm_fwd(const aptp_gemm_args* a, void* stream_) {
       const char* e = getenv("APTP_GEMM_TMA_STORE");
       tma_store = !(e && e[0] == '0');
     }
-    if (tma_store && a->a_mode == APTP_A_LINEAR && a->out_mode == APTP_OUT_BF16 &&
+    if (tma_store && a->a_mode == APTP_A_LINEAR && a->out_mode == APTP_OUT_BF16 && !(a->flags & APTP_EPI_GN_STATS) &&
         (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) {
       const uint64_t out_cols = (uint64_t)a->out_ld;  // columns addressable in a row (segments write disjoint column ranges)
       int rc = make_tmap_store64(&p.tmap_out, a->out, false, out_cols, (uint64_t)a->a_rows, (uint64_t)a->out_ld * 2);

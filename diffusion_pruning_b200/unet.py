@@ -1376,14 +1376,21 @@ class _Engine:
             return K.build_schedule(segs, bn, self.device, mode=A_CONV3X3, Ho=H, Wo=W)
         sched = self._sched(("res_c1", r.uid, H, W), build_c1)
         rv = self.temb_rowvec[:, self.m._temb_off[r.uid]:]
+        # norm2's statistics (of the bf16 values conv1 stores) come from conv1's epilogue too: no statistics pass over h1
+        cs_h1 = None
+        if (self.gn_epi and hw % 128 == 0 and K.conv_box(W, H)[2] == 1
+                and os.environ.get("APTP_GN_EPI_BF16", "1") != "0"):
+            nblk = B * (hw // 32)
+            cs_h1 = (self.buf("cs_h1_sum", nblk, r.cout, torch.float32), self.buf("cs_h1_sq", nblk, r.cout, torch.float32))
         self._gemm(sched, a1, pk["w1"], h1, a_ld=r.cin, a_k=r.cin, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W,
-                   k_tap_pitch=r.cin, out_ld=r.cout, rowvec=rv, rowvec_ld=self.m._temb_total, rows_per_sample=hw)
+                   k_tap_pitch=r.cin, out_ld=r.cout, rowvec=rv, rowvec_ld=self.m._temb_total, rows_per_sample=hw,
+                   colstat=cs_h1)
         # width gate (soft: fused multiplier) + norm2 + SiLU on the compacted tensor
         a2 = self.buf("gn_b", M, r.cout)
         gate = self._soft_gate(cidx["w"][0]) if not self.compact else None
         self.groupnorm(h1, r.cout, r.cout, B, hw, r.groups, gs, r.eps, pk["gamma2"], pk["beta2"], r.cout, a2, r.cout,
                        True, sample_seg=aux.get("seg_mid"),
-                       sample_channels=aux.get("ch_mid"), gate=gate, alg_elems=el_mid)
+                       sample_channels=aux.get("ch_mid"), gate=gate, alg_elems=el_mid, cs0=cs_h1)
         # shortcut: 1x1 conv over the bf16 copy of the (concatenated) input, written fp32 and added in place by conv2
         out = torch.empty(M, r.cout, device=self.device, dtype=torch.float32)
         # ... unless conv2 can take it as extra K steps of its own tiles (halo-mode convs: 8 x 16-pixel boxes, 2-SM scheme)

@@ -144,6 +144,11 @@ def grouped_gemm(a, w, out, sched, *, a_ld, a_k, a_rows, mode=A_LINEAR, batch=1,
         if out_mode == OUT_BF16:
             O = _view(out, re, out_ld, out_ld)
             O[rb:re, oco:oco + nst] = acc[:, :nst].to(torch.bfloat16)
+            if colstat is not None:  # statistics of the STORED (bf16-rounded) values
+                assert rows_per_sample % 128 == 0 and rb % rows_per_sample == 0
+                a32 = acc[:, :nst].to(torch.bfloat16).float().reshape((re - rb) // 32, 32, nst)
+                colstat[0][rb // 32: re // 32, oco:oco + nst] = a32.sum(1)
+                colstat[1][rb // 32: re // 32, oco:oco + nst] = (a32 * a32).sum(1)
             if rowstat_out is not None:  # per-row (sum, sumsq) per 32-column chunk of the stored values
                 assert oco % 32 == 0 and nst % 32 == 0
                 a32 = acc[:, :nst].reshape(re - rb, nst // 32, 32)

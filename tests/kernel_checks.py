@@ -478,6 +478,28 @@ def check_gemm_ln_fold(geglu=False, seed=0):
         _close(out, hg[:, :inner] * F.gelu(hg[:, inner:]), 5e-2, 3e-2, "ln-fold geglu")
 
 
+def check_conv_colstat_bf16(B=2, H=32, W=32, Cin=320, Cout=288, bn=160, seed=0):
+    """APTP_EPI_GN_STATS on a bf16 conv output (ResNet conv1 -> norm2): the partial planes hold the column sums of the
+    STORED (bf16-rounded) values; halo-tile boxes (8 x 16), ragged last column tile."""
+    hw, M = H * W, B * H * W
+    x = _rand(B, Cin, H, W, seed=seed).bfloat16()
+    a = x.permute(0, 2, 3, 1).reshape(M, Cin).contiguous()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=seed + 1).bfloat16()
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    b = _rand(Cout, seed=seed + 2)
+    out = torch.full((M, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    cs = (torch.full((M // 32, Cout), float("nan"), device=DEV), torch.full((M // 32, Cout), float("nan"), device=DEV))
+    sched = K.build_schedule([K.Segment(0, M, Cout, Cin // 64)], bn, DEV, mode=A_CONV3X3, Ho=H, Wo=W)
+    K.grouped_gemm(a, wp, out, sched, a_ld=Cin, a_k=Cin, a_rows=M, mode=A_CONV3X3, batch=B, H=H, W=W, k_tap_pitch=Cin,
+                   out_ld=Cout, bias=b, rows_per_sample=hw, colstat=cs)
+    K.check_abort()
+    ref = _conv_ref(x.float(), w.float(), b, 1).permute(0, 2, 3, 1).reshape(M, Cout)
+    _close(out, ref, 2e-2, 1e-2, "conv3x3 bf16 with column statistics")
+    o3 = out.float().reshape(B, hw, Cout)
+    _close(cs[0].reshape(B, hw // 32, Cout).sum(1), o3.sum(1), 2e-3, 1e-4, "bf16 column sums")
+    _close(cs[1].reshape(B, hw // 32, Cout).sum(1), (o3 * o3).sum(1), 2e-3, 1e-4, "bf16 column sums of squares")
+
+
 def check_gemm_colstat(conv=False, seed=0):
     """APTP_EPI_GN_STATS: per-channel (sum, sumsq) partials of the fp32 output gathered in the GEMM epilogue, then reduced
     per (sample, group) by aptp_groupnorm_stats_from_partials -- vs torch on the stored output (two-source cat case too)."""
@@ -603,6 +625,8 @@ ALL = [
     ("gemm_res_f32", check_gemm_res_f32),
     ("gemm_colstat", check_gemm_colstat),
     ("conv_colstat", lambda: check_gemm_colstat(conv=True)),
+    ("conv_colstat_bf16", check_conv_colstat_bf16),
+    ("conv_colstat_bf16_8x8box", lambda: check_conv_colstat_bf16(B=3, H=16, W=8, Cin=128, Cout=160, bn=160)),
     ("gemm_ln_fold", check_gemm_ln_fold),
     ("gemm_ln_fold_geglu", lambda: check_gemm_ln_fold(geglu=True)),
     ("conv_res_f32", lambda: check_gemm_res_f32(conv=True)),
