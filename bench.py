@@ -240,19 +240,28 @@ def run_ours(args):
     ms_e2e_dev = timed(step_e2e, args.steps)
     ms_e2e = ms_e2e_dev
     # per-kernel timing of the dominant kernel, live, with CUDA events on the launching stream
-    eng.profile = []
-    step_resident()
-    torch.cuda.synchronize()
-    prof = eng.profile
+    # (eager launches, each bracketed by two events. The GPU is first parked on a spin kernel so that the host has queued the
+    # whole forward before the first kernel runs -- otherwise an event pair also times the host's launch latency whenever
+    # the GPU catches up with the launching thread -- and every launch takes the median of three such passes.)
+    passes = []
+    for _ in range(3):
+        eng.profile = []
+        torch.cuda._sleep(int(60e6))  # ~35 ms at 1.7 GHz
+        step_resident()
+        torch.cuda.synchronize()
+        passes.append(eng.profile)
     eng.profile = None
+    prof = []
+    for i, (kind, a, b, fl, label) in enumerate(passes[0]):
+        ms = sorted(p_[i][1].elapsed_time(p_[i][2]) for p_ in passes)[1]
+        prof.append((kind, ms, fl, label))
     if os.environ.get("APTP_PROFILE_DUMP") and rank == 0:
         with open(os.environ["APTP_PROFILE_DUMP"], "w") as f:
-            for kind, a, b, fl, label in prof:
-                ms = a.elapsed_time(b)
+            for kind, ms, fl, label in prof:
                 f.write(f"{kind}\t{ms:.4f}\t{fl / 1e9:.2f}\t{fl / max(ms, 1e-6) / 1e9:.1f}\t{label}\n")
-    gemm = [(a.elapsed_time(b), fl) for kind, a, b, fl, _ in prof if kind == "gemm" and fl > 0]
-    attn = [(a.elapsed_time(b), fl) for kind, a, b, fl, _ in prof if kind == "attn"]
-    hbm = [(a.elapsed_time(b), nb) for kind, a, b, nb, _ in prof if kind == "hbm"]
+    gemm = [(ms, fl) for kind, ms, fl, _ in prof if kind == "gemm" and fl > 0]
+    attn = [(ms, fl) for kind, ms, fl, _ in prof if kind == "attn"]
+    hbm = [(ms, nb) for kind, ms, nb, _ in prof if kind == "hbm"]
     g_ms, g_fl = sum(x for x, _ in gemm), sum(f for _, f in gemm)
     a_ms, a_fl = sum(x for x, _ in attn), sum(f for _, f in attn)
     h_ms, h_bytes = sum(x for x, _ in hbm), sum(b for _, b in hbm)
