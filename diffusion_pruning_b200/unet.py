@@ -1394,7 +1394,8 @@ class _Engine:
         # shortcut: 1x1 conv over the bf16 copy of the (concatenated) input, written fp32 and added in place by conv2
         out = torch.empty(M, r.cout, device=self.device, dtype=torch.float32)
         # ... unless conv2 can take it as extra K steps of its own tiles (halo-mode convs: 8 x 16-pixel boxes, 2-SM scheme)
-        fuse_sc = (r.conv_shortcut is not None and W % 8 == 0 and H % 16 == 0 and 9 * r.cout >= 1280
+        fuse_sc = (r.conv_shortcut is not None and W % 8 == 0 and H % 16 == 0
+                   and 9 * r.cout >= int(os.environ.get("APTP_GEMM_2SM_MINK", "1280") or 1280)
                    and os.environ.get("APTP_SC_FUSE", "1") != "0" and os.environ.get("APTP_CONV_HALO", "1") != "0"
                    and os.environ.get("APTP_GEMM_1SM", "0") != "1")
         sc_kw = {}
