@@ -101,14 +101,18 @@ constexpr int HALO_BYTES = HALO_W * HALO_H * 128;         // 36 KB per 64-channe
 // Accumulator columns the MMAs of a tile compute: the LAST column tile of a bucket is ragged (kept widths are not
 // multiples of bn), so its MMAs run with N = the 32-column-rounded remainder instead of bn -- tensor time and operand reads
 // shrink with it (the weight box is still loaded whole). GEGLU tiles keep bn (their [h | g] halves sit at fixed columns).
-__device__ __forceinline__ int tile_mma_n(const aptp_gemm_seg& seg, int n0, int bn, bool geglu) {
+// The host may also give a bucket narrower, BALANCED tiles (tile flags bits 8..15 = width / 32: 320 columns under bn = 224
+// become 160 + 160 instead of 224 + 96 -- a 96-wide MMA moves the whole A tile for a third of the work).
+__device__ __forceinline__ int tile_mma_n(const aptp_gemm_seg& seg, int n0, int bn, bool geglu, int tflags) {
 #ifdef APTP_NO_RAGGED_N
   return bn;
 #else
   if (geglu) return bn;
+  const int w32 = (tflags >> 8) & 0xFF;
+  const int width = w32 ? w32 * 32 : bn;
   const int n_cols = seg.n_valid > seg.n_store ? seg.n_valid : seg.n_store;
   const int left = (n_cols - n0 + 31) & ~31;
-  return left < bn ? (left < 32 ? 32 : left) : bn;
+  return left < width ? (left < 32 ? 32 : left) : width;
 #endif
 }
 
@@ -384,7 +388,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
         // this CTA's half of the weight tile (2-SM: half of the columns the tile's MMAs really compute)
         const int b_row = seg.w_row_off + tile.n0 +
-                          (int)cta_rank * ((k2Sm ? tile_mma_n(seg, tile.n0, p.bn, kGeglu) : p.bn) >> 1);
+                          (int)cta_rank * ((k2Sm ? tile_mma_n(seg, tile.n0, p.bn, kGeglu, tile.flags) : p.bn) >> 1);
         if constexpr (k2Sm) {
           if (p.halo) {
             for (int kc = 0; kc < seg.k_chunks && ok; ++kc) {
@@ -416,7 +420,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
               }
             }
             // the 1x1 shortcut's K steps: plain box of the second tensor into the next A slot, W2 rows = output columns
-            const int b2_row = tile.n0 + (int)cta_rank * (tile_mma_n(seg, tile.n0, p.bn, kGeglu) >> 1);
+            const int b2_row = tile.n0 + (int)cta_rank * (tile_mma_n(seg, tile.n0, p.bn, kGeglu, tile.flags) >> 1);
             for (int kc = 0; kc < p.k2_chunks && ok; ++kc) {
               if (!mbar_wait(&aempty_bar[aslot], aphase ^ 1, p.abort_flag) ||
                   !mbar_wait(&empty_bar[stage], phase ^ 1, p.abort_flag)) {
@@ -515,7 +519,7 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int tflags = __shfl_sync(0xffffffffu, trec->flags, 0);
         if (tflags & APTP_TILE_SKIP) continue;
         const int k_chunks = __shfl_sync(0xffffffffu, segs[seg_id].k_chunks, 0);
-        const int n_mma = __shfl_sync(0xffffffffu, tile_mma_n(segs[seg_id], trec->n0, p.bn, kGeglu), 0);
+        const int n_mma = __shfl_sync(0xffffffffu, tile_mma_n(segs[seg_id], trec->n0, p.bn, kGeglu, tflags), 0);
         const uint32_t idesc = make_idesc_bf16(k2Sm ? 2 * BM : BM, (uint32_t)n_mma, 0, 0);
         const int kblocks = ((p.a_mode == APTP_A_LINEAR) ? 1 : 9) * k_chunks;
         if (!TRACE_WAIT(3, mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.abort_flag))) break;
@@ -679,7 +683,6 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr bool geglu = kGeglu;
-    const int out_cols_per_tile = geglu ? p.bn / 2 : p.bn;
     constexpr bool bf16_out = (kEpi == EPI_BF16 || kEpi == EPI_GEGLU);
     int ti = 0;
     bool st_pending = false;
@@ -780,6 +783,8 @@ grouped_gemm_kernel(const __grid_constant__ GemmParams p) {
       };
       // this tile's chunks are dealt round-robin to the EPI_PER_QUAD warps of the quadrant, continuing where the
       // previous tile stopped, so tiles whose chunk count is not a multiple of EPI_PER_QUAD still balance
+      const int w32_tile = (tile.flags >> 8) & 0xFF;  // balanced tiles: narrower than bn
+      const int out_cols_per_tile = geglu ? p.bn / 2 : (w32_tile ? w32_tile * 32 : p.bn);
       const int n_chunks = (out_cols_per_tile + 31) >> 5;
       const int c_first = (cpar + EPI_PER_QUAD - (int)(chunk_rot % EPI_PER_QUAD)) % EPI_PER_QUAD;
       chunk_rot += (uint32_t)n_chunks;

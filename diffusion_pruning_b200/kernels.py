@@ -201,14 +201,21 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
         mb = np.concatenate([m_bases, m_bases[-1:]]) if odd else m_bases
         n_pairs = len(mb) // 2
         m_pair = mb.reshape(n_pairs, 2)                                        # [pair, which]
-        n0 = (np.arange(n_tiles_n, dtype=np.int64) * bn)                       # [nt]
+        # column tiles of a bucket are BALANCED: N = 320 under bn = 224 becomes 160 + 160 rather than 224 + 96 (a narrow
+        # ragged tile moves the whole A tile through shared memory for a fraction of the work); width in flags bits 8..15
+        width, wflag = bn, 0
+        if not geglu and os.environ.get("APTP_BALANCED_TILES", "1") != "0":
+            ncols = max(s.n_valid, n_store)
+            width = min(bn, ((ncols + n_tiles_n - 1) // n_tiles_n + 31) // 32 * 32)
+            wflag = (width // 32) << 8 if width != bn else 0
+        n0 = (np.arange(n_tiles_n, dtype=np.int64) * width)                    # [nt]
         blk = np.empty((n_pairs, n_tiles_n, 2, 4), dtype=np.int32)
         blk[..., 0] = si
         blk[..., 1] = m_pair[:, None, :]
         blk[..., 2] = n0[None, :, None]
-        blk[..., 3] = 0
+        blk[..., 3] = wflag
         if odd:
-            blk[n_pairs - 1, :, 1, 3] = TILE_PLACEHOLDER
+            blk[n_pairs - 1, :, 1, 3] |= TILE_PLACEHOLDER
         # segments over the SAME rows (the q | k | v blocks of one expert bucket) share their A row tiles: their N tiles
         # are walked back to back per pair of row tiles, so A is fetched from DRAM once instead of once per block
         key = (s.row_begin, s.row_end) if mode == A_LINEAR else None

@@ -60,12 +60,17 @@ def choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False, 
         for n in n_values:
             if n <= 0:
                 continue
-            full, rem = divmod(n, cols)
             w_box = bn / 2.0 if two_sm else float(bn)
-            cost += full * (a_write + w_box + 128.0 + bn)
-            if rem:
-                n_mma = bn if geglu else min(bn, (rem + 31) // 32 * 32)
-                cost += a_write + w_box + 128.0 + n_mma
+            if geglu or os.environ.get("APTP_BALANCED_TILES", "1") == "0":
+                full, rem = divmod(n, cols)
+                cost += full * (a_write + w_box + 128.0 + bn)
+                if rem:
+                    n_mma = bn if geglu else min(bn, (rem + 31) // 32 * 32)
+                    cost += a_write + w_box + 128.0 + n_mma
+            else:  # balanced column tiles (kernels.build_schedule): nt tiles of the 32-rounded N / nt
+                nt = (n + bn - 1) // bn
+                width = min(bn, ((n + nt - 1) // nt + 31) // 32 * 32)
+                cost += nt * (a_write + w_box + 128.0 + width)
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = bn, cost
     return best or 128

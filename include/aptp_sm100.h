@@ -61,7 +61,8 @@ typedef struct aptp_gemm_tile {
   int32_t seg;    /* index into segs                                                              */
   int32_t m_base; /* linear: first row; conv: linear index of the top-left output pixel of the box */
   int32_t n0;     /* first packed weight row / accumulator column block of this tile              */
-  int32_t flags;  /* APTP_TILE_*                                                                   */
+  int32_t flags;  /* APTP_TILE_* in bits 0..7; bits 8..15: tile width / 32 when the bucket's column tiles are
+                     narrower than bn (balanced tiles; 0 = bn wide; not for GEGLU)                 */
 } aptp_gemm_tile;
 /* Tiles are consumed in PAIRS by a cluster of two CTAs that share (multicast) the weight tile: n_tiles is
  * even and tiles[2i], tiles[2i+1] have the same seg and n0 and different m_base. A bucket with an odd

@@ -32,7 +32,10 @@ def _check_tiles(sched: K.Schedule, mode, Ho, Wo, geglu):
         if len(mine) == 0:
             continue
         nt = (max(nv, ns) + cols - 1) // cols
-        assert set(mine[:, 2].tolist()) == {i * sched.bn for i in range(nt)}
+        w32 = int(mine[0, 3] >> 8) & 0xFF
+        width = w32 * 32 if w32 else sched.bn  # balanced tiles: narrower than bn, same count
+        assert width <= sched.bn and nt * (width // 2 if geglu else width) >= max(nv, ns)
+        assert set(mine[:, 2].tolist()) == {i * width for i in range(nt)}
         covered = np.zeros(re - rb, dtype=np.int32)
         for m in np.unique(mine[:, 1]):
             if mode == A_LINEAR:

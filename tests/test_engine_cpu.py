@@ -117,7 +117,7 @@ def test_a_stationary_tile_layout(monkeypatch):
                 assert open_run is None
                 open_run, exp_n0 = key, 0
             assert open_run == key and int(e[0, 2]) == exp_n0
-            exp_n0 += 128
+            exp_n0 += ((f >> 8) & 0xFF) * 32 or 128   # balanced tiles carry their width in flags bits 8..15
             seen[(key, int(e[0, 2]), int(e[1, 1]), int(e[1, 3]) & 1)] = seen.get((key, int(e[0, 2])), 0) + 1
             if f & KK.TILE_A_LAST:
                 open_run = None

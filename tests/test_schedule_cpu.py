@@ -9,12 +9,14 @@ from diffusion_pruning_b200 import plan as P
 from diffusion_pruning_b200._lib import A_CONV3X3, A_CONV3X3_S2, A_LINEAR
 
 
-def tile_mma_n(n_valid, n_store, n0, bn, geglu=False):
+def tile_mma_n(n_valid, n_store, n0, bn, geglu=False, flags=0):
     """Accumulator columns the MMAs of a tile compute (csrc/gemm_sm100.cu: tile_mma_n)."""
     if geglu:
         return bn
+    w32 = (flags >> 8) & 0xFF
+    width = w32 * 32 if w32 else bn
     left = (max(n_valid, n_store) - n0 + 31) // 32 * 32
-    return bn if left >= bn else max(left, 32)
+    return width if left >= width else max(left, 32)
 
 
 @pytest.mark.parametrize("geglu", [False, True])
@@ -36,7 +38,7 @@ def test_choose_bn_returns_a_legal_width_and_covers_every_column(geglu):
 
 
 def test_choose_bn_prefers_wide_tiles_when_the_remainder_is_cheap():
-    # N = 960 at K = 320: three 256-wide tiles + a ragged 192-wide one move less shared-memory traffic than 7.5 x 128
+    # N = 960 at K = 320: four (balanced) 256-wide tiles move less shared-memory traffic than 7.5 x 128
     assert P.choose_bn([960], k=320) == 256
     # N = 320 has no cheap split into 256 + 64: two 160-wide tiles
     assert P.choose_bn([320], k=320) == 160
@@ -69,6 +71,26 @@ def test_stride1_convs_take_halo_boxes_where_the_image_allows(H, W, expect, monk
     monkeypatch.setenv("APTP_CONV_HALO", "0")
     s0 = K.build_schedule([K.Segment(0, 2 * H * W, 64, 1)], 64, "cpu", mode=A_CONV3X3, Ho=H, Wo=W)
     assert s0.box == K.conv_box(W, H)
+
+
+def test_buckets_get_balanced_column_tiles(monkeypatch):
+    """N = 320 under bn = 224 -> 160 + 160 (width in flags bits 8..15), N = 192 -> one 192-wide tile; the MMAs of every tile
+    cover exactly the bucket's columns."""
+    monkeypatch.delenv("APTP_BALANCED_TILES", raising=False)
+    segs = [K.Segment(0, 256, 320, 5), K.Segment(256, 512, 192, 5, w_row_off=320), K.Segment(512, 768, 224, 5, w_row_off=640)]
+    s = K.build_schedule(segs, 224, "cpu", mode=A_LINEAR)
+    t = s.tiles.numpy()
+    for si, n in enumerate((320, 192, 224)):
+        mine = t[t[:, 0] == si]
+        n0s = sorted(set(mine[:, 2].tolist()))
+        widths = [tile_mma_n(n, n, n0, 224, flags=int(mine[0, 3])) for n0 in n0s]
+        assert sum(widths) >= n and all(w % 32 == 0 for w in widths)
+        assert [a + w for a, w in zip(n0s[:-1], widths[:-1])] == n0s[1:]   # tiles abut
+    assert sorted(set(t[t[:, 0] == 0][:, 2].tolist())) == [0, 160]
+    assert sorted(set(t[t[:, 0] == 1][:, 2].tolist())) == [0]
+    monkeypatch.setenv("APTP_BALANCED_TILES", "0")
+    s0 = K.build_schedule(segs, 224, "cpu", mode=A_LINEAR)
+    assert sorted(set(s0.tiles.numpy()[s0.tiles.numpy()[:, 0] == 0][:, 2].tolist())) == [0, 224]
 
 
 def test_stride2_convs_keep_the_generic_boxes():
