@@ -257,7 +257,10 @@ def build_schedule(segments: Sequence[Segment], bn: int, device, mode: int = A_L
         a_stat, a_pairs = int(kc_max), int(S)
     else:
         tl = np.concatenate([r.reshape(-1, 4) for r in runs], 0) if runs else np.zeros((0, 4), dtype=np.int32)
-    return Schedule(segs=upload(segs, device), tiles=upload(tl, device),
+    # one upload per schedule: [segs | tiles] as a single int32 array, the two tables are views of it
+    n_seg_words = segs.size
+    both = upload(np.concatenate([segs.reshape(-1), np.ascontiguousarray(tl, dtype=np.int32).reshape(-1)]), device)
+    return Schedule(segs=both[:n_seg_words].view(segs.shape), tiles=both[n_seg_words:].view(-1, 4),
                     n_segs=len(segments), n_tiles=int(tl.shape[0]), bn=bn, box=box, a_stat=a_stat, a_pairs=a_pairs,
                     flops=flops, bytes_in=bytes_in, out_elems=out_elems)
 

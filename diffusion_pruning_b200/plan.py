@@ -29,7 +29,23 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+_BN_CACHE: dict = {}
+
+
 def choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False, k: int = 0) -> int:
+    """Cached front end of _choose_bn (a re-structured forward asks ~170 times, mostly with the same arguments)."""
+    import os
+    key = (tuple(int(n) for n in n_values), multiple, bool(geglu), int(k), os.environ.get("APTP_BN_MODEL"),
+           os.environ.get("APTP_BN_OVERHEAD"), os.environ.get("APTP_BALANCED_TILES"))
+    bn = _BN_CACHE.get(key)
+    if bn is None:
+        if len(_BN_CACHE) > 4096:
+            _BN_CACHE.clear()
+        bn = _BN_CACHE[key] = _choose_bn(n_values, multiple, geglu, k)
+    return bn
+
+
+def _choose_bn(n_values: Sequence[int], multiple: int = 32, geglu: bool = False, k: int = 0) -> int:
     """Accumulator width for one launch from the shared-memory traffic of its tiles (the GEMM main
     loop is bound by the ~128 B/clk the TMA writes and the tensor core's operand reads share). Per K step a 128-row
     tile writes A + the weight box (bn rows; half of it per CTA in the 2-SM scheme, K*taps >= 1280; a quarter of A with
